@@ -1,0 +1,114 @@
+/* openglottal_b200 -- C ABI of the B200-native U-Net-only hot path.
+ *
+ * The reference (hari-krishnan/openglottal, pure Python) has no FFI of its own; its seam for
+ * this path is Python duck typing. Each entry point below names the reference interface it
+ * replaces (paths relative to the reference repository root):
+ *
+ *   ogl_unet_create / ogl_unet_load_state   openglottal/cli.py:61-65
+ *        UNet(1,1,(32,64,128,256)).to(device); load_state_dict(torch.load(...)); eval()
+ *        state-dict layout: openglottal/models/unet.py:18-33,50-72 (118 tensors)
+ *   ogl_unet_forward                        openglottal/models/unet.py:74-88 (UNet.forward)
+ *        + openglottal/utils.py:235-241 (u8/255, sigmoid, > threshold -> {0,255} mask)
+ *        + openglottal/features.py:238 (area = count(mask > 0))
+ *   ogl_features / ogl_features_f64         openglottal/features.py:38-68 (_kinematic_features)
+ *   ogl_bgr_to_gray                         openglottal/features.py:235 (cv2.COLOR_BGR2GRAY)
+ *
+ * Conventions: every function returns 0 on success and non-zero on failure; the message is
+ * available from ogl_last_error() (thread-local). All `*_dev` pointers are device pointers on
+ * the handle's device; the caller owns inputs, outputs and workspaces. Kernels are enqueued
+ * on `stream` (a cudaStream_t passed as void*) and never synchronise the device. There is no
+ * CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef OPENGLOTTAL_B200_H
+#define OPENGLOTTAL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OGL_VERSION 100 /* 0.1.0 */
+
+enum { OGL_DTYPE_U8 = 0, OGL_DTYPE_F32 = 1 };
+/* BF16: bf16 operands on tcgen05 tensor cores, fp32 accumulate (the product path).
+ * F32 : fp32 weights/activations on CUDA cores -- validation mode (logits within 1e-4 of the
+ *       reference); same folding, tiling-independent arithmetic. Not a timed path. */
+enum { OGL_PRECISION_BF16 = 0, OGL_PRECISION_F32 = 1 };
+
+typedef struct ogl_unet ogl_unet;
+
+/* Conv2d(3x3, bias=False) + BatchNorm2d, host pointers into the state dict. */
+typedef struct {
+    const float* weight;       /* [cout][cin][3][3]  "<prefix>.net.{0,3}.weight" */
+    const float* bn_weight;    /* [cout]             "<prefix>.net.{1,4}.weight" */
+    const float* bn_bias;      /* [cout]             "....bias"                  */
+    const float* running_mean; /* [cout]             "....running_mean"          */
+    const float* running_var;  /* [cout]             "....running_var"           */
+} ogl_conv_bn;
+
+/* ConvTranspose2d(2f, f, kernel_size=2, stride=2). */
+typedef struct {
+    const float* weight; /* [cin][cout][2][2]  "ups.{0,2,4,6}.weight" */
+    const float* bias;   /* [cout]             "ups.{0,2,4,6}.bias"   */
+} ogl_convt;
+
+/* The 118-entry state dict of UNet(1,1,(32,64,128,256)) (num_batches_tracked ignored). */
+typedef struct {
+    ogl_conv_bn downs[4][2];   /* downs.i.net.{0,1} / downs.i.net.{3,4}          */
+    ogl_conv_bn bottleneck[2]; /* bottleneck.net.{0,1} / .net.{3,4}              */
+    ogl_convt up_t[4];         /* ups.0, ups.2, ups.4, ups.6                     */
+    ogl_conv_bn up_c[4][2];    /* ups.1, ups.3, ups.5, ups.7  (.net.{0,1}/{3,4}) */
+    const float* head_weight;  /* [1][32][1][1] */
+    const float* head_bias;    /* [1] */
+    float bn_eps;              /* 1e-5 */
+} ogl_unet_state;
+
+int ogl_version(void);
+const char* ogl_last_error(void);
+
+/* Creates a handle bound to CUDA device `device` (fails when there is none). */
+int ogl_unet_create(ogl_unet** out, int device);
+int ogl_unet_destroy(ogl_unet* h);
+
+/* Folds BatchNorm (eval mode) into the convolutions in fp64, keeps an fp32 copy for the
+ * validation path, and packs bf16 tensor-core operands. Host pointers; copies synchronously. */
+int ogl_unet_load_state(ogl_unet* h, const ogl_unet_state* state);
+
+/* Bytes of device workspace ogl_unet_forward needs for n frames of h x w (h, w % 16 == 0). */
+size_t ogl_unet_workspace_bytes(const ogl_unet* h, int n, int height, int width, int precision);
+
+/* UNet forward + sigmoid/threshold + per-frame area for n gray frames [n][height][width]
+ * (u8 in 0..255, or f32 already scaled). Any of logits_dev [n][h][w] f32, mask_dev [n][h][w]
+ * u8 {0,255}, area_dev [n] int32 may be NULL. `threshold` is on the probability (0.5 in the
+ * reference); the kernel compares the fp32 logit against logit(threshold). */
+int ogl_unet_forward(ogl_unet* h, const void* frames_dev, int in_dtype, int n, int height,
+                     int width, void* workspace_dev, size_t workspace_bytes, float* logits_dev,
+                     uint8_t* mask_dev, int32_t* area_dev, float threshold, int precision,
+                     void* stream);
+
+/* Kinematic features of an area waveform of n >= 2 samples.
+ * out8_dev: {area_mean, area_std, area_range, open_quotient, f0, periodicity, cv, peak_bin};
+ * flags2_dev: {is_silent (reference returns None), f0_is_none (peak in first bin)}. */
+size_t ogl_features_workspace_bytes(int64_t n);
+int ogl_features(const int32_t* area_dev, int64_t n, double* out8_dev, int32_t* flags2_dev,
+                 void* workspace_dev, size_t workspace_bytes, void* stream);
+int ogl_features_f64(const double* area_dev, int64_t n, double* out8_dev, int32_t* flags2_dev,
+                     void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* cv2.COLOR_BGR2GRAY on interleaved u8 BGR pixels: (3735 B + 19235 G + 9798 R + 16384) >> 15. */
+int ogl_bgr_to_gray(const uint8_t* bgr_dev, uint8_t* gray_dev, int64_t pixels, void* stream);
+
+/* Unit-test hook: one tensor-core layer on fp32 NCHW device tensors (converted to the bf16
+ * kernel layout internally). kind: 0 conv3x3+bias+ReLU, 1 same + 2x2 max-pool (out_pool_dev),
+ * 3 ConvTranspose2d k2 s2 (+bias). src1_dev/c1 describe the second concat source (or NULL/0).
+ * weight_host is [cout][c0+c1][3][3] (conv) or [c0][cout][2][2] (convT), bias_host [cout]. */
+int ogl_debug_tc_layer(ogl_unet* h, int kind, const float* src0_dev, int c0, const float* src1_dev,
+                       int c1, const float* weight_host, const float* bias_host, int cout, int n,
+                       int height, int width, float* out_dev, float* out_pool_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPENGLOTTAL_B200_H */

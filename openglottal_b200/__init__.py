@@ -1,0 +1,31 @@
+"""openglottal_b200: B200-native drop-in for OpenGlottal's unet-only hot path.
+
+Public names mirror ``openglottal`` (/root/reference/openglottal/__init__.py) for the path
+this package accelerates: ``UNet``, ``extract_features_unet``, ``unet_segment_frame``,
+``_kinematic_features``; plus the batched / sharded entry points.
+"""
+__version__ = "0.1.0"
+
+from .unet import UNet
+from .utils import unet_segment_frame, unet_segment_frames, bgr_to_gray, load_frames_bgr, dice
+from .features import (
+    _kinematic_features,
+    kinematic_features_device,
+    segment_clip,
+    extract_features_unet,
+    extract_features_unet_frames,
+)
+
+__all__ = [
+    "UNet",
+    "unet_segment_frame",
+    "unet_segment_frames",
+    "bgr_to_gray",
+    "load_frames_bgr",
+    "dice",
+    "_kinematic_features",
+    "kinematic_features_device",
+    "segment_clip",
+    "extract_features_unet",
+    "extract_features_unet_frames",
+]

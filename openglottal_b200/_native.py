@@ -1,0 +1,113 @@
+"""ctypes binding of libopenglottal_b200.so (the C ABI in include/openglottal_b200.h).
+
+There is no CPU fallback: if the library is missing or no CUDA device is visible, every compute
+call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+from .build import LIB_PATH
+
+DTYPE_U8, DTYPE_F32 = 0, 1
+PRECISION_BF16, PRECISION_F32 = 0, 1
+
+_c_float_p = C.POINTER(C.c_float)
+
+
+class ConvBN(C.Structure):
+    _fields_ = [
+        ("weight", _c_float_p),
+        ("bn_weight", _c_float_p),
+        ("bn_bias", _c_float_p),
+        ("running_mean", _c_float_p),
+        ("running_var", _c_float_p),
+    ]
+
+
+class ConvT(C.Structure):
+    _fields_ = [("weight", _c_float_p), ("bias", _c_float_p)]
+
+
+class UNetState(C.Structure):
+    _fields_ = [
+        ("downs", (ConvBN * 2) * 4),
+        ("bottleneck", ConvBN * 2),
+        ("up_t", ConvT * 4),
+        ("up_c", (ConvBN * 2) * 4),
+        ("head_weight", _c_float_p),
+        ("head_bias", _c_float_p),
+        ("bn_eps", C.c_float),
+    ]
+
+
+# every symbol include/openglottal_b200.h declares
+EXPORTS = [
+    "ogl_version",
+    "ogl_last_error",
+    "ogl_unet_create",
+    "ogl_unet_destroy",
+    "ogl_unet_load_state",
+    "ogl_unet_workspace_bytes",
+    "ogl_unet_forward",
+    "ogl_features_workspace_bytes",
+    "ogl_features",
+    "ogl_features_f64",
+    "ogl_bgr_to_gray",
+    "ogl_debug_tc_layer",
+]
+
+_lib = None
+
+
+def library_path() -> Path:
+    return LIB_PATH
+
+
+def load() -> C.CDLL:
+    """Load the shared library (built by ``__graft_entry__.build()`` / ``build.build_library``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: run `python -m openglottal_b200.build` (needs nvcc). "
+            "openglottal_b200 has no CPU or PyTorch fallback."
+        )
+    lib = C.CDLL(str(LIB_PATH))
+    vp, i32, i64, sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
+    lib.ogl_version.restype = i32
+    lib.ogl_version.argtypes = []
+    lib.ogl_last_error.restype = C.c_char_p
+    lib.ogl_last_error.argtypes = []
+    lib.ogl_unet_create.restype = i32
+    lib.ogl_unet_create.argtypes = [C.POINTER(vp), i32]
+    lib.ogl_unet_destroy.restype = i32
+    lib.ogl_unet_destroy.argtypes = [vp]
+    lib.ogl_unet_load_state.restype = i32
+    lib.ogl_unet_load_state.argtypes = [vp, C.POINTER(UNetState)]
+    lib.ogl_unet_workspace_bytes.restype = sz
+    lib.ogl_unet_workspace_bytes.argtypes = [vp, i32, i32, i32, i32]
+    lib.ogl_unet_forward.restype = i32
+    lib.ogl_unet_forward.argtypes = [vp, vp, i32, i32, i32, i32, vp, sz, vp, vp, vp, C.c_float,
+                                     i32, vp]
+    lib.ogl_features_workspace_bytes.restype = sz
+    lib.ogl_features_workspace_bytes.argtypes = [i64]
+    lib.ogl_features.restype = i32
+    lib.ogl_features.argtypes = [vp, i64, vp, vp, vp, sz, vp]
+    lib.ogl_features_f64.restype = i32
+    lib.ogl_features_f64.argtypes = [vp, i64, vp, vp, vp, sz, vp]
+    lib.ogl_bgr_to_gray.restype = i32
+    lib.ogl_bgr_to_gray.argtypes = [vp, vp, i64, vp]
+    lib.ogl_debug_tc_layer.restype = i32
+    lib.ogl_debug_tc_layer.argtypes = [vp, i32, vp, i32, vp, i32, _c_float_p, _c_float_p, i32,
+                                       i32, i32, i32, vp, vp, vp]
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().ogl_last_error()
+        raise RuntimeError("openglottal_b200: " + (msg.decode() if msg else f"error {rc}"))

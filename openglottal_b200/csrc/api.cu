@@ -1,0 +1,544 @@
+// C ABI of libopenglottal_b200.so (see include/openglottal_b200.h): handle management,
+// BatchNorm folding + operand packing, and the layer schedule of the U-Net forward
+// (/root/reference/openglottal/models/unet.py:74-88).
+#include "../../include/openglottal_b200.h"
+#include "internal.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace ogl {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+int fail(const std::string& msg) {
+    g_err = msg;
+    return 1;
+}
+int fail_cuda(cudaError_t e, const char* what) {
+    g_err = std::string("CUDA error: ") + cudaGetErrorString(e) + " at " + what;
+    return 1;
+}
+int launch_features_f64(const double* area, int64_t n, double* out8, int32_t* flags2, void* ws,
+                        size_t ws_bytes, cudaStream_t stream);
+
+namespace {
+
+constexpr int kFeat[4] = {32, 64, 128, 256};
+
+struct F32Conv {   // fp32 folded conv3x3 (validation path), PyTorch layout
+    float* w = nullptr;  // [cout][cin][9]
+    float* b = nullptr;  // [cout]
+    int cin = 0, cout = 0;
+};
+struct F32ConvT {
+    float* w = nullptr;  // [cin][cout][2][2]
+    float* b = nullptr;
+    int cin = 0, cout = 0;
+};
+
+__global__ void bgr_to_gray_kernel(const uint8_t* __restrict__ bgr, uint8_t* __restrict__ gray,
+                                   long long pixels) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < pixels;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int b = bgr[3 * i], g = bgr[3 * i + 1], r = bgr[3 * i + 2];
+        gray[i] = static_cast<uint8_t>((3735 * b + 19235 * g + 9798 * r + 16384) >> 15);
+    }
+}
+
+}  // namespace
+}  // namespace ogl
+
+using namespace ogl;
+
+struct ogl_unet {
+    int device = 0;
+    int num_sms = 148;
+    bool loaded = false;
+    // bf16 tensor-core path
+    float* stem_w = nullptr;  // [32][9] folded fp32
+    float* stem_b = nullptr;  // [32]
+    TcLayer down_c2[4];       // downs.i.net.3 (+pool)
+    TcLayer down_c1[4];       // downs.i.net.0 for i = 1..3 (index 0 unused: stem)
+    TcLayer bott[2];
+    TcLayer up_t[4];
+    TcLayer up_c[4][2];
+    float* head_w = nullptr;  // [32] device
+    float head_b = 0.f;
+    // fp32 validation path
+    F32Conv f_down[4][2], f_bott[2], f_up[4][2];
+    F32ConvT f_upt[4];
+    std::vector<void*> allocs;
+};
+
+namespace {
+
+template <typename T>
+int dev_upload(ogl_unet* h, const std::vector<T>& host, T** out) {
+    void* p = nullptr;
+    OGL_CUDA(cudaMalloc(&p, host.size() * sizeof(T)));
+    h->allocs.push_back(p);
+    OGL_CUDA(cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = static_cast<T*>(p);
+    return 0;
+}
+
+void free_all(ogl_unet* h) {
+    for (void* p : h->allocs) cudaFree(p);
+    h->allocs.clear();
+    h->loaded = false;
+}
+
+// eval-mode BatchNorm folded into the preceding bias-free conv, in fp64:
+//   s = gamma / sqrt(var + eps);  W' = W * s[co];  b' = beta - mean * s
+void fold_conv_bn(const ogl_conv_bn& L, int cout, int cin, double eps, std::vector<float>* w,
+                  std::vector<float>* b) {
+    w->resize(static_cast<size_t>(cout) * cin * 9);
+    b->resize(cout);
+    for (int co = 0; co < cout; ++co) {
+        const double s = static_cast<double>(L.bn_weight[co]) /
+                         std::sqrt(static_cast<double>(L.running_var[co]) + eps);
+        (*b)[co] = static_cast<float>(static_cast<double>(L.bn_bias[co]) -
+                                      static_cast<double>(L.running_mean[co]) * s);
+        const size_t base = static_cast<size_t>(co) * cin * 9;
+        for (size_t k = 0; k < static_cast<size_t>(cin) * 9; ++k)
+            (*w)[base + k] = static_cast<float>(static_cast<double>(L.weight[base + k]) * s);
+    }
+}
+
+__nv_bfloat16 to_bf16(float v) { return __float2bfloat16_rn(v); }
+
+// conv3x3 weights [cout][cin][3][3] -> [pass][tap][cin/8][N][8] bf16
+std::vector<__nv_bfloat16> pack_conv(const std::vector<float>& w, int cout, int cin, int N) {
+    const int npass = cout / N, kc = cin / 8;
+    std::vector<__nv_bfloat16> out(static_cast<size_t>(cout) * cin * 9);
+    for (int pass = 0; pass < npass; ++pass)
+        for (int tap = 0; tap < 9; ++tap)
+            for (int c = 0; c < kc; ++c)
+                for (int n = 0; n < N; ++n)
+                    for (int e = 0; e < 8; ++e) {
+                        const int co = pass * N + n, ci = c * 8 + e;
+                        const size_t dst =
+                            ((((static_cast<size_t>(pass) * 9 + tap) * kc + c) * N + n) * 8) + e;
+                        out[dst] = to_bf16(w[(static_cast<size_t>(co) * cin + ci) * 9 + tap]);
+                    }
+    return out;
+}
+
+// convT weights [cin][cout][2][2] -> GEMM columns j = (dy*2+dx)*cout + co, layout
+// [pass][tap=0][cin/8][N][8] bf16
+std::vector<__nv_bfloat16> pack_convt(const float* w, int cin, int cout, int N) {
+    const int ntot = 4 * cout, npass = ntot / N, kc = cin / 8;
+    std::vector<__nv_bfloat16> out(static_cast<size_t>(ntot) * cin);
+    for (int pass = 0; pass < npass; ++pass)
+        for (int c = 0; c < kc; ++c)
+            for (int n = 0; n < N; ++n)
+                for (int e = 0; e < 8; ++e) {
+                    const int j = pass * N + n, q = j / cout, co = j % cout, ci = c * 8 + e;
+                    const size_t dst = (((static_cast<size_t>(pass) * kc + c) * N + n) * 8) + e;
+                    out[dst] = to_bf16(w[(static_cast<size_t>(ci) * cout + co) * 4 + q]);
+                }
+    return out;
+}
+
+int build_tc_conv(ogl_unet* h, const std::vector<float>& w, const std::vector<float>& b, int cin0,
+                  int cin1, int cout, int epi, TcLayer* L) {
+    L->cin0 = cin0;
+    L->cin1 = cin1;
+    L->cout = cout;
+    L->taps = 9;
+    L->N = cout < 128 ? cout : 128;
+    L->npass = cout / L->N;
+    L->epi = epi;
+    if (dev_upload(h, pack_conv(w, cout, cin0 + cin1, L->N), &L->wpack)) return 1;
+    return dev_upload(h, b, &L->bias);
+}
+
+int build_f32_conv(ogl_unet* h, const std::vector<float>& w, const std::vector<float>& b, int cin,
+                   int cout, F32Conv* L) {
+    L->cin = cin;
+    L->cout = cout;
+    if (dev_upload(h, w, &L->w)) return 1;
+    return dev_upload(h, b, &L->b);
+}
+
+int check_conv_bn(const ogl_conv_bn& L) {
+    return (L.weight && L.bn_weight && L.bn_bias && L.running_mean && L.running_var) ? 0 : 1;
+}
+
+// ---- workspace plan: per level T (temp), S (skip), U (up / decoder out); P3, T4, B4 at the
+// bottom. P_l (pooled level l) aliases U_{l+1}, which is only written later by the decoder.
+struct Plan {
+    size_t T[5], S[4], U[4], P3, B4, total;
+};
+Plan make_plan(int n, int H, int W, size_t elem) {
+    Plan p;
+    size_t o = 0;
+    auto take = [&](size_t bytes) {
+        size_t r = o;
+        o += (bytes + 255) & ~static_cast<size_t>(255);
+        return r;
+    };
+    for (int l = 0; l < 4; ++l) {
+        const size_t bytes = static_cast<size_t>(n) * kFeat[l] * (H >> l) * (W >> l) * elem;
+        p.T[l] = take(bytes);
+        p.S[l] = take(bytes);
+        p.U[l] = take(bytes);
+    }
+    const size_t b4 = static_cast<size_t>(n) * 512 * (H >> 4) * (W >> 4) * elem;
+    p.T[4] = take(b4);
+    p.B4 = take(b4);
+    p.P3 = take(b4 / 2);
+    p.total = o;
+    return p;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ogl_version(void) { return OGL_VERSION; }
+const char* ogl_last_error(void) { return g_err.c_str(); }
+
+int ogl_unet_create(ogl_unet** out, int device) {
+    if (!out) return fail("ogl_unet_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail("no CUDA device available: openglottal_b200 has no CPU fallback");
+    if (device < 0 || device >= count) return fail("ogl_unet_create: bad device index");
+    OGL_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    OGL_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(std::string("openglottal_b200 is built for sm_100a (B200); found ") + prop.name);
+    if (conv_tc_init()) return 1;
+    ogl_unet* h = new ogl_unet();
+    h->device = device;
+    h->num_sms = prop.multiProcessorCount;
+    *out = h;
+    return 0;
+}
+
+int ogl_unet_destroy(ogl_unet* h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    free_all(h);
+    delete h;
+    return 0;
+}
+
+int ogl_unet_load_state(ogl_unet* h, const ogl_unet_state* st) {
+    if (!h || !st) return fail("ogl_unet_load_state: NULL argument");
+    OGL_CUDA(cudaSetDevice(h->device));
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 2; ++j)
+            if (check_conv_bn(st->downs[i][j]) || check_conv_bn(st->up_c[i][j]))
+                return fail("ogl_unet_load_state: missing conv/bn tensor");
+    if (check_conv_bn(st->bottleneck[0]) || check_conv_bn(st->bottleneck[1]) || !st->head_weight ||
+        !st->head_bias)
+        return fail("ogl_unet_load_state: missing tensor");
+    for (int i = 0; i < 4; ++i)
+        if (!st->up_t[i].weight || !st->up_t[i].bias)
+            return fail("ogl_unet_load_state: missing convT tensor");
+    free_all(h);
+    const double eps = st->bn_eps;
+    std::vector<float> w, b;
+
+    // encoder
+    int cin = 1;
+    for (int i = 0; i < 4; ++i) {
+        const int f = kFeat[i];
+        fold_conv_bn(st->downs[i][0], f, cin, eps, &w, &b);
+        if (build_f32_conv(h, w, b, cin, f, &h->f_down[i][0])) return 1;
+        if (i == 0) {
+            if (dev_upload(h, w, &h->stem_w) || dev_upload(h, b, &h->stem_b)) return 1;
+        } else {
+            if (build_tc_conv(h, w, b, cin, 0, f, EPI_RELU, &h->down_c1[i])) return 1;
+        }
+        fold_conv_bn(st->downs[i][1], f, f, eps, &w, &b);
+        if (build_f32_conv(h, w, b, f, f, &h->f_down[i][1])) return 1;
+        if (build_tc_conv(h, w, b, f, 0, f, EPI_RELU_POOL, &h->down_c2[i])) return 1;
+        cin = f;
+    }
+    // bottleneck 256 -> 512 -> 512
+    fold_conv_bn(st->bottleneck[0], 512, 256, eps, &w, &b);
+    if (build_f32_conv(h, w, b, 256, 512, &h->f_bott[0])) return 1;
+    if (build_tc_conv(h, w, b, 256, 0, 512, EPI_RELU, &h->bott[0])) return 1;
+    fold_conv_bn(st->bottleneck[1], 512, 512, eps, &w, &b);
+    if (build_f32_conv(h, w, b, 512, 512, &h->f_bott[1])) return 1;
+    if (build_tc_conv(h, w, b, 512, 0, 512, EPI_RELU, &h->bott[1])) return 1;
+    // decoder: up_t[k] / up_c[k] act at level l = 3 - k
+    for (int k = 0; k < 4; ++k) {
+        const int f = kFeat[3 - k];
+        {
+            const ogl_convt& T = st->up_t[k];
+            std::vector<float> tw(T.weight, T.weight + static_cast<size_t>(2 * f) * f * 4);
+            std::vector<float> tb(T.bias, T.bias + f);
+            h->f_upt[k].cin = 2 * f;
+            h->f_upt[k].cout = f;
+            if (dev_upload(h, tw, &h->f_upt[k].w) || dev_upload(h, tb, &h->f_upt[k].b)) return 1;
+            TcLayer* L = &h->up_t[k];
+            L->cin0 = 2 * f;
+            L->cin1 = 0;
+            L->cout = f;
+            L->taps = 1;
+            L->N = f < 128 ? f : 128;
+            L->npass = 4 * f / L->N;
+            L->epi = EPI_CONVT;
+            if (dev_upload(h, pack_convt(T.weight, 2 * f, f, L->N), &L->wpack)) return 1;
+            if (dev_upload(h, tb, &L->bias)) return 1;
+        }
+        fold_conv_bn(st->up_c[k][0], f, 2 * f, eps, &w, &b);
+        if (build_f32_conv(h, w, b, 2 * f, f, &h->f_up[k][0])) return 1;
+        if (build_tc_conv(h, w, b, f, f, f, EPI_RELU, &h->up_c[k][0])) return 1;
+        fold_conv_bn(st->up_c[k][1], f, f, eps, &w, &b);
+        if (build_f32_conv(h, w, b, f, f, &h->f_up[k][1])) return 1;
+        if (build_tc_conv(h, w, b, f, 0, f, k == 3 ? EPI_HEAD : EPI_RELU, &h->up_c[k][1]))
+            return 1;
+    }
+    std::vector<float> hw(st->head_weight, st->head_weight + 32);
+    if (dev_upload(h, hw, &h->head_w)) return 1;
+    h->head_b = st->head_bias[0];
+    h->loaded = true;
+    return 0;
+}
+
+size_t ogl_unet_workspace_bytes(const ogl_unet* h, int n, int height, int width, int precision) {
+    (void)h;
+    if (n <= 0 || height <= 0 || width <= 0) return 0;
+    const size_t elem = precision == OGL_PRECISION_F32 ? 4 : 2;
+    Plan p = make_plan(n, height, width, elem);
+    size_t extra = 0;
+    if (precision == OGL_PRECISION_F32) {
+        // fp32 path also needs the scaled input plane and pooled level-0..2 tensors
+        extra = static_cast<size_t>(n) * height * width * 4 + 256;
+    }
+    return p.total + extra + 256;
+}
+
+int ogl_unet_forward(ogl_unet* h, const void* frames_dev, int in_dtype, int n, int height,
+                     int width, void* workspace_dev, size_t workspace_bytes, float* logits_dev,
+                     uint8_t* mask_dev, int32_t* area_dev, float threshold, int precision,
+                     void* stream_v) {
+    if (!h) return fail("ogl_unet_forward: NULL handle");
+    if (!h->loaded) return fail("ogl_unet_forward: no weights loaded (ogl_unet_load_state)");
+    if (!frames_dev || !workspace_dev) return fail("ogl_unet_forward: NULL frames/workspace");
+    if (n <= 0) return fail("ogl_unet_forward: n must be positive");
+    if (height % 16 || width % 16 || height <= 0 || width <= 0)
+        return fail("ogl_unet_forward: height and width must be positive multiples of 16");
+    if (in_dtype != OGL_DTYPE_U8 && in_dtype != OGL_DTYPE_F32)
+        return fail("ogl_unet_forward: in_dtype must be OGL_DTYPE_U8 or OGL_DTYPE_F32");
+    if (!(threshold > 0.f && threshold < 1.f))
+        return fail("ogl_unet_forward: threshold must be in (0, 1)");
+    if (precision != OGL_PRECISION_BF16 && precision != OGL_PRECISION_F32)
+        return fail("ogl_unet_forward: unknown precision mode");
+    if (workspace_bytes < ogl_unet_workspace_bytes(h, n, height, width, precision))
+        return fail("ogl_unet_forward: workspace too small");
+    if (reinterpret_cast<uintptr_t>(workspace_dev) & 255)
+        return fail("ogl_unet_forward: workspace must be 256-byte aligned");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    const float thr = static_cast<float>(
+        std::log(static_cast<double>(threshold) / (1.0 - static_cast<double>(threshold))));
+    const int H = height, W = width;
+    uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
+    if (area_dev) OGL_CUDA(cudaMemsetAsync(area_dev, 0, sizeof(int32_t) * n, stream));
+
+    if (precision == OGL_PRECISION_BF16) {
+        const Plan p = make_plan(n, H, W, 2);
+        auto B = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(ws + off); };
+        __nv_bfloat16* P[4] = {B(p.U[1]), B(p.U[2]), B(p.U[3]), B(p.P3)};
+        if (launch_stem(frames_dev, in_dtype, h->stem_w, h->stem_b, n, H, W, B(p.T[0]), stream))
+            return 1;
+        for (int l = 0; l < 4; ++l) {
+            const int hh = H >> l, ww = W >> l;
+            if (l > 0 && launch_conv_tc(h->down_c1[l], P[l - 1], nullptr, n, hh, ww, B(p.T[l]),
+                                        nullptr, nullptr, h->num_sms, stream))
+                return 1;
+            if (launch_conv_tc(h->down_c2[l], B(p.T[l]), nullptr, n, hh, ww, B(p.S[l]), P[l],
+                               nullptr, h->num_sms, stream))
+                return 1;
+        }
+        if (launch_conv_tc(h->bott[0], P[3], nullptr, n, H >> 4, W >> 4, B(p.T[4]), nullptr,
+                           nullptr, h->num_sms, stream))
+            return 1;
+        if (launch_conv_tc(h->bott[1], B(p.T[4]), nullptr, n, H >> 4, W >> 4, B(p.B4), nullptr,
+                           nullptr, h->num_sms, stream))
+            return 1;
+        const __nv_bfloat16* below = B(p.B4);
+        HeadParams hp;
+        hp.w = h->head_w;
+        hp.b = h->head_b;
+        hp.logit_thr = thr;
+        hp.logits = logits_dev;
+        hp.mask = mask_dev;
+        hp.area = area_dev;
+        for (int k = 0; k < 4; ++k) {
+            const int l = 3 - k;
+            const int hh = H >> l, ww = W >> l;
+            if (launch_conv_tc(h->up_t[k], below, nullptr, n, hh / 2, ww / 2, B(p.U[l]), nullptr,
+                               nullptr, h->num_sms, stream))
+                return 1;
+            if (launch_conv_tc(h->up_c[k][0], B(p.S[l]), B(p.U[l]), n, hh, ww, B(p.T[l]), nullptr,
+                               nullptr, h->num_sms, stream))
+                return 1;
+            if (launch_conv_tc(h->up_c[k][1], B(p.T[l]), nullptr, n, hh, ww, B(p.U[l]), nullptr,
+                               k == 3 ? &hp : nullptr, h->num_sms, stream))
+                return 1;
+            below = B(p.U[l]);
+        }
+        return 0;
+    }
+
+    // ------------------------------------------------ fp32 validation path (NCHW)
+    const Plan p = make_plan(n, H, W, 4);
+    auto F = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
+    float* x0 = F(p.total);  // scaled input [n][1][H][W]
+    float* P[4] = {F(p.U[1]), F(p.U[2]), F(p.U[3]), F(p.P3)};
+    if (launch_f32_input(frames_dev, in_dtype, static_cast<int64_t>(n) * H * W, x0, stream))
+        return 1;
+    const float* cur = x0;
+    int cin = 1;
+    for (int l = 0; l < 4; ++l) {
+        const int hh = H >> l, ww = W >> l, f = kFeat[l];
+        if (launch_f32_conv3x3(cur, cin, nullptr, 0, h->f_down[l][0].w, h->f_down[l][0].b,
+                               F(p.T[l]), n, f, hh, ww, 1, stream))
+            return 1;
+        if (launch_f32_conv3x3(F(p.T[l]), f, nullptr, 0, h->f_down[l][1].w, h->f_down[l][1].b,
+                               F(p.S[l]), n, f, hh, ww, 1, stream))
+            return 1;
+        if (launch_f32_maxpool(F(p.S[l]), P[l], n * f, hh, ww, stream)) return 1;
+        cur = P[l];
+        cin = f;
+    }
+    if (launch_f32_conv3x3(P[3], 256, nullptr, 0, h->f_bott[0].w, h->f_bott[0].b, F(p.T[4]), n,
+                           512, H >> 4, W >> 4, 1, stream))
+        return 1;
+    if (launch_f32_conv3x3(F(p.T[4]), 512, nullptr, 0, h->f_bott[1].w, h->f_bott[1].b, F(p.B4), n,
+                           512, H >> 4, W >> 4, 1, stream))
+        return 1;
+    const float* below = F(p.B4);
+    for (int k = 0; k < 4; ++k) {
+        const int l = 3 - k;
+        const int hh = H >> l, ww = W >> l, f = kFeat[l];
+        if (launch_f32_convt(below, h->f_upt[k].w, h->f_upt[k].b, F(p.U[l]), n, 2 * f, f, hh / 2,
+                             ww / 2, stream))
+            return 1;
+        if (launch_f32_conv3x3(F(p.S[l]), f, F(p.U[l]), f, h->f_up[k][0].w, h->f_up[k][0].b,
+                               F(p.T[l]), n, f, hh, ww, 1, stream))
+            return 1;
+        if (launch_f32_conv3x3(F(p.T[l]), f, nullptr, 0, h->f_up[k][1].w, h->f_up[k][1].b,
+                               F(p.U[l]), n, f, hh, ww, 1, stream))
+            return 1;
+        below = F(p.U[l]);
+    }
+    return launch_f32_head(below, h->head_w, h->head_b, thr, n, 32, H, W, logits_dev, mask_dev,
+                           area_dev, stream);
+}
+
+size_t ogl_features_workspace_bytes(int64_t n) { return features_workspace_bytes(n); }
+
+int ogl_features(const int32_t* area_dev, int64_t n, double* out8_dev, int32_t* flags2_dev,
+                 void* workspace_dev, size_t workspace_bytes, void* stream) {
+    if (!area_dev || !out8_dev || !flags2_dev || !workspace_dev)
+        return fail("ogl_features: NULL argument");
+    return launch_features(area_dev, n, out8_dev, flags2_dev, workspace_dev, workspace_bytes,
+                           static_cast<cudaStream_t>(stream));
+}
+
+int ogl_features_f64(const double* area_dev, int64_t n, double* out8_dev, int32_t* flags2_dev,
+                     void* workspace_dev, size_t workspace_bytes, void* stream) {
+    if (!area_dev || !out8_dev || !flags2_dev || !workspace_dev)
+        return fail("ogl_features_f64: NULL argument");
+    return launch_features_f64(area_dev, n, out8_dev, flags2_dev, workspace_dev, workspace_bytes,
+                               static_cast<cudaStream_t>(stream));
+}
+
+int ogl_bgr_to_gray(const uint8_t* bgr_dev, uint8_t* gray_dev, int64_t pixels, void* stream) {
+    if (!bgr_dev || !gray_dev || pixels < 0) return fail("ogl_bgr_to_gray: bad argument");
+    if (pixels == 0) return 0;
+    long long g = (pixels + 255) / 256;
+    if (g > 148 * 16) g = 148 * 16;
+    bgr_to_gray_kernel<<<static_cast<int>(g), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        bgr_dev, gray_dev, pixels);
+    OGL_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int ogl_debug_tc_layer(ogl_unet* h, int kind, const float* src0_dev, int c0, const float* src1_dev,
+                       int c1, const float* weight_host, const float* bias_host, int cout, int n,
+                       int height, int width, float* out_dev, float* out_pool_dev,
+                       void* stream_v) {
+    if (!h || !src0_dev || !weight_host || !bias_host || !out_dev)
+        return fail("ogl_debug_tc_layer: NULL argument");
+    if (kind != EPI_RELU && kind != EPI_RELU_POOL && kind != EPI_CONVT)
+        return fail("ogl_debug_tc_layer: kind must be 0, 1 or 3");
+    if (c0 % 32 || c1 % 32 || cout % 32) return fail("ogl_debug_tc_layer: channels % 32 != 0");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    OGL_CUDA(cudaSetDevice(h->device));
+    const int cin = c0 + c1;
+    TcLayer L;
+    L.cin0 = c0;
+    L.cin1 = c1;
+    L.cout = cout;
+    L.N = cout < 128 ? cout : 128;
+    L.epi = kind;
+    std::vector<__nv_bfloat16> pk;
+    if (kind == EPI_CONVT) {
+        L.taps = 1;
+        L.npass = 4 * cout / L.N;
+        pk = pack_convt(weight_host, cin, cout, L.N);
+    } else {
+        L.taps = 9;
+        L.npass = cout / L.N;
+        std::vector<float> w(weight_host, weight_host + static_cast<size_t>(cout) * cin * 9);
+        pk = pack_conv(w, cout, cin, L.N);
+    }
+    const size_t hw = static_cast<size_t>(height) * width;
+    const int oh = kind == EPI_CONVT ? 2 * height : height;
+    const int ow = kind == EPI_CONVT ? 2 * width : width;
+    __nv_bfloat16 *d_w = nullptr, *d_s0 = nullptr, *d_s1 = nullptr, *d_o = nullptr, *d_p = nullptr;
+    float* d_b = nullptr;
+    int rc = 1;
+    do {
+        if (cudaMalloc(&d_w, pk.size() * 2) != cudaSuccess) break;
+        if (cudaMalloc(&d_b, cout * 4) != cudaSuccess) break;
+        if (cudaMalloc(&d_s0, n * c0 * hw * 2) != cudaSuccess) break;
+        if (c1 && cudaMalloc(&d_s1, n * c1 * hw * 2) != cudaSuccess) break;
+        if (cudaMalloc(&d_o, static_cast<size_t>(n) * cout * oh * ow * 2) != cudaSuccess) break;
+        if (kind == EPI_RELU_POOL && cudaMalloc(&d_p, n * cout * hw / 4 * 2) != cudaSuccess) break;
+        cudaMemcpyAsync(d_w, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice, stream);
+        cudaMemcpyAsync(d_b, bias_host, cout * 4, cudaMemcpyHostToDevice, stream);
+        cudaStreamSynchronize(stream);
+        L.wpack = d_w;
+        L.bias = d_b;
+        if (launch_nchw_to_c8(src0_dev, d_s0, n, c0, height, width, stream)) break;
+        if (c1 && launch_nchw_to_c8(src1_dev, d_s1, n, c1, height, width, stream)) break;
+        if (launch_conv_tc(L, d_s0, d_s1, n, height, width, d_o, d_p, nullptr, h->num_sms, stream))
+            break;
+        if (launch_c8_to_nchw(d_o, out_dev, n, cout, oh, ow, stream)) break;
+        if (kind == EPI_RELU_POOL && out_pool_dev &&
+            launch_c8_to_nchw(d_p, out_pool_dev, n, cout, height / 2, width / 2, stream))
+            break;
+        cudaError_t e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) {
+            fail_cuda(e, "ogl_debug_tc_layer");
+            break;
+        }
+        rc = 0;
+    } while (0);
+    if (rc && g_err.empty()) fail("ogl_debug_tc_layer: allocation or launch failed");
+    cudaFree(d_w);
+    cudaFree(d_b);
+    cudaFree(d_s0);
+    cudaFree(d_s1);
+    cudaFree(d_o);
+    cudaFree(d_p);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,480 @@
+// Implicit-GEMM conv3x3 / convT2x2 on the sm_100a tensor cores (tcgen05 + TMEM), fed by TMA.
+//
+// Replaces, per fused group, the PyTorch calls of the reference U-Net
+// (/root/reference/openglottal/models/unet.py:24-29 Conv2d+BatchNorm2d+ReLU, :59,79 MaxPool2d,
+//  :69,82 ConvTranspose2d, :86 torch.cat, :72,88 1x1 head; utils.py:237,241 sigmoid+threshold;
+//  features.py:238 np.sum of the mask).
+//
+// GEMM view: D[pixels, Cout] = sum over taps (dy,dx) and channels of
+//            A_tap[pixels, Cin] * W_tap[Cin, Cout].
+//   * M = 128 pixels = an 8(x) x 16(y) patch; a CTA tile is S sub-tiles of 16x16 px
+//     (2 patches each), so up to 4 accumulators of N columns live in TMEM (double-buffered
+//     when 2*S*N <= 256 so the epilogue of tile i overlaps the MMAs of tile i+1).
+//   * A operand: one TMA box per (sub-tile, 32-channel block) brings the 18x18 halo tile of
+//     4 channel planes; the 9 taps are 9 start-address offsets into that one tile
+//     (zero padding = TMA out-of-bounds fill). Nothing is re-read per tap.
+//   * B operand: host-packed weights, streamed per (32-channel block, tap) with 1-D bulk copies.
+//   * torch.cat([skip, up]) is two tensor maps walked back to back in the K loop.
+//   * Warp roles: w0 = activation TMA producer, w1 = MMA issuer, w2 = TMEM allocator,
+//     w3 = weight producer, w4..7 = epilogue (TMEM -> regs -> bias/ReLU/pool/head -> HBM).
+#include "internal.h"
+#include "ptx.cuh"
+
+#include <cuda.h>
+#include <cstdio>
+#include <cstring>
+
+namespace ogl {
+
+namespace {
+
+constexpr int kHalo = 18;                          // 16 + 2
+constexpr int kPlaneBytes = kHalo * kHalo * 16;    // one 8-channel plane of a halo tile
+constexpr int kSubBytes = 4 * kPlaneBytes;         // 32 channels of one 16x16 sub-tile (20736 B)
+constexpr int kThreads = 256;
+constexpr int kTmemCols = 512;
+
+struct ConvParams {
+    const __nv_bfloat16* wpack;
+    const float* bias;
+    __nv_bfloat16* out;
+    __nv_bfloat16* out_pool;
+    const float* head_w;
+    float* logits;
+    uint8_t* mask;
+    int32_t* area;
+    float head_b, logit_thr;
+    int kb0, kb1;    // 32-channel K blocks taken from source 0 / source 1
+    int taps;        // 9 or 1
+    int N, npass;    // MMA N per pass, number of passes over N_total
+    int cout;        // channels of the output tensor
+    int H, W, B;     // resolution of the INPUT feature map
+    int S;           // sub-tiles (16x16 px) per CTA tile
+    int tiles_x, tiles_y, total_sub, num_tiles;
+    int na, nw;      // ring depths
+    int acc_bufs;    // 1 or 2 TMEM accumulator sets
+};
+
+struct SubTile {
+    int n, y0, x0;
+};
+__device__ __forceinline__ SubTile decode_sub(const ConvParams& p, int st) {
+    SubTile s;
+    int tx = st % p.tiles_x;
+    int r = st / p.tiles_x;
+    int ty = r % p.tiles_y;
+    s.n = r / p.tiles_y;
+    s.y0 = ty * 16;
+    s.x0 = tx * 16;
+    return s;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
+    __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a),
+                               *reinterpret_cast<__nv_bfloat162*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+               const ConvParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
+
+    const uint32_t a_stage_bytes = static_cast<uint32_t>(p.S) * kSubBytes;
+    const uint32_t w_stage_bytes = 64u * static_cast<uint32_t>(p.N);
+    const uint32_t a_ring = smem_base;
+    const uint32_t w_ring = a_ring + p.na * a_stage_bytes;
+    const uint32_t bar_base = w_ring + p.nw * w_stage_bytes;  // 8 B aligned (sizes are x64)
+    const uint32_t a_full = bar_base;
+    const uint32_t a_empty = a_full + 8u * p.na;
+    const uint32_t w_full = a_empty + 8u * p.na;
+    const uint32_t w_empty = w_full + 8u * p.nw;
+    const uint32_t acc_full = w_empty + 8u * p.nw;
+    const uint32_t acc_empty = acc_full + 16u;
+    const uint32_t tmem_slot = acc_empty + 16u;
+    const uint32_t bias_s = tmem_slot + 16u;  // floats: bias[cout] then head_w[32]
+    // generic pointers to the small fp32 tables
+    float* bias_sp = reinterpret_cast<float*>(smem_raw + (bias_s - smem_u32(smem_raw)));
+    volatile uint32_t* tmem_slot_p =
+        reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int kb_total = p.kb0 + p.kb1;
+    const int items = p.npass * p.num_tiles;
+
+    // ---------------------------------------------------------------- setup
+    for (int i = threadIdx.x; i < p.cout; i += kThreads) bias_sp[i] = p.bias[i];
+    if (EPI == EPI_HEAD) {
+        if (threadIdx.x < 32) bias_sp[p.cout + threadIdx.x] = p.head_w[threadIdx.x];
+    }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA0);
+        tma_prefetch_desc(&tmA1);
+        for (int i = 0; i < p.na; ++i) {
+            mbar_init(a_full + 8u * i, 1);
+            mbar_init(a_empty + 8u * i, 1);
+        }
+        for (int i = 0; i < p.nw; ++i) {
+            mbar_init(w_full + 8u * i, 1);
+            mbar_init(w_empty + 8u * i, 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(acc_full + 8u * i, 1);
+            mbar_init(acc_empty + 8u * i, 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_p;
+
+    if (warp == 0) {
+        // ================================================ activation producer
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int item = blockIdx.x; item < items; item += gridDim.x) {
+                const int tile = item % p.num_tiles;
+                for (int kb = 0; kb < kb_total; ++kb, ++it) {
+                    const uint32_t s = it % p.na;
+                    const uint32_t ph = (it / p.na) & 1u;
+                    mbar_wait(a_empty + 8u * s, ph ^ 1u);
+                    mbar_arrive_expect_tx(a_full + 8u * s, a_stage_bytes);
+                    const CUtensorMap* tm = kb < p.kb0 ? &tmA0 : &tmA1;
+                    const int plane0 = (kb < p.kb0 ? kb : kb - p.kb0) * 4;
+                    for (int sub = 0; sub < p.S; ++sub) {
+                        int st = tile * p.S + sub;
+                        if (st >= p.total_sub) st = p.total_sub - 1;  // tail: load a duplicate
+                        const SubTile t = decode_sub(p, st);
+                        tma_load_4d(a_ring + s * a_stage_bytes + sub * kSubBytes, tm,
+                                    a_full + 8u * s, (t.x0 - 1) * 8, t.y0 - 1, plane0, t.n);
+                    }
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ==================================================== weight producer
+        if (lane == 0) {
+            uint32_t it = 0;
+            const uint8_t* wbytes = reinterpret_cast<const uint8_t*>(p.wpack);
+            for (int item = blockIdx.x; item < items; item += gridDim.x) {
+                const int pass = item / p.num_tiles;
+                for (int kb = 0; kb < kb_total; ++kb) {
+                    for (int tap = 0; tap < p.taps; ++tap, ++it) {
+                        const uint32_t s = it % p.nw;
+                        const uint32_t ph = (it / p.nw) & 1u;
+                        mbar_wait(w_empty + 8u * s, ph ^ 1u);
+                        mbar_arrive_expect_tx(w_full + 8u * s, w_stage_bytes);
+                        const size_t off =
+                            (static_cast<size_t>(pass * p.taps + tap) * kb_total + kb) *
+                            w_stage_bytes;
+                        bulk_load(w_ring + s * w_stage_bytes, wbytes + off, w_stage_bytes,
+                                  w_full + 8u * s);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ========================================================= MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(p.N);
+            const uint32_t lbo_a = kPlaneBytes, sbo_a = kHalo * 16;
+            const uint32_t lbo_b = 16u * p.N, sbo_b = 128u;
+            const int mtiles = 2 * p.S;
+            const uint32_t acc_cols = static_cast<uint32_t>(mtiles * p.N);
+            uint32_t ita = 0, itw = 0, li = 0;
+            for (int item = blockIdx.x; item < items; item += gridDim.x, ++li) {
+                const uint32_t buf = li % p.acc_bufs;
+                const uint32_t aph = (li / p.acc_bufs) & 1u;
+                mbar_wait(acc_empty + 8u * buf, aph ^ 1u);
+                tc_fence_after();
+                const uint32_t d0 = tmem_base + buf * acc_cols;
+                for (int kb = 0; kb < kb_total; ++kb, ++ita) {
+                    const uint32_t sa = ita % p.na;
+                    mbar_wait(a_full + 8u * sa, (ita / p.na) & 1u);
+                    tc_fence_after();
+                    const uint32_t abase = a_ring + sa * a_stage_bytes;
+                    for (int tap = 0; tap < p.taps; ++tap, ++itw) {
+                        const uint32_t sw = itw % p.nw;
+                        mbar_wait(w_full + 8u * sw, (itw / p.nw) & 1u);
+                        tc_fence_after();
+                        const int dy = p.taps == 9 ? tap / 3 : 1;
+                        const int dx = p.taps == 9 ? tap % 3 : 1;
+                        const uint32_t wbase = w_ring + sw * w_stage_bytes;
+                        const uint32_t tap_off = static_cast<uint32_t>(dy * kHalo + dx) * 16u;
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {  // two K=16 steps per 32-channel block
+                            const uint64_t bdesc =
+                                make_smem_desc(wbase + j * 2u * lbo_b, lbo_b, sbo_b);
+                            const uint32_t acc_flag = (kb | tap | j) != 0 ? 1u : 0u;
+                            for (int mt = 0; mt < mtiles; ++mt) {
+                                const uint32_t aaddr = abase + (mt >> 1) * kSubBytes +
+                                                       j * 2u * lbo_a + tap_off +
+                                                       (mt & 1) * 128u;
+                                umma_bf16(d0 + mt * p.N, make_smem_desc(aaddr, lbo_a, sbo_a),
+                                          bdesc, idesc, acc_flag);
+                            }
+                        }
+                        umma_commit(w_empty + 8u * sw);
+                    }
+                    umma_commit(a_empty + 8u * sa);
+                }
+                umma_commit(acc_full + 8u * buf);
+            }
+        }
+    } else if (warp >= 4) {
+        // =========================================================== epilogue
+        const int et = threadIdx.x - 128;          // TMEM lane == pixel index inside a patch
+        const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
+        const int py = et >> 3, px = et & 7;
+        const int mtiles = 2 * p.S;
+        const uint32_t acc_cols = static_cast<uint32_t>(mtiles * p.N);
+        const int OH = EPI == EPI_CONVT ? 2 * p.H : p.H;
+        const int OW = EPI == EPI_CONVT ? 2 * p.W : p.W;
+        uint32_t li = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x, ++li) {
+            const int tile = item % p.num_tiles;
+            const int pass = item / p.num_tiles;
+            const uint32_t buf = li % p.acc_bufs;
+            const uint32_t aph = (li / p.acc_bufs) & 1u;
+            mbar_wait(acc_full + 8u * buf, aph);
+            tc_fence_after();
+            for (int mt = 0; mt < mtiles; ++mt) {
+                const int st = tile * p.S + (mt >> 1);
+                const bool valid = st < p.total_sub;  // warp-uniform
+                const SubTile t = decode_sub(p, valid ? st : p.total_sub - 1);
+                const int y = t.y0 + py;
+                const int x = t.x0 + (mt & 1) * 8 + px;
+                const uint32_t tcol = tmem_base + lane_sel + buf * acc_cols + mt * p.N;
+                float zacc = 0.f;
+                for (int c0 = 0; c0 < p.N; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld32(tcol + c0, r);
+                    tmem_ld_wait();
+                    // column -> output channel
+                    int co0;  // first output channel of these 32 columns
+                    int qy = 0, qx = 0;
+                    if (EPI == EPI_CONVT) {
+                        const int col = pass * p.N + c0;
+                        const int q = col / p.cout;
+                        co0 = col - q * p.cout;
+                        qy = q >> 1;
+                        qx = q & 1;
+                    } else {
+                        co0 = pass * p.N + c0;
+                    }
+                    float v[32];
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        float f = __uint_as_float(r[c]) + bias_sp[co0 + c];
+                        if (EPI != EPI_CONVT) f = fmaxf(f, 0.f);
+                        v[c] = f;
+                    }
+                    if (EPI == EPI_HEAD) {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c)
+                            zacc = fmaf(v[c], bias_sp[p.cout + c0 + c], zacc);
+                    } else {
+                        const int oy = EPI == EPI_CONVT ? 2 * y + qy : y;
+                        const int ox = EPI == EPI_CONVT ? 2 * x + qx : x;
+                        const size_t plane = static_cast<size_t>(OH) * OW * 8;
+                        __nv_bfloat16* optr =
+                            p.out + (static_cast<size_t>(t.n) * (p.cout >> 3) + (co0 >> 3)) * plane +
+                            (static_cast<size_t>(oy) * OW + ox) * 8;
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            uint4 q4;
+                            q4.x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]);
+                            q4.y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
+                            q4.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]);
+                            q4.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
+                            if (valid) *reinterpret_cast<uint4*>(optr + g * plane) = q4;
+                            if (EPI == EPI_RELU_POOL) {
+                                // 2x2 max over (x^1, y^1): lanes ^1 and ^8 of this warp
+                                uint4 m4;
+                                m4.x = max_bf16x2(q4.x, __shfl_xor_sync(0xffffffffu, q4.x, 1));
+                                m4.y = max_bf16x2(q4.y, __shfl_xor_sync(0xffffffffu, q4.y, 1));
+                                m4.z = max_bf16x2(q4.z, __shfl_xor_sync(0xffffffffu, q4.z, 1));
+                                m4.w = max_bf16x2(q4.w, __shfl_xor_sync(0xffffffffu, q4.w, 1));
+                                m4.x = max_bf16x2(m4.x, __shfl_xor_sync(0xffffffffu, m4.x, 8));
+                                m4.y = max_bf16x2(m4.y, __shfl_xor_sync(0xffffffffu, m4.y, 8));
+                                m4.z = max_bf16x2(m4.z, __shfl_xor_sync(0xffffffffu, m4.z, 8));
+                                m4.w = max_bf16x2(m4.w, __shfl_xor_sync(0xffffffffu, m4.w, 8));
+                                if (valid && ((px & 1) == 0) && ((py & 1) == 0)) {
+                                    const int PH = p.H >> 1, PW = p.W >> 1;
+                                    const size_t pplane = static_cast<size_t>(PH) * PW * 8;
+                                    __nv_bfloat16* pp =
+                                        p.out_pool +
+                                        (static_cast<size_t>(t.n) * (p.cout >> 3) + (co0 >> 3) + g) *
+                                            pplane +
+                                        (static_cast<size_t>(y >> 1) * PW + (x >> 1)) * 8;
+                                    *reinterpret_cast<uint4*>(pp) = m4;
+                                }
+                            }
+                        }
+                    }
+                }
+                if (EPI == EPI_HEAD) {
+                    const float z = zacc + p.head_b;
+                    const bool on = valid && (z > p.logit_thr);
+                    const size_t pix = (static_cast<size_t>(t.n) * p.H + y) * p.W + x;
+                    if (valid && p.logits) p.logits[pix] = z;
+                    if (valid && p.mask) p.mask[pix] = on ? 255 : 0;
+                    const uint32_t bal = __ballot_sync(0xffffffffu, on);
+                    if (lane == 0 && p.area && bal) atomicAdd(p.area + t.n, __popc(bal));
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(acc_empty + 8u * buf);
+        }
+    }
+
+    // ------------------------------------------------------------- teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+constexpr int kMaxSmem = 227 * 1024;
+
+// Tensor map over a C8-planar activation tensor [B][C/8][H][W][8] bf16:
+// dims (innermost first) = (W*8, H, C/8, B); box = (18*8, 18, 4, 1).
+int make_act_map(CUtensorMap* tm, const __nv_bfloat16* base, int B, int C, int H, int W) {
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(W) * 8, static_cast<cuuint64_t>(H),
+                          static_cast<cuuint64_t>(C / 8), static_cast<cuuint64_t>(B)};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(W) * 16,
+                             static_cast<cuuint64_t>(W) * 16 * H,
+                             static_cast<cuuint64_t>(W) * 16 * H * (C / 8)};
+    cuuint32_t box[4] = {kHalo * 8, kHalo, 4, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                          const_cast<__nv_bfloat16*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d) for B=%d C=%d H=%d W=%d",
+                 static_cast<int>(r), B, C, H, W);
+        return fail(buf);
+    }
+    return 0;
+}
+
+template <int EPI>
+int launch_epi(const CUtensorMap& tm0, const CUtensorMap& tm1, const ConvParams& p, int grid,
+               size_t smem, cudaStream_t stream) {
+    conv_tc_kernel<EPI><<<grid, kThreads, smem, stream>>>(tm0, tm1, p);
+    OGL_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+int conv_tc_init() {
+    if (!g_encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        OGL_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess)
+            return fail("cuTensorMapEncodeTiled entry point not available");
+        g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    OGL_CUDA(cudaFuncSetAttribute(conv_tc_kernel<EPI_RELU>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    OGL_CUDA(cudaFuncSetAttribute(conv_tc_kernel<EPI_RELU_POOL>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    OGL_CUDA(cudaFuncSetAttribute(conv_tc_kernel<EPI_HEAD>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    OGL_CUDA(cudaFuncSetAttribute(conv_tc_kernel<EPI_CONVT>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    return 0;
+}
+
+int launch_conv_tc(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloat16* src1, int B,
+                   int H, int W, __nv_bfloat16* out, __nv_bfloat16* out_pool,
+                   const HeadParams* head, int num_sms, cudaStream_t stream) {
+    if (!g_encode) return fail("conv_tc_init() was not called");
+    if (H % 16 || W % 16) return fail("tensor-core conv needs H and W to be multiples of 16");
+    if (L.cin0 % 32 || L.cin1 % 32 || L.N % 32 || L.N > 128)
+        return fail("tensor-core conv needs Cin % 32 == 0 and N in {32,64,96,128}");
+    if (L.epi == EPI_RELU_POOL && !out_pool) return fail("pool epilogue needs out_pool");
+    if (L.epi == EPI_HEAD && (!head || L.cout != 32 || L.npass != 1))
+        return fail("head epilogue needs Cout == 32 in one pass");
+
+    ConvParams p;
+    memset(&p, 0, sizeof p);
+    p.wpack = L.wpack;
+    p.bias = L.bias;
+    p.out = out;
+    p.out_pool = out_pool;
+    if (head) {
+        p.head_w = head->w;
+        p.head_b = head->b;
+        p.logit_thr = head->logit_thr;
+        p.logits = head->logits;
+        p.mask = head->mask;
+        p.area = head->area;
+    }
+    p.kb0 = L.cin0 / 32;
+    p.kb1 = L.cin1 / 32;
+    p.taps = L.taps;
+    p.N = L.N;
+    p.npass = L.npass;
+    p.cout = L.cout;
+    p.H = H;
+    p.W = W;
+    p.B = B;
+    p.S = 2;
+    p.tiles_x = W / 16;
+    p.tiles_y = H / 16;
+    p.total_sub = B * p.tiles_x * p.tiles_y;
+    p.num_tiles = (p.total_sub + p.S - 1) / p.S;
+    p.acc_bufs = (2 * p.S * p.N <= 256) ? 2 : 1;
+    p.na = 3;
+    const size_t a_bytes = static_cast<size_t>(p.na) * p.S * kSubBytes;
+    const size_t w_stage = 64u * p.N;
+    const size_t fixed = 128 /*align slack*/ + 8 * 2 * p.na + 16 + 16 + 16 +
+                         sizeof(float) * (L.cout + 32) + 64;
+    int nw = static_cast<int>((kMaxSmem - a_bytes - fixed - 8 * 2 * 12) / w_stage);
+    if (nw > 12) nw = 12;
+    if (nw < 2) return fail("not enough shared memory for the weight ring");
+    p.nw = nw;
+    const size_t smem = a_bytes + nw * w_stage + fixed + 8 * 2 * nw;
+    if (smem > static_cast<size_t>(kMaxSmem)) return fail("shared memory budget exceeded");
+
+    CUtensorMap tm0, tm1;
+    if (make_act_map(&tm0, src0, B, L.cin0, H, W)) return 1;
+    if (L.cin1 > 0) {
+        if (make_act_map(&tm1, src1, B, L.cin1, H, W)) return 1;
+    } else {
+        tm1 = tm0;
+    }
+    const int items = p.npass * p.num_tiles;
+    const int grid = items < num_sms ? items : num_sms;
+    switch (L.epi) {
+        case EPI_RELU: return launch_epi<EPI_RELU>(tm0, tm1, p, grid, smem, stream);
+        case EPI_RELU_POOL: return launch_epi<EPI_RELU_POOL>(tm0, tm1, p, grid, smem, stream);
+        case EPI_HEAD: return launch_epi<EPI_HEAD>(tm0, tm1, p, grid, smem, stream);
+        case EPI_CONVT: return launch_epi<EPI_CONVT>(tm0, tm1, p, grid, smem, stream);
+    }
+    return fail("unknown epilogue");
+}
+
+}  // namespace ogl

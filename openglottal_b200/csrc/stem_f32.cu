@@ -1,0 +1,304 @@
+// CUDA-core kernels: the Cin=1 stem of the bf16 path, the fp32 validation path
+// (precision_mode = OGL_PRECISION_F32: fp32 weights/activations, FFMA, NCHW), and the
+// layout converters used by the unit tests.
+//
+// Reference semantics restated here:
+//   utils.py:235       x = u8.astype(float32) / 255.0
+//   unet.py:24-29      y = relu(bn(conv3x3(x)))  (BN folded into W', b' by the host)
+//   unet.py:59,79      max_pool2d(2, 2)
+//   unet.py:69,82      out[n,co,2y+dy,2x+dx] = b[co] + sum_ci x[n,ci,y,x] * W[ci,co,dy,dx]
+//   unet.py:86         cat([skip, up], dim=1)  -> two source pointers
+//   unet.py:72,88      logits = conv1x1(x) + b;  utils.py:237,241 sigmoid(z) > thr <=> z > logit(thr)
+//   features.py:238    area = count(mask > 0)
+#include "internal.h"
+
+namespace ogl {
+
+namespace {
+
+__device__ __forceinline__ float load_gray(const void* frames, int in_dtype, size_t idx) {
+    if (in_dtype == 0) {
+        const float v = static_cast<float>(static_cast<const uint8_t*>(frames)[idx]);
+        return __fdiv_rn(v, 255.0f);  // same rounding as numpy float32 / 255.0
+    }
+    return static_cast<const float*>(frames)[idx];
+}
+
+// ------------------------------------------------------------------- stem
+// One thread per pixel: 9 taps -> 32 channels in fp32, written as 4 planes of 8 bf16.
+__global__ void __launch_bounds__(256)
+stem_kernel(const void* __restrict__ frames, int in_dtype, const float* __restrict__ w,
+            const float* __restrict__ b, int B, int H, int W, __nv_bfloat16* __restrict__ out) {
+    __shared__ float ws[32 * 9];
+    __shared__ float bs[32];
+    for (int i = threadIdx.x; i < 288; i += blockDim.x) ws[i] = w[i];
+    if (threadIdx.x < 32) bs[threadIdx.x] = b[threadIdx.x];
+    __syncthreads();
+    const size_t total = static_cast<size_t>(B) * H * W;
+    for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int x = static_cast<int>(idx % W);
+        const int y = static_cast<int>((idx / W) % H);
+        const size_t n = idx / (static_cast<size_t>(W) * H);
+        float in[9];
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+                const int yy = y + dy - 1, xx = x + dx - 1;
+                in[dy * 3 + dx] = (yy >= 0 && yy < H && xx >= 0 && xx < W)
+                                      ? load_gray(frames, in_dtype,
+                                                  (n * H + yy) * static_cast<size_t>(W) + xx)
+                                      : 0.f;
+            }
+        const size_t plane = static_cast<size_t>(H) * W * 8;
+        __nv_bfloat16* o = out + n * 4 * plane + (static_cast<size_t>(y) * W + x) * 8;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            float v[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int co = g * 8 + c;
+                float acc = 0.f;
+#pragma unroll
+                for (int t = 0; t < 9; ++t) acc = fmaf(in[t], ws[co * 9 + t], acc);
+                v[c] = fmaxf(acc + bs[co], 0.f);
+            }
+            uint4 q;
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]);
+            __nv_bfloat162 h1 = __floats2bfloat162_rn(v[2], v[3]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]);
+            __nv_bfloat162 h3 = __floats2bfloat162_rn(v[6], v[7]);
+            q.x = *reinterpret_cast<uint32_t*>(&h0);
+            q.y = *reinterpret_cast<uint32_t*>(&h1);
+            q.z = *reinterpret_cast<uint32_t*>(&h2);
+            q.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(o + g * plane) = q;
+        }
+    }
+}
+
+// ---------------------------------------------------------- fp32 validation
+__global__ void f32_input_kernel(const void* __restrict__ frames, int in_dtype, int64_t count,
+                                 float* __restrict__ out) {
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < count;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+        out[i] = load_gray(frames, in_dtype, static_cast<size_t>(i));
+}
+
+// Direct conv3x3, pad 1. Block = 16x16 output pixels x 8 output channels of one frame; the
+// input tile (18x18) of each input channel is staged in shared memory.
+constexpr int kFc = 8;
+__global__ void __launch_bounds__(256)
+f32_conv3x3_kernel(const float* __restrict__ src0, int c0, const float* __restrict__ src1, int c1,
+                   const float* __restrict__ w, const float* __restrict__ b,
+                   float* __restrict__ out, int cout, int H, int W, int relu) {
+    __shared__ float tile[18][18 + 1];
+    __shared__ float wsm[kFc][9];
+    const int tiles_x = (W + 15) / 16;
+    const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+    const int cog = blockIdx.y;  // group of kFc output channels
+    const int n = blockIdx.z;
+    const int lx = threadIdx.x & 15, ly = threadIdx.x >> 4;
+    const int x = tx * 16 + lx, y = ty * 16 + ly;
+    const int cin = c0 + c1;
+    float acc[kFc];
+#pragma unroll
+    for (int k = 0; k < kFc; ++k) acc[k] = 0.f;
+    for (int ci = 0; ci < cin; ++ci) {
+        const float* src = ci < c0 ? src0 + (static_cast<size_t>(n) * c0 + ci) * H * W
+                                   : src1 + (static_cast<size_t>(n) * c1 + (ci - c0)) * H * W;
+        __syncthreads();
+        for (int i = threadIdx.x; i < 18 * 18; i += 256) {
+            const int hy = i / 18, hx = i % 18;
+            const int yy = ty * 16 + hy - 1, xx = tx * 16 + hx - 1;
+            tile[hy][hx] =
+                (yy >= 0 && yy < H && xx >= 0 && xx < W) ? src[static_cast<size_t>(yy) * W + xx] : 0.f;
+        }
+        if (threadIdx.x < kFc * 9) {
+            const int k = threadIdx.x / 9, t = threadIdx.x % 9;
+            const int co = cog * kFc + k;
+            wsm[k][t] = co < cout ? w[(static_cast<size_t>(co) * cin + ci) * 9 + t] : 0.f;
+        }
+        __syncthreads();
+        float in[9];
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) in[dy * 3 + dx] = tile[ly + dy][lx + dx];
+#pragma unroll
+        for (int k = 0; k < kFc; ++k)
+#pragma unroll
+            for (int t = 0; t < 9; ++t) acc[k] = fmaf(in[t], wsm[k][t], acc[k]);
+    }
+    if (x < W && y < H) {
+#pragma unroll
+        for (int k = 0; k < kFc; ++k) {
+            const int co = cog * kFc + k;
+            if (co < cout) {
+                float v = acc[k] + b[co];
+                if (relu) v = fmaxf(v, 0.f);
+                out[((static_cast<size_t>(n) * cout + co) * H + y) * W + x] = v;
+            }
+        }
+    }
+}
+
+__global__ void f32_maxpool_kernel(const float* __restrict__ in, float* __restrict__ out, int BC,
+                                   int H, int W) {
+    const int OH = H / 2, OW = W / 2;
+    const size_t total = static_cast<size_t>(BC) * OH * OW;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int ox = static_cast<int>(i % OW);
+        const int oy = static_cast<int>((i / OW) % OH);
+        const size_t bc = i / (static_cast<size_t>(OW) * OH);
+        const float* p = in + (bc * H + 2 * oy) * W + 2 * ox;
+        out[i] = fmaxf(fmaxf(p[0], p[1]), fmaxf(p[W], p[W + 1]));
+    }
+}
+
+// ConvTranspose2d k=2 s=2: thread per output element.
+__global__ void f32_convt_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                 const float* __restrict__ b, float* __restrict__ out, int B,
+                                 int cin, int cout, int H, int W) {
+    const int OH = 2 * H, OW = 2 * W;
+    const size_t total = static_cast<size_t>(B) * cout * OH * OW;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int ox = static_cast<int>(i % OW);
+        const int oy = static_cast<int>((i / OW) % OH);
+        const int co = static_cast<int>((i / (static_cast<size_t>(OW) * OH)) % cout);
+        const size_t n = i / (static_cast<size_t>(OW) * OH * cout);
+        const int y = oy >> 1, x = ox >> 1, dy = oy & 1, dx = ox & 1;
+        float acc = 0.f;
+        const float* ip = in + (n * cin * H + y) * W + x;
+        const float* wp = w + (static_cast<size_t>(co) * 2 + dy) * 2 + dx;
+        for (int ci = 0; ci < cin; ++ci)
+            acc = fmaf(ip[static_cast<size_t>(ci) * H * W], wp[static_cast<size_t>(ci) * cout * 4], acc);
+        out[i] = acc + b[co];
+    }
+}
+
+__global__ void f32_head_kernel(const float* __restrict__ in, const float* __restrict__ w, float b,
+                                float thr, int C, int H, int W, float* __restrict__ logits,
+                                uint8_t* __restrict__ mask, int32_t* __restrict__ area) {
+    // grid.y = frame; block reduces its pixel count and does one atomic.
+    const int n = blockIdx.y;
+    const size_t hw = static_cast<size_t>(H) * W;
+    int cnt = 0;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < hw;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        float z = 0.f;
+        for (int c = 0; c < C; ++c) z = fmaf(in[(static_cast<size_t>(n) * C + c) * hw + i], w[c], z);
+        z += b;
+        const bool on = z > thr;
+        if (logits) logits[n * hw + i] = z;
+        if (mask) mask[n * hw + i] = on ? 255 : 0;
+        cnt += on ? 1 : 0;
+    }
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0 && area && cnt) atomicAdd(area + n, cnt);
+}
+
+// ------------------------------------------------------- layout converters
+__global__ void nchw_to_c8_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                  int B, int C, int H, int W) {
+    const size_t total = static_cast<size_t>(B) * C * H * W;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int x = static_cast<int>(i % W);
+        const int y = static_cast<int>((i / W) % H);
+        const int c = static_cast<int>((i / (static_cast<size_t>(W) * H)) % C);
+        const size_t n = i / (static_cast<size_t>(W) * H * C);
+        out[(((n * (C / 8) + c / 8) * H + y) * W + x) * 8 + (c & 7)] = __float2bfloat16_rn(in[i]);
+    }
+}
+__global__ void c8_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out,
+                                  int B, int C, int H, int W) {
+    const size_t total = static_cast<size_t>(B) * C * H * W;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int x = static_cast<int>(i % W);
+        const int y = static_cast<int>((i / W) % H);
+        const int c = static_cast<int>((i / (static_cast<size_t>(W) * H)) % C);
+        const size_t n = i / (static_cast<size_t>(W) * H * C);
+        out[i] = __bfloat162float(in[(((n * (C / 8) + c / 8) * H + y) * W + x) * 8 + (c & 7)]);
+    }
+}
+
+inline int grid_for(size_t total, int block = 256, int cap = 148 * 16) {
+    size_t g = (total + block - 1) / block;
+    if (g > static_cast<size_t>(cap)) g = cap;
+    if (g < 1) g = 1;
+    return static_cast<int>(g);
+}
+
+}  // namespace
+
+int launch_stem(const void* frames, int in_dtype, const float* w, const float* b, int B, int H,
+                int W, __nv_bfloat16* out, cudaStream_t stream) {
+    const size_t total = static_cast<size_t>(B) * H * W;
+    stem_kernel<<<grid_for(total, 256, 148 * 8), 256, 0, stream>>>(frames, in_dtype, w, b, B, H, W,
+                                                                   out);
+    OGL_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_f32_input(const void* frames, int in_dtype, int64_t count, float* out,
+                     cudaStream_t stream) {
+    f32_input_kernel<<<grid_for(static_cast<size_t>(count)), 256, 0, stream>>>(frames, in_dtype,
+                                                                              count, out);
+    OGL_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_f32_conv3x3(const float* src0, int c0, const float* src1, int c1, const float* w,
+                       const float* b, float* out, int B, int cout, int H, int W, int relu,
+                       cudaStream_t stream) {
+    dim3 grid(((W + 15) / 16) * ((H + 15) / 16), (cout + kFc - 1) / kFc, B);
+    f32_conv3x3_kernel<<<grid, 256, 0, stream>>>(src0, c0, src1, c1, w, b, out, cout, H, W, relu);
+    OGL_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_f32_maxpool(const float* in, float* out, int BC, int H, int W, cudaStream_t stream) {
+    f32_maxpool_kernel<<<grid_for(static_cast<size_t>(BC) * (H / 2) * (W / 2)), 256, 0, stream>>>(
+        in, out, BC, H, W);
+    OGL_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_f32_convt(const float* in, const float* w, const float* b, float* out, int B, int cin,
+                     int cout, int H, int W, cudaStream_t stream) {
+    f32_convt_kernel<<<grid_for(static_cast<size_t>(B) * cout * 4 * H * W), 256, 0, stream>>>(
+        in, w, b, out, B, cin, cout, H, W);
+    OGL_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_f32_head(const float* in, const float* w, float b, float thr, int B, int C, int H,
+                    int W, float* logits, uint8_t* mask, int32_t* area, cudaStream_t stream) {
+    const size_t hw = static_cast<size_t>(H) * W;
+    dim3 grid(grid_for(hw, 256, 64), B);
+    f32_head_kernel<<<grid, 256, 0, stream>>>(in, w, b, thr, C, H, W, logits, mask, area);
+    OGL_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_nchw_to_c8(const float* in, __nv_bfloat16* out, int B, int C, int H, int W,
+                      cudaStream_t stream) {
+    nchw_to_c8_kernel<<<grid_for(static_cast<size_t>(B) * C * H * W), 256, 0, stream>>>(in, out, B,
+                                                                                       C, H, W);
+    OGL_CUDA(cudaGetLastError());
+    return 0;
+}
+int launch_c8_to_nchw(const __nv_bfloat16* in, float* out, int B, int C, int H, int W,
+                      cudaStream_t stream) {
+    c8_to_nchw_kernel<<<grid_for(static_cast<size_t>(B) * C * H * W), 256, 0, stream>>>(in, out, B,
+                                                                                       C, H, W);
+    OGL_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace ogl

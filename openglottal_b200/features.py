@@ -1,0 +1,218 @@
+"""unet-only pipeline and kinematic features, mirroring /root/reference/openglottal/features.py.
+
+* ``_kinematic_features``      <- features.py:38-68  (same dict, same None / ValueError cases)
+* ``extract_features_unet``    <- features.py:202-247 (same signature and return value)
+* ``extract_features_unet_frames`` is the raw-frame entry point the video wrapper, the bench and
+  the multi-GPU launcher share: batches stream from pinned host memory, frames are sharded by
+  contiguous ranges over ranks, and only the int32 area vector is gathered (NCCL).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native, sharding
+from .unet import UNet
+from .utils import _require_native, bgr_to_gray, load_frames_bgr
+
+_FEATURE_KEYS = ("area_mean", "area_std", "area_range", "open_quotient", "f0", "periodicity", "cv")
+
+
+def _features_from_device(area_dev: torch.Tensor):
+    """Runs the CUDA feature kernels on an int32 or float64 CUDA vector of n >= 2 samples.
+    Returns (out8 numpy float64, flags numpy int32) after one D2H copy."""
+    lib = _native.load()
+    n = area_dev.numel()
+    dev = area_dev.device
+    nbytes = lib.ogl_features_workspace_bytes(n)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    out = torch.empty(8, dtype=torch.float64, device=dev)
+    flags = torch.empty(2, dtype=torch.int32, device=dev)
+    fn = lib.ogl_features if area_dev.dtype == torch.int32 else lib.ogl_features_f64
+    with torch.cuda.device(dev):
+        _native.check(fn(area_dev.data_ptr(), n, out.data_ptr(), flags.data_ptr(), ws.data_ptr(),
+                         ws.numel(), torch.cuda.current_stream().cuda_stream))
+    return out.cpu().numpy(), flags.cpu().numpy()
+
+
+def _assemble(out8: np.ndarray, flags: np.ndarray, area_f64: np.ndarray) -> dict | None:
+    if flags[0]:
+        return None  # silent waveform (features.py:45-46)
+    return {
+        "area_mean": np.float64(out8[0]),
+        "area_std": np.float64(out8[1]),
+        "area_range": np.float64(out8[2]),
+        "open_quotient": float(out8[3]),
+        "f0": None if flags[1] else float(out8[4]),
+        "periodicity": float(out8[5]),
+        "cv": np.float64(out8[6]),
+        "_area": area_f64,
+    }
+
+
+def kinematic_features_device(area: torch.Tensor) -> dict | None:
+    """Features of an int32 CUDA area vector (the hot-path form). ``_area`` is the float64 copy
+    the reference returns."""
+    if area.device.type != "cuda" or area.dtype != torch.int32 or area.dim() != 1:
+        raise ValueError("expected a 1-D int32 CUDA tensor")
+    n = area.numel()
+    if n == 0:
+        raise ValueError("zero-size array to reduction operation maximum which has no identity")
+    area_host = area.cpu().numpy().astype(np.float64)
+    if n == 1:
+        if area_host[0] == 0:
+            return None
+        raise ValueError("attempt to get argmax of an empty sequence")  # as the reference does
+    out8, flags = _features_from_device(area.contiguous())
+    return _assemble(out8, flags, area_host)
+
+
+def _kinematic_features(area_wave) -> dict | None:
+    """Reference-compatible entry: list/array of per-frame areas -> feature dict or ``None``.
+
+    Edge cases follow /root/reference/openglottal/features.py:44-54 exactly: empty input and
+    n == 1 (non-silent) raise ``ValueError`` as numpy does there; an all-zero waveform gives
+    ``None``. The arithmetic runs on the GPU in fp64.
+    """
+    area = np.array(area_wave, dtype=np.float64)
+    if area.ndim != 1:
+        raise ValueError("area_wave must be one-dimensional")
+    if area.size == 0:
+        raise ValueError("zero-size array to reduction operation maximum which has no identity")
+    if area.max() == 0:
+        return None
+    if area.size == 1:
+        raise ValueError("attempt to get argmax of an empty sequence")
+    if not torch.cuda.is_available():
+        raise RuntimeError("openglottal_b200._kinematic_features needs a CUDA device (no CPU path)")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    exact_int = bool(np.all(area == np.round(area)) and np.abs(area).max() < 2**31)
+    if exact_int:
+        t = torch.from_numpy(area.astype(np.int32)).to(dev)
+    else:
+        t = torch.from_numpy(area).to(dev)
+    out8, flags = _features_from_device(t)
+    return _assemble(out8, flags, area)
+
+
+def segment_clip(frames_gray, model: UNet, batch: int = 512, threshold: float = 0.5,
+                 want_masks: bool = False):
+    """Area waveform (and optionally masks) of a clip of ``(N, H, W)`` uint8 gray frames.
+
+    Host input (numpy / CPU tensor) is streamed batch by batch from pinned memory on a copy
+    stream, double-buffered against the compute stream; CUDA input is used in place.
+    Returns ``(area int32 CUDA (N,), masks uint8 CUDA (N,H,W) | None)``.
+    """
+    model = _require_native(model)
+    dev = model._device()
+    if isinstance(frames_gray, np.ndarray):
+        frames_gray = torch.from_numpy(np.ascontiguousarray(frames_gray))
+    if frames_gray.dtype != torch.uint8 or frames_gray.dim() != 3:
+        raise ValueError("expected (N, H, W) uint8 frames")
+    n, hgt, wid = frames_gray.shape
+    if n == 0:
+        raise ValueError("no frames")
+    area = torch.empty(n, dtype=torch.int32, device=dev)
+    masks = torch.empty((n, hgt, wid), dtype=torch.uint8, device=dev) if want_masks else None
+    if frames_gray.device.type == "cuda":
+        for i0 in range(0, n, batch):
+            _, m, a = model.run(frames_gray[i0:i0 + batch], threshold=threshold,
+                                want_mask=want_masks)
+            area[i0:i0 + batch] = a
+            if want_masks:
+                masks[i0:i0 + batch] = m
+        return area, masks
+
+    host = frames_gray if frames_gray.is_pinned() else frames_gray.pin_memory()
+    compute = torch.cuda.current_stream(dev)
+    copy = torch.cuda.Stream(device=dev)
+    bufs = [torch.empty((min(batch, n), hgt, wid), dtype=torch.uint8, device=dev) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+    starts = list(range(0, n, batch))
+
+    def issue_copy(k: int) -> None:
+        i0 = starts[k]
+        m = min(batch, n - i0)
+        with torch.cuda.stream(copy):
+            if k >= 2:
+                copy.wait_event(freed[k % 2])
+            bufs[k % 2][:m].copy_(host[i0:i0 + m], non_blocking=True)
+            ready[k % 2].record(copy)
+
+    issue_copy(0)
+    for k, i0 in enumerate(starts):
+        if k + 1 < len(starts):
+            issue_copy(k + 1)
+        m = min(batch, n - i0)
+        compute.wait_event(ready[k % 2])
+        _, mk, a = model.run(bufs[k % 2][:m], threshold=threshold, want_mask=want_masks)
+        freed[k % 2].record(compute)
+        area[i0:i0 + m] = a
+        if want_masks:
+            masks[i0:i0 + m] = mk
+    return area, masks
+
+
+def extract_features_unet_frames(frames_gray, model: UNet, batch: int = 512,
+                                 threshold: float = 0.5, group=None) -> dict | None:
+    """unet-only pipeline on raw gray frames ``(N, H, W)`` uint8 (H, W multiples of 16).
+
+    With ``torch.distributed`` initialised (one process per GPU) every rank passes the FULL clip
+    (or at least its own shard, see ``sharding.shard_range``); each rank segments its contiguous
+    frame range and the int32 areas are all-gathered, so every rank returns the same dict.
+    """
+    n = frames_gray.shape[0]
+    rank, world = sharding.rank_world(group)
+    lo, hi = sharding.shard_range(n, rank, world)
+    if hi > lo:
+        local, _ = segment_clip(frames_gray[lo:hi], model, batch=batch, threshold=threshold)
+    else:
+        local = torch.empty(0, dtype=torch.int32, device=model._device())
+    area = sharding.gather_area(local, n, group)
+    return kinematic_features_device(area)
+
+
+def extract_features_unet(avi_path: str, detector, model, device=None) -> dict | None:
+    """Drop-in for ``openglottal.extract_features_unet`` (features.py:202-247).
+
+    ``detector is None`` (unet-only) is the accelerated path. With a detector the per-frame
+    masks come from the native kernels and the reference's bbox gating (features.py:240-245)
+    is applied on the host; the detector itself (Ultralytics YOLO) stays with the reference.
+    """
+    import cv2
+
+    model = _require_native(model)
+    dev = model._device()
+    frames_bgr = load_frames_bgr(avi_path)
+    if not frames_bgr:
+        return None
+    hgt, wid = frames_bgr[0].shape[:2]
+    native_size = (hgt, wid) == (256, 256)
+
+    if detector is None and native_size:
+        bgr = torch.from_numpy(np.stack(frames_bgr)).pin_memory().to(dev, non_blocking=True)
+        area, _ = segment_clip(bgr_to_gray(bgr), model)
+        return kinematic_features_device(area)
+
+    # Reference-resize semantics for other frame sizes and for the gated variant.
+    from .utils import unet_segment_frame
+
+    if detector is not None:
+        detector.reset()
+    area_wave: list[float] = []
+    for frm in frames_bgr:
+        gray = cv2.cvtColor(frm, cv2.COLOR_BGR2GRAY)
+        mask = unet_segment_frame(gray, model, dev)
+        if detector is None:
+            area_wave.append(float(np.sum(mask > 0)))
+        else:
+            box = detector.detect(frm)
+            if box is None:
+                area_wave.append(0.0)
+            else:
+                x1, y1, x2, y2 = box
+                area_wave.append(float(np.sum(mask[y1:y2, x1:x2] > 0)))
+    return _kinematic_features(area_wave)

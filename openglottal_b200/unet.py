@@ -1,0 +1,220 @@
+"""Drop-in for ``openglottal.UNet`` whose forward runs on hand-written sm_100a kernels.
+
+Mirrors /root/reference/openglottal/models/unet.py:36-88: same constructor signature, the same
+parameter/buffer tree (118 state-dict entries: ``downs.i.net.{0,1,3,4}.*``, ``ups.{0..7}.*``,
+``bottleneck.net.*``, ``head.*``) so ``load_state_dict(torch.load(path, weights_only=True))``
+(/root/reference/openglottal/cli.py:61-65) works unchanged. The forward pass is NOT PyTorch:
+BatchNorm is folded into the convolutions at pack time and the whole network runs through
+``libopenglottal_b200.so`` (tcgen05 implicit-GEMM convs, fused pool/head epilogues).
+There is no CPU path and no training path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _native
+
+_FEATURES = (32, 64, 128, 256)
+
+
+def _conv_bn_relu_x2(cin: int, cout: int) -> nn.Module:
+    """Container with the reference's parameter names: ``net.0`` conv, ``net.1`` BN, ``net.3``
+    conv, ``net.4`` BN (indices 2 and 5 are the parameter-free ReLUs)."""
+    block = nn.Module()
+    block.net = nn.Sequential(
+        nn.Conv2d(cin, cout, 3, padding=1, bias=False),
+        nn.BatchNorm2d(cout),
+        nn.ReLU(inplace=True),
+        nn.Conv2d(cout, cout, 3, padding=1, bias=False),
+        nn.BatchNorm2d(cout),
+        nn.ReLU(inplace=True),
+    )
+    return block
+
+
+class UNet(nn.Module):
+    """B200-native U-Net for binary glottal segmentation (1-channel in, 1-channel logits out).
+
+    Parameters match ``openglottal.UNet``; only ``UNet(1, 1, (32, 64, 128, 256))`` -- the
+    architecture every shipped checkpoint and the CLI use -- is implemented natively.
+    """
+
+    def __init__(self, in_ch: int = 1, out_ch: int = 1,
+                 features: tuple[int, ...] = _FEATURES) -> None:
+        super().__init__()
+        if in_ch != 1 or out_ch != 1 or tuple(features) != _FEATURES:
+            raise NotImplementedError(
+                "openglottal_b200.UNet implements UNet(1, 1, (32, 64, 128, 256)) only "
+                f"(got in_ch={in_ch}, out_ch={out_ch}, features={tuple(features)})")
+        self.downs = nn.ModuleList()
+        self.ups = nn.ModuleList()
+        self.pool = nn.MaxPool2d(2, 2)  # parameter-free; kept so the module tree matches
+        ch = in_ch
+        for f in features:
+            self.downs.append(_conv_bn_relu_x2(ch, f))
+            ch = f
+        self.bottleneck = _conv_bn_relu_x2(ch, 2 * ch)
+        for f in reversed(features):
+            self.ups.append(nn.ConvTranspose2d(2 * f, f, kernel_size=2, stride=2))
+            self.ups.append(_conv_bn_relu_x2(2 * f, f))
+        self.head = nn.Conv2d(features[0], out_ch, 1)
+
+        self.precision = "bf16"      # "bf16" (tensor cores) or "fp32" (validation mode)
+        self.max_batch = 512         # frames per native call; larger inputs are chunked
+        self._handle = None
+        self._handle_device = None
+        self._packed_sig = None
+        self._workspace = None
+        self._keepalive = None
+
+    # ------------------------------------------------------------------ native plumbing
+    def _device(self) -> torch.device:
+        return self.head.weight.device
+
+    def _ensure_handle(self) -> C.c_void_p:
+        dev = self._device()
+        if dev.type != "cuda":
+            raise RuntimeError(
+                "openglottal_b200.UNet runs on CUDA (B200) only; move the module with "
+                ".to('cuda'). There is no CPU fallback -- use the reference for CPU.")
+        index = dev.index if dev.index is not None else torch.cuda.current_device()
+        if self._handle is not None and self._handle_device == index:
+            return self._handle
+        self._release()
+        lib = _native.load()
+        h = C.c_void_p()
+        _native.check(lib.ogl_unet_create(C.byref(h), index))
+        self._handle, self._handle_device, self._packed_sig = h, index, None
+        return h
+
+    def _release(self) -> None:
+        if self._handle is not None:
+            _native.load().ogl_unet_destroy(self._handle)
+        self._handle = None
+        self._packed_sig = None
+
+    def __del__(self):  # pragma: no cover - best effort
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def _signature(self):
+        return tuple((t.data_ptr(), t._version) for t in self.state_dict(keep_vars=True).values())
+
+    def _pack_if_needed(self) -> None:
+        h = self._ensure_handle()
+        sig = self._signature()
+        if sig == self._packed_sig:
+            return
+        keep = []
+
+        def host(t: torch.Tensor):
+            a = t.detach().to(device="cpu", dtype=torch.float32).contiguous()
+            keep.append(a)
+            return C.cast(a.data_ptr(), C.POINTER(C.c_float))
+
+        def conv_bn(dst, seq, ci: int, bi: int) -> None:
+            conv, bn = seq[ci], seq[bi]
+            dst.weight = host(conv.weight)
+            dst.bn_weight = host(bn.weight)
+            dst.bn_bias = host(bn.bias)
+            dst.running_mean = host(bn.running_mean)
+            dst.running_var = host(bn.running_var)
+
+        st = _native.UNetState()
+        for i in range(4):
+            conv_bn(st.downs[i][0], self.downs[i].net, 0, 1)
+            conv_bn(st.downs[i][1], self.downs[i].net, 3, 4)
+            st.up_t[i].weight = host(self.ups[2 * i].weight)
+            st.up_t[i].bias = host(self.ups[2 * i].bias)
+            conv_bn(st.up_c[i][0], self.ups[2 * i + 1].net, 0, 1)
+            conv_bn(st.up_c[i][1], self.ups[2 * i + 1].net, 3, 4)
+        conv_bn(st.bottleneck[0], self.bottleneck.net, 0, 1)
+        conv_bn(st.bottleneck[1], self.bottleneck.net, 3, 4)
+        st.head_weight = host(self.head.weight)
+        st.head_bias = host(self.head.bias)
+        st.bn_eps = float(self.downs[0].net[1].eps)
+        _native.check(_native.load().ogl_unet_load_state(h, C.byref(st)))
+        self._packed_sig = sig
+
+    def _precision_code(self) -> int:
+        if self.precision == "bf16":
+            return _native.PRECISION_BF16
+        if self.precision == "fp32":
+            return _native.PRECISION_F32
+        raise ValueError(f"precision must be 'bf16' or 'fp32', got {self.precision!r}")
+
+    def _get_workspace(self, nbytes: int, device: torch.device) -> torch.Tensor:
+        ws = self._workspace
+        if ws is None or ws.numel() < nbytes or ws.device != device:
+            self._workspace = None
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            self._workspace = ws
+        return ws
+
+    # ------------------------------------------------------------------ public API
+    def run(self, frames: torch.Tensor, threshold: float = 0.5, want_logits: bool = False,
+            want_mask: bool = True, want_area: bool = True):
+        """Batched hot path: gray frames -> (logits | None, mask | None, area | None).
+
+        ``frames``: CUDA tensor ``(N, H, W)`` uint8 in 0..255 (scaled by 1/255 inside the
+        kernel, /root/reference/openglottal/utils.py:235) or float32 already scaled.
+        Returns f32 logits ``(N, H, W)``, u8 masks in {0, 255}
+        (utils.py:241) and int32 per-frame areas (features.py:238).
+        """
+        if self.training:
+            raise RuntimeError("openglottal_b200.UNet is inference-only: call .eval() first "
+                               "(training stays with the reference implementation)")
+        if frames.dim() != 3:
+            raise ValueError(f"expected (N, H, W) frames, got shape {tuple(frames.shape)}")
+        if frames.dtype == torch.uint8:
+            in_dtype = _native.DTYPE_U8
+        elif frames.dtype == torch.float32:
+            in_dtype = _native.DTYPE_F32
+        else:
+            raise TypeError(f"frames must be uint8 or float32, got {frames.dtype}")
+        dev = self._device()
+        if frames.device != dev:
+            raise RuntimeError(f"frames are on {frames.device} but the model is on {dev}")
+        n, hgt, wid = frames.shape
+        if n == 0:
+            raise ValueError("no frames")
+        if hgt % 16 or wid % 16:
+            raise ValueError(f"H and W must be multiples of 16 (got {hgt}x{wid}); resize first")
+        if not (0.0 < threshold < 1.0) or math.isnan(threshold):
+            raise ValueError("threshold must be in (0, 1)")
+        self._pack_if_needed()
+        lib = _native.load()
+        frames = frames.contiguous()
+        logits = torch.empty((n, hgt, wid), dtype=torch.float32, device=dev) if want_logits else None
+        mask = torch.empty((n, hgt, wid), dtype=torch.uint8, device=dev) if want_mask else None
+        area = torch.empty((n,), dtype=torch.int32, device=dev) if want_area else None
+        prec = self._precision_code()
+        chunk = min(n, self.max_batch if prec == _native.PRECISION_BF16 else min(self.max_batch, 16))
+        nbytes = lib.ogl_unet_workspace_bytes(self._handle, chunk, hgt, wid, prec)
+        ws = self._get_workspace(nbytes, dev)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream().cuda_stream
+            for i0 in range(0, n, chunk):
+                m = min(chunk, n - i0)
+                _native.check(lib.ogl_unet_forward(
+                    self._handle, frames[i0:i0 + m].data_ptr(), in_dtype, m, hgt, wid,
+                    ws.data_ptr(), ws.numel(),
+                    logits[i0:i0 + m].data_ptr() if want_logits else None,
+                    mask[i0:i0 + m].data_ptr() if want_mask else None,
+                    area[i0:i0 + m].data_ptr() if want_area else None,
+                    float(threshold), prec, stream))
+        return logits, mask, area
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """``(N, 1, H, W)`` float32 (or uint8) -> raw logits ``(N, 1, H, W)`` float32
+        (/root/reference/openglottal/models/unet.py:74-88)."""
+        if x.dim() != 4 or x.shape[1] != 1:
+            raise ValueError(f"expected (N, 1, H, W) input, got shape {tuple(x.shape)}")
+        logits, _, _ = self.run(x[:, 0], want_logits=True, want_mask=False, want_area=False)
+        return logits.unsqueeze(1)

@@ -1,0 +1,103 @@
+"""Per-kernel parity of the tcgen05 implicit-GEMM layers against torch.nn.functional on the
+same bf16-rounded operands (fp32 accumulate on both sides), called through the C ABI
+(ogl_debug_tc_layer). Tolerance: the kernel stores bf16, so |err| <= 2^-8 * |ref| + 1e-3."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+@pytest.fixture(scope="module")
+def handle(lib):
+    from openglottal_b200 import _native
+
+    h = C.c_void_p()
+    _native.check(lib.ogl_unet_create(C.byref(h), 0))
+    yield h
+    lib.ogl_unet_destroy(h)
+
+
+def _run_layer(lib, handle, kind, x0, x1, w, b, cout):
+    from openglottal_b200 import _native
+
+    n, c0, hgt, wid = x0.shape
+    c1 = 0 if x1 is None else x1.shape[1]
+    oh, ow = (2 * hgt, 2 * wid) if kind == 3 else (hgt, wid)
+    out = torch.full((n, cout, oh, ow), float("nan"), device="cuda")
+    pool = torch.full((n, cout, hgt // 2, wid // 2), float("nan"), device="cuda") if kind == 1 else None
+    wh = w.contiguous().cpu()
+    bh = b.contiguous().cpu()
+    rc = lib.ogl_debug_tc_layer(
+        handle, kind, x0.data_ptr(), c0, None if x1 is None else x1.data_ptr(), c1,
+        C.cast(wh.data_ptr(), C.POINTER(C.c_float)), C.cast(bh.data_ptr(), C.POINTER(C.c_float)),
+        cout, n, hgt, wid, out.data_ptr(), None if pool is None else pool.data_ptr(), None)
+    _native.check(rc)
+    torch.cuda.synchronize()
+    return out, pool
+
+
+def _report(name, got, ref):
+    err = (got - ref).abs()
+    tol = ref.abs() * 2.0 ** -7 + 2e-3
+    bad = err > tol
+    nan = torch.isnan(got).sum().item()
+    msg = (f"{name}: max|err|={err.max().item():.4g} ref_rms={ref.pow(2).mean().sqrt().item():.4g} "
+           f"bad={bad.sum().item()}/{bad.numel()} nan={nan}")
+    if bad.any():
+        idx = bad.nonzero()
+        msg += f" first_bad={idx[0].tolist()} per-channel bad={bad.sum((0, 2, 3)).tolist()[:16]}"
+        msg += f" per-row bad={bad.sum((0, 1, 3)).tolist()[:20]} per-col bad={bad.sum((0, 1, 2)).tolist()[:20]}"
+    print(msg)
+    assert nan == 0 and not bad.any(), msg
+
+
+CONV_CASES = [
+    # kind, c0, c1, cout, n, H, W
+    (0, 32, 0, 32, 2, 16, 16),
+    (0, 32, 0, 32, 2, 32, 48),
+    (0, 32, 0, 64, 3, 32, 32),
+    (1, 64, 0, 64, 2, 32, 32),
+    (0, 32, 32, 32, 2, 32, 32),
+    (0, 128, 128, 128, 1, 32, 32),
+    (0, 256, 0, 256, 3, 16, 16),
+    (1, 256, 0, 256, 2, 32, 32),
+    (0, 256, 0, 512, 5, 16, 16),
+    (0, 512, 0, 512, 2, 16, 16),
+]
+
+
+@pytest.mark.parametrize("kind,c0,c1,cout,n,hgt,wid", CONV_CASES)
+def test_conv3x3_tc(lib, handle, kind, c0, c1, cout, n, hgt, wid):
+    g = torch.Generator().manual_seed(c0 * 7 + cout + hgt)
+    cin = c0 + c1
+    x = _bf(torch.randn(n, cin, hgt, wid, generator=g))
+    w = _bf(torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (cin * 9)) ** 0.5)
+    b = torch.randn(cout, generator=g) * 0.1
+    ref = F.relu(F.conv2d(x.double(), w.double(), b.double(), padding=1)).float()
+    xc = x.cuda()
+    x0 = xc[:, :c0].contiguous()
+    x1 = xc[:, c0:].contiguous() if c1 else None
+    out, pool = _run_layer(lib, handle, kind, x0, x1, w, b, cout)
+    _report(f"conv {c0}+{c1}->{cout} {n}x{hgt}x{wid}", out.cpu(), ref)
+    if kind == 1:
+        _report("pooled", pool.cpu(), F.max_pool2d(_bf(ref), 2, 2))
+
+
+@pytest.mark.parametrize("cin,cout,n,hgt,wid", [(64, 32, 2, 16, 16), (512, 256, 3, 16, 16),
+                                                (128, 64, 1, 32, 48)])
+def test_convt2x2_tc(lib, handle, cin, cout, n, hgt, wid):
+    g = torch.Generator().manual_seed(cin + cout)
+    x = _bf(torch.randn(n, cin, hgt, wid, generator=g))
+    w = _bf(torch.randn(cin, cout, 2, 2, generator=g) * (1.0 / cin) ** 0.5)
+    b = torch.randn(cout, generator=g) * 0.1
+    ref = F.conv_transpose2d(x.double(), w.double(), b.double(), stride=2).float()
+    out, _ = _run_layer(lib, handle, 3, x.cuda(), None, w, b, cout)
+    _report(f"convT {cin}->{cout} {n}x{hgt}x{wid}", out.cpu(), ref)

@@ -1,0 +1,147 @@
+"""CPU: host-side logic -- C-ABI exports, state-dict tree, sharding (incl. world_size-2 gloo),
+loud failures without a GPU. No compute calls into the library here."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from openglottal_b200 import _native
+
+    header = (ROOT / "include" / "openglottal_b200.h").read_text()
+    declared = set(re.findall(r"\b(ogl_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_native.EXPORTS), declared ^ set(_native.EXPORTS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.ogl_version() == 100
+
+
+def test_struct_layout_matches_header():
+    from openglottal_b200 import _native
+
+    ptr = C.sizeof(C.c_void_p)
+    assert C.sizeof(_native.ConvBN) == 5 * ptr
+    assert C.sizeof(_native.ConvT) == 2 * ptr
+    # 18 conv+bn, 4 convT, head w/b, eps (padded)
+    assert C.sizeof(_native.UNetState) == (18 * 5 + 4 * 2 + 2) * ptr + ptr
+
+
+def test_module_tree_matches_reference_state_dict(calibrated_sd):
+    import openglottal_b200 as ogl
+
+    m = ogl.UNet()
+    sd = m.state_dict()
+    assert len(sd) == 118
+    assert sum(p.numel() for p in m.parameters()) == 7_762_465
+    assert set(sd) == set(calibrated_sd)
+    for k, v in calibrated_sd.items():
+        assert sd[k].shape == v.shape, k
+    m.load_state_dict(calibrated_sd, strict=True)
+    keys = list(sd)
+    assert keys[0] == "downs.0.net.0.weight" and keys[-1] == "head.bias"
+    assert keys.index("ups.0.weight") < keys.index("bottleneck.net.0.weight") < keys.index("head.weight")
+    assert sd["ups.0.weight"].shape == (512, 256, 2, 2)
+    assert sd["ups.7.net.0.weight"].shape == (32, 64, 3, 3)
+
+
+def test_no_cpu_fallback(lib):
+    import openglottal_b200 as ogl
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    h = C.c_void_p()
+    assert lib.ogl_unet_create(C.byref(h), 0) != 0
+    assert b"no CUDA device" in lib.ogl_last_error()
+    m = ogl.UNet().eval()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(1, 1, 32, 32))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ogl._kinematic_features([1.0, 2.0, 3.0])
+    # reference-identical edge cases are decided before any device work
+    assert ogl._kinematic_features([0.0] * 4) is None
+    with pytest.raises(ValueError):
+        ogl._kinematic_features([3.0])
+
+
+def test_product_does_not_import_oracle():
+    pkg = ROOT / "openglottal_b200"
+    for p in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.h")):
+        text = p.read_text()
+        assert "import oracle" not in text and "from oracle" not in text, p
+
+
+def test_shard_ranges_cover_and_are_contiguous():
+    from openglottal_b200 import sharding
+
+    for n in (0, 1, 7, 8, 9, 2000, 100_000, 1_000_003):
+        for world in (1, 2, 3, 4, 8):
+            edges = [sharding.shard_range(n, r, world) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == n
+            for (a, b), (c, d) in zip(edges, edges[1:]):
+                assert b == c and a <= b and c <= d
+            assert max(b - a for a, b in edges) == sharding.shard_size(n, world) or n == 0
+    with pytest.raises(ValueError):
+        sharding.shard_range(10, 2, 2)
+
+
+_GLOO_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["OGL_ROOT"])
+from openglottal_b200 import sharding
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % os.environ["OGL_PORT"],
+                        rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+rank, world = sharding.rank_world()
+for n in (9, 10, 1, 1001):
+    full = (torch.arange(n, dtype=torch.int32) * 7 + 3)
+    lo, hi = sharding.shard_range(n, rank, world)
+    got = sharding.gather_area(full[lo:hi].clone(), n)
+    assert torch.equal(got, full), (n, rank, got[:5])
+dist.barrier()
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gather_area_gloo(world, tmp_path):
+    port = 29500 + (os.getpid() % 2000) + world
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), OGL_PORT=str(port),
+                   OGL_ROOT=str(ROOT), CUDA_VISIBLE_DEVICES="")
+        procs.append(subprocess.Popen([sys.executable, "-c", _GLOO_WORKER], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
+    for p in procs:
+        out, _ = p.communicate(timeout=120)
+        assert p.returncode == 0, out.decode()
+        assert b"ok" in out
+
+
+def test_cli_rejects_out_of_scope_requests(capsys):
+    from openglottal_b200 import cli
+
+    with pytest.raises(SystemExit):
+        cli.main(["run", "x.avi", "--pipeline", "vft", "--unet-weights", "w.pt"])
+    with pytest.raises(SystemExit):
+        cli.main(["run", "x.avi", "--pipeline", "unet-only"])          # weights required
+    with pytest.raises(SystemExit):
+        cli.main(["run", "x.avi", "--unet-weights", "w.pt", "--device", "cpu"])
+
+
+def test_dice_matches_reference_definition():
+    from openglottal_b200 import dice
+
+    a = np.zeros((4, 4), np.uint8)
+    assert dice(a, a) == 1.0
+    b = a.copy(); b[0, :2] = 255
+    c = a.copy(); c[0, 1:3] = 255
+    assert dice(b, c) == pytest.approx(0.5)

@@ -1,0 +1,117 @@
+"""CPU: the oracle restatement is pinned against fixtures generated from the UNMODIFIED reference
+(tests/golden/make_golden.py, run in the build container where /root/reference exists)."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+GOLDEN = Path(__file__).parent / "golden"
+
+
+def test_forward_oracle_matches_reference_logits(calibrated_sd):
+    from oracle import unet_oracle as uo
+
+    g = np.load(GOLDEN / "unet_forward.npz")
+    got = uo.ref_forward(calibrated_sd, uo.frames_to_input(g["frames"])).numpy()
+    assert got.shape == g["logits"].shape
+    # same torch ops in the same order; allow for a different CPU conv kernel selection
+    assert np.abs(got - g["logits"]).max() <= 1e-4
+
+
+def test_folded_fp32_matches_reference_logits(calibrated_sd):
+    from oracle import unet_oracle as uo
+
+    g = np.load(GOLDEN / "unet_forward.npz")
+    got = uo.folded_forward(calibrated_sd, uo.frames_to_input(g["frames"]), bf16=False).numpy()
+    assert np.abs(got - g["logits"]).max() <= 2e-4
+
+
+def test_bitmodel_is_close_but_not_identical(calibrated_sd):
+    from oracle import unet_oracle as uo
+
+    g = np.load(GOLDEN / "unet_forward.npz")
+    got = uo.folded_forward(calibrated_sd, uo.frames_to_input(g["frames"]), bf16=True).numpy()
+    err = np.abs(got - g["logits"]).max()
+    assert 1e-4 < err < 0.5
+
+
+def test_segment_frame_oracle_matches_reference_masks(calibrated_sd):
+    from oracle import unet_oracle as uo
+
+    g = np.load(GOLDEN / "segment_frame.npz")
+    for name, shape in (("256", (256, 256)), ("96", (96, 128))):
+        frame = g["f" + name]
+        ref = np.unpackbits(g["m" + name])[: shape[0] * shape[1]].reshape(shape).astype(bool)
+        got = uo.segment_frame(calibrated_sd, frame) > 0
+        assert got.shape == shape
+        assert (got != ref).sum() <= 2, name     # borderline pixels only
+
+
+def test_pipeline_oracle_matches_reference_features(calibrated_sd):
+    import cv2
+    from oracle import unet_oracle as uo
+    from oracle.features_oracle import kinematic_features
+
+    ref = json.loads((GOLDEN / "pipeline.json").read_text())
+    cap = cv2.VideoCapture(str(GOLDEN / "pipeline_clip.avi"))
+    frames = []
+    while True:
+        ok, frm = cap.read()
+        if not ok:
+            break
+        frames.append(cv2.cvtColor(frm, cv2.COLOR_BGR2GRAY))
+    cap.release()
+    assert len(frames) == 30
+    wave = uo.area_wave(calibrated_sd, frames)
+    assert np.abs(np.array(wave) - np.array(ref["_area"])).max() <= 2
+    feats = kinematic_features(ref["_area"])
+    for k in ("area_mean", "area_std", "area_range", "open_quotient", "periodicity", "cv"):
+        assert feats[k] == pytest.approx(ref[k], rel=1e-12, abs=1e-12), k
+    assert feats["f0"] == ref["f0"]
+
+
+def test_features_oracle_matches_reference_kats():
+    from oracle.features_oracle import kinematic_features
+
+    kats = json.loads((GOLDEN / "features_kat.json").read_text())
+    assert len(kats) >= 10
+    for case in kats:
+        for exact in (False, True):
+            if case["raises"]:
+                with pytest.raises(ValueError):
+                    kinematic_features(case["input"], exact_correlate=exact)
+                continue
+            got = kinematic_features(case["input"], exact_correlate=exact)
+            ref = case["output"]
+            if ref is None:
+                assert got is None
+                continue
+            for k in ("area_mean", "area_std", "area_range", "open_quotient", "cv"):
+                assert got[k] == pytest.approx(ref[k], rel=1e-13, abs=1e-13), k
+            assert got["periodicity"] == pytest.approx(ref["periodicity"], rel=1e-9, abs=1e-12)
+            assert got["f0"] == ref["f0"]
+
+
+def test_survey_appendix_c_values():
+    """Spot values quoted in SURVEY.md App. C (generated from the reference)."""
+    from oracle.features_oracle import kinematic_features
+
+    t = np.arange(500)
+    f = kinematic_features(np.floor(np.maximum(0, 300 * np.sin(2 * np.pi * t / 20))))
+    assert f["area_mean"] == 94.5 and f["f0"] == 0.05 and f["open_quotient"] == 0.45
+    assert f["periodicity"] == pytest.approx(0.9599999999999985, rel=1e-12)
+    f = kinematic_features([5.0, 7.0])
+    assert f["f0"] is None and f["periodicity"] == pytest.approx(-0.4999999975, rel=1e-9)
+
+
+def test_synthetic_fixtures_are_reproducible():
+    from oracle import synth
+
+    a = synth.calibrated_state(0)
+    b = synth.calibrated_state(0)
+    assert all(torch.equal(a[k], b[k]) for k in a) and len(a) == 118
+    f1, m1 = synth.glottis_clip(3, 64, 64, seed=5)
+    f2, _ = synth.glottis_clip(3, 64, 64, seed=5)
+    assert np.array_equal(f1, f2) and set(np.unique(m1)) <= {0, 255}
