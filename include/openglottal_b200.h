@@ -88,6 +88,13 @@ int ogl_unet_forward(ogl_unet* h, const void* frames_dev, int in_dtype, int n, i
                      uint8_t* mask_dev, int32_t* area_dev, float threshold, int precision,
                      void* stream);
 
+/* Optional per-launch timing of the bf16 path (CUDA events on the caller's stream between the
+ * 22 launches of one forward; used by bench.py for the roofline numbers).
+ * ogl_unet_layer_times synchronises on the last event of the most recent profiled forward. */
+int ogl_unet_set_profiling(ogl_unet* h, int enable);
+int ogl_unet_layer_times(ogl_unet* h, float* ms_out, int capacity, int* count_out);
+const char* ogl_unet_layer_name(int index);
+
 /* Kinematic features of an area waveform of n >= 2 samples.
  * out8_dev: {area_mean, area_std, area_range, open_quotient, f0, periodicity, cv, peak_bin};
  * flags2_dev: {is_silent (reference returns None), f0_is_none (peak in first bin)}. */

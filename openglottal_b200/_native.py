@@ -51,6 +51,9 @@ EXPORTS = [
     "ogl_unet_load_state",
     "ogl_unet_workspace_bytes",
     "ogl_unet_forward",
+    "ogl_unet_set_profiling",
+    "ogl_unet_layer_times",
+    "ogl_unet_layer_name",
     "ogl_features_workspace_bytes",
     "ogl_features",
     "ogl_features_f64",
@@ -92,6 +95,12 @@ def load() -> C.CDLL:
     lib.ogl_unet_forward.restype = i32
     lib.ogl_unet_forward.argtypes = [vp, vp, i32, i32, i32, i32, vp, sz, vp, vp, vp, C.c_float,
                                      i32, vp]
+    lib.ogl_unet_set_profiling.restype = i32
+    lib.ogl_unet_set_profiling.argtypes = [vp, i32]
+    lib.ogl_unet_layer_times.restype = i32
+    lib.ogl_unet_layer_times.argtypes = [vp, _c_float_p, i32, C.POINTER(i32)]
+    lib.ogl_unet_layer_name.restype = C.c_char_p
+    lib.ogl_unet_layer_name.argtypes = [i32]
     lib.ogl_features_workspace_bytes.restype = sz
     lib.ogl_features_workspace_bytes.argtypes = [i64]
     lib.ogl_features.restype = i32

@@ -72,6 +72,10 @@ struct ogl_unet {
     F32Conv f_down[4][2], f_bott[2], f_up[4][2];
     F32ConvT f_upt[4];
     std::vector<void*> allocs;
+    // optional per-launch timing (ogl_unet_set_profiling)
+    bool profile = false;
+    std::vector<cudaEvent_t> events;
+    int n_events = 0;
 };
 
 namespace {
@@ -196,6 +200,19 @@ Plan make_plan(int n, int H, int W, size_t elem) {
     return p;
 }
 
+constexpr int kMaxLaunches = 40;
+const char* const kLayerNames[] = {
+    "stem", "downs.0.net.3+pool", "downs.1.net.0", "downs.1.net.3+pool", "downs.2.net.0",
+    "downs.2.net.3+pool", "downs.3.net.0", "downs.3.net.3+pool", "bottleneck.net.0",
+    "bottleneck.net.3", "ups.0(convT)", "ups.1.net.0(cat)", "ups.1.net.3", "ups.2(convT)",
+    "ups.3.net.0(cat)", "ups.3.net.3", "ups.4(convT)", "ups.5.net.0(cat)", "ups.5.net.3",
+    "ups.6(convT)", "ups.7.net.0(cat)", "ups.7.net.3+head"};
+
+inline void mark(ogl_unet* h, cudaStream_t stream) {
+    if (h->profile && h->n_events < static_cast<int>(h->events.size()))
+        cudaEventRecord(h->events[h->n_events++], stream);
+}
+
 }  // namespace
 
 extern "C" {
@@ -228,6 +245,7 @@ int ogl_unet_destroy(ogl_unet* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     free_all(h);
+    for (auto& e : h->events) cudaEventDestroy(e);
     delete h;
     return 0;
 }
@@ -352,23 +370,32 @@ int ogl_unet_forward(ogl_unet* h, const void* frames_dev, int in_dtype, int n, i
         const Plan p = make_plan(n, H, W, 2);
         auto B = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(ws + off); };
         __nv_bfloat16* P[4] = {B(p.U[1]), B(p.U[2]), B(p.U[3]), B(p.P3)};
+        h->n_events = 0;
+        mark(h, stream);
         if (launch_stem(frames_dev, in_dtype, h->stem_w, h->stem_b, n, H, W, B(p.T[0]), stream))
             return 1;
+        mark(h, stream);
         for (int l = 0; l < 4; ++l) {
             const int hh = H >> l, ww = W >> l;
-            if (l > 0 && launch_conv_tc(h->down_c1[l], P[l - 1], nullptr, n, hh, ww, B(p.T[l]),
-                                        nullptr, nullptr, h->num_sms, stream))
-                return 1;
+            if (l > 0) {
+                if (launch_conv_tc(h->down_c1[l], P[l - 1], nullptr, n, hh, ww, B(p.T[l]), nullptr,
+                                   nullptr, h->num_sms, stream))
+                    return 1;
+                mark(h, stream);
+            }
             if (launch_conv_tc(h->down_c2[l], B(p.T[l]), nullptr, n, hh, ww, B(p.S[l]), P[l],
                                nullptr, h->num_sms, stream))
                 return 1;
+            mark(h, stream);
         }
         if (launch_conv_tc(h->bott[0], P[3], nullptr, n, H >> 4, W >> 4, B(p.T[4]), nullptr,
                            nullptr, h->num_sms, stream))
             return 1;
+        mark(h, stream);
         if (launch_conv_tc(h->bott[1], B(p.T[4]), nullptr, n, H >> 4, W >> 4, B(p.B4), nullptr,
                            nullptr, h->num_sms, stream))
             return 1;
+        mark(h, stream);
         const __nv_bfloat16* below = B(p.B4);
         HeadParams hp;
         hp.w = h->head_w;
@@ -383,12 +410,15 @@ int ogl_unet_forward(ogl_unet* h, const void* frames_dev, int in_dtype, int n, i
             if (launch_conv_tc(h->up_t[k], below, nullptr, n, hh / 2, ww / 2, B(p.U[l]), nullptr,
                                nullptr, h->num_sms, stream))
                 return 1;
+            mark(h, stream);
             if (launch_conv_tc(h->up_c[k][0], B(p.S[l]), B(p.U[l]), n, hh, ww, B(p.T[l]), nullptr,
                                nullptr, h->num_sms, stream))
                 return 1;
+            mark(h, stream);
             if (launch_conv_tc(h->up_c[k][1], B(p.T[l]), nullptr, n, hh, ww, B(p.U[l]), nullptr,
                                k == 3 ? &hp : nullptr, h->num_sms, stream))
                 return 1;
+            mark(h, stream);
             below = B(p.U[l]);
         }
         return 0;
@@ -440,6 +470,35 @@ int ogl_unet_forward(ogl_unet* h, const void* frames_dev, int in_dtype, int n, i
                            area_dev, stream);
 }
 
+int ogl_unet_set_profiling(ogl_unet* h, int enable) {
+    if (!h) return fail("ogl_unet_set_profiling: NULL handle");
+    OGL_CUDA(cudaSetDevice(h->device));
+    if (enable && h->events.empty()) {
+        h->events.resize(kMaxLaunches);
+        for (auto& e : h->events) OGL_CUDA(cudaEventCreate(&e));
+    }
+    h->profile = enable != 0;
+    h->n_events = 0;
+    return 0;
+}
+
+int ogl_unet_layer_times(ogl_unet* h, float* ms_out, int capacity, int* count_out) {
+    if (!h || !ms_out || !count_out) return fail("ogl_unet_layer_times: NULL argument");
+    *count_out = 0;
+    if (!h->profile || h->n_events < 2) return fail("ogl_unet_layer_times: no profiled forward");
+    OGL_CUDA(cudaEventSynchronize(h->events[h->n_events - 1]));
+    const int n = h->n_events - 1;
+    for (int i = 0; i < n && i < capacity; ++i)
+        OGL_CUDA(cudaEventElapsedTime(ms_out + i, h->events[i], h->events[i + 1]));
+    *count_out = n < capacity ? n : capacity;
+    return 0;
+}
+
+const char* ogl_unet_layer_name(int index) {
+    const int n = static_cast<int>(sizeof(kLayerNames) / sizeof(kLayerNames[0]));
+    return (index >= 0 && index < n) ? kLayerNames[index] : "";
+}
+
 size_t ogl_features_workspace_bytes(int64_t n) { return features_workspace_bytes(n); }
 
 int ogl_features(const int32_t* area_dev, int64_t n, double* out8_dev, int32_t* flags2_dev,
@@ -473,6 +532,7 @@ int ogl_debug_tc_layer(ogl_unet* h, int kind, const float* src0_dev, int c0, con
                        int c1, const float* weight_host, const float* bias_host, int cout, int n,
                        int height, int width, float* out_dev, float* out_pool_dev,
                        void* stream_v) {
+    g_err.clear();
     if (!h || !src0_dev || !weight_host || !bias_host || !out_dev)
         return fail("ogl_debug_tc_layer: NULL argument");
     if (kind != EPI_RELU && kind != EPI_RELU_POOL && kind != EPI_CONVT)

@@ -249,10 +249,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             tc_fence_after();
             for (int mt = 0; mt < mtiles; ++mt) {
                 const int st = tile * p.S + (mt >> 1);
-                const bool valid = st < p.total_sub;  // warp-uniform
-                const SubTile t = decode_sub(p, valid ? st : p.total_sub - 1);
+                const bool in_range = st < p.total_sub;  // warp-uniform
+                const SubTile t = decode_sub(p, in_range ? st : p.total_sub - 1);
                 const int y = t.y0 + py;
                 const int x = t.x0 + (mt & 1) * 8 + px;
+                // partial tiles at the right / bottom edge: compute everything, store nothing
+                const bool valid = in_range && y < p.H && x < p.W;
                 const uint32_t tcol = tmem_base + lane_sel + buf * acc_cols + mt * p.N;
                 float zacc = 0.f;
                 for (int c0 = 0; c0 < p.N; c0 += 32) {
@@ -411,7 +413,9 @@ int launch_conv_tc(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloa
                    int H, int W, __nv_bfloat16* out, __nv_bfloat16* out_pool,
                    const HeadParams* head, int num_sms, cudaStream_t stream) {
     if (!g_encode) return fail("conv_tc_init() was not called");
-    if (H % 16 || W % 16) return fail("tensor-core conv needs H and W to be multiples of 16");
+    if (H < 1 || W < 1) return fail("tensor-core conv needs a non-empty feature map");
+    if (L.epi == EPI_RELU_POOL && (H % 2 || W % 2))
+        return fail("fused 2x2 max-pool needs even H and W");
     if (L.cin0 % 32 || L.cin1 % 32 || L.N % 32 || L.N > 128)
         return fail("tensor-core conv needs Cin % 32 == 0 and N in {32,64,96,128}");
     if (L.epi == EPI_RELU_POOL && !out_pool) return fail("pool epilogue needs out_pool");
@@ -442,8 +446,8 @@ int launch_conv_tc(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloa
     p.W = W;
     p.B = B;
     p.S = 2;
-    p.tiles_x = W / 16;
-    p.tiles_y = H / 16;
+    p.tiles_x = (W + 15) / 16;
+    p.tiles_y = (H + 15) / 16;
     p.total_sub = B * p.tiles_x * p.tiles_y;
     p.num_tiles = (p.total_sub + p.S - 1) / p.S;
     p.acc_bufs = (2 * p.S * p.N <= 256) ? 2 : 1;
