@@ -71,7 +71,7 @@ class ClockSampler(threading.Thread):
         self.samples: list[int] = []
         self.reasons: set[str] = set()
         self.max_mhz = None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         self.ok = False
         try:
             import pynvml
@@ -95,7 +95,7 @@ class ClockSampler(threading.Thread):
             nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
             nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
         }
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
@@ -104,10 +104,10 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._halt.wait(0.05)
 
     def stop(self) -> dict:
-        self._stop.set()
+        self._halt.set()
         if self.is_alive():
             self.join(timeout=2)
         if not self.samples:

@@ -184,50 +184,55 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
     } else if (warp == 1) {
         // ========================================================= MMA issuer
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(p.N);
-            const uint32_t lbo_a = kPlaneBytes, sbo_a = kHalo * 16;
-            const uint32_t lbo_b = 16u * p.N, sbo_b = 128u;
-            const int mtiles = 2 * p.S;
-            const uint32_t acc_cols = static_cast<uint32_t>(mtiles * p.N);
-            uint32_t ita = 0, itw = 0, li = 0;
-            for (int item = blockIdx.x; item < items; item += gridDim.x, ++li) {
-                const uint32_t buf = li % p.acc_bufs;
-                const uint32_t aph = (li / p.acc_bufs) & 1u;
-                mbar_wait(acc_empty + 8u * buf, aph ^ 1u);
-                tc_fence_after();
-                const uint32_t d0 = tmem_base + buf * acc_cols;
-                for (int kb = 0; kb < kb_total; ++kb, ++ita) {
-                    const uint32_t sa = ita % p.na;
-                    mbar_wait(a_full + 8u * sa, (ita / p.na) & 1u);
+        // The whole warp walks the loops (all values warp-uniform); one elected lane issues.
+        // Descriptors differ only in their start-address field, so each MMA is one 32-bit add.
+        const uint32_t idesc = make_idesc_bf16(p.N);
+        constexpr uint32_t lbo_a = kPlaneBytes, sbo_a = kHalo * 16;
+        const uint32_t lbo_b = 16u * p.N, sbo_b = 128u;
+        const uint64_t adesc0 = make_smem_desc(0, lbo_a, sbo_a);
+        const uint64_t bdesc0 = make_smem_desc(0, lbo_b, sbo_b);
+        const uint32_t acc_cols = static_cast<uint32_t>(4 * p.N);
+        const uint32_t bstep = (2u * lbo_b) >> 4;   // second K=16 half of a 32-channel block
+        uint32_t ita = 0, itw = 0, li = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x, ++li) {
+            const uint32_t buf = li % p.acc_bufs;
+            const uint32_t aph = (li / p.acc_bufs) & 1u;
+            mbar_wait(acc_empty + 8u * buf, aph ^ 1u);
+            tc_fence_after();
+            const uint32_t d0 = tmem_base + buf * acc_cols;
+            for (int kb = 0; kb < kb_total; ++kb, ++ita) {
+                const uint32_t sa = ita % p.na;
+                mbar_wait(a_full + 8u * sa, (ita / p.na) & 1u);
+                const uint32_t abase = a_ring + sa * a_stage_bytes;
+                for (int tap = 0; tap < p.taps; ++tap, ++itw) {
+                    const uint32_t sw = itw % p.nw;
+                    mbar_wait(w_full + 8u * sw, (itw / p.nw) & 1u);
                     tc_fence_after();
-                    const uint32_t abase = a_ring + sa * a_stage_bytes;
-                    for (int tap = 0; tap < p.taps; ++tap, ++itw) {
-                        const uint32_t sw = itw % p.nw;
-                        mbar_wait(w_full + 8u * sw, (itw / p.nw) & 1u);
-                        tc_fence_after();
-                        const int dy = p.taps == 9 ? tap / 3 : 1;
-                        const int dx = p.taps == 9 ? tap % 3 : 1;
-                        const uint32_t wbase = w_ring + sw * w_stage_bytes;
-                        const uint32_t tap_off = static_cast<uint32_t>(dy * kHalo + dx) * 16u;
+                    const int dy = p.taps == 9 ? tap / 3 : 1;
+                    const int dx = p.taps == 9 ? tap % 3 : 1;
+                    const uint64_t ad =
+                        adesc0 + ((abase + static_cast<uint32_t>(dy * kHalo + dx) * 16u) >> 4);
+                    const uint64_t bd = bdesc0 + ((w_ring + sw * w_stage_bytes) >> 4);
+                    const uint32_t first = (kb | tap) != 0 ? 1u : 0u;
+                    if (elect_one()) {
 #pragma unroll
-                        for (int j = 0; j < 2; ++j) {  // two K=16 steps per 32-channel block
-                            const uint64_t bdesc =
-                                make_smem_desc(wbase + j * 2u * lbo_b, lbo_b, sbo_b);
-                            const uint32_t acc_flag = (kb | tap | j) != 0 ? 1u : 0u;
-                            for (int mt = 0; mt < mtiles; ++mt) {
-                                const uint32_t aaddr = abase + (mt >> 1) * kSubBytes +
-                                                       j * 2u * lbo_a + tap_off +
-                                                       (mt & 1) * 128u;
-                                umma_bf16(d0 + mt * p.N, make_smem_desc(aaddr, lbo_a, sbo_a),
-                                          bdesc, idesc, acc_flag);
+                        for (int j = 0; j < 2; ++j) {
+#pragma unroll
+                            for (int mt = 0; mt < 4; ++mt) {
+                                constexpr uint32_t kSubStep = kSubBytes >> 4;
+                                const uint32_t aoff = (mt >> 1) * kSubStep +
+                                                      j * ((2u * lbo_a) >> 4) + (mt & 1) * 8u;
+                                umma_bf16(d0 + mt * p.N, ad + aoff, bd + j * bstep, idesc,
+                                          j ? 1u : first);
                             }
                         }
                         umma_commit(w_empty + 8u * sw);
+                        if (tap == p.taps - 1) umma_commit(a_empty + 8u * sa);
+                        if (tap == p.taps - 1 && kb == kb_total - 1)
+                            umma_commit(acc_full + 8u * buf);
                     }
-                    umma_commit(a_empty + 8u * sa);
+                    __syncwarp();
                 }
-                umma_commit(acc_full + 8u * buf);
             }
         }
     } else if (warp >= 4) {
@@ -445,7 +450,7 @@ int launch_conv_tc(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloa
     p.H = H;
     p.W = W;
     p.B = B;
-    p.S = 2;
+    p.S = 2;  // the MMA issuer is unrolled for 2 sub-tiles = 4 accumulators
     p.tiles_x = (W + 15) / 16;
     p.tiles_y = (H + 15) / 16;
     p.total_sub = B * p.tiles_x * p.tiles_y;
