@@ -59,8 +59,7 @@ struct ogl_unet {
     int num_sms = 148;
     bool loaded = false;
     // bf16 tensor-core path
-    float* stem_w = nullptr;  // [32][9] folded fp32
-    float* stem_b = nullptr;  // [32]
+    StemWeights stem;         // folded fp32 [32][9] + [32], passed by value to the stem kernel
     TcLayer down_c2[4];       // downs.i.net.3 (+pool)
     TcLayer down_c1[4];       // downs.i.net.0 for i = 1..3 (index 0 unused: stem)
     TcLayer bott[2];
@@ -115,36 +114,43 @@ void fold_conv_bn(const ogl_conv_bn& L, int cout, int cin, double eps, std::vect
 
 __nv_bfloat16 to_bf16(float v) { return __float2bfloat16_rn(v); }
 
-// conv3x3 weights [cout][cin][3][3] -> [pass][tap][cin/8][N][8] bf16
+// conv3x3 weights [cout][cin][3][3] -> [pass][cin/32][tap][4][N][8] bf16: one contiguous
+// 64*N-byte block per (32-channel block, tap), taps of a block adjacent so several can be
+// fetched with one bulk copy.
 std::vector<__nv_bfloat16> pack_conv(const std::vector<float>& w, int cout, int cin, int N) {
-    const int npass = cout / N, kc = cin / 8;
+    const int npass = cout / N, kb = cin / 32;
     std::vector<__nv_bfloat16> out(static_cast<size_t>(cout) * cin * 9);
     for (int pass = 0; pass < npass; ++pass)
-        for (int tap = 0; tap < 9; ++tap)
-            for (int c = 0; c < kc; ++c)
-                for (int n = 0; n < N; ++n)
-                    for (int e = 0; e < 8; ++e) {
-                        const int co = pass * N + n, ci = c * 8 + e;
-                        const size_t dst =
-                            ((((static_cast<size_t>(pass) * 9 + tap) * kc + c) * N + n) * 8) + e;
-                        out[dst] = to_bf16(w[(static_cast<size_t>(co) * cin + ci) * 9 + tap]);
-                    }
+        for (int b = 0; b < kb; ++b)
+            for (int tap = 0; tap < 9; ++tap)
+                for (int c = 0; c < 4; ++c)
+                    for (int n = 0; n < N; ++n)
+                        for (int e = 0; e < 8; ++e) {
+                            const int co = pass * N + n, ci = b * 32 + c * 8 + e;
+                            const size_t dst =
+                                (((((static_cast<size_t>(pass) * kb + b) * 9 + tap) * 4 + c) * N + n) * 8) + e;
+                            out[dst] = to_bf16(w[(static_cast<size_t>(co) * cin + ci) * 9 + tap]);
+                        }
     return out;
 }
 
-// convT weights [cin][cout][2][2] -> GEMM columns j = (dy*2+dx)*cout + co, layout
-// [pass][tap=0][cin/8][N][8] bf16
+// ConvTranspose2d weights [cin][cout][2][2]: pass = (dy, block of cb = N/2 output channels),
+// GEMM column n of a pass = dx * cb + (co - blk*cb); layout [pass][cin/32][4][N][8] bf16.
+int convt_n(int cout) { return 2 * (cout < 64 ? cout : 64); }
 std::vector<__nv_bfloat16> pack_convt(const float* w, int cin, int cout, int N) {
-    const int ntot = 4 * cout, npass = ntot / N, kc = cin / 8;
-    std::vector<__nv_bfloat16> out(static_cast<size_t>(ntot) * cin);
+    const int cb = N / 2, nblk = cout / cb, npass = 2 * nblk, kb = cin / 32;
+    std::vector<__nv_bfloat16> out(static_cast<size_t>(4) * cout * cin);
     for (int pass = 0; pass < npass; ++pass)
-        for (int c = 0; c < kc; ++c)
-            for (int n = 0; n < N; ++n)
-                for (int e = 0; e < 8; ++e) {
-                    const int j = pass * N + n, q = j / cout, co = j % cout, ci = c * 8 + e;
-                    const size_t dst = (((static_cast<size_t>(pass) * kc + c) * N + n) * 8) + e;
-                    out[dst] = to_bf16(w[(static_cast<size_t>(ci) * cout + co) * 4 + q]);
-                }
+        for (int b = 0; b < kb; ++b)
+            for (int c = 0; c < 4; ++c)
+                for (int n = 0; n < N; ++n)
+                    for (int e = 0; e < 8; ++e) {
+                        const int dy = pass / nblk, blk = pass % nblk;
+                        const int dx = n / cb, co = blk * cb + n % cb, ci = b * 32 + c * 8 + e;
+                        const size_t dst =
+                            ((((static_cast<size_t>(pass) * kb + b) * 4 + c) * N + n) * 8) + e;
+                        out[dst] = to_bf16(w[(static_cast<size_t>(ci) * cout + co) * 4 + dy * 2 + dx]);
+                    }
     return out;
 }
 
@@ -274,7 +280,8 @@ int ogl_unet_load_state(ogl_unet* h, const ogl_unet_state* st) {
         fold_conv_bn(st->downs[i][0], f, cin, eps, &w, &b);
         if (build_f32_conv(h, w, b, cin, f, &h->f_down[i][0])) return 1;
         if (i == 0) {
-            if (dev_upload(h, w, &h->stem_w) || dev_upload(h, b, &h->stem_b)) return 1;
+            memcpy(h->stem.w, w.data(), sizeof h->stem.w);
+            memcpy(h->stem.b, b.data(), sizeof h->stem.b);
         } else {
             if (build_tc_conv(h, w, b, cin, 0, f, EPI_RELU, &h->down_c1[i])) return 1;
         }
@@ -305,7 +312,7 @@ int ogl_unet_load_state(ogl_unet* h, const ogl_unet_state* st) {
             L->cin1 = 0;
             L->cout = f;
             L->taps = 1;
-            L->N = f < 128 ? f : 128;
+            L->N = convt_n(f);
             L->npass = 4 * f / L->N;
             L->epi = EPI_CONVT;
             if (dev_upload(h, pack_convt(T.weight, 2 * f, f, L->N), &L->wpack)) return 1;
@@ -372,7 +379,7 @@ int ogl_unet_forward(ogl_unet* h, const void* frames_dev, int in_dtype, int n, i
         __nv_bfloat16* P[4] = {B(p.U[1]), B(p.U[2]), B(p.U[3]), B(p.P3)};
         h->n_events = 0;
         mark(h, stream);
-        if (launch_stem(frames_dev, in_dtype, h->stem_w, h->stem_b, n, H, W, B(p.T[0]), stream))
+        if (launch_stem(frames_dev, in_dtype, h->stem, n, H, W, B(p.T[0]), stream))
             return 1;
         mark(h, stream);
         for (int l = 0; l < 4; ++l) {
@@ -545,7 +552,7 @@ int ogl_debug_tc_layer(ogl_unet* h, int kind, const float* src0_dev, int c0, con
     L.cin0 = c0;
     L.cin1 = c1;
     L.cout = cout;
-    L.N = cout < 128 ? cout : 128;
+    L.N = kind == EPI_CONVT ? convt_n(cout) : (cout < 128 ? cout : 128);
     L.epi = kind;
     std::vector<__nv_bfloat16> pk;
     if (kind == EPI_CONVT) {

@@ -13,7 +13,9 @@
 //   * A operand: one TMA box per (sub-tile, 32-channel block) brings the 18x18 halo tile of
 //     4 channel planes; the 9 taps are 9 start-address offsets into that one tile
 //     (zero padding = TMA out-of-bounds fill). Nothing is re-read per tap.
-//   * B operand: host-packed weights, streamed per (32-channel block, tap) with 1-D bulk copies.
+//   * B operand: host-packed weights [pass][32-ch block][tap][4][N][8], streamed with 1-D bulk
+//     copies, TPS taps per stage (9 for N <= 64, 3 for N = 128, 1 for convT) so the issuer
+//     pays one barrier wait per 8*TPS MMAs.
 //   * torch.cat([skip, up]) is two tensor maps walked back to back in the K loop.
 //   * Warp roles: w0 = activation TMA producer, w1 = MMA issuer, w2 = TMEM allocator,
 //     w3 = weight producer, w4..7 = epilogue (TMEM -> regs -> bias/ReLU/pool/head -> HBM).
@@ -79,7 +81,7 @@ __device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
     return *reinterpret_cast<uint32_t*>(&r);
 }
 
-template <int EPI>
+template <int EPI, int TPS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const ConvParams p) {
@@ -87,7 +89,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
 
     const uint32_t a_stage_bytes = static_cast<uint32_t>(p.S) * kSubBytes;
-    const uint32_t w_stage_bytes = 64u * static_cast<uint32_t>(p.N);
+    const uint32_t w_tap_bytes = 64u * static_cast<uint32_t>(p.N);
+    const uint32_t w_stage_bytes = TPS * w_tap_bytes;
     const uint32_t a_ring = smem_base;
     const uint32_t w_ring = a_ring + p.na * a_stage_bytes;
     const uint32_t bar_base = w_ring + p.nw * w_stage_bytes;  // 8 B aligned (sizes are x64)
@@ -168,14 +171,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             for (int item = blockIdx.x; item < items; item += gridDim.x) {
                 const int pass = item / p.num_tiles;
                 for (int kb = 0; kb < kb_total; ++kb) {
-                    for (int tap = 0; tap < p.taps; ++tap, ++it) {
+                    for (int tg = 0; tg < p.taps / TPS; ++tg, ++it) {
                         const uint32_t s = it % p.nw;
                         const uint32_t ph = (it / p.nw) & 1u;
                         mbar_wait(w_empty + 8u * s, ph ^ 1u);
                         mbar_arrive_expect_tx(w_full + 8u * s, w_stage_bytes);
                         const size_t off =
-                            (static_cast<size_t>(pass * p.taps + tap) * kb_total + kb) *
-                            w_stage_bytes;
+                            (static_cast<size_t>(pass * kb_total + kb) * p.taps + tg * TPS) *
+                            w_tap_bytes;
                         bulk_load(w_ring + s * w_stage_bytes, wbytes + off, w_stage_bytes,
                                   w_full + 8u * s);
                     }
@@ -204,32 +207,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 const uint32_t sa = ita % p.na;
                 mbar_wait(a_full + 8u * sa, (ita / p.na) & 1u);
                 const uint32_t abase = a_ring + sa * a_stage_bytes;
-                for (int tap = 0; tap < p.taps; ++tap, ++itw) {
+                for (int tg = 0; tg < p.taps / TPS; ++tg, ++itw) {
                     const uint32_t sw = itw % p.nw;
                     mbar_wait(w_full + 8u * sw, (itw / p.nw) & 1u);
                     tc_fence_after();
-                    const int dy = p.taps == 9 ? tap / 3 : 1;
-                    const int dx = p.taps == 9 ? tap % 3 : 1;
-                    const uint64_t ad =
-                        adesc0 + ((abase + static_cast<uint32_t>(dy * kHalo + dx) * 16u) >> 4);
+                    // TPS == 9: all taps unrolled; TPS == 3: tg is the tap row dy; TPS == 1: convT
+                    const uint32_t row_off =
+                        TPS == 3 ? static_cast<uint32_t>(tg) * kHalo * 16u : 0u;
+                    const uint64_t ad = adesc0 + ((abase + row_off) >> 4);
                     const uint64_t bd = bdesc0 + ((w_ring + sw * w_stage_bytes) >> 4);
-                    const uint32_t first = (kb | tap) != 0 ? 1u : 0u;
+                    const uint32_t first = (kb | tg) != 0 ? 1u : 0u;
+                    const bool last_tg = tg == p.taps / TPS - 1;
                     if (elect_one()) {
 #pragma unroll
-                        for (int j = 0; j < 2; ++j) {
+                        for (int t = 0; t < TPS; ++t) {
+                            // tap offset inside the halo tile, in 16-byte units
+                            constexpr int kCenter = kHalo + 1;
+                            const uint32_t toff = TPS == 9   ? (t / 3) * kHalo + (t % 3)
+                                                  : TPS == 3 ? t
+                                                             : kCenter;
 #pragma unroll
-                            for (int mt = 0; mt < 4; ++mt) {
-                                constexpr uint32_t kSubStep = kSubBytes >> 4;
-                                const uint32_t aoff = (mt >> 1) * kSubStep +
-                                                      j * ((2u * lbo_a) >> 4) + (mt & 1) * 8u;
-                                umma_bf16(d0 + mt * p.N, ad + aoff, bd + j * bstep, idesc,
-                                          j ? 1u : first);
+                            for (int j = 0; j < 2; ++j) {
+#pragma unroll
+                                for (int mt = 0; mt < 4; ++mt) {
+                                    constexpr uint32_t kSubStep = kSubBytes >> 4;
+                                    const uint32_t aoff = toff + (mt >> 1) * kSubStep +
+                                                          j * ((2u * lbo_a) >> 4) + (mt & 1) * 8u;
+                                    umma_bf16(d0 + mt * p.N, ad + aoff,
+                                              bd + (t * 4u * p.N + j * bstep), idesc,
+                                              (t | j) ? 1u : first);
+                                }
                             }
                         }
                         umma_commit(w_empty + 8u * sw);
-                        if (tap == p.taps - 1) umma_commit(a_empty + 8u * sa);
-                        if (tap == p.taps - 1 && kb == kb_total - 1)
-                            umma_commit(acc_full + 8u * buf);
+                        if (last_tg) umma_commit(a_empty + 8u * sa);
+                        if (last_tg && kb == kb_total - 1) umma_commit(acc_full + 8u * buf);
                     }
                     __syncwarp();
                 }
@@ -262,40 +274,57 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 const bool valid = in_range && y < p.H && x < p.W;
                 const uint32_t tcol = tmem_base + lane_sel + buf * acc_cols + mt * p.N;
                 float zacc = 0.f;
-                for (int c0 = 0; c0 < p.N; c0 += 32) {
+                if (EPI == EPI_CONVT) {
+                    // pass = (dy, block of cb output channels); columns = [dx][cb]. One thread
+                    // owns output pixels (2y+dy, 2x) and (2y+dy, 2x+1): 32 contiguous bytes.
+                    const int cb = p.N >> 1;
+                    const int nblk = p.cout / cb;
+                    const int qy = pass / nblk;
+                    const int blk = pass - qy * nblk;
+                    const size_t plane = static_cast<size_t>(OH) * OW * 8;
+                    for (int c0 = 0; c0 < cb; c0 += 32) {
+                        uint32_t r0[32], r1[32];
+                        tmem_ld32(tcol + c0, r0);
+                        tmem_ld32(tcol + cb + c0, r1);
+                        tmem_ld_wait();
+                        const int co0 = blk * cb + c0;
+                        __nv_bfloat16* optr =
+                            p.out + (static_cast<size_t>(t.n) * (p.cout >> 3) + (co0 >> 3)) * plane +
+                            (static_cast<size_t>(2 * y + qy) * OW + 2 * x) * 8;
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            uint32_t q[8];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float b0 = bias_sp[co0 + g * 8 + 2 * e];
+                                const float b1 = bias_sp[co0 + g * 8 + 2 * e + 1];
+                                q[e] = pack_bf16x2(__uint_as_float(r0[g * 8 + 2 * e]) + b0,
+                                                   __uint_as_float(r0[g * 8 + 2 * e + 1]) + b1);
+                                q[4 + e] = pack_bf16x2(__uint_as_float(r1[g * 8 + 2 * e]) + b0,
+                                                       __uint_as_float(r1[g * 8 + 2 * e + 1]) + b1);
+                            }
+                            if (valid) st_global_256(optr + g * plane, q);
+                        }
+                    }
+                }
+                for (int c0 = 0; EPI != EPI_CONVT && c0 < p.N; c0 += 32) {
                     uint32_t r[32];
                     tmem_ld32(tcol + c0, r);
                     tmem_ld_wait();
-                    // column -> output channel
-                    int co0;  // first output channel of these 32 columns
-                    int qy = 0, qx = 0;
-                    if (EPI == EPI_CONVT) {
-                        const int col = pass * p.N + c0;
-                        const int q = col / p.cout;
-                        co0 = col - q * p.cout;
-                        qy = q >> 1;
-                        qx = q & 1;
-                    } else {
-                        co0 = pass * p.N + c0;
-                    }
+                    const int co0 = pass * p.N + c0;  // first output channel of these columns
                     float v[32];
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        float f = __uint_as_float(r[c]) + bias_sp[co0 + c];
-                        if (EPI != EPI_CONVT) f = fmaxf(f, 0.f);
-                        v[c] = f;
-                    }
+                    for (int c = 0; c < 32; ++c)
+                        v[c] = fmaxf(__uint_as_float(r[c]) + bias_sp[co0 + c], 0.f);
                     if (EPI == EPI_HEAD) {
 #pragma unroll
                         for (int c = 0; c < 32; ++c)
                             zacc = fmaf(v[c], bias_sp[p.cout + c0 + c], zacc);
                     } else {
-                        const int oy = EPI == EPI_CONVT ? 2 * y + qy : y;
-                        const int ox = EPI == EPI_CONVT ? 2 * x + qx : x;
                         const size_t plane = static_cast<size_t>(OH) * OW * 8;
                         __nv_bfloat16* optr =
                             p.out + (static_cast<size_t>(t.n) * (p.cout >> 3) + (co0 >> 3)) * plane +
-                            (static_cast<size_t>(oy) * OW + ox) * 8;
+                            (static_cast<size_t>(y) * OW + x) * 8;
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
                             uint4 q4;
@@ -384,13 +413,20 @@ int make_act_map(CUtensorMap* tm, const __nv_bfloat16* base, int B, int C, int H
     return 0;
 }
 
-template <int EPI>
+template <int EPI, int TPS>
 int launch_epi(const CUtensorMap& tm0, const CUtensorMap& tm1, const ConvParams& p, int grid,
                size_t smem, cudaStream_t stream) {
-    conv_tc_kernel<EPI><<<grid, kThreads, smem, stream>>>(tm0, tm1, p);
+    conv_tc_kernel<EPI, TPS><<<grid, kThreads, smem, stream>>>(tm0, tm1, p);
     OGL_CUDA(cudaGetLastError());
     return 0;
 }
+template <int EPI, int TPS>
+int set_smem_attr() {
+    OGL_CUDA(cudaFuncSetAttribute(conv_tc_kernel<EPI, TPS>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    return 0;
+}
+inline int taps_per_stage(const TcLayer& L) { return L.taps == 1 ? 1 : (L.N <= 64 ? 9 : 3); }
 
 }  // namespace
 
@@ -403,14 +439,10 @@ int conv_tc_init() {
             return fail("cuTensorMapEncodeTiled entry point not available");
         g_encode = reinterpret_cast<EncodeTiledFn>(fn);
     }
-    OGL_CUDA(cudaFuncSetAttribute(conv_tc_kernel<EPI_RELU>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    OGL_CUDA(cudaFuncSetAttribute(conv_tc_kernel<EPI_RELU_POOL>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    OGL_CUDA(cudaFuncSetAttribute(conv_tc_kernel<EPI_HEAD>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    OGL_CUDA(cudaFuncSetAttribute(conv_tc_kernel<EPI_CONVT>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    if (set_smem_attr<EPI_RELU, 9>() || set_smem_attr<EPI_RELU, 3>() ||
+        set_smem_attr<EPI_RELU_POOL, 9>() || set_smem_attr<EPI_RELU_POOL, 3>() ||
+        set_smem_attr<EPI_HEAD, 9>() || set_smem_attr<EPI_CONVT, 1>())
+        return 1;
     return 0;
 }
 
@@ -421,8 +453,10 @@ int launch_conv_tc(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloa
     if (H < 1 || W < 1) return fail("tensor-core conv needs a non-empty feature map");
     if (L.epi == EPI_RELU_POOL && (H % 2 || W % 2))
         return fail("fused 2x2 max-pool needs even H and W");
-    if (L.cin0 % 32 || L.cin1 % 32 || L.N % 32 || L.N > 128)
-        return fail("tensor-core conv needs Cin % 32 == 0 and N in {32,64,96,128}");
+    if (L.cin0 % 32 || L.cin1 % 32 || (L.N != 32 && L.N != 64 && L.N != 128))
+        return fail("tensor-core conv needs Cin % 32 == 0 and N in {32,64,128}");
+    if (L.epi == EPI_CONVT && (L.taps != 1 || L.cout % (L.N / 2)))
+        return fail("convT layer: N must be 2 * (a divisor block of Cout)");
     if (L.epi == EPI_RELU_POOL && !out_pool) return fail("pool epilogue needs out_pool");
     if (L.epi == EPI_HEAD && (!head || L.cout != 32 || L.npass != 1))
         return fail("head epilogue needs Cout == 32 in one pass");
@@ -456,16 +490,23 @@ int launch_conv_tc(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloa
     p.total_sub = B * p.tiles_x * p.tiles_y;
     p.num_tiles = (p.total_sub + p.S - 1) / p.S;
     p.acc_bufs = (2 * p.S * p.N <= 256) ? 2 : 1;
+    const int tps = taps_per_stage(L);
+    const size_t w_stage = static_cast<size_t>(tps) * 64u * p.N;
+    const size_t tables = sizeof(float) * (L.cout + 32);
+    auto smem_need = [&](int na, int nw) {
+        return static_cast<size_t>(128 /*align slack*/ + na * p.S * kSubBytes + nw * w_stage +
+                                   16 * (na + nw) + 48 + tables + 64);
+    };
+    // ring depths: as many weight stages as fit beside 3 activation stages (2 when the
+    // weight stages are large), at least 2 and at most 8
     p.na = 3;
-    const size_t a_bytes = static_cast<size_t>(p.na) * p.S * kSubBytes;
-    const size_t w_stage = 64u * p.N;
-    const size_t fixed = 128 /*align slack*/ + 8 * 2 * p.na + 16 + 16 + 16 +
-                         sizeof(float) * (L.cout + 32) + 64;
-    int nw = static_cast<int>((kMaxSmem - a_bytes - fixed - 8 * 2 * 12) / w_stage);
-    if (nw > 12) nw = 12;
-    if (nw < 2) return fail("not enough shared memory for the weight ring");
-    p.nw = nw;
-    const size_t smem = a_bytes + nw * w_stage + fixed + 8 * 2 * nw;
+    p.nw = 8;
+    while (p.nw > 2 && smem_need(p.na, p.nw) > static_cast<size_t>(kMaxSmem)) --p.nw;
+    if (p.nw < 3 && w_stage > 30000) {
+        p.na = 2;
+        p.nw = 3;
+    }
+    const size_t smem = smem_need(p.na, p.nw);
     if (smem > static_cast<size_t>(kMaxSmem)) return fail("shared memory budget exceeded");
 
     CUtensorMap tm0, tm1;
@@ -477,12 +518,14 @@ int launch_conv_tc(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloa
     }
     const int items = p.npass * p.num_tiles;
     const int grid = items < num_sms ? items : num_sms;
-    switch (L.epi) {
-        case EPI_RELU: return launch_epi<EPI_RELU>(tm0, tm1, p, grid, smem, stream);
-        case EPI_RELU_POOL: return launch_epi<EPI_RELU_POOL>(tm0, tm1, p, grid, smem, stream);
-        case EPI_HEAD: return launch_epi<EPI_HEAD>(tm0, tm1, p, grid, smem, stream);
-        case EPI_CONVT: return launch_epi<EPI_CONVT>(tm0, tm1, p, grid, smem, stream);
-    }
+    if (L.epi == EPI_CONVT) return launch_epi<EPI_CONVT, 1>(tm0, tm1, p, grid, smem, stream);
+    if (L.epi == EPI_HEAD) return launch_epi<EPI_HEAD, 9>(tm0, tm1, p, grid, smem, stream);
+    if (L.epi == EPI_RELU)
+        return tps == 9 ? launch_epi<EPI_RELU, 9>(tm0, tm1, p, grid, smem, stream)
+                        : launch_epi<EPI_RELU, 3>(tm0, tm1, p, grid, smem, stream);
+    if (L.epi == EPI_RELU_POOL)
+        return tps == 9 ? launch_epi<EPI_RELU_POOL, 9>(tm0, tm1, p, grid, smem, stream)
+                        : launch_epi<EPI_RELU_POOL, 3>(tm0, tm1, p, grid, smem, stream);
     return fail("unknown epilogue");
 }
 

@@ -33,7 +33,7 @@ enum Epilogue : int {
 };
 
 struct TcLayer {
-    __nv_bfloat16* wpack = nullptr;  // [npass][taps][Cin/8][N][8] bf16 (device)
+    __nv_bfloat16* wpack = nullptr;  // [npass][Cin/32][taps][4][N][8] bf16 (device)
     float* bias = nullptr;           // [cout] fp32 (device)
     int cin0 = 0, cin1 = 0;          // channels of source 0 (skip / only) and source 1 (up)
     int cout = 0;                    // channels of the output tensor
@@ -58,9 +58,12 @@ int launch_conv_tc(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloa
                    const HeadParams* head, int num_sms, cudaStream_t stream);
 
 // stem: u8 / f32 gray -> conv3x3(1->32)+bias+ReLU in fp32 -> C8-planar bf16
-int launch_stem(const void* frames, int in_dtype, const float* w /*[32][9]*/,
-                const float* b /*[32]*/, int B, int H, int W, __nv_bfloat16* out,
-                cudaStream_t stream);
+struct StemWeights {  // passed by value: lives in the kernel-parameter constant bank
+    float w[32 * 9];
+    float b[32];
+};
+int launch_stem(const void* frames, int in_dtype, const StemWeights& sw, int B, int H, int W,
+                __nv_bfloat16* out, cudaStream_t stream);
 
 // fp32 validation path (NCHW fp32 activations, FFMA kernels)
 int launch_f32_input(const void* frames, int in_dtype, int64_t count, float* out,

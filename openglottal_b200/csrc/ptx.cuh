@@ -138,6 +138,13 @@ __device__ __forceinline__ void tmem_ld_wait() {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 32-byte global store (one full sector per thread).
+__device__ __forceinline__ void st_global_256(void* ptr, const uint32_t (&q)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(q[0]),
+                 "r"(q[1]), "r"(q[2]), "r"(q[3]), "r"(q[4]), "r"(q[5]), "r"(q[6]), "r"(q[7])
+                 : "memory");
+}
+
 // Shared-memory matrix descriptor, K-major, SWIZZLE_NONE ("interleave") canonical layout:
 // in 16-byte units ((8,n),2):((1,SBO),LBO) -- 8 rows x 16 B are one contiguous 128 B core
 // matrix, SBO = byte step between 8-row groups, LBO = byte step between the two 8-element

@@ -26,14 +26,11 @@ __device__ __forceinline__ float load_gray(const void* frames, int in_dtype, siz
 
 // ------------------------------------------------------------------- stem
 // One thread per pixel: 9 taps -> 32 channels in fp32, written as 4 planes of 8 bf16.
+// The 288 folded weights arrive as a by-value kernel parameter, so every FFMA takes its
+// weight straight from the constant bank (no LDS / LDG in the inner loop).
 __global__ void __launch_bounds__(256)
-stem_kernel(const void* __restrict__ frames, int in_dtype, const float* __restrict__ w,
-            const float* __restrict__ b, int B, int H, int W, __nv_bfloat16* __restrict__ out) {
-    __shared__ float ws[32 * 9];
-    __shared__ float bs[32];
-    for (int i = threadIdx.x; i < 288; i += blockDim.x) ws[i] = w[i];
-    if (threadIdx.x < 32) bs[threadIdx.x] = b[threadIdx.x];
-    __syncthreads();
+stem_kernel(const void* __restrict__ frames, int in_dtype, const __grid_constant__ StemWeights sw,
+            int B, int H, int W, __nv_bfloat16* __restrict__ out) {
     const size_t total = static_cast<size_t>(B) * H * W;
     for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -61,8 +58,8 @@ stem_kernel(const void* __restrict__ frames, int in_dtype, const float* __restri
                 const int co = g * 8 + c;
                 float acc = 0.f;
 #pragma unroll
-                for (int t = 0; t < 9; ++t) acc = fmaf(in[t], ws[co * 9 + t], acc);
-                v[c] = fmaxf(acc + bs[co], 0.f);
+                for (int t = 0; t < 9; ++t) acc = fmaf(in[t], sw.w[co * 9 + t], acc);
+                v[c] = fmaxf(acc + sw.b[co], 0.f);
             }
             uint4 q;
             __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]);
@@ -236,10 +233,10 @@ inline int grid_for(size_t total, int block = 256, int cap = 148 * 16) {
 
 }  // namespace
 
-int launch_stem(const void* frames, int in_dtype, const float* w, const float* b, int B, int H,
-                int W, __nv_bfloat16* out, cudaStream_t stream) {
+int launch_stem(const void* frames, int in_dtype, const StemWeights& sw, int B, int H, int W,
+                __nv_bfloat16* out, cudaStream_t stream) {
     const size_t total = static_cast<size_t>(B) * H * W;
-    stem_kernel<<<grid_for(total, 256, 148 * 8), 256, 0, stream>>>(frames, in_dtype, w, b, B, H, W,
+    stem_kernel<<<grid_for(total, 256, 148 * 8), 256, 0, stream>>>(frames, in_dtype, sw, B, H, W,
                                                                    out);
     OGL_CUDA(cudaGetLastError());
     return 0;
