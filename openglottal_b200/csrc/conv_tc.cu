@@ -18,7 +18,8 @@
 //     pays one barrier wait per 8*TPS MMAs.
 //   * torch.cat([skip, up]) is two tensor maps walked back to back in the K loop.
 //   * Warp roles: w0 = activation TMA producer, w1 = MMA issuer, w2 = TMEM allocator,
-//     w3 = weight producer, w4..7 = epilogue (TMEM -> regs -> bias/ReLU/pool/head -> HBM).
+//     w3 = weight producer, w4..11 = epilogue (TMEM -> regs -> bias/ReLU/pool/head -> HBM);
+//     epilogue warp w reads TMEM lanes 32*(w%4).. and handles sub-tile (w-4)/4 of each tile.
 #include "internal.h"
 #include "ptx.cuh"
 
@@ -33,7 +34,8 @@ namespace {
 constexpr int kHalo = 18;                          // 16 + 2
 constexpr int kPlaneBytes = kHalo * kHalo * 16;    // one 8-channel plane of a halo tile
 constexpr int kSubBytes = 4 * kPlaneBytes;         // 32 channels of one 16x16 sub-tile (20736 B)
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;       // 4 control warps + 8 epilogue warps
+constexpr int kEpiThreads = 256;
 constexpr int kTmemCols = 512;
 
 struct ConvParams {
@@ -53,6 +55,7 @@ struct ConvParams {
     int H, W, B;     // resolution of the INPUT feature map
     int S;           // sub-tiles (16x16 px) per CTA tile
     int tiles_x, tiles_y, total_sub, num_tiles;
+    unsigned long long magic_tx, magic_tpf;  // ceil(2^40 / d) for d = tiles_x, tiles_x*tiles_y
     int na, nw;      // ring depths
     int acc_bufs;    // 1 or 2 TMEM accumulator sets
 };
@@ -60,14 +63,17 @@ struct ConvParams {
 struct SubTile {
     int n, y0, x0;
 };
+// sub-tile index -> (frame, y0, x0); divisions by multiply-shift (exact for st * d < 2^40)
 __device__ __forceinline__ SubTile decode_sub(const ConvParams& p, int st) {
     SubTile s;
-    int tx = st % p.tiles_x;
-    int r = st / p.tiles_x;
-    int ty = r % p.tiles_y;
-    s.n = r / p.tiles_y;
-    s.y0 = ty * 16;
-    s.x0 = tx * 16;
+    const unsigned u = static_cast<unsigned>(st);
+    const unsigned n = static_cast<unsigned>((u * p.magic_tpf) >> 40);
+    const unsigned rem = u - n * static_cast<unsigned>(p.tiles_x * p.tiles_y);
+    const unsigned ty = static_cast<unsigned>((rem * p.magic_tx) >> 40);
+    const unsigned tx = rem - ty * static_cast<unsigned>(p.tiles_x);
+    s.n = static_cast<int>(n);
+    s.y0 = static_cast<int>(ty) * 16;
+    s.x0 = static_cast<int>(tx) * 16;
     return s;
 }
 
@@ -130,7 +136,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(acc_full + 8u * i, 1);
-            mbar_init(acc_empty + 8u * i, 128);
+            mbar_init(acc_empty + 8u * i, kEpiThreads);
         }
         fence_barrier_init();
     }
@@ -249,11 +255,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
     } else if (warp >= 4) {
         // =========================================================== epilogue
-        const int et = threadIdx.x - 128;          // TMEM lane == pixel index inside a patch
+        const int et = (threadIdx.x - 128) & 127;  // TMEM lane == pixel index inside a patch
+        const int esub = (threadIdx.x - 128) >> 7; // which sub-tile (pair of patches) this warp owns
         const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
         const int py = et >> 3, px = et & 7;
-        const int mtiles = 2 * p.S;
-        const uint32_t acc_cols = static_cast<uint32_t>(mtiles * p.N);
+        const uint32_t acc_cols = static_cast<uint32_t>(4 * p.N);
         const int OH = EPI == EPI_CONVT ? 2 * p.H : p.H;
         const int OW = EPI == EPI_CONVT ? 2 * p.W : p.W;
         uint32_t li = 0;
@@ -262,14 +268,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const int pass = item / p.num_tiles;
             const uint32_t buf = li % p.acc_bufs;
             const uint32_t aph = (li / p.acc_bufs) & 1u;
+            const int st = tile * p.S + esub;
+            const bool in_range = st < p.total_sub;  // warp-uniform
+            const SubTile t = decode_sub(p, in_range ? st : p.total_sub - 1);
             mbar_wait(acc_full + 8u * buf, aph);
             tc_fence_after();
-            for (int mt = 0; mt < mtiles; ++mt) {
-                const int st = tile * p.S + (mt >> 1);
-                const bool in_range = st < p.total_sub;  // warp-uniform
-                const SubTile t = decode_sub(p, in_range ? st : p.total_sub - 1);
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                const int mt = esub * 2 + half;
                 const int y = t.y0 + py;
-                const int x = t.x0 + (mt & 1) * 8 + px;
+                const int x = t.x0 + half * 8 + px;
                 // partial tiles at the right / bottom edge: compute everything, store nothing
                 const bool valid = in_range && y < p.H && x < p.W;
                 const uint32_t tcol = tmem_base + lane_sel + buf * acc_cols + mt * p.N;
@@ -296,8 +304,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                             uint32_t q[8];
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
-                                const float b0 = bias_sp[co0 + g * 8 + 2 * e];
-                                const float b1 = bias_sp[co0 + g * 8 + 2 * e + 1];
+                                const float2 b2 =
+                                    *reinterpret_cast<const float2*>(bias_sp + co0 + g * 8 + 2 * e);
+                                const float b0 = b2.x, b1 = b2.y;
                                 q[e] = pack_bf16x2(__uint_as_float(r0[g * 8 + 2 * e]) + b0,
                                                    __uint_as_float(r0[g * 8 + 2 * e + 1]) + b1);
                                 q[4 + e] = pack_bf16x2(__uint_as_float(r1[g * 8 + 2 * e]) + b0,
@@ -314,12 +323,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     const int co0 = pass * p.N + c0;  // first output channel of these columns
                     float v[32];
 #pragma unroll
-                    for (int c = 0; c < 32; ++c)
-                        v[c] = fmaxf(__uint_as_float(r[c]) + bias_sp[co0 + c], 0.f);
+                    for (int c4 = 0; c4 < 8; ++c4) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(bias_sp + co0 + 4 * c4);
+                        v[4 * c4 + 0] = fmaxf(__uint_as_float(r[4 * c4 + 0]) + b4.x, 0.f);
+                        v[4 * c4 + 1] = fmaxf(__uint_as_float(r[4 * c4 + 1]) + b4.y, 0.f);
+                        v[4 * c4 + 2] = fmaxf(__uint_as_float(r[4 * c4 + 2]) + b4.z, 0.f);
+                        v[4 * c4 + 3] = fmaxf(__uint_as_float(r[4 * c4 + 3]) + b4.w, 0.f);
+                    }
                     if (EPI == EPI_HEAD) {
 #pragma unroll
-                        for (int c = 0; c < 32; ++c)
-                            zacc = fmaf(v[c], bias_sp[p.cout + c0 + c], zacc);
+                        for (int c4 = 0; c4 < 8; ++c4) {
+                            const float4 h4 =
+                                *reinterpret_cast<const float4*>(bias_sp + p.cout + c0 + 4 * c4);
+                            zacc = fmaf(v[4 * c4 + 0], h4.x, zacc);
+                            zacc = fmaf(v[4 * c4 + 1], h4.y, zacc);
+                            zacc = fmaf(v[4 * c4 + 2], h4.z, zacc);
+                            zacc = fmaf(v[4 * c4 + 3], h4.w, zacc);
+                        }
                     } else {
                         const size_t plane = static_cast<size_t>(OH) * OW * 8;
                         __nv_bfloat16* optr =
@@ -489,6 +509,10 @@ int launch_conv_tc(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloa
     p.tiles_y = (H + 15) / 16;
     p.total_sub = B * p.tiles_x * p.tiles_y;
     p.num_tiles = (p.total_sub + p.S - 1) / p.S;
+    p.magic_tx = ((1ull << 40) / static_cast<unsigned long long>(p.tiles_x)) + 1;
+    p.magic_tpf = ((1ull << 40) / static_cast<unsigned long long>(p.tiles_x * p.tiles_y)) + 1;
+    if (static_cast<unsigned long long>(p.total_sub) * (p.tiles_x * p.tiles_y) >= (1ull << 40))
+        return fail("batch too large for the tile decoder");
     p.acc_bufs = (2 * p.S * p.N <= 256) ? 2 : 1;
     const int tps = taps_per_stage(L);
     const size_t w_stage = static_cast<size_t>(tps) * 64u * p.N;

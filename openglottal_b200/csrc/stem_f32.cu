@@ -31,6 +31,10 @@ __device__ __forceinline__ float load_gray(const void* frames, int in_dtype, siz
 __global__ void __launch_bounds__(256)
 stem_kernel(const void* __restrict__ frames, int in_dtype, const __grid_constant__ StemWeights sw,
             int B, int H, int W, __nv_bfloat16* __restrict__ out) {
+    // u8 -> float32(v) / 255.0f (IEEE division, as numpy does) through a 256-entry table
+    __shared__ float lut[256];
+    lut[threadIdx.x] = __fdiv_rn(static_cast<float>(threadIdx.x), 255.0f);
+    __syncthreads();
     const size_t total = static_cast<size_t>(B) * H * W;
     for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -43,10 +47,12 @@ stem_kernel(const void* __restrict__ frames, int in_dtype, const __grid_constant
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx) {
                 const int yy = y + dy - 1, xx = x + dx - 1;
-                in[dy * 3 + dx] = (yy >= 0 && yy < H && xx >= 0 && xx < W)
-                                      ? load_gray(frames, in_dtype,
-                                                  (n * H + yy) * static_cast<size_t>(W) + xx)
-                                      : 0.f;
+                const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+                const size_t at = (n * H + (ok ? yy : y)) * static_cast<size_t>(W) + (ok ? xx : x);
+                float v;
+                if (in_dtype == 0) v = lut[static_cast<const uint8_t*>(frames)[at]];
+                else v = static_cast<const float*>(frames)[at];
+                in[dy * 3 + dx] = ok ? v : 0.f;
             }
         const size_t plane = static_cast<size_t>(H) * W * 8;
         __nv_bfloat16* o = out + n * 4 * plane + (static_cast<size_t>(y) * W + x) * 8;
