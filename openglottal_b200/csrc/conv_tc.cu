@@ -25,6 +25,7 @@
 
 #include <cuda.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace ogl {
@@ -58,6 +59,8 @@ struct ConvParams {
     unsigned long long magic_tx, magic_tpf;  // ceil(2^40 / d) for d = tiles_x, tiles_x*tiles_y
     int na, nw;      // ring depths
     int acc_bufs;    // 1 or 2 TMEM accumulator sets
+    int dbg;         // experiment switches (OGL_DBG): 1 no MMA, 2 no stores, 4 no epilogue math,
+                     // 8 no activation TMA, 16 no weight copies. Results are garbage when set.
 };
 
 struct SubTile {
@@ -156,6 +159,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     const uint32_t s = it % p.na;
                     const uint32_t ph = (it / p.na) & 1u;
                     mbar_wait(a_empty + 8u * s, ph ^ 1u);
+                    if (p.dbg & 8) {
+                        mbar_arrive(a_full + 8u * s);
+                        continue;
+                    }
                     mbar_arrive_expect_tx(a_full + 8u * s, a_stage_bytes);
                     const CUtensorMap* tm = kb < p.kb0 ? &tmA0 : &tmA1;
                     const int plane0 = (kb < p.kb0 ? kb : kb - p.kb0) * 4;
@@ -181,6 +188,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                         const uint32_t s = it % p.nw;
                         const uint32_t ph = (it / p.nw) & 1u;
                         mbar_wait(w_empty + 8u * s, ph ^ 1u);
+                        if (p.dbg & 16) {
+                            mbar_arrive(w_full + 8u * s);
+                            continue;
+                        }
                         mbar_arrive_expect_tx(w_full + 8u * s, w_stage_bytes);
                         const size_t off =
                             (static_cast<size_t>(pass * kb_total + kb) * p.taps + tg * TPS) *
@@ -227,6 +238,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     if (elect_one()) {
 #pragma unroll
                         for (int t = 0; t < TPS; ++t) {
+                            if (p.dbg & 1) break;
                             // tap offset inside the halo tile, in 16-byte units
                             constexpr int kCenter = kHalo + 1;
                             const uint32_t toff = TPS == 9   ? (t / 3) * kHalo + (t % 3)
@@ -275,11 +287,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             tc_fence_after();
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {
+                if (p.dbg & 4) break;
                 const int mt = esub * 2 + half;
                 const int y = t.y0 + py;
                 const int x = t.x0 + half * 8 + px;
                 // partial tiles at the right / bottom edge: compute everything, store nothing
-                const bool valid = in_range && y < p.H && x < p.W;
+                const bool valid = in_range && y < p.H && x < p.W && !(p.dbg & 2);
                 const uint32_t tcol = tmem_base + lane_sel + buf * acc_cols + mt * p.N;
                 float zacc = 0.f;
                 if (EPI == EPI_CONVT) {
@@ -514,6 +527,8 @@ int launch_conv_tc(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloa
     if (static_cast<unsigned long long>(p.total_sub) * (p.tiles_x * p.tiles_y) >= (1ull << 40))
         return fail("batch too large for the tile decoder");
     p.acc_bufs = (2 * p.S * p.N <= 256) ? 2 : 1;
+    static const int dbg_env = getenv("OGL_DBG") ? atoi(getenv("OGL_DBG")) : 0;
+    p.dbg = dbg_env;
     const int tps = taps_per_stage(L);
     const size_t w_stage = static_cast<size_t>(tps) * 64u * p.N;
     const size_t tables = sizeof(float) * (L.cout + 32);
@@ -530,6 +545,11 @@ int launch_conv_tc(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloa
         p.na = 2;
         p.nw = 3;
     }
+    static const int na_env = getenv("OGL_NA") ? atoi(getenv("OGL_NA")) : 0;
+    static const int nw_env = getenv("OGL_NW") ? atoi(getenv("OGL_NW")) : 0;
+    if (na_env > 0) p.na = na_env;
+    if (nw_env > 0) p.nw = nw_env;
+    while (p.nw > 2 && smem_need(p.na, p.nw) > static_cast<size_t>(kMaxSmem)) --p.nw;
     const size_t smem = smem_need(p.na, p.nw);
     if (smem > static_cast<size_t>(kMaxSmem)) return fail("shared memory budget exceeded");
 
