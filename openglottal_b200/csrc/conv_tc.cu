@@ -90,14 +90,14 @@ __device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
     return *reinterpret_cast<uint32_t*>(&r);
 }
 
-template <int EPI, int TPS>
+template <int EPI, int TPS, int S>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const ConvParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
 
-    const uint32_t a_stage_bytes = static_cast<uint32_t>(p.S) * kSubBytes;
+    constexpr uint32_t a_stage_bytes = static_cast<uint32_t>(S) * kSubBytes;
     const uint32_t w_tap_bytes = 64u * static_cast<uint32_t>(p.N);
     const uint32_t w_stage_bytes = TPS * w_tap_bytes;
     const uint32_t a_ring = smem_base;
@@ -166,8 +166,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     mbar_arrive_expect_tx(a_full + 8u * s, a_stage_bytes);
                     const CUtensorMap* tm = kb < p.kb0 ? &tmA0 : &tmA1;
                     const int plane0 = (kb < p.kb0 ? kb : kb - p.kb0) * 4;
-                    for (int sub = 0; sub < p.S; ++sub) {
-                        int st = tile * p.S + sub;
+                    for (int sub = 0; sub < S; ++sub) {
+                        int st = tile * S + sub;
                         if (st >= p.total_sub) st = p.total_sub - 1;  // tail: load a duplicate
                         const SubTile t = decode_sub(p, st);
                         tma_load_4d(a_ring + s * a_stage_bytes + sub * kSubBytes, tm,
@@ -211,7 +211,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const uint32_t lbo_b = 16u * p.N, sbo_b = 128u;
         const uint64_t adesc0 = make_smem_desc(0, lbo_a, sbo_a);
         const uint64_t bdesc0 = make_smem_desc(0, lbo_b, sbo_b);
-        const uint32_t acc_cols = static_cast<uint32_t>(4 * p.N);
+        const uint32_t acc_cols = static_cast<uint32_t>(2 * S * p.N);
         const uint32_t bstep = (2u * lbo_b) >> 4;   // second K=16 half of a 32-channel block
         uint32_t ita = 0, itw = 0, li = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x, ++li) {
@@ -247,7 +247,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
                             for (int j = 0; j < 2; ++j) {
 #pragma unroll
-                                for (int mt = 0; mt < 4; ++mt) {
+                                for (int mt = 0; mt < 2 * S; ++mt) {
                                     constexpr uint32_t kSubStep = kSubBytes >> 4;
                                     const uint32_t aoff = toff + (mt >> 1) * kSubStep +
                                                           j * ((2u * lbo_a) >> 4) + (mt & 1) * 8u;
@@ -268,10 +268,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     } else if (warp >= 4) {
         // =========================================================== epilogue
         const int et = (threadIdx.x - 128) & 127;  // TMEM lane == pixel index inside a patch
-        const int esub = (threadIdx.x - 128) >> 7; // which sub-tile (pair of patches) this warp owns
+        const int egrp = (threadIdx.x - 128) >> 7; // warp group: S == 2 -> one sub-tile (both
+                                                   // x-halves); S == 1 -> one x-half of the tile
+        const int esub = S == 2 ? egrp : 0;
         const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
         const int py = et >> 3, px = et & 7;
-        const uint32_t acc_cols = static_cast<uint32_t>(4 * p.N);
+        const uint32_t acc_cols = static_cast<uint32_t>(2 * S * p.N);
         const int OH = EPI == EPI_CONVT ? 2 * p.H : p.H;
         const int OW = EPI == EPI_CONVT ? 2 * p.W : p.W;
         uint32_t li = 0;
@@ -280,14 +282,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const int pass = item / p.num_tiles;
             const uint32_t buf = li % p.acc_bufs;
             const uint32_t aph = (li / p.acc_bufs) & 1u;
-            const int st = tile * p.S + esub;
+            const int st = tile * S + esub;
             const bool in_range = st < p.total_sub;  // warp-uniform
             const SubTile t = decode_sub(p, in_range ? st : p.total_sub - 1);
             mbar_wait(acc_full + 8u * buf, aph);
             tc_fence_after();
 #pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
+            for (int hh = 0; hh < S; ++hh) {
                 if (p.dbg & 4) break;
+                const int half = S == 2 ? hh : egrp;
                 const int mt = esub * 2 + half;
                 const int y = t.y0 + py;
                 const int x = t.x0 + half * 8 + px;
@@ -449,13 +452,18 @@ int make_act_map(CUtensorMap* tm, const __nv_bfloat16* base, int B, int C, int H
 template <int EPI, int TPS>
 int launch_epi(const CUtensorMap& tm0, const CUtensorMap& tm1, const ConvParams& p, int grid,
                size_t smem, cudaStream_t stream) {
-    conv_tc_kernel<EPI, TPS><<<grid, kThreads, smem, stream>>>(tm0, tm1, p);
+    if (p.S == 1)
+        conv_tc_kernel<EPI, TPS, 1><<<grid, kThreads, smem, stream>>>(tm0, tm1, p);
+    else
+        conv_tc_kernel<EPI, TPS, 2><<<grid, kThreads, smem, stream>>>(tm0, tm1, p);
     OGL_CUDA(cudaGetLastError());
     return 0;
 }
 template <int EPI, int TPS>
 int set_smem_attr() {
-    OGL_CUDA(cudaFuncSetAttribute(conv_tc_kernel<EPI, TPS>,
+    OGL_CUDA(cudaFuncSetAttribute(conv_tc_kernel<EPI, TPS, 1>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    OGL_CUDA(cudaFuncSetAttribute(conv_tc_kernel<EPI, TPS, 2>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     return 0;
 }
@@ -517,7 +525,10 @@ int launch_conv_tc(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloa
     p.H = H;
     p.W = W;
     p.B = B;
-    p.S = 2;  // the MMA issuer is unrolled for 2 sub-tiles = 4 accumulators
+    // 2 sub-tiles (4 accumulators) per tile, except N = 128 where 4 x 128 columns would fill
+    // TMEM and serialise the epilogue behind the main loop: 1 sub-tile, double-buffered
+    static const int s_env = getenv("OGL_S128") ? atoi(getenv("OGL_S128")) : 2;
+    p.S = (L.N == 128) ? s_env : 2;
     p.tiles_x = (W + 15) / 16;
     p.tiles_y = (H + 15) / 16;
     p.total_sub = B * p.tiles_x * p.tiles_y;

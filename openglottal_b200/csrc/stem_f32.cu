@@ -25,9 +25,9 @@ __device__ __forceinline__ float load_gray(const void* frames, int in_dtype, siz
 }
 
 // ------------------------------------------------------------------- stem
-// One thread per pixel: 9 taps -> 32 channels in fp32, written as 4 planes of 8 bf16.
-// The 288 folded weights arrive as a by-value kernel parameter, so every FFMA takes its
-// weight straight from the constant bank (no LDS / LDG in the inner loop).
+// Generic form (f32 input): one thread per pixel, 9 taps -> 32 channels in fp32, written as
+// 4 planes of 8 bf16. The 288 folded weights arrive as a by-value kernel parameter, so every
+// FFMA takes its weight straight from the constant bank (no LDS / LDG in the inner loop).
 __global__ void __launch_bounds__(256)
 stem_kernel(const void* __restrict__ frames, int in_dtype, const __grid_constant__ StemWeights sw,
             int B, int H, int W, __nv_bfloat16* __restrict__ out) {
@@ -77,6 +77,86 @@ stem_kernel(const void* __restrict__ frames, int in_dtype, const __grid_constant
             q.z = *reinterpret_cast<uint32_t*>(&h2);
             q.w = *reinterpret_cast<uint32_t*>(&h3);
             *reinterpret_cast<uint4*>(o + g * plane) = q;
+        }
+    }
+}
+
+// u8 form (the hot path): one warp per image row, one thread per 4 consecutive pixels.
+// The three input rows arrive as one aligned 32-bit load each; the left/right neighbour bytes
+// come from the adjacent lanes by shuffle (warp-edge lanes load them). sw.w holds the folded
+// weights already divided by 255 (utils.py:235), so the bytes are used as integers-in-fp32.
+// 1152 FFMAs (constant-bank weights) per 4 pixels; bias rides in as the first addend; ReLU is a
+// packed bf16x2 max after rounding; each channel group stores 64 contiguous bytes per thread.
+__global__ void __launch_bounds__(256)
+stem_u8_kernel(const uint8_t* __restrict__ frames, const __grid_constant__ StemWeights sw,
+               int rows_total, int H, int W, __nv_bfloat16* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int warps_per_grid = gridDim.x * (blockDim.x >> 5);
+    const int Q = W >> 2;  // quads per row
+    const size_t plane = static_cast<size_t>(H) * W * 8;
+    for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows_total;
+         row += warps_per_grid) {
+        const int n = row / H;
+        const int y = row - n * H;
+        const uint8_t* base = frames + static_cast<size_t>(row) * W;
+        for (int q0 = 0; q0 < Q; q0 += 32) {
+            const int xq = q0 + lane;
+            const bool act = xq < Q;
+            float in[3][6];
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+                const int yy = y + dy - 1;
+                const bool rowok = yy >= 0 && yy < H;  // warp-uniform
+                const uint8_t* rp = base + (dy - 1) * W;
+                uint32_t w = 0;
+                if (rowok && act) w = *reinterpret_cast<const uint32_t*>(rp + 4 * xq);
+                uint32_t lw = __shfl_up_sync(0xffffffffu, w, 1);
+                uint32_t rw = __shfl_down_sync(0xffffffffu, w, 1);
+                uint32_t lb = lw >> 24, rb = rw & 0xffu;
+                if (lane == 0) lb = (rowok && act && xq > 0) ? rp[4 * xq - 1] : 0u;
+                if (lane == 31 || xq + 1 >= Q) rb = (rowok && act && xq + 1 < Q) ? rp[4 * xq + 4] : 0u;
+                in[dy][0] = static_cast<float>(lb);
+                in[dy][1] = static_cast<float>(w & 0xffu);
+                in[dy][2] = static_cast<float>((w >> 8) & 0xffu);
+                in[dy][3] = static_cast<float>((w >> 16) & 0xffu);
+                in[dy][4] = static_cast<float>(w >> 24);
+                in[dy][5] = static_cast<float>(rb);
+            }
+            if (!act) continue;
+            __nv_bfloat16* o = out + static_cast<size_t>(n) * 4 * plane +
+                               (static_cast<size_t>(y) * W + 4 * xq) * 8;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                uint32_t pk[4][4];  // [pixel][channel pair]
+#pragma unroll
+                for (int c2 = 0; c2 < 4; ++c2) {
+                    float acc[2][4];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int co = g * 8 + c2 * 2 + e;
+#pragma unroll
+                        for (int px = 0; px < 4; ++px) {
+                            float a = sw.b[co];
+#pragma unroll
+                            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                                for (int dx = 0; dx < 3; ++dx)
+                                    a = fmaf(in[dy][px + dx], sw.w[co * 9 + dy * 3 + dx], a);
+                            acc[e][px] = a;
+                        }
+                    }
+                    const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+                    for (int px = 0; px < 4; ++px) {
+                        __nv_bfloat162 h = __hmax2(__floats2bfloat162_rn(acc[0][px], acc[1][px]), zero);
+                        pk[px][c2] = *reinterpret_cast<uint32_t*>(&h);
+                    }
+                }
+                uint4* dst = reinterpret_cast<uint4*>(o + g * plane);
+#pragma unroll
+                for (int px = 0; px < 4; ++px)
+                    dst[px] = make_uint4(pk[px][0], pk[px][1], pk[px][2], pk[px][3]);
+            }
         }
     }
 }
@@ -242,8 +322,21 @@ inline int grid_for(size_t total, int block = 256, int cap = 148 * 16) {
 int launch_stem(const void* frames, int in_dtype, const StemWeights& sw, int B, int H, int W,
                 __nv_bfloat16* out, cudaStream_t stream) {
     const size_t total = static_cast<size_t>(B) * H * W;
-    stem_kernel<<<grid_for(total, 256, 148 * 8), 256, 0, stream>>>(frames, in_dtype, sw, B, H, W,
-                                                                   out);
+    if (in_dtype == 0 && W % 4 == 0) {
+        // hot path: weights pre-scaled by 1/255 (in fp64, rounded once) so the u8 values are
+        // used directly; differs from fl(v/255)*w by ~1 ulp of fp32, far below bf16 rounding
+        StemWeights scaled = sw;
+        for (int i = 0; i < 32 * 9; ++i)
+            scaled.w[i] = static_cast<float>(static_cast<double>(sw.w[i]) / 255.0);
+        const int rows = B * H;
+        int grid = (rows + 7) / 8;
+        if (grid > 148 * 6) grid = 148 * 6;
+        stem_u8_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint8_t*>(frames), scaled, rows,
+                                                 H, W, out);
+    } else {
+        stem_kernel<<<grid_for(total, 256, 148 * 8), 256, 0, stream>>>(frames, in_dtype, sw, B, H,
+                                                                       W, out);
+    }
     OGL_CUDA(cudaGetLastError());
     return 0;
 }
