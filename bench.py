@@ -36,30 +36,50 @@ METRIC = "unet_only_frames_per_sec_256x256_bf16"
 FEATS = (32, 64, 128, 256)
 
 
-def layer_flops(hgt: int, wid: int) -> list[float]:
-    """Algorithmic FLOPs per frame of each of the 22 launches (2 x MACs of the reference
-    formulation). Order = ogl_unet_layer_name()."""
+def module_flops(hgt: int, wid: int) -> dict[str, float]:
+    """Algorithmic FLOPs per frame of every reference module on the path (2 x MACs of the
+    reference formulation, /root/reference/openglottal/models/unet.py:50-72),
+    keyed by the names ogl_unet_launch_name() uses."""
     def conv(cin, cout, h, w):
         return 2.0 * 9 * cin * cout * h * w
 
     def convt(cin, cout, h, w):      # h, w = INPUT resolution
         return 2.0 * 4 * cin * cout * h * w
 
-    fl = [conv(1, 32, hgt, wid), conv(32, 32, hgt, wid)]
+    fl = {"stem": conv(1, 32, hgt, wid), "downs.0.net.3+pool": conv(32, 32, hgt, wid)}
     cin = 32
     for lvl in range(1, 4):
         f = FEATS[lvl]
         h, w = hgt >> lvl, wid >> lvl
-        fl += [conv(cin, f, h, w), conv(f, f, h, w)]
+        fl[f"downs.{lvl}.net.0"] = conv(cin, f, h, w)
+        fl[f"downs.{lvl}.net.3+pool"] = conv(f, f, h, w)
         cin = f
-    fl += [conv(256, 512, hgt >> 4, wid >> 4), conv(512, 512, hgt >> 4, wid >> 4)]
+    fl["bottleneck.net.0"] = conv(256, 512, hgt >> 4, wid >> 4)
+    fl["bottleneck.net.3"] = conv(512, 512, hgt >> 4, wid >> 4)
     for k in range(4):
         lvl = 3 - k
         f = FEATS[lvl]
         h, w = hgt >> lvl, wid >> lvl
-        fl += [convt(2 * f, f, h // 2, w // 2), conv(2 * f, f, h, w), conv(f, f, h, w)]
-    fl[-1] += 2.0 * 32 * hgt * wid   # 1x1 head fused into the last conv
+        fl[f"ups.{2 * k}(convT)"] = convt(2 * f, f, h // 2, w // 2)
+        fl[f"ups.{2 * k + 1}.net.0(cat)"] = conv(2 * f, f, h, w)
+        fl[f"ups.{2 * k + 1}.net.3"] = conv(f, f, h, w)
+    fl["ups.7.net.3+head"] = fl.pop("ups.7.net.3") + 2.0 * 32 * hgt * wid   # 1x1 head fused in
     return fl
+
+
+def launch_flops(name: str, fl: dict[str, float]) -> float:
+    """A launch that computes several reference modules is named 'a+b' with module names
+    (module names may themselves contain '+', e.g. 'downs.0.net.3+pool')."""
+    if name in fl:
+        return fl[name]
+    for i, ch in enumerate(name):
+        if ch == "+" and name[:i] in fl:
+            return fl[name[:i]] + launch_flops(name[i + 1:], fl)
+    raise KeyError(f"launch {name!r} does not name reference modules")
+
+
+def layer_flops(hgt: int, wid: int) -> list[float]:
+    return list(module_flops(hgt, wid).values())
 
 
 class ClockSampler(threading.Thread):
@@ -278,19 +298,22 @@ def run_native(args) -> None:
     # ---- per-launch timing (roofline of the dominant kernel), same workload, events between
     # launches on the launching stream
     _native.check(lib.ogl_unet_set_profiling(model._handle, 1))
-    nl = 22
-    acc = np.zeros(nl)
     prof_steps = min(steps, 10)
     buf = (C.c_float * 64)()
     cnt = C.c_int(0)
+    acc = None
     for i in range(prof_steps):
         step_dev(i, None)
         _native.check(lib.ogl_unet_layer_times(model._handle, buf, 64, C.byref(cnt)))
-        acc += np.array(buf[:nl])
+        v = np.array(buf[:cnt.value])
+        acc = v if acc is None else acc + v
     _native.check(lib.ogl_unet_set_profiling(model._handle, 0))
+    nl = cnt.value
     layer_ms = acc / prof_steps
-    fl = np.array(layer_flops(HGT, WID)) * BATCH
-    names = [lib.ogl_unet_layer_name(i).decode() for i in range(nl)]
+    names = [lib.ogl_unet_launch_name(model._handle, i).decode() for i in range(nl)]
+    mfl = module_flops(HGT, WID)
+    fl = np.array([launch_flops(n_, mfl) for n_ in names]) * BATCH
+    assert abs(fl.sum() / BATCH - sum(mfl.values())) < 1.0, "launch names do not cover the path"
     tc_ms = float(layer_ms[1:].sum())
     tc_flops = float(fl[1:].sum())
     peaks = {}
@@ -306,10 +329,12 @@ def run_native(args) -> None:
     if tr.exists():
         traffic = json.loads(tr.read_text()).get("dram_bytes_per_launch_avg")
     roofline = {
-        "bound": "tensor", "kernel": "conv_tc_kernel (21 launches/step: 18 conv3x3 + 4 convT - stem)",
+        "bound": "tensor",
+        "kernel": f"conv_tc_kernel + s2d_tc_kernel ({nl - 1} tcgen05 launches/step: every conv3x3, "
+                  "ConvTranspose2d and the head; the Cin=1 stem is CUDA-core)",
         "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
         "peak_source": f"{which} bf16_tflops_sustained", "traffic": traffic,
-        "flops_per_launch_avg": tc_flops / 21, "ms_per_launch_avg": tc_ms / 21,
+        "flops_per_launch_avg": tc_flops / (nl - 1), "ms_per_launch_avg": tc_ms / (nl - 1),
         "tc_share_of_step": tc_ms / float(layer_ms.sum()),
     }
     layers = [{"layer": n_, "ms": float(m), "tflops": float(f / (m * 1e-3) / 1e12) if m > 0 else None}
@@ -353,7 +378,7 @@ def run_native(args) -> None:
         "e2e": {"value": e2e_value, "unit": "frames/s",
                 "h2d_bytes_per_step": BATCH * HGT * WID, "d2h_bytes_per_step": BATCH * 4,
                 "matches_device_run": same},
-        "gpu_launches": steps * 22 + 70,
+        "gpu_launches": steps * (nl + 1) + 70,
         "roofline": roofline,
         "clocks": clocks,
         "pct_of_tc_roofline": 100.0 * (value / world) * sum(layer_flops(HGT, WID)) / (peak_tf * 1e12),

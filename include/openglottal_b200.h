@@ -89,11 +89,19 @@ int ogl_unet_forward(ogl_unet* h, const void* frames_dev, int in_dtype, int n, i
                      void* stream);
 
 /* Optional per-launch timing of the bf16 path (CUDA events on the caller's stream between the
- * 22 launches of one forward; used by bench.py for the roofline numbers).
- * ogl_unet_layer_times synchronises on the last event of the most recent profiled forward. */
+ * launches of one forward; used by bench.py for the roofline numbers).
+ * ogl_unet_layer_times synchronises on the last event of the most recent profiled forward.
+ * ogl_unet_launch_count / _name describe the launches of the most recent bf16 forward, each
+ * named after the reference modules (openglottal/models/unet.py:50-72) it computes. */
 int ogl_unet_set_profiling(ogl_unet* h, int enable);
 int ogl_unet_layer_times(ogl_unet* h, float* ms_out, int capacity, int* count_out);
-const char* ogl_unet_layer_name(int index);
+int ogl_unet_launch_count(const ogl_unet* h);
+const char* ogl_unet_launch_name(const ogl_unet* h, int index);
+
+/* Kernel schedule of the full-resolution level of the bf16 path. 1 (default): space-to-depth
+ * GEMMs with ConvTranspose2d ups.6 composed into ups.7.net.0 (20 launches); 0: the direct
+ * per-tap form used at the other levels (22 launches). Same results within bf16 rounding. */
+int ogl_unet_set_schedule(ogl_unet* h, int s2d_level0);
 
 /* Kinematic features of an area waveform of n >= 2 samples.
  * out8_dev: {area_mean, area_std, area_range, open_quotient, f0, periodicity, cv, peak_bin};
@@ -114,6 +122,27 @@ int ogl_bgr_to_gray(const uint8_t* bgr_dev, uint8_t* gray_dev, int64_t pixels, v
 int ogl_debug_tc_layer(ogl_unet* h, int kind, const float* src0_dev, int c0, const float* src1_dev,
                        int c1, const float* weight_host, const float* bias_host, int cout, int n,
                        int height, int width, float* out_dev, float* out_pool_dev, void* stream);
+
+/* Unit-test hook for the space-to-depth layers of the full-resolution level (Cout = 32).
+ * src_dev [n][cin_s][H][W] f32; below_dev [n][64][H/2][W/2] f32 with wt_host [64][32][2][2] and
+ * bt_host [32] (ConvTranspose2d composed in front of the conv; all three NULL for a plain
+ * conv); w3_host [32][cin_s (+32)][3][3], b3_host [32]. kind: 0 conv+bias+ReLU, 1 + max-pool. */
+int ogl_debug_s2d_layer(ogl_unet* h, int kind, const float* src_dev, int cin_s,
+                        const float* below_dev, const float* w3_host, const float* b3_host,
+                        const float* wt_host, const float* bt_host, int n, int height, int width,
+                        float* out_dev, float* out_pool_dev, void* stream);
+
+
+/* Host-only (no device needed): the MMA program build_s2d_host makes for a space-to-depth
+ * layer, for CPU emulation in the tests. ops_out: 4 x uint32 per op {a_off | dcol << 16 |
+ * src << 24 | accumulate << 25, b_off16 | N << 16, idesc, 0}; stages_out: 3 ints per stage
+ * {source (0 S2D, 1 below), first 8-channel plane, end op}; btab_out [3][3][32]. Any output
+ * pointer may be NULL to query sizes. */
+int ogl_debug_s2d_program(const float* w3_host, const float* b3_host, int cin_s,
+                          const float* wt_host, const float* bt_host, uint8_t* wblob_out,
+                          size_t wblob_capacity, size_t* wblob_bytes, uint32_t* ops_out,
+                          int ops_capacity, int* n_ops, int* stages_out, int* n_stages,
+                          float* btab_out);
 
 #ifdef __cplusplus
 }

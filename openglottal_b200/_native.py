@@ -53,12 +53,16 @@ EXPORTS = [
     "ogl_unet_forward",
     "ogl_unet_set_profiling",
     "ogl_unet_layer_times",
-    "ogl_unet_layer_name",
+    "ogl_unet_launch_count",
+    "ogl_unet_launch_name",
+    "ogl_unet_set_schedule",
     "ogl_features_workspace_bytes",
     "ogl_features",
     "ogl_features_f64",
     "ogl_bgr_to_gray",
     "ogl_debug_tc_layer",
+    "ogl_debug_s2d_layer",
+    "ogl_debug_s2d_program",
 ]
 
 _lib = None
@@ -99,8 +103,12 @@ def load() -> C.CDLL:
     lib.ogl_unet_set_profiling.argtypes = [vp, i32]
     lib.ogl_unet_layer_times.restype = i32
     lib.ogl_unet_layer_times.argtypes = [vp, _c_float_p, i32, C.POINTER(i32)]
-    lib.ogl_unet_layer_name.restype = C.c_char_p
-    lib.ogl_unet_layer_name.argtypes = [i32]
+    lib.ogl_unet_launch_count.restype = i32
+    lib.ogl_unet_launch_count.argtypes = [vp]
+    lib.ogl_unet_launch_name.restype = C.c_char_p
+    lib.ogl_unet_launch_name.argtypes = [vp, i32]
+    lib.ogl_unet_set_schedule.restype = i32
+    lib.ogl_unet_set_schedule.argtypes = [vp, i32]
     lib.ogl_features_workspace_bytes.restype = sz
     lib.ogl_features_workspace_bytes.argtypes = [i64]
     lib.ogl_features.restype = i32
@@ -112,6 +120,13 @@ def load() -> C.CDLL:
     lib.ogl_debug_tc_layer.restype = i32
     lib.ogl_debug_tc_layer.argtypes = [vp, i32, vp, i32, vp, i32, _c_float_p, _c_float_p, i32,
                                        i32, i32, i32, vp, vp, vp]
+    lib.ogl_debug_s2d_layer.restype = i32
+    lib.ogl_debug_s2d_layer.argtypes = [vp, i32, vp, i32, vp, _c_float_p, _c_float_p, _c_float_p,
+                                        _c_float_p, i32, i32, i32, vp, vp, vp]
+    lib.ogl_debug_s2d_program.restype = i32
+    lib.ogl_debug_s2d_program.argtypes = [_c_float_p, _c_float_p, i32, _c_float_p, _c_float_p, vp,
+                                          sz, C.POINTER(sz), vp, i32, C.POINTER(i32), vp,
+                                          C.POINTER(i32), vp]
     _lib = lib
     return lib
 

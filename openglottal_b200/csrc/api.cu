@@ -6,6 +6,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -66,7 +67,12 @@ struct ogl_unet {
     TcLayer up_t[4];
     TcLayer up_c[4][2];
     float* head_w = nullptr;  // [32] device
+    float head_w_host[32] = {0};
     float head_b = 0.f;
+    // full-resolution level as space-to-depth GEMMs (s2d_tc.cu): downs.0.net.3 (+pool),
+    // ups.6 (convT) composed into ups.7.net.0, ups.7.net.3 (+head)
+    S2dLayer s2d_down, s2d_up0, s2d_up1;
+    bool use_s2d = true;
     // fp32 validation path
     F32Conv f_down[4][2], f_bott[2], f_up[4][2];
     F32ConvT f_upt[4];
@@ -75,6 +81,7 @@ struct ogl_unet {
     bool profile = false;
     std::vector<cudaEvent_t> events;
     int n_events = 0;
+    std::vector<const char*> launch_names;  // of the most recent bf16 forward
 };
 
 namespace {
@@ -167,6 +174,25 @@ int build_tc_conv(ogl_unet* h, const std::vector<float>& w, const std::vector<fl
     return dev_upload(h, b, &L->bias);
 }
 
+int build_s2d_layer(ogl_unet* h, const std::vector<float>& w3, const std::vector<float>& b3,
+                    int cin_s, const float* wt, const float* bt, int cin_b, int epi, S2dLayer* L) {
+    S2dHost hs;
+    if (build_s2d_host(w3.data(), b3.data(), cin_s, wt, bt, cin_b, &hs)) return 1;
+    *L = S2dLayer();
+    L->wbytes = static_cast<uint32_t>(hs.wblob.size());
+    L->n_stages = hs.n_stages;
+    for (int i = 0; i < kS2dMaxStages; ++i) {
+        L->stage_src[i] = hs.stage_src[i];
+        L->stage_plane0[i] = hs.stage_plane0[i];
+    }
+    L->cin_s = cin_s;
+    L->cin_b = wt ? cin_b : 0;
+    L->epi = epi;
+    for (int i = 0; i < 32; ++i) L->bias_host[i] = hs.btab[4 * 32 + i];
+    if (dev_upload(h, hs.wblob, &L->wblob)) return 1;
+    return dev_upload(h, hs.btab, &L->btab);
+}
+
 int build_f32_conv(ogl_unet* h, const std::vector<float>& w, const std::vector<float>& b, int cin,
                    int cout, F32Conv* L) {
     L->cin = cin;
@@ -207,14 +233,17 @@ Plan make_plan(int n, int H, int W, size_t elem) {
 }
 
 constexpr int kMaxLaunches = 40;
-const char* const kLayerNames[] = {
-    "stem", "downs.0.net.3+pool", "downs.1.net.0", "downs.1.net.3+pool", "downs.2.net.0",
-    "downs.2.net.3+pool", "downs.3.net.0", "downs.3.net.3+pool", "bottleneck.net.0",
-    "bottleneck.net.3", "ups.0(convT)", "ups.1.net.0(cat)", "ups.1.net.3", "ups.2(convT)",
-    "ups.3.net.0(cat)", "ups.3.net.3", "ups.4(convT)", "ups.5.net.0(cat)", "ups.5.net.3",
-    "ups.6(convT)", "ups.7.net.0(cat)", "ups.7.net.3+head"};
+const char* const kDownC1[4] = {"stem", "downs.1.net.0", "downs.2.net.0", "downs.3.net.0"};
+const char* const kDownC2[4] = {"downs.0.net.3+pool", "downs.1.net.3+pool", "downs.2.net.3+pool",
+                                "downs.3.net.3+pool"};
+const char* const kUpT[4] = {"ups.0(convT)", "ups.2(convT)", "ups.4(convT)", "ups.6(convT)"};
+const char* const kUpC1[4] = {"ups.1.net.0(cat)", "ups.3.net.0(cat)", "ups.5.net.0(cat)",
+                              "ups.7.net.0(cat)"};
+const char* const kUpC2[4] = {"ups.1.net.3", "ups.3.net.3", "ups.5.net.3", "ups.7.net.3+head"};
 
-inline void mark(ogl_unet* h, cudaStream_t stream) {
+// closes the launch that was just enqueued: its name, and (when profiling) an event after it
+inline void mark(ogl_unet* h, cudaStream_t stream, const char* name) {
+    if (name) h->launch_names.push_back(name);
     if (h->profile && h->n_events < static_cast<int>(h->events.size()))
         cudaEventRecord(h->events[h->n_events++], stream);
 }
@@ -239,8 +268,9 @@ int ogl_unet_create(ogl_unet** out, int device) {
     OGL_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10)
         return fail(std::string("openglottal_b200 is built for sm_100a (B200); found ") + prop.name);
-    if (conv_tc_init()) return 1;
+    if (conv_tc_init() || s2d_tc_init()) return 1;
     ogl_unet* h = new ogl_unet();
+    if (const char* e = getenv("OGL_S2D")) h->use_s2d = atoi(e) != 0;
     h->device = device;
     h->num_sms = prop.multiProcessorCount;
     *out = h;
@@ -288,6 +318,8 @@ int ogl_unet_load_state(ogl_unet* h, const ogl_unet_state* st) {
         fold_conv_bn(st->downs[i][1], f, f, eps, &w, &b);
         if (build_f32_conv(h, w, b, f, f, &h->f_down[i][1])) return 1;
         if (build_tc_conv(h, w, b, f, 0, f, EPI_RELU_POOL, &h->down_c2[i])) return 1;
+        if (i == 0 && build_s2d_layer(h, w, b, 32, nullptr, nullptr, 0, EPI_RELU_POOL, &h->s2d_down))
+            return 1;
         cin = f;
     }
     // bottleneck 256 -> 512 -> 512
@@ -321,13 +353,19 @@ int ogl_unet_load_state(ogl_unet* h, const ogl_unet_state* st) {
         fold_conv_bn(st->up_c[k][0], f, 2 * f, eps, &w, &b);
         if (build_f32_conv(h, w, b, 2 * f, f, &h->f_up[k][0])) return 1;
         if (build_tc_conv(h, w, b, f, f, f, EPI_RELU, &h->up_c[k][0])) return 1;
+        if (k == 3 && build_s2d_layer(h, w, b, 32, st->up_t[k].weight, st->up_t[k].bias, 64,
+                                      EPI_RELU, &h->s2d_up0))
+            return 1;
         fold_conv_bn(st->up_c[k][1], f, f, eps, &w, &b);
         if (build_f32_conv(h, w, b, f, f, &h->f_up[k][1])) return 1;
         if (build_tc_conv(h, w, b, f, 0, f, k == 3 ? EPI_HEAD : EPI_RELU, &h->up_c[k][1]))
             return 1;
+        if (k == 3 && build_s2d_layer(h, w, b, 32, nullptr, nullptr, 0, EPI_HEAD, &h->s2d_up1))
+            return 1;
     }
     std::vector<float> hw(st->head_weight, st->head_weight + 32);
     if (dev_upload(h, hw, &h->head_w)) return 1;
+    memcpy(h->head_w_host, hw.data(), sizeof h->head_w_host);
     h->head_b = st->head_bias[0];
     h->loaded = true;
     return 0;
@@ -378,34 +416,42 @@ int ogl_unet_forward(ogl_unet* h, const void* frames_dev, int in_dtype, int n, i
         auto B = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(ws + off); };
         __nv_bfloat16* P[4] = {B(p.U[1]), B(p.U[2]), B(p.U[3]), B(p.P3)};
         h->n_events = 0;
-        mark(h, stream);
-        if (launch_stem(frames_dev, in_dtype, h->stem, n, H, W, B(p.T[0]), stream))
+        h->launch_names.clear();
+        const bool s2d = h->use_s2d;
+        mark(h, stream, nullptr);
+        if (launch_stem(frames_dev, in_dtype, h->stem, n, H, W, B(p.T[0]), s2d, stream))
             return 1;
-        mark(h, stream);
+        mark(h, stream, kDownC1[0]);
         for (int l = 0; l < 4; ++l) {
             const int hh = H >> l, ww = W >> l;
             if (l > 0) {
                 if (launch_conv_tc(h->down_c1[l], P[l - 1], nullptr, n, hh, ww, B(p.T[l]), nullptr,
                                    nullptr, h->num_sms, stream))
                     return 1;
-                mark(h, stream);
+                mark(h, stream, kDownC1[l]);
             }
-            if (launch_conv_tc(h->down_c2[l], B(p.T[l]), nullptr, n, hh, ww, B(p.S[l]), P[l],
-                               nullptr, h->num_sms, stream))
+            if (l == 0 && s2d) {
+                if (launch_s2d_tc(h->s2d_down, B(p.T[0]), nullptr, n, H, W, B(p.S[0]), P[0],
+                                  nullptr, h->num_sms, stream))
+                    return 1;
+            } else if (launch_conv_tc(h->down_c2[l], B(p.T[l]), nullptr, n, hh, ww, B(p.S[l]),
+                                      P[l], nullptr, h->num_sms, stream)) {
                 return 1;
-            mark(h, stream);
+            }
+            mark(h, stream, kDownC2[l]);
         }
         if (launch_conv_tc(h->bott[0], P[3], nullptr, n, H >> 4, W >> 4, B(p.T[4]), nullptr,
                            nullptr, h->num_sms, stream))
             return 1;
-        mark(h, stream);
+        mark(h, stream, "bottleneck.net.0");
         if (launch_conv_tc(h->bott[1], B(p.T[4]), nullptr, n, H >> 4, W >> 4, B(p.B4), nullptr,
                            nullptr, h->num_sms, stream))
             return 1;
-        mark(h, stream);
+        mark(h, stream, "bottleneck.net.3");
         const __nv_bfloat16* below = B(p.B4);
         HeadParams hp;
         hp.w = h->head_w;
+        hp.w_host = h->head_w_host;
         hp.b = h->head_b;
         hp.logit_thr = thr;
         hp.logits = logits_dev;
@@ -414,18 +460,30 @@ int ogl_unet_forward(ogl_unet* h, const void* frames_dev, int in_dtype, int n, i
         for (int k = 0; k < 4; ++k) {
             const int l = 3 - k;
             const int hh = H >> l, ww = W >> l;
+            if (l == 0 && s2d) {
+                // ups.6 is composed into ups.7.net.0: reads the skip (S2D) and the level-1 tensor
+                if (launch_s2d_tc(h->s2d_up0, B(p.S[0]), below, n, H, W, B(p.T[0]), nullptr,
+                                  nullptr, h->num_sms, stream))
+                    return 1;
+                mark(h, stream, "ups.6(convT)+ups.7.net.0(cat)");
+                if (launch_s2d_tc(h->s2d_up1, B(p.T[0]), nullptr, n, H, W, nullptr, nullptr, &hp,
+                                  h->num_sms, stream))
+                    return 1;
+                mark(h, stream, kUpC2[k]);
+                break;
+            }
             if (launch_conv_tc(h->up_t[k], below, nullptr, n, hh / 2, ww / 2, B(p.U[l]), nullptr,
                                nullptr, h->num_sms, stream))
                 return 1;
-            mark(h, stream);
+            mark(h, stream, kUpT[k]);
             if (launch_conv_tc(h->up_c[k][0], B(p.S[l]), B(p.U[l]), n, hh, ww, B(p.T[l]), nullptr,
                                nullptr, h->num_sms, stream))
                 return 1;
-            mark(h, stream);
+            mark(h, stream, kUpC1[k]);
             if (launch_conv_tc(h->up_c[k][1], B(p.T[l]), nullptr, n, hh, ww, B(p.U[l]), nullptr,
                                k == 3 ? &hp : nullptr, h->num_sms, stream))
                 return 1;
-            mark(h, stream);
+            mark(h, stream, kUpC2[k]);
             below = B(p.U[l]);
         }
         return 0;
@@ -501,9 +559,19 @@ int ogl_unet_layer_times(ogl_unet* h, float* ms_out, int capacity, int* count_ou
     return 0;
 }
 
-const char* ogl_unet_layer_name(int index) {
-    const int n = static_cast<int>(sizeof(kLayerNames) / sizeof(kLayerNames[0]));
-    return (index >= 0 && index < n) ? kLayerNames[index] : "";
+int ogl_unet_launch_count(const ogl_unet* h) {
+    return h ? static_cast<int>(h->launch_names.size()) : 0;
+}
+
+const char* ogl_unet_launch_name(const ogl_unet* h, int index) {
+    if (!h || index < 0 || index >= static_cast<int>(h->launch_names.size())) return "";
+    return h->launch_names[index];
+}
+
+int ogl_unet_set_schedule(ogl_unet* h, int s2d_level0) {
+    if (!h) return fail("ogl_unet_set_schedule: NULL handle");
+    h->use_s2d = s2d_level0 != 0;
+    return 0;
 }
 
 size_t ogl_features_workspace_bytes(int64_t n) { return features_workspace_bytes(n); }
@@ -603,6 +671,111 @@ int ogl_debug_tc_layer(ogl_unet* h, int kind, const float* src0_dev, int c0, con
     cudaFree(d_b);
     cudaFree(d_s0);
     cudaFree(d_s1);
+    cudaFree(d_o);
+    cudaFree(d_p);
+    return rc;
+}
+
+int ogl_debug_s2d_program(const float* w3_host, const float* b3_host, int cin_s,
+                          const float* wt_host, const float* bt_host, uint8_t* wblob_out,
+                          size_t wblob_capacity, size_t* wblob_bytes, uint32_t* ops_out,
+                          int ops_capacity, int* n_ops, int* stages_out, int* n_stages,
+                          float* btab_out) {
+    g_err.clear();
+    if (!w3_host || !b3_host || !wblob_bytes || !n_ops || !n_stages)
+        return fail("ogl_debug_s2d_program: NULL argument");
+    S2dHost hs;
+    if (build_s2d_host(w3_host, b3_host, cin_s, wt_host, bt_host, wt_host ? 64 : 0, &hs)) return 1;
+    *wblob_bytes = hs.wblob.size();
+    *n_ops = static_cast<int>(hs.ops.size());
+    *n_stages = hs.n_stages;
+    if (wblob_out) {
+        if (wblob_capacity < hs.wblob.size()) return fail("ogl_debug_s2d_program: wblob too small");
+        memcpy(wblob_out, hs.wblob.data(), hs.wblob.size());
+    }
+    if (ops_out) {
+        if (ops_capacity < *n_ops) return fail("ogl_debug_s2d_program: ops buffer too small");
+        memcpy(ops_out, hs.ops.data(), hs.ops.size() * sizeof(S2dOp));
+    }
+    if (stages_out)
+        for (int i = 0; i < hs.n_stages; ++i) {
+            stages_out[3 * i] = hs.stage_src[i];
+            stages_out[3 * i + 1] = hs.stage_plane0[i];
+            stages_out[3 * i + 2] = hs.stage_op_end[i];
+        }
+    if (btab_out) memcpy(btab_out, hs.btab.data(), hs.btab.size() * sizeof(float));
+    return 0;
+}
+
+int ogl_debug_s2d_layer(ogl_unet* h, int kind, const float* src_dev, int cin_s,
+                        const float* below_dev, const float* w3_host, const float* b3_host,
+                        const float* wt_host, const float* bt_host, int n, int height, int width,
+                        float* out_dev, float* out_pool_dev, void* stream_v) {
+    g_err.clear();
+    if (!h || !src_dev || !w3_host || !b3_host || !out_dev)
+        return fail("ogl_debug_s2d_layer: NULL argument");
+    if (kind != EPI_RELU && kind != EPI_RELU_POOL)
+        return fail("ogl_debug_s2d_layer: kind must be 0 or 1");
+    if ((below_dev != nullptr) != (wt_host != nullptr) || (wt_host && !bt_host))
+        return fail("ogl_debug_s2d_layer: below, wt and bt come together");
+    if (height % 16 || width % 16) return fail("ogl_debug_s2d_layer: H, W must be multiples of 16");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    OGL_CUDA(cudaSetDevice(h->device));
+    const int cin_b = wt_host ? 64 : 0;
+    const int cin3 = cin_s + (wt_host ? 32 : 0);
+    std::vector<float> w3(w3_host, w3_host + static_cast<size_t>(32) * cin3 * 9);
+    std::vector<float> b3(b3_host, b3_host + 32);
+    S2dHost hs;
+    if (build_s2d_host(w3.data(), b3.data(), cin_s, wt_host, bt_host, cin_b, &hs)) return 1;
+    const size_t hw = static_cast<size_t>(height) * width;
+    uint8_t* d_w = nullptr;
+    float* d_bt = nullptr;
+    __nv_bfloat16 *d_s = nullptr, *d_b = nullptr, *d_o = nullptr, *d_p = nullptr;
+    int rc = 1;
+    do {
+        if (cudaMalloc(&d_w, hs.wblob.size()) != cudaSuccess) break;
+        if (cudaMalloc(&d_bt, hs.btab.size() * 4) != cudaSuccess) break;
+        if (cudaMalloc(&d_s, n * cin_s * hw * 2) != cudaSuccess) break;
+        if (cin_b && cudaMalloc(&d_b, n * cin_b * hw / 4 * 2) != cudaSuccess) break;
+        if (cudaMalloc(&d_o, n * 32 * hw * 2) != cudaSuccess) break;
+        if (kind == EPI_RELU_POOL && cudaMalloc(&d_p, n * 32 * hw / 4 * 2) != cudaSuccess) break;
+        cudaMemcpyAsync(d_w, hs.wblob.data(), hs.wblob.size(), cudaMemcpyHostToDevice, stream);
+        cudaMemcpyAsync(d_bt, hs.btab.data(), hs.btab.size() * 4, cudaMemcpyHostToDevice, stream);
+        cudaStreamSynchronize(stream);
+        S2dLayer L;
+        L.wblob = d_w;
+        L.wbytes = static_cast<uint32_t>(hs.wblob.size());
+        L.n_stages = hs.n_stages;
+        for (int i = 0; i < kS2dMaxStages; ++i) {
+            L.stage_src[i] = hs.stage_src[i];
+            L.stage_plane0[i] = hs.stage_plane0[i];
+        }
+        L.btab = d_bt;
+        for (int i = 0; i < 32; ++i) L.bias_host[i] = hs.btab[4 * 32 + i];
+        L.cin_s = cin_s;
+        L.cin_b = cin_b;
+        L.epi = kind;
+        if (launch_nchw_to_c8(src_dev, d_s, n, cin_s, height, width, stream, true)) break;
+        if (cin_b && launch_nchw_to_c8(below_dev, d_b, n, cin_b, height / 2, width / 2, stream))
+            break;
+        if (launch_s2d_tc(L, d_s, d_b, n, height, width, d_o, d_p, nullptr, h->num_sms, stream))
+            break;
+        if (launch_c8_to_nchw(d_o, out_dev, n, 32, height, width, stream, true)) break;
+        if (kind == EPI_RELU_POOL && out_pool_dev &&
+            launch_c8_to_nchw(d_p, out_pool_dev, n, 32, height / 2, width / 2, stream))
+            break;
+        cudaError_t e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) {
+            fail_cuda(e, "ogl_debug_s2d_layer");
+            break;
+        }
+        rc = 0;
+    } while (0);
+    if (rc && g_err.empty()) fail("ogl_debug_s2d_layer: allocation or launch failed");
+    cudaFree(d_w);
+    cudaFree(d_bt);
+    cudaFree(d_s);
+    cudaFree(d_b);
     cudaFree(d_o);
     cudaFree(d_p);
     return rc;

@@ -209,7 +209,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const uint32_t idesc = make_idesc_bf16(p.N);
         constexpr uint32_t lbo_a = kPlaneBytes, sbo_a = kHalo * 16;
         const uint32_t lbo_b = 16u * p.N, sbo_b = 128u;
-        const uint64_t adesc0 = make_smem_desc(0, lbo_a, sbo_a);
+        // dbg 32 (experiment): every A core matrix 128-byte aligned (SBO 256, no tap offset)
+        const uint64_t adesc0 = make_smem_desc(0, lbo_a, (p.dbg & 32) ? 256u : sbo_a);
         const uint64_t bdesc0 = make_smem_desc(0, lbo_b, sbo_b);
         const uint32_t acc_cols = static_cast<uint32_t>(2 * S * p.N);
         const uint32_t bstep = (2u * lbo_b) >> 4;   // second K=16 half of a 32-channel block
@@ -230,7 +231,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     tc_fence_after();
                     // TPS == 9: all taps unrolled; TPS == 3: tg is the tap row dy; TPS == 1: convT
                     const uint32_t row_off =
-                        TPS == 3 ? static_cast<uint32_t>(tg) * kHalo * 16u : 0u;
+                        (TPS == 3 && !(p.dbg & 32)) ? static_cast<uint32_t>(tg) * kHalo * 16u : 0u;
                     const uint64_t ad = adesc0 + ((abase + row_off) >> 4);
                     const uint64_t bd = bdesc0 + ((w_ring + sw * w_stage_bytes) >> 4);
                     const uint32_t first = (kb | tg) != 0 ? 1u : 0u;
@@ -241,9 +242,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                             if (p.dbg & 1) break;
                             // tap offset inside the halo tile, in 16-byte units
                             constexpr int kCenter = kHalo + 1;
-                            const uint32_t toff = TPS == 9   ? (t / 3) * kHalo + (t % 3)
-                                                  : TPS == 3 ? t
-                                                             : kCenter;
+                            const uint32_t toff = (p.dbg & 32) ? 0u
+                                                  : TPS == 9   ? (t / 3) * kHalo + (t % 3)
+                                                  : TPS == 3   ? t
+                                                               : kCenter;
 #pragma unroll
                             for (int j = 0; j < 2; ++j) {
 #pragma unroll
@@ -470,6 +472,30 @@ int set_smem_attr() {
 inline int taps_per_stage(const TcLayer& L) { return L.taps == 1 ? 1 : (L.N <= 64 ? 9 : 3); }
 
 }  // namespace
+
+int encode_bf16_map(void* tensor_map, const void* base, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box) {
+    if (!g_encode) return fail("conv_tc_init() was not called");
+    cuuint64_t d[5], st[4];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) {
+        d[i] = dims[i];
+        bx[i] = box[i];
+        es[i] = 1;
+        if (i < rank - 1) st[i] = strides_bytes[i];
+    }
+    CUresult r = g_encode(static_cast<CUtensorMap*>(tensor_map), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                          static_cast<cuuint32_t>(rank), const_cast<void*>(base), d, st, bx, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d) for a rank-%d map",
+                 static_cast<int>(r), rank);
+        return fail(buf);
+    }
+    return 0;
+}
 
 int conv_tc_init() {
     if (!g_encode) {

@@ -5,6 +5,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <string>
+#include <vector>
 
 namespace ogl {
 
@@ -45,6 +46,7 @@ struct TcLayer {
 
 struct HeadParams {
     const float* w = nullptr;  // [32] device
+    const float* w_host = nullptr;  // the same on the host (s2d kernels take it as a parameter)
     float b = 0.f;
     float logit_thr = 0.f;
     float* logits = nullptr;   // [B][H][W] or null
@@ -57,13 +59,63 @@ int launch_conv_tc(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloa
                    int H, int W, __nv_bfloat16* out, __nv_bfloat16* out_pool,
                    const HeadParams* head, int num_sms, cudaStream_t stream);
 
+// ------------------------------------------------------------------ full-resolution level
+// The tensor-core convs at full resolution (Cout = 32) run on tensors stored "space-to-depth"
+// (S2D): [frame][C/8][phase = (y&1)*2 + (x&1)][H/2][W/2][8]. A GEMM row is a half-resolution
+// position and the accumulator columns are (output phase, cout) = 128, so one input phase at
+// one half-resolution offset feeds 1, 2 or 4 output phases with ONE MMA of N = 32/64/96/128
+// (16 MMAs per 16-channel slab instead of 36 N = 32 ones whose shared-memory operand reads
+// bound the tensor pipe). The ConvTranspose2d(k2,s2) in front of the
+// decoder's first conv is composed into it: its 2x2 phases are exactly the S2D phases, so
+// conv3x3(up) becomes 9 half-resolution offsets of the 64-channel tensor below with weights
+// multiplied at load time (fp64, rounded once to bf16).
+struct S2dOp {        // one tcgen05.mma of the per-tile program, as the host packer lists it (the
+                      // kernel unrolls the same table at compile time; tests emulate this list)
+    uint32_t w0;      // a_off (16-B units inside the stage) | dcol << 16 | src << 24 | acc << 25
+    uint32_t b_lo;    // B offset in the weight blob (16-B units) | (LBO >> 4) << 16
+    uint32_t idesc;   // instruction descriptor (carries N)
+    uint32_t pad;
+};
+constexpr int kS2dMaxStages = 8;
+struct S2dLayer {
+    uint8_t* wblob = nullptr;  // device: B tiles in op order
+    uint32_t wbytes = 0;
+    int n_stages = 0;          // activation stages (TMA boxes) per tile
+    int stage_src[kS2dMaxStages] = {0};     // 0: S2D source, 1: plain half-resolution source
+    int stage_plane0[kS2dMaxStages] = {0};  // first 8-channel plane of the box
+    float* btab = nullptr;     // [3][3][32] device: bias per (row class, column class)
+    float bias_host[32] = {0}; // bias of interior pixels (btab[1][1]), passed as kernel parameter
+    int cin_s = 0, cin_b = 0;
+    int epi = EPI_RELU;        // EPI_RELU / EPI_RELU_POOL / EPI_HEAD
+};
+struct S2dHost {               // host-side result of build_s2d_host, uploaded by the caller
+    std::vector<uint8_t> wblob;
+    std::vector<S2dOp> ops;
+    int n_stages = 0;
+    int stage_src[kS2dMaxStages] = {0}, stage_plane0[kS2dMaxStages] = {0},
+        stage_op_end[kS2dMaxStages] = {0};
+    std::vector<float> btab;
+};
+// w3: folded conv weights [32][cin_s + (wt ? 32 : 0)][3][3], b3 [32]; wt: ConvTranspose2d weights
+// [cin_b][32][2][2] with bias bt [32], or null.
+int build_s2d_host(const float* w3, const float* b3, int cin_s, const float* wt, const float* bt,
+                   int cin_b, S2dHost* out);
+int s2d_tc_init();
+// src_s2d: [B][cin_s/8][4][H/2][W/2][8]; below: [B][cin_b/8][H/2][W/2][8] or null. H, W = full res.
+int launch_s2d_tc(const S2dLayer& L, const __nv_bfloat16* src_s2d, const __nv_bfloat16* below,
+                  int B, int H, int W, __nv_bfloat16* out_s2d, __nv_bfloat16* out_pool,
+                  const HeadParams* head, int num_sms, cudaStream_t stream);
+// cuTensorMapEncodeTiled for a bf16 tensor (conv_tc.cu owns the driver entry point)
+int encode_bf16_map(void* tensor_map, const void* base, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box);
+
 // stem: u8 / f32 gray -> conv3x3(1->32)+bias+ReLU in fp32 -> C8-planar bf16
 struct StemWeights {  // passed by value: lives in the kernel-parameter constant bank
     float w[32 * 9];
     float b[32];
 };
 int launch_stem(const void* frames, int in_dtype, const StemWeights& sw, int B, int H, int W,
-                __nv_bfloat16* out, cudaStream_t stream);
+                __nv_bfloat16* out, bool s2d, cudaStream_t stream);
 
 // fp32 validation path (NCHW fp32 activations, FFMA kernels)
 int launch_f32_input(const void* frames, int in_dtype, int64_t count, float* out,
@@ -83,9 +135,10 @@ int launch_features(const int32_t* area, int64_t n, double* out8, int32_t* flags
                     size_t ws_bytes, cudaStream_t stream);
 
 // debugging / unit-test helpers: layout conversion NCHW f32 <-> C8-planar bf16
+// (s2d = true: the space-to-depth form of the same tensor)
 int launch_nchw_to_c8(const float* in, __nv_bfloat16* out, int B, int C, int H, int W,
-                      cudaStream_t stream);
+                      cudaStream_t stream, bool s2d = false);
 int launch_c8_to_nchw(const __nv_bfloat16* in, float* out, int B, int C, int H, int W,
-                      cudaStream_t stream);
+                      cudaStream_t stream, bool s2d = false);
 
 }  // namespace ogl

@@ -1,0 +1,659 @@
+// Full-resolution conv3x3 layers (Cout = 32) as space-to-depth GEMMs on tcgen05 / TMEM.
+//
+// Replaces, at the first U-Net level, /root/reference/openglottal/models/unet.py:24-29
+// (downs.0.net.3 + the MaxPool2d of :59,79; ups.7.net.0 with the ConvTranspose2d ups.6 of
+// :69,82 and the torch.cat of :86 composed in; ups.7.net.3 + the 1x1 head of :72,88 +
+// utils.py:237,241 sigmoid/threshold + features.py:238 area).
+//
+// Tensors are stored S2D (internal.h): [frame][C/8][phase][H/2][W/2][8]. A CTA tile is 128
+// half-resolution positions (8 in x, 16 in y) = 512 pixels; its accumulator is 128 TMEM lanes x
+// 128 columns = (output phase, cout). For input phase q at half-resolution offset o the taps
+// that exist are those with 2*o + q - p in {-1,0,1}^2, so ONE MMA with A = that phase plane
+// shifted by o serves every output phase p it reaches: N = 128 (4 phases), 64, 96 (two phases
+// whose columns are not adjacent: the block between them is zero weights) or 32.
+//   * The shape of every MMA of a tile (A offset, B offset, N, columns) is a compile-time
+//     table (s2d_shape / below_shape) shared by the host packer and the issuer, whose loop is
+//     fully unrolled so that all tcgen05.mma operands sit in uniform registers (measured:
+//     85 cycles per MMA when they come through R2UR, max(N/2, 32 + N/4) when they do not).
+//   * Weights (80 KB for Cin = 32, 152 KB with the composed transposed conv) are loaded into
+//     shared memory ONCE per CTA and stay resident; only activations stream (TMA, ring of
+//     23 KB stages = 8 planes of a 10x18 halo tile).
+//   * 4 accumulator buffers in TMEM; two epilogue warp groups take alternate tiles, so the
+//     epilogue of two tiles overlaps the MMAs of the next two.
+//   * Epilogue per thread = one half-resolution position: 4 phases x 32 channels. The 2x2
+//     max-pool is a max over the 4 phases held by the same thread (no shuffles); the head is
+//     four dot products on the fp32 values.
+#include "internal.h"
+#include "ptx.cuh"
+
+#include <cuda.h>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+namespace ogl {
+
+namespace {
+
+constexpr int kTW = 8, kTH = 16;               // tile: 8 x 16 half-resolution positions
+constexpr int kHW = kTW + 2, kHH = kTH + 2;    // with halo: 10 x 18
+constexpr int kPlane = kHW * kHH * 16;         // one 8-channel plane of a halo tile (2880 B)
+constexpr int kSlot = 8 * kPlane;              // one activation stage (23040 B)
+constexpr int kThreads = 384;                  // 4 control warps + 2 epilogue groups of 4 warps
+constexpr int kAccBufs = 4;
+constexpr int kMaxSmem = 227 * 1024;
+constexpr uint32_t kWChunk = 16384;            // weight bulk-copy granule
+
+// ---- MMA shapes (compile-time, host + device) ------------------------------------------
+// 1-D structure of a 3x3 stride-1 conv on phase-separated data: input phase q at
+// half-resolution offset o sits at full-resolution coordinate 2*o + q relative to the output
+// position's even pixel; output phase p uses it through tap d = 2*o + q - p + 1 if 0 <= d <= 2.
+__host__ __device__ constexpr int tap_of(int o, int q, int p) {
+    const int d = 2 * o + q - p + 1;
+    return (d >= 0 && d <= 2) ? d : -1;
+}
+// the four (offset, phase) pairs of one axis; the one reaching both output phases comes first so
+// that op 0 of a tile is the N = 128 one that initialises every accumulator column
+__host__ __device__ constexpr int combo_o(int i) { return i == 2 ? -1 : (i == 3 ? 1 : 0); }
+__host__ __device__ constexpr int combo_q(int i) { return (i == 1 || i == 2) ? 1 : 0; }
+__host__ __device__ constexpr int below_o(int i) { return i == 0 ? 0 : (i == 1 ? -1 : 1); }
+// bit p set: output phase p of this axis is reached
+__host__ __device__ constexpr int set_s2d(int i) {
+    return (tap_of(combo_o(i), combo_q(i), 0) >= 0 ? 1 : 0) |
+           (tap_of(combo_o(i), combo_q(i), 1) >= 0 ? 2 : 0);
+}
+__host__ __device__ constexpr int set_below(int i) {  // through either phase of `up`
+    return ((tap_of(below_o(i), 0, 0) >= 0 || tap_of(below_o(i), 1, 0) >= 0) ? 1 : 0) |
+           ((tap_of(below_o(i), 0, 1) >= 0 || tap_of(below_o(i), 1, 1) >= 0) ? 2 : 0);
+}
+struct OpShape {
+    int a_off;  // 16-byte units from the stage base (below: from the slab's first plane)
+    int dcol;   // first accumulator column
+    int n;      // MMA N
+};
+__host__ __device__ constexpr OpShape shape_from_sets(int ys, int xs, int a_off) {
+    int pmin = 4, pmax = -1;
+    for (int pp = 0; pp < 4; ++pp)
+        if (((ys >> (pp >> 1)) & 1) && ((xs >> (pp & 1)) & 1)) {
+            pmin = pp < pmin ? pp : pmin;
+            pmax = pp > pmax ? pp : pmax;
+        }
+    return OpShape{a_off, pmin * 32, (pmax - pmin + 1) * 32};
+}
+// op c = cy * 4 + cx of an S2D slab (16 per 16-channel slab)
+__host__ __device__ constexpr OpShape s2d_shape(int c) {
+    const int cy = c >> 2, cx = c & 3;
+    return shape_from_sets(set_s2d(cy), set_s2d(cx),
+                           (combo_q(cy) * 2 + combo_q(cx)) * (kPlane / 16) +
+                               (1 + combo_o(cy)) * kHW + (1 + combo_o(cx)));
+}
+// op i = iy * 3 + ix of a slab of the tensor below (9 per 16-channel slab)
+__host__ __device__ constexpr OpShape below_shape(int i) {
+    return shape_from_sets(set_below(i / 3), set_below(i % 3),
+                           (1 + below_o(i / 3)) * kHW + (1 + below_o(i % 3)));
+}
+// B offsets inside a slab's weight block, 16-byte units (an N-column block is N * 32 bytes)
+__host__ __device__ constexpr int s2d_boff(int c) {
+    int o = 0;
+    for (int i = 0; i < c; ++i) o += 2 * s2d_shape(i).n;
+    return o;
+}
+__host__ __device__ constexpr int below_boff(int i) {
+    int o = 0;
+    for (int j = 0; j < i; ++j) o += 2 * below_shape(j).n;
+    return o;
+}
+constexpr int kS2dSlabUnits = s2d_boff(16);      // 2560 (40 KB)
+constexpr int kBelowSlabUnits = below_boff(9);   // 1152 (18 KB)
+static_assert(kS2dSlabUnits == 2560 && kBelowSlabUnits == 1152, "weight block sizes");
+static_assert(s2d_shape(0).n == 128 && s2d_shape(0).dcol == 0, "op 0 must initialise all columns");
+
+struct S2dParams {
+    const uint8_t* wblob;
+    const float* btab;     // [3][3][32]: bias per (row class, column class), border pixels only
+    float bias[32];        // bias of interior pixels (= btab[1][1]); constant-bank operands
+    float head_w[32];      // 1x1 head weights (EPI_HEAD)
+    int border_bias;       // the bias of border pixels differs (composed transposed conv)
+    float* logits;
+    uint8_t* mask;
+    int32_t* area;
+    __nv_bfloat16* out;
+    __nv_bfloat16* out_pool;
+    uint32_t wbytes;
+    int n_stages;     // activation stages per tile: n_s2d slabs, then (has_below) the tensor below
+    int n_s2d, has_below;
+    int stage_src[kS2dMaxStages], stage_plane0[kS2dMaxStages];
+    float head_b, logit_thr;
+    int H2, W2, B;
+    int tiles_x, tiles_y, num_tiles;
+    unsigned long long magic_tx, magic_tpf;
+    int nslots;
+    int dbg;  // 1 no MMA, 2 no stores, 4 no epilogue work
+};
+
+struct Tile {
+    int n, y0, x0;
+};
+__device__ __forceinline__ Tile decode_tile(const S2dParams& p, int tile) {
+    Tile t;
+    const unsigned u = static_cast<unsigned>(tile);
+    const unsigned n = static_cast<unsigned>((u * p.magic_tpf) >> 40);
+    const unsigned rem = u - n * static_cast<unsigned>(p.tiles_x * p.tiles_y);
+    const unsigned ty = static_cast<unsigned>((rem * p.magic_tx) >> 40);
+    const unsigned tx = rem - ty * static_cast<unsigned>(p.tiles_x);
+    t.n = static_cast<int>(n);
+    t.y0 = static_cast<int>(ty) * kTH;
+    t.x0 = static_cast<int>(tx) * kTW;
+    return t;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
+    __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a),
+                               *reinterpret_cast<__nv_bfloat162*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(kThreads, 1)
+s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmB,
+              const S2dParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t smem_base = (raw + 127u) & ~127u;
+    const uint32_t w_s = smem_base;                                   // resident weights
+    const uint32_t a_ring = w_s + ((p.wbytes + 127u) & ~127u);        // activation stages
+    const uint32_t btab_s = a_ring + static_cast<uint32_t>(p.nslots) * kSlot;
+    const uint32_t bar_base = btab_s + 9u * 32u * 4u;
+    const uint32_t w_full = bar_base;
+    const uint32_t a_full = w_full + 8u;
+    const uint32_t a_empty = a_full + 8u * p.nslots;
+    const uint32_t acc_full = a_empty + 8u * p.nslots;
+    const uint32_t acc_empty = acc_full + 8u * kAccBufs;
+    const uint32_t tmem_slot = acc_empty + 8u * kAccBufs;
+    uint8_t* gen = smem_raw - raw;  // generic pointer = gen + shared address
+    float* btab_sp = reinterpret_cast<float*>(gen + btab_s);
+    volatile uint32_t* tmem_slot_p = reinterpret_cast<volatile uint32_t*>(gen + tmem_slot);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    // ---------------------------------------------------------------- setup
+    for (int i = threadIdx.x; i < 9 * 32; i += kThreads) btab_sp[i] = p.btab[i];
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmS);
+        tma_prefetch_desc(&tmB);
+        mbar_init(w_full, 1);
+        for (int i = 0; i < p.nslots; ++i) {
+            mbar_init(a_full + 8u * i, 1);
+            mbar_init(a_empty + 8u * i, 1);
+        }
+        for (int i = 0; i < kAccBufs; ++i) {
+            mbar_init(acc_full + 8u * i, 1);
+            mbar_init(acc_empty + 8u * i, 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_p;
+
+    if (warp == 0) {
+        // ================================================ activation producer
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const Tile t = decode_tile(p, tile);
+                for (int s = 0; s < p.n_stages; ++s, ++it) {
+                    const uint32_t slot = it % p.nslots;
+                    const uint32_t ph = (it / p.nslots) & 1u;
+                    mbar_wait(a_empty + 8u * slot, ph ^ 1u);
+                    mbar_arrive_expect_tx(a_full + 8u * slot, kSlot);
+                    const uint32_t dst = a_ring + slot * kSlot;
+                    if (p.stage_src[s] == 0)
+                        tma_load_5d(dst, &tmS, a_full + 8u * slot, (t.x0 - 1) * 8, t.y0 - 1, 0,
+                                    p.stage_plane0[s], t.n);
+                    else
+                        tma_load_4d(dst, &tmB, a_full + 8u * slot, (t.x0 - 1) * 8, t.y0 - 1,
+                                    p.stage_plane0[s], t.n);
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ================================================== weights, once per CTA
+        if (lane == 0) {
+            mbar_arrive_expect_tx(w_full, p.wbytes);
+            for (uint32_t off = 0; off < p.wbytes; off += kWChunk) {
+                const uint32_t n = p.wbytes - off < kWChunk ? p.wbytes - off : kWChunk;
+                bulk_load(w_s + off, p.wblob + off, n, w_full);
+            }
+        }
+    } else if (warp == 1) {
+        // ========================================================= MMA issuer
+        // The whole warp walks the loops (all values warp-uniform); one elected lane issues.
+        // descriptor halves that never change: A (two LBOs: S2D stage / plain stage), B
+        constexpr uint32_t a_hi = ((kHW * 16u) >> 4) | (1u << 14);           // SBO = one halo row
+        constexpr uint32_t a_lbo_s2d = ((4u * kPlane) >> 4) << 16;          // plane pair of a phase
+        constexpr uint32_t a_lbo_plain = (static_cast<uint32_t>(kPlane) >> 4) << 16;
+        constexpr uint64_t b_hi = static_cast<uint64_t>((128u >> 4) | (1u << 14)) << 32;
+        const uint32_t w_lo = w_s >> 4;
+        mbar_wait(w_full, 0);
+        uint32_t ita = 0, li = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++li) {
+            const uint32_t buf = li % kAccBufs;
+            const uint32_t aph = (li / kAccBufs) & 1u;
+            mbar_wait(acc_empty + 8u * buf, aph ^ 1u);
+            tc_fence_after();
+            const uint32_t d0 = tmem_base + buf * 128u;
+            for (int s = 0; s < p.n_s2d; ++s, ++ita) {
+                const uint32_t slot = ita % p.nslots;
+                mbar_wait(a_full + 8u * slot, (ita / p.nslots) & 1u);
+                tc_fence_after();
+                const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) |
+                                    (((a_ring + slot * kSlot) >> 4) | a_lbo_s2d);
+                const uint64_t bd = b_hi | (w_lo + static_cast<uint32_t>(s) * kS2dSlabUnits);
+                const uint32_t first = s != 0 ? 1u : 0u;
+                const bool last = (s == p.n_s2d - 1) && !p.has_below;
+                if (elect_one()) {
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        if (p.dbg & 1) break;
+                        const OpShape sh = s2d_shape(c);
+                        // LBO of B = 16 * N bytes -> (N) in the descriptor's bits 16..29
+                        umma_bf16(d0 + sh.dcol, ad + sh.a_off,
+                                  bd + (s2d_boff(c) + (static_cast<uint32_t>(sh.n) << 16)),
+                                  make_idesc_bf16(sh.n), c ? 1u : first);
+                    }
+                    umma_commit(a_empty + 8u * slot);
+                    if (last) umma_commit(acc_full + 8u * buf);
+                }
+                __syncwarp();
+            }
+            if (p.has_below) {
+                const uint32_t slot = ita % p.nslots;
+                mbar_wait(a_full + 8u * slot, (ita / p.nslots) & 1u);
+                tc_fence_after();
+                const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) |
+                                    (((a_ring + slot * kSlot) >> 4) | a_lbo_plain);
+                const uint64_t bd =
+                    b_hi | (w_lo + static_cast<uint32_t>(p.n_s2d) * kS2dSlabUnits);
+                if (elect_one()) {
+#pragma unroll
+                    for (int k16 = 0; k16 < 4; ++k16) {
+#pragma unroll
+                        for (int i = 0; i < 9; ++i) {
+                            if (p.dbg & 1) break;
+                            const OpShape sh = below_shape(i);
+                            umma_bf16(d0 + sh.dcol, ad + (2 * k16 * (kPlane / 16) + sh.a_off),
+                                      bd + (k16 * kBelowSlabUnits + below_boff(i) +
+                                            (static_cast<uint32_t>(sh.n) << 16)),
+                                      make_idesc_bf16(sh.n), 1u);
+                        }
+                    }
+                    umma_commit(a_empty + 8u * slot);
+                    umma_commit(acc_full + 8u * buf);
+                }
+                __syncwarp();
+                ++ita;
+            }
+        }
+    } else if (warp >= 4) {
+        // =========================================================== epilogue
+        const int et = (threadIdx.x - 128) & 127;   // TMEM lane = position inside the tile
+        const int grp = (threadIdx.x - 128) >> 7;   // takes tiles with (li & 1) == grp
+        const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;
+        const int py = et >> 3, px = et & 7;
+        const int H = 2 * p.H2, W = 2 * p.W2;
+        const size_t plane = static_cast<size_t>(p.H2) * p.W2 * 8;  // one phase of one 8-ch group
+        uint32_t li = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++li) {
+            if (static_cast<int>(li & 1u) != grp) continue;
+            const uint32_t buf = li % kAccBufs;
+            const uint32_t aph = (li / kAccBufs) & 1u;
+            const Tile t = decode_tile(p, tile);
+            const int Y = t.y0 + py, X = t.x0 + px;
+            const bool valid = Y < p.H2 && X < p.W2 && !(p.dbg & 2);
+            mbar_wait(acc_full + 8u * buf, aph);
+            tc_fence_after();
+            const uint32_t tcol = tmem_base + lane_sel + buf * 128u;
+            uint32_t mx[16];
+            float zprev = 0.f;
+            bool onprev = false;
+            int cnt = 0;
+#pragma unroll 1
+            for (int ph = 0; ph < 4; ++ph) {
+                if (p.dbg & 4) break;
+                uint32_t r[32];
+                tmem_ld32(tcol + ph * 32, r);
+                tmem_ld_wait();
+                const int y = 2 * Y + (ph >> 1), x = 2 * X + (ph & 1);
+                const int ry = y == 0 ? 0 : (y == H - 1 ? 2 : 1);
+                const int rx = x == 0 ? 0 : (x == W - 1 ? 2 : 1);
+                float v[32];
+                // bias + ReLU. Interior pixels (every lane of nearly every warp) take the bias
+                // straight from the constant bank; only warps touching the image border of a
+                // layer with a composed transposed conv read their per-class bias from smem.
+                const bool plain = !p.border_bias || (ry == 1 && rx == 1);
+                if (__all_sync(0xffffffffu, plain)) {
+#pragma unroll
+                    for (int k = 0; k < 32; ++k)
+                        v[k] = fmaxf(__uint_as_float(r[k]) + p.bias[k], 0.f);
+                } else {
+                    const float* bp = btab_sp + (ry * 3 + rx) * 32;
+#pragma unroll
+                    for (int k = 0; k < 32; ++k)
+                        v[k] = fmaxf(__uint_as_float(r[k]) + bp[k], 0.f);
+                }
+                if (EPI == EPI_HEAD) {
+                    float z = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) z = fmaf(v[k], p.head_w[k], z);
+                    z += p.head_b;
+                    const bool on = valid && (z > p.logit_thr);
+                    const uint32_t bal = __ballot_sync(0xffffffffu, on);
+                    cnt += __popc(bal);
+                    if (ph & 1) {
+                        // pixels (y, 2X) and (y, 2X+1) leave together
+                        const size_t pix = (static_cast<size_t>(t.n) * H + y) * W + 2 * X;
+                        if (valid && p.logits)
+                            *reinterpret_cast<float2*>(p.logits + pix) = make_float2(zprev, z);
+                        if (valid && p.mask)
+                            *reinterpret_cast<uint16_t*>(p.mask + pix) =
+                                static_cast<uint16_t>((onprev ? 0x00ffu : 0u) | (on ? 0xff00u : 0u));
+                    }
+                    zprev = z;
+                    onprev = on;
+                } else {
+                    __nv_bfloat16* optr =
+                        p.out + ((static_cast<size_t>(t.n) * 4) * 4 + ph) * plane +
+                        (static_cast<size_t>(Y) * p.W2 + X) * 8;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        uint4 q4;
+                        q4.x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]);
+                        q4.y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
+                        q4.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]);
+                        q4.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
+                        if (valid) *reinterpret_cast<uint4*>(optr + g * 4 * plane) = q4;
+                        if (EPI == EPI_RELU_POOL) {
+                            if (ph == 0) {
+                                mx[g * 4 + 0] = q4.x;
+                                mx[g * 4 + 1] = q4.y;
+                                mx[g * 4 + 2] = q4.z;
+                                mx[g * 4 + 3] = q4.w;
+                            } else {
+                                mx[g * 4 + 0] = max_bf16x2(mx[g * 4 + 0], q4.x);
+                                mx[g * 4 + 1] = max_bf16x2(mx[g * 4 + 1], q4.y);
+                                mx[g * 4 + 2] = max_bf16x2(mx[g * 4 + 2], q4.z);
+                                mx[g * 4 + 3] = max_bf16x2(mx[g * 4 + 3], q4.w);
+                            }
+                        }
+                    }
+                }
+            }
+            if (EPI == EPI_RELU_POOL && valid && !(p.dbg & 4)) {
+                // pooled tensor: plain C8-planar at half resolution
+                __nv_bfloat16* pp = p.out_pool + (static_cast<size_t>(t.n) * 4) * plane +
+                                    (static_cast<size_t>(Y) * p.W2 + X) * 8;
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                    *reinterpret_cast<uint4*>(pp + g * plane) =
+                        make_uint4(mx[g * 4 + 0], mx[g * 4 + 1], mx[g * 4 + 2], mx[g * 4 + 3]);
+            }
+            if (EPI == EPI_HEAD) {
+                if (lane == 0 && p.area && cnt) atomicAdd(p.area + t.n, cnt);
+            }
+            tc_fence_before();
+            mbar_arrive(acc_empty + 8u * buf);
+        }
+    }
+
+    // ------------------------------------------------------------- teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+inline uint16_t bf16_bits(double v) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(static_cast<float>(v));
+    uint16_t b;
+    memcpy(&b, &h, 2);
+    return b;
+}
+
+}  // namespace
+
+int build_s2d_host(const float* w3, const float* b3, int cin_s, const float* wt, const float* bt,
+                   int cin_b, S2dHost* out) {
+    if (cin_s <= 0 || cin_s % 16) return fail("s2d layer: Cin of the S2D source must be a multiple of 16");
+    if (wt && cin_b != 64) return fail("s2d layer: the composed ConvTranspose2d needs 64 input channels");
+    const int cin3 = cin_s + (wt ? 32 : 0);
+    auto W3 = [&](int co, int ci, int dy, int dx) -> double {
+        return w3[((static_cast<size_t>(co) * cin3 + ci) * 3 + dy) * 3 + dx];
+    };
+    out->wblob.clear();
+    out->ops.clear();
+    int n_stages = 0;
+
+    // One MMA: its shape comes from the table the kernel unrolls (s2d_shape / below_shape); the
+    // B block [2][N][8] holds, for column n = (phase - first phase) * 32 + cout, the weight
+    // through which this A reaches that output phase, or zero when it does not.
+    auto emit = [&](const OpShape& sh, uint32_t a_extra, int src, int ys, int xs, size_t want_off,
+                    auto&& weight /* (k, py, px, cout) -> double */) -> int {
+        const int N = sh.n, pmin = sh.dcol / 32;
+        const size_t b_off = out->wblob.size();
+        if (b_off != want_off) return fail("s2d layer: weight block offset differs from the kernel's table");
+        out->wblob.resize(b_off + static_cast<size_t>(N) * 32);
+        uint16_t* B = reinterpret_cast<uint16_t*>(out->wblob.data() + b_off);
+        for (int kh = 0; kh < 2; ++kh)
+            for (int n = 0; n < N; ++n)
+                for (int e = 0; e < 8; ++e) {
+                    const int pp = pmin + n / 32, c = n % 32;
+                    double v = 0.0;
+                    if (((ys >> (pp >> 1)) & 1) && ((xs >> (pp & 1)) & 1))
+                        v = weight(kh * 8 + e, pp >> 1, pp & 1, c);
+                    B[(static_cast<size_t>(kh) * N + n) * 8 + e] = bf16_bits(v);
+                }
+        S2dOp op;
+        op.w0 = (static_cast<uint32_t>(sh.a_off) + a_extra) | (static_cast<uint32_t>(sh.dcol) << 16) |
+                (static_cast<uint32_t>(src) << 24) | ((out->ops.empty() ? 0u : 1u) << 25);
+        op.b_lo = static_cast<uint32_t>(b_off >> 4) | (static_cast<uint32_t>(N) << 16);  // LBO = 16 N
+        op.idesc = make_idesc_bf16(N);
+        op.pad = 0;
+        out->ops.push_back(op);
+        return 0;
+    };
+
+    // ---- S2D source: one stage per 16-channel slab, 16 ops each
+    for (int s = 0; s < cin_s / 16; ++s) {
+        if (n_stages >= kS2dMaxStages - 1) return fail("s2d layer: too many stages");
+        for (int c = 0; c < 16; ++c) {
+            const int cy = c >> 2, cx = c & 3;
+            const int oy = combo_o(cy), qy = combo_q(cy), ox = combo_o(cx), qx = combo_q(cx);
+            const size_t want = (static_cast<size_t>(s) * kS2dSlabUnits + s2d_boff(c)) * 16;
+            if (emit(s2d_shape(c), 0, 0, set_s2d(cy), set_s2d(cx), want,
+                     [&](int k, int py, int px, int co) {
+                         return W3(co, s * 16 + k, tap_of(oy, qy, py), tap_of(ox, qx, px));
+                     }))
+                return 1;
+        }
+        out->stage_src[n_stages] = 0;
+        out->stage_plane0[n_stages] = 2 * s;
+        out->stage_op_end[n_stages] = static_cast<int>(out->ops.size());
+        ++n_stages;
+    }
+    // ---- composed ConvTranspose2d: one stage = all 64 channels of the tensor below,
+    // 4 slabs x 9 half-resolution offsets. `up` phase q at offset o is wt[., ., q] applied to
+    // below[Y + o], so the weight from below channel k to (output phase p, cout) is
+    // sum over the q that p reaches at this offset, and over the 32 `up` channels.
+    if (wt) {
+        auto WT = [&](int ci, int co, int qy, int qx) -> double {
+            return wt[((static_cast<size_t>(ci) * 32 + co) * 2 + qy) * 2 + qx];
+        };
+        const size_t base = static_cast<size_t>(cin_s / 16) * kS2dSlabUnits;
+        for (int k16 = 0; k16 < cin_b / 16; ++k16)
+            for (int i = 0; i < 9; ++i) {
+                const int oy = below_o(i / 3), ox = below_o(i % 3);
+                const size_t want = (base + static_cast<size_t>(k16) * kBelowSlabUnits + below_boff(i)) * 16;
+                if (emit(below_shape(i), static_cast<uint32_t>(2 * k16 * (kPlane / 16)), 1,
+                         set_below(i / 3), set_below(i % 3), want,
+                         [&](int k, int py, int px, int co) {
+                             double acc = 0.0;
+                             for (int qy = 0; qy < 2; ++qy) {
+                                 const int dy = tap_of(oy, qy, py);
+                                 if (dy < 0) continue;
+                                 for (int qx = 0; qx < 2; ++qx) {
+                                     const int dx = tap_of(ox, qx, px);
+                                     if (dx < 0) continue;
+                                     for (int cm = 0; cm < 32; ++cm)
+                                         acc += WT(k16 * 16 + k, cm, qy, qx) * W3(co, cin_s + cm, dy, dx);
+                                 }
+                             }
+                             return acc;
+                         }))
+                    return 1;
+            }
+        out->stage_src[n_stages] = 1;
+        out->stage_plane0[n_stages] = 0;
+        out->stage_op_end[n_stages] = static_cast<int>(out->ops.size());
+        ++n_stages;
+    }
+    out->n_stages = n_stages;
+    // ---- bias per (row class, column class): the transposed conv's bias reaches an output
+    // pixel only through the taps that fall inside the image (zero padding of `up`)
+    out->btab.assign(9 * 32, 0.f);
+    for (int ry = 0; ry < 3; ++ry)
+        for (int rx = 0; rx < 3; ++rx)
+            for (int c = 0; c < 32; ++c) {
+                double v = b3[c];
+                if (wt)
+                    for (int dy = 0; dy < 3; ++dy) {
+                        if ((ry == 0 && dy == 0) || (ry == 2 && dy == 2)) continue;
+                        for (int dx = 0; dx < 3; ++dx) {
+                            if ((rx == 0 && dx == 0) || (rx == 2 && dx == 2)) continue;
+                            for (int cm = 0; cm < 32; ++cm) v += W3(c, cin_s + cm, dy, dx) * bt[cm];
+                        }
+                    }
+                out->btab[(ry * 3 + rx) * 32 + c] = static_cast<float>(v);
+            }
+    return 0;
+}
+
+int s2d_tc_init() {
+    OGL_CUDA(cudaFuncSetAttribute(s2d_tc_kernel<EPI_RELU>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    OGL_CUDA(cudaFuncSetAttribute(s2d_tc_kernel<EPI_RELU_POOL>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    OGL_CUDA(cudaFuncSetAttribute(s2d_tc_kernel<EPI_HEAD>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    return 0;
+}
+
+int launch_s2d_tc(const S2dLayer& L, const __nv_bfloat16* src_s2d, const __nv_bfloat16* below,
+                  int B, int H, int W, __nv_bfloat16* out_s2d, __nv_bfloat16* out_pool,
+                  const HeadParams* head, int num_sms, cudaStream_t stream) {
+    if (H < 2 || W < 2 || H % 2 || W % 2) return fail("s2d layer needs even, non-empty H and W");
+    if ((W / 2) % 8) return fail("s2d layer needs W to be a multiple of 16");
+    if (!src_s2d || L.n_stages < 1 || !L.wblob || !L.btab)
+        return fail("s2d layer is not built");
+    if (L.cin_b > 0 && !below) return fail("s2d layer: the tensor below is missing");
+    if (L.epi == EPI_RELU_POOL && !out_pool) return fail("pool epilogue needs out_pool");
+    if (L.epi == EPI_HEAD && !head) return fail("head epilogue needs head parameters");
+    if (L.epi != EPI_HEAD && !out_s2d) return fail("s2d layer: no output tensor");
+
+    S2dParams p;
+    memset(&p, 0, sizeof p);
+    p.wblob = L.wblob;
+    p.wbytes = L.wbytes;
+    p.n_stages = L.n_stages;
+    p.has_below = L.stage_src[L.n_stages - 1] == 1 ? 1 : 0;
+    p.n_s2d = L.n_stages - p.has_below;
+    for (int i = 0; i < kS2dMaxStages; ++i) {
+        p.stage_src[i] = L.stage_src[i];
+        p.stage_plane0[i] = L.stage_plane0[i];
+    }
+    if (p.n_s2d != L.cin_s / 16 || (p.has_below != 0) != (L.cin_b > 0) ||
+        L.wbytes != (static_cast<uint32_t>(p.n_s2d) * kS2dSlabUnits +
+                     (p.has_below ? 4u * kBelowSlabUnits : 0u)) * 16u)
+        return fail("s2d layer: program does not match the kernel's compile-time tables");
+    p.btab = L.btab;
+    p.border_bias = L.cin_b > 0 ? 1 : 0;
+    for (int i = 0; i < 32; ++i) p.bias[i] = L.bias_host[i];
+    if (head) {
+        if (L.epi == EPI_HEAD && !head->w_host) return fail("head epilogue needs the host weights");
+        for (int i = 0; i < 32 && head->w_host; ++i) p.head_w[i] = head->w_host[i];
+        p.head_b = head->b;
+        p.logit_thr = head->logit_thr;
+        p.logits = head->logits;
+        p.mask = head->mask;
+        p.area = head->area;
+    }
+    p.out = out_s2d;
+    p.out_pool = out_pool;
+    p.H2 = H / 2;
+    p.W2 = W / 2;
+    p.B = B;
+    p.tiles_x = (p.W2 + kTW - 1) / kTW;
+    p.tiles_y = (p.H2 + kTH - 1) / kTH;
+    const long long total = static_cast<long long>(B) * p.tiles_x * p.tiles_y;
+    if (total * (p.tiles_x * p.tiles_y) >= (1ll << 40) || total > 0x7fffffffll)
+        return fail("batch too large for the tile decoder");
+    p.num_tiles = static_cast<int>(total);
+    p.magic_tx = ((1ull << 40) / static_cast<unsigned long long>(p.tiles_x)) + 1;
+    p.magic_tpf = ((1ull << 40) / static_cast<unsigned long long>(p.tiles_x * p.tiles_y)) + 1;
+    static const int dbg_env = getenv("OGL_DBG") ? atoi(getenv("OGL_DBG")) : 0;
+    p.dbg = dbg_env;
+
+    const size_t fixed = 128 + ((L.wbytes + 127u) & ~127u) + 9 * 32 * 4 + 8 +
+                         16 * kAccBufs + 16 + 64;
+    int nslots = 6;
+    static const int ns_env = getenv("OGL_S2D_SLOTS") ? atoi(getenv("OGL_S2D_SLOTS")) : 0;
+    if (ns_env > 0) nslots = ns_env;
+    while (nslots > 2 && fixed + static_cast<size_t>(nslots) * (kSlot + 16) > kMaxSmem) --nslots;
+    const size_t smem = fixed + static_cast<size_t>(nslots) * (kSlot + 16);
+    if (smem > static_cast<size_t>(kMaxSmem)) return fail("s2d layer: shared memory budget exceeded");
+    p.nslots = nslots;
+
+    CUtensorMap tmS, tmB;
+    {
+        const uint64_t W2 = p.W2, H2 = p.H2;
+        const uint64_t dims[5] = {W2 * 8, H2, 4, static_cast<uint64_t>(L.cin_s / 8),
+                                  static_cast<uint64_t>(B)};
+        const uint64_t str[4] = {W2 * 16, W2 * 16 * H2, W2 * 16 * H2 * 4,
+                                 W2 * 16 * H2 * 4 * (L.cin_s / 8)};
+        const uint32_t box[5] = {kHW * 8, kHH, 4, 2, 1};
+        if (encode_bf16_map(&tmS, src_s2d, 5, dims, str, box)) return 1;
+    }
+    if (L.cin_b > 0) {
+        const uint64_t W2 = p.W2, H2 = p.H2;
+        const uint64_t dims[4] = {W2 * 8, H2, static_cast<uint64_t>(L.cin_b / 8),
+                                  static_cast<uint64_t>(B)};
+        const uint64_t str[3] = {W2 * 16, W2 * 16 * H2, W2 * 16 * H2 * (L.cin_b / 8)};
+        const uint32_t box[4] = {kHW * 8, kHH, 8, 1};
+        if (encode_bf16_map(&tmB, below, 4, dims, str, box)) return 1;
+    } else {
+        tmB = tmS;
+    }
+    const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+    if (L.epi == EPI_RELU)
+        s2d_tc_kernel<EPI_RELU><<<grid, kThreads, smem, stream>>>(tmS, tmB, p);
+    else if (L.epi == EPI_RELU_POOL)
+        s2d_tc_kernel<EPI_RELU_POOL><<<grid, kThreads, smem, stream>>>(tmS, tmB, p);
+    else if (L.epi == EPI_HEAD)
+        s2d_tc_kernel<EPI_HEAD><<<grid, kThreads, smem, stream>>>(tmS, tmB, p);
+    else
+        return fail("s2d layer: unknown epilogue");
+    OGL_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace ogl

@@ -24,13 +24,23 @@ __device__ __forceinline__ float load_gray(const void* frames, int in_dtype, siz
     return static_cast<const float*>(frames)[idx];
 }
 
+// Element offset of pixel (y, x) inside one 8-channel group of a [H][W][8] plane, or of its
+// space-to-depth form [phase][H/2][W/2][8] (internal.h); the group stride is H*W*8 for both.
+__device__ __forceinline__ size_t pix_off(int y, int x, int H, int W, int s2d) {
+    if (s2d) {
+        const size_t hw2 = static_cast<size_t>(H >> 1) * (W >> 1);
+        return ((((y & 1) * 2 + (x & 1)) * hw2) + static_cast<size_t>(y >> 1) * (W >> 1) + (x >> 1)) * 8;
+    }
+    return (static_cast<size_t>(y) * W + x) * 8;
+}
+
 // ------------------------------------------------------------------- stem
 // Generic form (f32 input): one thread per pixel, 9 taps -> 32 channels in fp32, written as
 // 4 planes of 8 bf16. The 288 folded weights arrive as a by-value kernel parameter, so every
 // FFMA takes its weight straight from the constant bank (no LDS / LDG in the inner loop).
 __global__ void __launch_bounds__(256)
 stem_kernel(const void* __restrict__ frames, int in_dtype, const __grid_constant__ StemWeights sw,
-            int B, int H, int W, __nv_bfloat16* __restrict__ out) {
+            int B, int H, int W, __nv_bfloat16* __restrict__ out, int s2d) {
     // u8 -> float32(v) / 255.0f (IEEE division, as numpy does) through a 256-entry table
     __shared__ float lut[256];
     lut[threadIdx.x] = __fdiv_rn(static_cast<float>(threadIdx.x), 255.0f);
@@ -55,7 +65,7 @@ stem_kernel(const void* __restrict__ frames, int in_dtype, const __grid_constant
                 in[dy * 3 + dx] = ok ? v : 0.f;
             }
         const size_t plane = static_cast<size_t>(H) * W * 8;
-        __nv_bfloat16* o = out + n * 4 * plane + (static_cast<size_t>(y) * W + x) * 8;
+        __nv_bfloat16* o = out + n * 4 * plane + pix_off(y, x, H, W, s2d);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             float v[8];
@@ -89,7 +99,7 @@ stem_kernel(const void* __restrict__ frames, int in_dtype, const __grid_constant
 // packed bf16x2 max after rounding; each channel group stores 64 contiguous bytes per thread.
 __global__ void __launch_bounds__(256)
 stem_u8_kernel(const uint8_t* __restrict__ frames, const __grid_constant__ StemWeights sw,
-               int rows_total, int H, int W, __nv_bfloat16* __restrict__ out) {
+               int rows_total, int H, int W, __nv_bfloat16* __restrict__ out, int s2d) {
     const int lane = threadIdx.x & 31;
     const int warps_per_grid = gridDim.x * (blockDim.x >> 5);
     const int Q = W >> 2;  // quads per row
@@ -123,8 +133,9 @@ stem_u8_kernel(const uint8_t* __restrict__ frames, const __grid_constant__ StemW
                 in[dy][5] = static_cast<float>(rb);
             }
             if (!act) continue;
-            __nv_bfloat16* o = out + static_cast<size_t>(n) * 4 * plane +
-                               (static_cast<size_t>(y) * W + 4 * xq) * 8;
+            // s2d: even pixels (4xq, 4xq+2) are neighbours in phase (y&1, 0), odd ones in (y&1, 1)
+            __nv_bfloat16* o = out + static_cast<size_t>(n) * 4 * plane + pix_off(y, 4 * xq, H, W, s2d);
+            const size_t odd = static_cast<size_t>(H >> 1) * (W >> 1) * 8;  // phase (., 1) - (., 0)
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
                 uint32_t pk[4][4];  // [pixel][channel pair]
@@ -153,9 +164,17 @@ stem_u8_kernel(const uint8_t* __restrict__ frames, const __grid_constant__ StemW
                     }
                 }
                 uint4* dst = reinterpret_cast<uint4*>(o + g * plane);
+                if (s2d) {
+                    uint4* dso = reinterpret_cast<uint4*>(o + g * plane + odd);
+                    dst[0] = make_uint4(pk[0][0], pk[0][1], pk[0][2], pk[0][3]);
+                    dst[1] = make_uint4(pk[2][0], pk[2][1], pk[2][2], pk[2][3]);
+                    dso[0] = make_uint4(pk[1][0], pk[1][1], pk[1][2], pk[1][3]);
+                    dso[1] = make_uint4(pk[3][0], pk[3][1], pk[3][2], pk[3][3]);
+                } else {
 #pragma unroll
-                for (int px = 0; px < 4; ++px)
-                    dst[px] = make_uint4(pk[px][0], pk[px][1], pk[px][2], pk[px][3]);
+                    for (int px = 0; px < 4; ++px)
+                        dst[px] = make_uint4(pk[px][0], pk[px][1], pk[px][2], pk[px][3]);
+                }
             }
         }
     }
@@ -286,7 +305,7 @@ __global__ void f32_head_kernel(const float* __restrict__ in, const float* __res
 
 // ------------------------------------------------------- layout converters
 __global__ void nchw_to_c8_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
-                                  int B, int C, int H, int W) {
+                                  int B, int C, int H, int W, int s2d) {
     const size_t total = static_cast<size_t>(B) * C * H * W;
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -294,11 +313,12 @@ __global__ void nchw_to_c8_kernel(const float* __restrict__ in, __nv_bfloat16* _
         const int y = static_cast<int>((i / W) % H);
         const int c = static_cast<int>((i / (static_cast<size_t>(W) * H)) % C);
         const size_t n = i / (static_cast<size_t>(W) * H * C);
-        out[(((n * (C / 8) + c / 8) * H + y) * W + x) * 8 + (c & 7)] = __float2bfloat16_rn(in[i]);
+        out[(n * (C / 8) + c / 8) * H * W * 8 + pix_off(y, x, H, W, s2d) + (c & 7)] =
+            __float2bfloat16_rn(in[i]);
     }
 }
 __global__ void c8_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out,
-                                  int B, int C, int H, int W) {
+                                  int B, int C, int H, int W, int s2d) {
     const size_t total = static_cast<size_t>(B) * C * H * W;
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -306,7 +326,8 @@ __global__ void c8_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, float* _
         const int y = static_cast<int>((i / W) % H);
         const int c = static_cast<int>((i / (static_cast<size_t>(W) * H)) % C);
         const size_t n = i / (static_cast<size_t>(W) * H * C);
-        out[i] = __bfloat162float(in[(((n * (C / 8) + c / 8) * H + y) * W + x) * 8 + (c & 7)]);
+        out[i] = __bfloat162float(
+            in[(n * (C / 8) + c / 8) * H * W * 8 + pix_off(y, x, H, W, s2d) + (c & 7)]);
     }
 }
 
@@ -320,8 +341,9 @@ inline int grid_for(size_t total, int block = 256, int cap = 148 * 16) {
 }  // namespace
 
 int launch_stem(const void* frames, int in_dtype, const StemWeights& sw, int B, int H, int W,
-                __nv_bfloat16* out, cudaStream_t stream) {
+                __nv_bfloat16* out, bool s2d, cudaStream_t stream) {
     const size_t total = static_cast<size_t>(B) * H * W;
+    if (s2d && (H % 2 || W % 2)) return fail("space-to-depth stem output needs even H and W");
     if (in_dtype == 0 && W % 4 == 0) {
         // hot path: weights pre-scaled by 1/255 (in fp64, rounded once) so the u8 values are
         // used directly; differs from fl(v/255)*w by ~1 ulp of fp32, far below bf16 rounding
@@ -332,10 +354,10 @@ int launch_stem(const void* frames, int in_dtype, const StemWeights& sw, int B, 
         int grid = (rows + 7) / 8;
         if (grid > 148 * 6) grid = 148 * 6;
         stem_u8_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint8_t*>(frames), scaled, rows,
-                                                 H, W, out);
+                                                 H, W, out, s2d ? 1 : 0);
     } else {
         stem_kernel<<<grid_for(total, 256, 148 * 8), 256, 0, stream>>>(frames, in_dtype, sw, B, H,
-                                                                       W, out);
+                                                                       W, out, s2d ? 1 : 0);
     }
     OGL_CUDA(cudaGetLastError());
     return 0;
@@ -383,16 +405,16 @@ int launch_f32_head(const float* in, const float* w, float b, float thr, int B, 
 }
 
 int launch_nchw_to_c8(const float* in, __nv_bfloat16* out, int B, int C, int H, int W,
-                      cudaStream_t stream) {
-    nchw_to_c8_kernel<<<grid_for(static_cast<size_t>(B) * C * H * W), 256, 0, stream>>>(in, out, B,
-                                                                                       C, H, W);
+                      cudaStream_t stream, bool s2d) {
+    nchw_to_c8_kernel<<<grid_for(static_cast<size_t>(B) * C * H * W), 256, 0, stream>>>(
+        in, out, B, C, H, W, s2d ? 1 : 0);
     OGL_CUDA(cudaGetLastError());
     return 0;
 }
 int launch_c8_to_nchw(const __nv_bfloat16* in, float* out, int B, int C, int H, int W,
-                      cudaStream_t stream) {
-    c8_to_nchw_kernel<<<grid_for(static_cast<size_t>(B) * C * H * W), 256, 0, stream>>>(in, out, B,
-                                                                                       C, H, W);
+                      cudaStream_t stream, bool s2d) {
+    c8_to_nchw_kernel<<<grid_for(static_cast<size_t>(B) * C * H * W), 256, 0, stream>>>(
+        in, out, B, C, H, W, s2d ? 1 : 0);
     OGL_CUDA(cudaGetLastError());
     return 0;
 }

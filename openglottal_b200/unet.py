@@ -65,6 +65,8 @@ class UNet(nn.Module):
 
         self.precision = "bf16"      # "bf16" (tensor cores) or "fp32" (validation mode)
         self.max_batch = 512         # frames per native call; larger inputs are chunked
+        self.schedule = "s2d"        # full-resolution level: "s2d" (space-to-depth GEMMs, the
+                                     # default) or "direct" (per-tap form of the other levels)
         self._handle = None
         self._handle_device = None
         self._packed_sig = None
@@ -188,8 +190,11 @@ class UNet(nn.Module):
             raise ValueError(f"H and W must be multiples of 16 (got {hgt}x{wid}); resize first")
         if not (0.0 < threshold < 1.0) or math.isnan(threshold):
             raise ValueError("threshold must be in (0, 1)")
+        if self.schedule not in ("s2d", "direct"):
+            raise ValueError(f"schedule must be 's2d' or 'direct', got {self.schedule!r}")
         self._pack_if_needed()
         lib = _native.load()
+        _native.check(lib.ogl_unet_set_schedule(self._handle, 1 if self.schedule == "s2d" else 0))
         frames = frames.contiguous()
         logits = torch.empty((n, hgt, wid), dtype=torch.float32, device=dev) if want_logits else None
         mask = torch.empty((n, hgt, wid), dtype=torch.uint8, device=dev) if want_mask else None

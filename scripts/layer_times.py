@@ -26,6 +26,7 @@ model = ogl.UNet().to("cuda")
 model.load_state_dict(sd)
 model.eval()
 model.max_batch = batch
+model.schedule = "direct" if os.environ.get("OGL_S2D", "1") == "0" else "s2d"
 lib = _native.load()
 g = torch.Generator().manual_seed(0)
 frames = torch.randint(0, 256, (4 * batch, hgt, wid), dtype=torch.uint8, generator=g).cuda()
@@ -49,7 +50,7 @@ for i in range(steps):
     v = np.array(buf[:cnt.value])
     acc = v if acc is None else acc + v
 acc /= steps
-names = [lib.ogl_unet_layer_name(i).decode() for i in range(cnt.value)]
+names = [lib.ogl_unet_launch_name(model._handle, i).decode() for i in range(cnt.value)]
 print(json.dumps({"tag": tag, "env": {k: v for k, v in os.environ.items() if k.startswith("OGL_")},
                   "batch": batch, "ms_step": total, "fps": batch / total * 1e3,
                   "layers": dict(zip(names, [round(float(x), 4) for x in acc]))}))

@@ -101,3 +101,65 @@ def test_convt2x2_tc(lib, handle, cin, cout, n, hgt, wid):
     ref = F.conv_transpose2d(x.double(), w.double(), b.double(), stride=2).float()
     out, _ = _run_layer(lib, handle, 3, x.cuda(), None, w, b, cout)
     _report(f"convT {cin}->{cout} {n}x{hgt}x{wid}", out.cpu(), ref)
+
+
+# ------------------------------------------------------------------ space-to-depth layers
+def _run_s2d(lib, handle, kind, x, below, w3, b3, wt, bt):
+    from openglottal_b200 import _native
+
+    fp = C.POINTER(C.c_float)
+    n, cin_s, hgt, wid = x.shape
+    out = torch.full((n, 32, hgt, wid), float("nan"), device="cuda")
+    pool = torch.full((n, 32, hgt // 2, wid // 2), float("nan"), device="cuda") if kind == 1 else None
+    host = [t.contiguous().cpu().float() if t is not None else None for t in (w3, b3, wt, bt)]
+    ptr = lambda t: None if t is None else C.cast(t.data_ptr(), fp)
+    xd = x.cuda().contiguous()
+    bd = None if below is None else below.cuda().contiguous()
+    rc = lib.ogl_debug_s2d_layer(handle, kind, xd.data_ptr(), cin_s,
+                                 None if bd is None else bd.data_ptr(), ptr(host[0]), ptr(host[1]),
+                                 ptr(host[2]), ptr(host[3]), n, hgt, wid, out.data_ptr(),
+                                 None if pool is None else pool.data_ptr(), None)
+    _native.check(rc)
+    torch.cuda.synchronize()
+    return out, pool
+
+
+@pytest.mark.parametrize("kind,cin_s,n,hgt,wid", [
+    (0, 32, 2, 16, 16), (0, 32, 3, 32, 48), (1, 32, 2, 48, 32), (0, 16, 1, 16, 32),
+    (1, 32, 5, 64, 64), (0, 32, 40, 64, 64), (1, 32, 2, 256, 256)])
+def test_s2d_conv3x3(lib, handle, kind, cin_s, n, hgt, wid):
+    g = torch.Generator().manual_seed(cin_s * 3 + hgt + n)
+    x = _bf(torch.randn(n, cin_s, hgt, wid, generator=g))
+    w = _bf(torch.randn(32, cin_s, 3, 3, generator=g) * (2.0 / (cin_s * 9)) ** 0.5)
+    b = torch.randn(32, generator=g) * 0.1
+    ref = F.relu(F.conv2d(x.double(), w.double(), b.double(), padding=1)).float()
+    out, pool = _run_s2d(lib, handle, kind, x, None, w, b, None, None)
+    _report(f"s2d conv {cin_s}->32 {n}x{hgt}x{wid}", out.cpu(), ref)
+    if kind == 1:
+        _report("s2d pooled", pool.cpu(), F.max_pool2d(_bf(ref), 2, 2))
+
+
+@pytest.mark.parametrize("n,hgt,wid", [(2, 32, 32), (3, 48, 80), (2, 256, 256)])
+def test_s2d_conv3x3_with_composed_convt(lib, handle, n, hgt, wid):
+    """ups.6 + cat + ups.7.net.0 (unet.py:82-87) in one launch. The composed weights are
+    rounded to bf16 once (instead of `up` being rounded), hence the wider tolerance."""
+    g = torch.Generator().manual_seed(hgt + wid)
+    skip = _bf(torch.randn(n, 32, hgt, wid, generator=g))
+    below = _bf(torch.randn(n, 64, hgt // 2, wid // 2, generator=g))
+    w3 = _bf(torch.randn(32, 64, 3, 3, generator=g) * (2.0 / (64 * 9)) ** 0.5)
+    b3 = torch.randn(32, generator=g) * 0.1
+    wt = _bf(torch.randn(64, 32, 2, 2, generator=g) * (1.0 / 64) ** 0.5)
+    bt = torch.randn(32, generator=g) * 0.5
+    up = F.conv_transpose2d(below.double(), wt.double(), bt.double(), stride=2)
+    ref = F.relu(F.conv2d(torch.cat([skip.double(), up], 1), w3.double(), b3.double(), padding=1)).float()
+    out, _ = _run_s2d(lib, handle, 0, skip, below, w3, b3, wt, bt)
+    got = out.cpu()
+    err = (got - ref).abs()
+    msg = f"s2d composed {n}x{hgt}x{wid}: max|err|={err.max().item():.4g} mean={err.mean().item():.3g}"
+    print(msg)
+    assert not torch.isnan(got).any()
+    assert err.max() <= 2e-2 * max(1.0, ref.abs().max().item() / 2) and err.mean() <= 3e-3, msg
+    # border pixels carry the bias table: check them separately
+    edge = torch.ones_like(err, dtype=torch.bool)
+    edge[:, :, 1:-1, 1:-1] = False
+    assert err[edge].max() <= 2e-2 * max(1.0, ref.abs().max().item() / 2), msg

@@ -76,6 +76,31 @@ def test_bf16_matches_bitmodel(native_model, trained_sd):
     assert err.max() <= 3e-2 and err.mean() <= 2e-3
 
 
+def test_direct_schedule_matches_bitmodel_and_s2d(native_model, trained_sd):
+    """The per-tap form of the full-resolution level (schedule "direct") against its own
+    bit-model, and the two schedules against each other (masks equal up to boundary pixels)."""
+    from oracle import unet_oracle as uo
+
+    frames = _clip(3)
+    dev = torch.from_numpy(frames).cuda()
+    lg_s2d, m_s2d, a_s2d = native_model.run(dev, want_logits=True)
+    native_model.schedule = "direct"
+    try:
+        lg, m, a = native_model.run(dev, want_logits=True)
+    finally:
+        native_model.schedule = "s2d"
+    bit = uo.folded_forward(trained_sd, uo.frames_to_input(frames), bf16=True,
+                            composed_level0=False)[:, 0].numpy()
+    err = np.abs(lg.cpu().numpy() - bit)
+    print("direct vs bit-model max|err|", err.max(), "mean", err.mean())
+    assert err.max() <= 3e-2 and err.mean() <= 2e-3
+    d = (lg - lg_s2d).abs()
+    print("direct vs s2d max|diff|", d.max().item(), "mean", d.mean().item())
+    assert d.max().item() <= 5e-2 and d.mean().item() <= 3e-3
+    assert (m != m_s2d).sum().item() <= 1e-4 * m.numel()
+    assert np.array_equal(a.cpu().numpy(), (m.cpu().numpy() > 0).reshape(3, -1).sum(1))
+
+
 def test_bf16_matches_reference_within_north_star(native_model, trained_sd):
     from oracle import unet_oracle as uo
     from openglottal_b200 import dice
