@@ -59,6 +59,7 @@ struct ConvParams {
     unsigned long long magic_tx, magic_tpf;  // ceil(2^40 / d) for d = tiles_x, tiles_x*tiles_y
     int na, nw;      // ring depths
     int acc_bufs;    // 1 or 2 TMEM accumulator sets
+    int split;       // N = 128, S = 2: per-accumulator barriers (see kSplit in the kernel)
     int dbg;         // experiment switches (OGL_DBG): 1 no MMA, 2 no stores, 4 no epilogue math,
                      // 8 no activation TMA, 16 no weight copies. Results are garbage when set.
 };
@@ -108,8 +109,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const uint32_t w_full = a_empty + 8u * p.na;
     const uint32_t w_empty = w_full + 8u * p.nw;
     const uint32_t acc_full = w_empty + 8u * p.nw;
-    const uint32_t acc_empty = acc_full + 16u;
-    const uint32_t tmem_slot = acc_empty + 16u;
+    const uint32_t acc_empty = acc_full + 32u;
+    const uint32_t tmem_slot = acc_empty + 32u;
+    // N = 128 with 2 sub-tiles fills TMEM (4 x 128 columns), so the accumulator set cannot be
+    // double-buffered. Instead each of the 4 accumulators has its own full/empty barrier, the
+    // first and the last K block of a tile are issued accumulator-major, and all 8 epilogue
+    // warps drain one accumulator at a time (half of its columns per warp group): accumulator
+    // m is drained while the MMAs of accumulators m+1.. (last K block) and then those of the
+    // next tile's first K block (accumulators ..m-1) run.
+    const bool kSplit = (TPS == 3 && S == 2) && p.split;
     const uint32_t bias_s = tmem_slot + 16u;  // floats: bias[cout] then head_w[32]
     // generic pointers to the small fp32 tables
     float* bias_sp = reinterpret_cast<float*>(smem_raw + (bias_s - smem_u32(smem_raw)));
@@ -137,7 +145,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             mbar_init(w_full + 8u * i, 1);
             mbar_init(w_empty + 8u * i, 1);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < 4; ++i) {
             mbar_init(acc_full + 8u * i, 1);
             mbar_init(acc_empty + 8u * i, kEpiThreads);
         }
@@ -209,29 +217,78 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const uint32_t idesc = make_idesc_bf16(p.N);
         constexpr uint32_t lbo_a = kPlaneBytes, sbo_a = kHalo * 16;
         const uint32_t lbo_b = 16u * p.N, sbo_b = 128u;
-        // dbg 32 (experiment): every A core matrix 128-byte aligned (SBO 256, no tap offset)
-        const uint64_t adesc0 = make_smem_desc(0, lbo_a, (p.dbg & 32) ? 256u : sbo_a);
+        const uint64_t adesc0 = make_smem_desc(0, lbo_a, sbo_a);
         const uint64_t bdesc0 = make_smem_desc(0, lbo_b, sbo_b);
         const uint32_t acc_cols = static_cast<uint32_t>(2 * S * p.N);
         const uint32_t bstep = (2u * lbo_b) >> 4;   // second K=16 half of a 32-channel block
         uint32_t ita = 0, itw = 0, li = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x, ++li) {
-            const uint32_t buf = li % p.acc_bufs;
-            const uint32_t aph = (li / p.acc_bufs) & 1u;
-            mbar_wait(acc_empty + 8u * buf, aph ^ 1u);
-            tc_fence_after();
+            const uint32_t buf = kSplit ? 0u : li % p.acc_bufs;
+            const uint32_t aph = kSplit ? (li & 1u) : (li / p.acc_bufs) & 1u;
+            if (!kSplit) {
+                mbar_wait(acc_empty + 8u * buf, aph ^ 1u);
+                tc_fence_after();
+            }
             const uint32_t d0 = tmem_base + buf * acc_cols;
             for (int kb = 0; kb < kb_total; ++kb, ++ita) {
                 const uint32_t sa = ita % p.na;
                 mbar_wait(a_full + 8u * sa, (ita / p.na) & 1u);
                 const uint32_t abase = a_ring + sa * a_stage_bytes;
+                if (kSplit && (kb == 0 || kb == kb_total - 1)) {
+                    // accumulator-major K block: its three weight stages (one per tap row)
+                    // are held together; needs nw >= 3
+                    uint32_t wst[3];
+#pragma unroll
+                    for (int tg = 0; tg < 3; ++tg) {
+                        wst[tg] = (itw + tg) % p.nw;
+                        mbar_wait(w_full + 8u * wst[tg], ((itw + tg) / p.nw) & 1u);
+                    }
+                    tc_fence_after();
+                    for (int mt = 0; mt < 4; ++mt) {
+                        if (kb == 0) {
+                            mbar_wait(acc_empty + 8u * mt, aph ^ 1u);
+                            tc_fence_after();
+                        }
+                        if (elect_one()) {
+#pragma unroll
+                            for (int tg = 0; tg < 3; ++tg) {
+                                const uint64_t ad =
+                                    adesc0 + ((abase + static_cast<uint32_t>(tg) * kHalo * 16u) >> 4);
+                                const uint64_t bd = bdesc0 + ((w_ring + wst[tg] * w_stage_bytes) >> 4);
+#pragma unroll
+                                for (int t = 0; t < 3; ++t) {
+                                    if (p.dbg & 1) break;
+#pragma unroll
+                                    for (int j = 0; j < 2; ++j) {
+                                        constexpr uint32_t kSubStep = kSubBytes >> 4;
+                                        const uint32_t aoff = t + (mt >> 1) * kSubStep +
+                                                              j * ((2u * lbo_a) >> 4) + (mt & 1) * 8u;
+                                        umma_bf16(d0 + mt * p.N, ad + aoff,
+                                                  bd + (t * 4u * p.N + j * bstep), idesc,
+                                                  (kb | tg | t | j) ? 1u : 0u);
+                                    }
+                                }
+                            }
+                            if (kb == kb_total - 1) umma_commit(acc_full + 8u * mt);
+                        }
+                        __syncwarp();
+                    }
+                    if (elect_one()) {
+#pragma unroll
+                        for (int tg = 0; tg < 3; ++tg) umma_commit(w_empty + 8u * wst[tg]);
+                        umma_commit(a_empty + 8u * sa);
+                    }
+                    __syncwarp();
+                    itw += 3;
+                    continue;
+                }
                 for (int tg = 0; tg < p.taps / TPS; ++tg, ++itw) {
                     const uint32_t sw = itw % p.nw;
                     mbar_wait(w_full + 8u * sw, (itw / p.nw) & 1u);
                     tc_fence_after();
                     // TPS == 9: all taps unrolled; TPS == 3: tg is the tap row dy; TPS == 1: convT
                     const uint32_t row_off =
-                        (TPS == 3 && !(p.dbg & 32)) ? static_cast<uint32_t>(tg) * kHalo * 16u : 0u;
+                        TPS == 3 ? static_cast<uint32_t>(tg) * kHalo * 16u : 0u;
                     const uint64_t ad = adesc0 + ((abase + row_off) >> 4);
                     const uint64_t bd = bdesc0 + ((w_ring + sw * w_stage_bytes) >> 4);
                     const uint32_t first = (kb | tg) != 0 ? 1u : 0u;
@@ -242,10 +299,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                             if (p.dbg & 1) break;
                             // tap offset inside the halo tile, in 16-byte units
                             constexpr int kCenter = kHalo + 1;
-                            const uint32_t toff = (p.dbg & 32) ? 0u
-                                                  : TPS == 9   ? (t / 3) * kHalo + (t % 3)
-                                                  : TPS == 3   ? t
-                                                               : kCenter;
+                            const uint32_t toff = TPS == 9   ? (t / 3) * kHalo + (t % 3)
+                                                  : TPS == 3 ? t
+                                                             : kCenter;
 #pragma unroll
                             for (int j = 0; j < 2; ++j) {
 #pragma unroll
@@ -261,7 +317,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                         }
                         umma_commit(w_empty + 8u * sw);
                         if (last_tg) umma_commit(a_empty + 8u * sa);
-                        if (last_tg && kb == kb_total - 1) umma_commit(acc_full + 8u * buf);
+                        if (!kSplit && last_tg && kb == kb_total - 1)
+                            umma_commit(acc_full + 8u * buf);
                     }
                     __syncwarp();
                 }
@@ -282,25 +339,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         for (int item = blockIdx.x; item < items; item += gridDim.x, ++li) {
             const int tile = item % p.num_tiles;
             const int pass = item / p.num_tiles;
-            const uint32_t buf = li % p.acc_bufs;
-            const uint32_t aph = (li / p.acc_bufs) & 1u;
-            const int st = tile * S + esub;
-            const bool in_range = st < p.total_sub;  // warp-uniform
-            const SubTile t = decode_sub(p, in_range ? st : p.total_sub - 1);
-            mbar_wait(acc_full + 8u * buf, aph);
-            tc_fence_after();
+            const uint32_t buf = kSplit ? 0u : li % p.acc_bufs;
+            const uint32_t aph = kSplit ? (li & 1u) : (li / p.acc_bufs) & 1u;
+            if (!kSplit) {
+                mbar_wait(acc_full + 8u * buf, aph);
+                tc_fence_after();
+            }
 #pragma unroll 1
-            for (int hh = 0; hh < S; ++hh) {
-                if (p.dbg & 4) break;
-                const int half = S == 2 ? hh : egrp;
-                const int mt = esub * 2 + half;
+            for (int u = 0; u < (kSplit ? 4 : S); ++u) {
+                // split mode: every warp drains accumulator u (its group's half of the columns);
+                // otherwise a warp group owns one sub-tile (S == 2) or one x-half (S == 1)
+                const int sub = kSplit ? (u >> 1) : esub;
+                const int half = kSplit ? (u & 1) : (S == 2 ? u : egrp);
+                const int mt = sub * 2 + half;
+                const int st = tile * S + sub;
+                const bool in_range = st < p.total_sub;  // warp-uniform
+                const SubTile t = decode_sub(p, in_range ? st : p.total_sub - 1);
+                if (kSplit) {
+                    mbar_wait(acc_full + 8u * mt, aph);
+                    tc_fence_after();
+                }
+                const int c_begin = kSplit ? egrp * 64 : 0;
+                const int c_end = (p.dbg & 4) ? 0 : (kSplit ? c_begin + 64 : p.N);
                 const int y = t.y0 + py;
                 const int x = t.x0 + half * 8 + px;
                 // partial tiles at the right / bottom edge: compute everything, store nothing
                 const bool valid = in_range && y < p.H && x < p.W && !(p.dbg & 2);
                 const uint32_t tcol = tmem_base + lane_sel + buf * acc_cols + mt * p.N;
                 float zacc = 0.f;
-                if (EPI == EPI_CONVT) {
+                if (EPI == EPI_CONVT && c_end > 0) {
                     // pass = (dy, block of cb output channels); columns = [dx][cb]. One thread
                     // owns output pixels (2y+dy, 2x) and (2y+dy, 2x+1): 32 contiguous bytes.
                     const int cb = p.N >> 1;
@@ -334,7 +401,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                         }
                     }
                 }
-                for (int c0 = 0; EPI != EPI_CONVT && c0 < p.N; c0 += 32) {
+                for (int c0 = c_begin; EPI != EPI_CONVT && c0 < c_end; c0 += 32) {
                     uint32_t r[32];
                     tmem_ld32(tcol + c0, r);
                     tmem_ld_wait();
@@ -396,7 +463,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                         }
                     }
                 }
-                if (EPI == EPI_HEAD) {
+                if (EPI == EPI_HEAD && c_end > 0) {
                     const float z = zacc + p.head_b;
                     const bool on = valid && (z > p.logit_thr);
                     const size_t pix = (static_cast<size_t>(t.n) * p.H + y) * p.W + x;
@@ -405,9 +472,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     const uint32_t bal = __ballot_sync(0xffffffffu, on);
                     if (lane == 0 && p.area && bal) atomicAdd(p.area + t.n, __popc(bal));
                 }
+                if (kSplit) {
+                    tc_fence_before();
+                    mbar_arrive(acc_empty + 8u * mt);
+                }
             }
-            tc_fence_before();
-            mbar_arrive(acc_empty + 8u * buf);
+            if (!kSplit) {
+                tc_fence_before();
+                mbar_arrive(acc_empty + 8u * buf);
+            }
         }
     }
 
@@ -564,6 +637,8 @@ int launch_conv_tc(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloa
     if (static_cast<unsigned long long>(p.total_sub) * (p.tiles_x * p.tiles_y) >= (1ull << 40))
         return fail("batch too large for the tile decoder");
     p.acc_bufs = (2 * p.S * p.N <= 256) ? 2 : 1;
+    static const int split_env = getenv("OGL_SPLIT") ? atoi(getenv("OGL_SPLIT")) : 1;
+    p.split = split_env;
     static const int dbg_env = getenv("OGL_DBG") ? atoi(getenv("OGL_DBG")) : 0;
     p.dbg = dbg_env;
     const int tps = taps_per_stage(L);
@@ -571,7 +646,7 @@ int launch_conv_tc(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloa
     const size_t tables = sizeof(float) * (L.cout + 32);
     auto smem_need = [&](int na, int nw) {
         return static_cast<size_t>(128 /*align slack*/ + na * p.S * kSubBytes + nw * w_stage +
-                                   16 * (na + nw) + 48 + tables + 64);
+                                   16 * (na + nw) + 80 + tables + 64);
     };
     // ring depths: as many weight stages as fit beside 3 activation stages (2 when the
     // weight stages are large), at least 2 and at most 8
@@ -589,6 +664,8 @@ int launch_conv_tc(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloa
     while (p.nw > 2 && smem_need(p.na, p.nw) > static_cast<size_t>(kMaxSmem)) --p.nw;
     const size_t smem = smem_need(p.na, p.nw);
     if (smem > static_cast<size_t>(kMaxSmem)) return fail("shared memory budget exceeded");
+    if (tps == 3 && p.S == 2 && p.nw < 3)
+        return fail("N = 128 layers hold three weight stages at once: nw must be >= 3");
 
     CUtensorMap tm0, tm1;
     if (make_act_map(&tm0, src0, B, L.cin0, H, W)) return 1;
