@@ -59,6 +59,9 @@ struct ConvParams {
     unsigned long long magic_tx, magic_tpf;  // ceil(2^40 / d) for d = tiles_x, tiles_x*tiles_y
     int na, nw;      // ring depths
     int acc_bufs;    // 1 or 2 TMEM accumulator sets
+    int pass_fast;   // items ordered (tile, pass) with the pass fastest: the CTAs that re-read a
+                     // tile for its other passes run at the same time, so the re-reads hit L2;
+                     // with gridDim % npass == 0 each CTA still keeps one pass (its weights)
     int split;       // N = 128, S = 2: per-accumulator barriers (see kSplit in the kernel)
     int dbg;         // experiment switches (OGL_DBG): 1 no MMA, 2 no stores, 4 no epilogue math,
                      // 8 no activation TMA, 16 no weight copies. Results are garbage when set.
@@ -162,7 +165,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (lane == 0) {
             uint32_t it = 0;
             for (int item = blockIdx.x; item < items; item += gridDim.x) {
-                const int tile = item % p.num_tiles;
+                const int tile = p.pass_fast ? item / p.npass : item % p.num_tiles;
                 for (int kb = 0; kb < kb_total; ++kb, ++it) {
                     const uint32_t s = it % p.na;
                     const uint32_t ph = (it / p.na) & 1u;
@@ -190,7 +193,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             uint32_t it = 0;
             const uint8_t* wbytes = reinterpret_cast<const uint8_t*>(p.wpack);
             for (int item = blockIdx.x; item < items; item += gridDim.x) {
-                const int pass = item / p.num_tiles;
+                const int pass = p.pass_fast ? item % p.npass : item / p.num_tiles;
                 for (int kb = 0; kb < kb_total; ++kb) {
                     for (int tg = 0; tg < p.taps / TPS; ++tg, ++it) {
                         const uint32_t s = it % p.nw;
@@ -337,8 +340,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int OW = EPI == EPI_CONVT ? 2 * p.W : p.W;
         uint32_t li = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x, ++li) {
-            const int tile = item % p.num_tiles;
-            const int pass = item / p.num_tiles;
+            const int tile = p.pass_fast ? item / p.npass : item % p.num_tiles;
+            const int pass = p.pass_fast ? item % p.npass : item / p.num_tiles;
             const uint32_t buf = kSplit ? 0u : li % p.acc_bufs;
             const uint32_t aph = kSplit ? (li & 1u) : (li / p.acc_bufs) & 1u;
             if (!kSplit) {
@@ -624,10 +627,12 @@ int launch_conv_tc(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloa
     p.H = H;
     p.W = W;
     p.B = B;
-    // 2 sub-tiles (4 accumulators) per tile, except N = 128 where 4 x 128 columns would fill
-    // TMEM and serialise the epilogue behind the main loop: 1 sub-tile, double-buffered
+    // 2 sub-tiles (4 accumulators) per tile. Measured alternatives (experiment switches):
+    // 1 sub-tile for N = 128 (OGL_S128=1) or for the transposed conv (OGL_ST=1) doubles the
+    // weight traffic per pixel and is slower although TMEM could then be double-buffered.
     static const int s_env = getenv("OGL_S128") ? atoi(getenv("OGL_S128")) : 2;
-    p.S = (L.N == 128) ? s_env : 2;
+    static const int st_env = getenv("OGL_ST") ? atoi(getenv("OGL_ST")) : 2;
+    p.S = (L.taps == 1 && L.N == 128) ? st_env : ((L.N == 128) ? s_env : 2);
     p.tiles_x = (W + 15) / 16;
     p.tiles_y = (H + 15) / 16;
     p.total_sub = B * p.tiles_x * p.tiles_y;
@@ -676,6 +681,8 @@ int launch_conv_tc(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloa
     }
     const int items = p.npass * p.num_tiles;
     const int grid = items < num_sms ? items : num_sms;
+    static const int pf_env = getenv("OGL_PASSFAST") ? atoi(getenv("OGL_PASSFAST")) : 1;
+    p.pass_fast = (pf_env && p.npass > 1 && grid % p.npass == 0) ? 1 : 0;
     if (L.epi == EPI_CONVT) return launch_epi<EPI_CONVT, 1>(tm0, tm1, p, grid, smem, stream);
     if (L.epi == EPI_HEAD) return launch_epi<EPI_HEAD, 9>(tm0, tm1, p, grid, smem, stream);
     if (L.epi == EPI_RELU)
