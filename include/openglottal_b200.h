@@ -115,6 +115,35 @@ int ogl_features_f64(const double* area_dev, int64_t n, double* out8_dev, int32_
 /* cv2.COLOR_BGR2GRAY on interleaved u8 BGR pixels: (3735 B + 19235 G + 9798 R + 16384) >> 15. */
 int ogl_bgr_to_gray(const uint8_t* bgr_dev, uint8_t* gray_dev, int64_t pixels, void* stream);
 
+/* ---- callers around the U-Net (all bit-exact, integer work) ---------------------------------
+ * Detection-gated area, openglottal/features.py:240-245:
+ *   area[i] = count(mask[i][y1:y2, x1:x2] > 0) with Python slice semantics for the box
+ *   {x1, y1, x2, y2} = boxes_dev[4 i ..]; has_box_dev[i] == 0 (detector returned None) gives 0.
+ *   has_box_dev may be NULL (every frame has a box). */
+int ogl_mask_area_boxes(const uint8_t* mask_dev, int n, int height, int width,
+                        const int32_t* boxes_dev, const uint8_t* has_box_dev, int32_t* area_dev,
+                        void* stream);
+
+/* yolo-crop+unet pipeline, scripts/infer.py:222-248. geom_dev holds 8 int32 per frame:
+ * {x1, y1, x2, y2 (crop bounds, 0 <= x1 < x2 <= width ...), pad_top, pad_left, content_h,
+ * content_w} as openglottal/utils.py:103-131 (letterbox_with_info) computes them; content_h == 0
+ * marks a frame without a usable box.
+ *   ogl_letterbox_crops : out[i] = letterbox(gray[i][y1:y2, x1:x2], size) (cv2 INTER_NEAREST,
+ *                         zero padding), out_dev [n][size][size] u8.
+ *   ogl_unletterbox_area: mask_orig = unletterbox(mask_cs[i]) (utils.py:170-186, INTER_NEAREST)
+ *                         at the crop's size; area[i] = count(mask_orig > 0); full_mask_dev
+ *                         [n][height][width] (or NULL) = zeros with mask_orig pasted at the box. */
+int ogl_letterbox_crops(const uint8_t* gray_dev, int n, int height, int width,
+                        const int32_t* geom_dev, int size, uint8_t* out_dev, void* stream);
+int ogl_unletterbox_area(const uint8_t* mask_cs_dev, int n, int size, const int32_t* geom_dev,
+                         int height, int width, uint8_t* full_mask_dev, int32_t* area_dev,
+                         void* stream);
+
+/* Batched evaluation, openglottal/utils.py:191-206: counts_dev[3 i ..] = {|pred & gt|, |pred|,
+ * |gt|} over (value > 0); dice = 2 I / (P + G), iou = I / (P + G - I), 1.0 when empty. */
+int ogl_mask_overlap_counts(const uint8_t* pred_dev, const uint8_t* gt_dev, int n, int64_t pixels,
+                            int32_t* counts_dev, void* stream);
+
 /* Unit-test hook: one tensor-core layer on fp32 NCHW device tensors (converted to the bf16
  * kernel layout internally). kind: 0 conv3x3+bias+ReLU, 1 same + 2x2 max-pool (out_pool_dev),
  * 3 ConvTranspose2d k2 s2 (+bias). src1_dev/c1 describe the second concat source (or NULL/0).

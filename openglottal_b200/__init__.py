@@ -7,13 +7,27 @@ this package accelerates: ``UNet``, ``extract_features_unet``, ``unet_segment_fr
 __version__ = "0.1.0"
 
 from .unet import UNet
-from .utils import unet_segment_frame, unet_segment_frames, bgr_to_gray, load_frames_bgr, dice
+from .utils import (
+    unet_segment_frame,
+    unet_segment_frames,
+    bgr_to_gray,
+    load_frames_bgr,
+    dice,
+    iou,
+    dice_iou_batch,
+    gated_area,
+    letterbox_geometry,
+    letterbox_crops,
+    unletterbox_area,
+    segment_crops,
+)
 from .features import (
     _kinematic_features,
     kinematic_features_device,
     segment_clip,
     extract_features_unet,
     extract_features_unet_frames,
+    extract_features_yolo_crop_unet,
 )
 
 __all__ = [
@@ -23,9 +37,17 @@ __all__ = [
     "bgr_to_gray",
     "load_frames_bgr",
     "dice",
+    "iou",
+    "dice_iou_batch",
+    "gated_area",
+    "letterbox_geometry",
+    "letterbox_crops",
+    "unletterbox_area",
+    "segment_crops",
     "_kinematic_features",
     "kinematic_features_device",
     "segment_clip",
     "extract_features_unet",
     "extract_features_unet_frames",
+    "extract_features_yolo_crop_unet",
 ]

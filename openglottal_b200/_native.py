@@ -60,6 +60,10 @@ EXPORTS = [
     "ogl_features",
     "ogl_features_f64",
     "ogl_bgr_to_gray",
+    "ogl_mask_area_boxes",
+    "ogl_letterbox_crops",
+    "ogl_unletterbox_area",
+    "ogl_mask_overlap_counts",
     "ogl_debug_tc_layer",
     "ogl_debug_s2d_layer",
     "ogl_debug_s2d_program",
@@ -117,6 +121,14 @@ def load() -> C.CDLL:
     lib.ogl_features_f64.argtypes = [vp, i64, vp, vp, vp, sz, vp]
     lib.ogl_bgr_to_gray.restype = i32
     lib.ogl_bgr_to_gray.argtypes = [vp, vp, i64, vp]
+    lib.ogl_mask_area_boxes.restype = i32
+    lib.ogl_mask_area_boxes.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp]
+    lib.ogl_letterbox_crops.restype = i32
+    lib.ogl_letterbox_crops.argtypes = [vp, i32, i32, i32, vp, i32, vp, vp]
+    lib.ogl_unletterbox_area.restype = i32
+    lib.ogl_unletterbox_area.argtypes = [vp, i32, i32, vp, i32, i32, vp, vp, vp]
+    lib.ogl_mask_overlap_counts.restype = i32
+    lib.ogl_mask_overlap_counts.argtypes = [vp, vp, i32, i64, vp, vp]
     lib.ogl_debug_tc_layer.restype = i32
     lib.ogl_debug_tc_layer.argtypes = [vp, i32, vp, i32, vp, i32, _c_float_p, _c_float_p, i32,
                                        i32, i32, i32, vp, vp, vp]

@@ -10,7 +10,7 @@ PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_DIR = PKG_DIR / "lib"
 LIB_PATH = LIB_DIR / "libopenglottal_b200.so"
-SOURCES = ["api.cu", "conv_tc.cu", "s2d_tc.cu", "stem_f32.cu", "features.cu"]
+SOURCES = ["api.cu", "conv_tc.cu", "s2d_tc.cu", "stem_f32.cu", "features.cu", "frame_ops.cu"]
 HEADERS = ["internal.h", "ptx.cuh", "../../include/openglottal_b200.h"]
 
 NVCC_FLAGS = [

@@ -603,6 +603,69 @@ int ogl_bgr_to_gray(const uint8_t* bgr_dev, uint8_t* gray_dev, int64_t pixels, v
     return 0;
 }
 
+namespace {
+constexpr int kFramesPerLaunch = 32768;  // grid.y limit
+}
+
+int ogl_mask_area_boxes(const uint8_t* mask_dev, int n, int height, int width,
+                        const int32_t* boxes_dev, const uint8_t* has_box_dev, int32_t* area_dev,
+                        void* stream) {
+    if (!mask_dev || !boxes_dev || !area_dev || n < 0 || height <= 0 || width <= 0)
+        return fail("ogl_mask_area_boxes: bad argument");
+    const size_t hw = static_cast<size_t>(height) * width;
+    for (int i = 0; i < n; i += kFramesPerLaunch) {
+        const int m = n - i < kFramesPerLaunch ? n - i : kFramesPerLaunch;
+        if (launch_mask_area_boxes(mask_dev + i * hw, m, height, width, boxes_dev + 4 * i,
+                                   has_box_dev ? has_box_dev + i : nullptr, area_dev + i,
+                                   static_cast<cudaStream_t>(stream)))
+            return 1;
+    }
+    return 0;
+}
+
+int ogl_letterbox_crops(const uint8_t* gray_dev, int n, int height, int width,
+                        const int32_t* geom_dev, int size, uint8_t* out_dev, void* stream) {
+    if (!gray_dev || !geom_dev || !out_dev || n < 0 || height <= 0 || width <= 0 || size <= 0)
+        return fail("ogl_letterbox_crops: bad argument");
+    const size_t hw = static_cast<size_t>(height) * width, ss = static_cast<size_t>(size) * size;
+    for (int i = 0; i < n; i += kFramesPerLaunch) {
+        const int m = n - i < kFramesPerLaunch ? n - i : kFramesPerLaunch;
+        if (launch_letterbox_crops(gray_dev + i * hw, m, height, width, geom_dev + 8 * i, size,
+                                   out_dev + i * ss, static_cast<cudaStream_t>(stream)))
+            return 1;
+    }
+    return 0;
+}
+
+int ogl_unletterbox_area(const uint8_t* mask_cs_dev, int n, int size, const int32_t* geom_dev,
+                         int height, int width, uint8_t* full_mask_dev, int32_t* area_dev,
+                         void* stream) {
+    if (!mask_cs_dev || !geom_dev || !area_dev || n < 0 || height <= 0 || width <= 0 || size <= 0)
+        return fail("ogl_unletterbox_area: bad argument");
+    const size_t hw = static_cast<size_t>(height) * width, ss = static_cast<size_t>(size) * size;
+    for (int i = 0; i < n; i += kFramesPerLaunch) {
+        const int m = n - i < kFramesPerLaunch ? n - i : kFramesPerLaunch;
+        if (launch_unletterbox_area(mask_cs_dev + i * ss, m, size, geom_dev + 8 * i, height, width,
+                                    full_mask_dev ? full_mask_dev + i * hw : nullptr, area_dev + i,
+                                    static_cast<cudaStream_t>(stream)))
+            return 1;
+    }
+    return 0;
+}
+
+int ogl_mask_overlap_counts(const uint8_t* pred_dev, const uint8_t* gt_dev, int n, int64_t pixels,
+                            int32_t* counts_dev, void* stream) {
+    if (!pred_dev || !gt_dev || !counts_dev || n < 0 || pixels <= 0 || pixels > 0x7fffffffLL)
+        return fail("ogl_mask_overlap_counts: bad argument");
+    for (int i = 0; i < n; i += kFramesPerLaunch) {
+        const int m = n - i < kFramesPerLaunch ? n - i : kFramesPerLaunch;
+        if (launch_overlap_counts(pred_dev + i * pixels, gt_dev + i * pixels, m, pixels,
+                                  counts_dev + 3 * i, static_cast<cudaStream_t>(stream)))
+            return 1;
+    }
+    return 0;
+}
+
 int ogl_debug_tc_layer(ogl_unet* h, int kind, const float* src0_dev, int c0, const float* src1_dev,
                        int c1, const float* weight_host, const float* bias_host, int cout, int n,
                        int height, int width, float* out_dev, float* out_pool_dev,

@@ -134,6 +134,16 @@ size_t features_workspace_bytes(int64_t n);
 int launch_features(const int32_t* area, int64_t n, double* out8, int32_t* flags2, void* ws,
                     size_t ws_bytes, cudaStream_t stream);
 
+// mask / frame operators around the U-Net (frame_ops.cu); n <= 65535 per launch
+int launch_mask_area_boxes(const uint8_t* mask, int n, int H, int W, const int32_t* boxes,
+                           const uint8_t* has_box, int32_t* area, cudaStream_t stream);
+int launch_letterbox_crops(const uint8_t* gray, int n, int H, int W, const int32_t* geom, int size,
+                           uint8_t* out, cudaStream_t stream);
+int launch_unletterbox_area(const uint8_t* mask_cs, int n, int size, const int32_t* geom, int H,
+                            int W, uint8_t* full, int32_t* area, cudaStream_t stream);
+int launch_overlap_counts(const uint8_t* pred, const uint8_t* gt, int n, long long pixels,
+                          int32_t* counts, cudaStream_t stream);
+
 // debugging / unit-test helpers: layout conversion NCHW f32 <-> C8-planar bf16
 // (s2d = true: the space-to-depth form of the same tensor)
 int launch_nchw_to_c8(const float* in, __nv_bfloat16* out, int B, int C, int H, int W,

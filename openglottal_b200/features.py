@@ -175,14 +175,41 @@ def extract_features_unet_frames(frames_gray, model: UNet, batch: int = 512,
     return kinematic_features_device(area)
 
 
+def _masks_reference_resize(frames_gray: list, model: UNet, threshold: float = 0.5,
+                            batch: int = 256) -> list:
+    """Masks of arbitrary-size gray frames with the reference's resize semantics
+    (/root/reference/openglottal/utils.py:234-241), batched: cv2 squash to 256x256 on the host,
+    ONE native forward per batch, sigmoid, cv2 bilinear resize of the probability map back,
+    threshold. Returns a list of ``(H, W)`` uint8 numpy masks."""
+    import cv2
+
+    dev = model._device()
+    out = []
+    for i0 in range(0, len(frames_gray), batch):
+        chunk = frames_gray[i0:i0 + batch]
+        inp = np.stack([cv2.resize(f, (256, 256), interpolation=cv2.INTER_LINEAR) for f in chunk])
+        logits, _, _ = model.run(torch.from_numpy(inp).to(dev), want_logits=True, want_mask=False,
+                                 want_area=False)
+        prob = torch.sigmoid(logits).cpu().numpy()
+        for f, pr in zip(chunk, prob):
+            hgt, wid = f.shape
+            if (hgt, wid) != (256, 256):
+                pr = cv2.resize(pr, (wid, hgt), interpolation=cv2.INTER_LINEAR)
+            out.append((pr > threshold).astype(np.uint8) * 255)
+    return out
+
+
 def extract_features_unet(avi_path: str, detector, model, device=None) -> dict | None:
     """Drop-in for ``openglottal.extract_features_unet`` (features.py:202-247).
 
-    ``detector is None`` (unet-only) is the accelerated path. With a detector the per-frame
-    masks come from the native kernels and the reference's bbox gating (features.py:240-245)
-    is applied on the host; the detector itself (Ultralytics YOLO) stays with the reference.
+    ``detector is None`` (unet-only) is the accelerated path. With a detector the masks come
+    from the native kernels in batches, the detector (the reference's Ultralytics
+    ``TemporalDetector``, or anything with ``reset()`` / ``detect(frame_bgr)``) is called once
+    per frame in order as the reference does, and the bbox gating of features.py:240-245 runs
+    as one CUDA reduction over the batch of masks.
     """
     import cv2
+    from .utils import gated_area
 
     model = _require_native(model)
     dev = model._device()
@@ -192,27 +219,43 @@ def extract_features_unet(avi_path: str, detector, model, device=None) -> dict |
     hgt, wid = frames_bgr[0].shape[:2]
     native_size = (hgt, wid) == (256, 256)
 
-    if detector is None and native_size:
-        bgr = torch.from_numpy(np.stack(frames_bgr)).pin_memory().to(dev, non_blocking=True)
-        area, _ = segment_clip(bgr_to_gray(bgr), model)
-        return kinematic_features_device(area)
-
-    # Reference-resize semantics for other frame sizes and for the gated variant.
-    from .utils import unet_segment_frame
-
+    boxes = None
     if detector is not None:
         detector.reset()
-    area_wave: list[float] = []
-    for frm in frames_bgr:
-        gray = cv2.cvtColor(frm, cv2.COLOR_BGR2GRAY)
-        mask = unet_segment_frame(gray, model, dev)
-        if detector is None:
-            area_wave.append(float(np.sum(mask > 0)))
-        else:
-            box = detector.detect(frm)
-            if box is None:
-                area_wave.append(0.0)
-            else:
-                x1, y1, x2, y2 = box
-                area_wave.append(float(np.sum(mask[y1:y2, x1:x2] > 0)))
-    return _kinematic_features(area_wave)
+        boxes = [detector.detect(frm) for frm in frames_bgr]
+
+    if native_size:
+        bgr = torch.from_numpy(np.stack(frames_bgr)).pin_memory().to(dev, non_blocking=True)
+        area, masks = segment_clip(bgr_to_gray(bgr), model, want_masks=boxes is not None)
+        if boxes is not None:
+            area = gated_area(masks, boxes)
+        return kinematic_features_device(area)
+
+    # other frame sizes: reference-resize semantics (squash to 256x256, upsample the probability)
+    grays = [cv2.cvtColor(frm, cv2.COLOR_BGR2GRAY) for frm in frames_bgr]
+    masks_np = _masks_reference_resize(grays, model)
+    masks = torch.from_numpy(np.stack(masks_np)).to(dev)
+    if boxes is None:
+        boxes = [(0, 0, wid, hgt)] * len(masks_np)
+    return kinematic_features_device(gated_area(masks, boxes))
+
+
+def extract_features_yolo_crop_unet(avi_path: str, detector, model, device=None,
+                                    crop_size: int = 256) -> dict | None:
+    """Area waveform + features of the ``yolo-crop+unet`` pipeline
+    (/root/reference/scripts/infer.py:222-248): per frame, the detector's box is cropped from the
+    gray frame, letterboxed to ``crop_size``, segmented by the crop-trained U-Net, un-letterboxed
+    and counted; frames without a box count 0. Cropping, letterboxing, un-letterboxing and
+    counting run on the GPU for the whole clip; the detector is the caller's."""
+    from .utils import segment_crops
+
+    model = _require_native(model)
+    dev = model._device()
+    frames_bgr = load_frames_bgr(avi_path)
+    if not frames_bgr:
+        return None
+    detector.reset()
+    boxes = [detector.detect(frm) for frm in frames_bgr]
+    bgr = torch.from_numpy(np.stack(frames_bgr)).pin_memory().to(dev, non_blocking=True)
+    area, _ = segment_crops(bgr_to_gray(bgr), boxes, model, size=crop_size)
+    return kinematic_features_device(area)

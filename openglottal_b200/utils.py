@@ -112,6 +112,185 @@ def unet_segment_frame(frame_gray: np.ndarray, model, device=None,
     return (prob > threshold).astype(np.uint8) * 255
 
 
+# ---------------------------------------------------------------------------------------------
+# Callers around the U-Net: detection-gated area, the yolo-crop+unet geometry, batched metrics
+# ---------------------------------------------------------------------------------------------
+def _stream(dev: torch.device):
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def gated_area(masks: torch.Tensor, boxes) -> torch.Tensor:
+    """Detection-gated areas, /root/reference/openglottal/features.py:240-245, batched.
+
+    ``masks``: ``(N, H, W)`` uint8 CUDA; ``boxes``: sequence of N entries, each ``None`` (the
+    detector found nothing: area 0) or ``(x1, y1, x2, y2)`` ints with Python slice semantics
+    ``mask[y1:y2, x1:x2]``. Returns int32 CUDA ``(N,)``.
+    """
+    from . import _native
+
+    if masks.device.type != "cuda" or masks.dtype != torch.uint8 or masks.dim() != 3:
+        raise ValueError("expected (N, H, W) uint8 CUDA masks")
+    n, hgt, wid = masks.shape
+    if len(boxes) != n:
+        raise ValueError(f"{len(boxes)} boxes for {n} masks")
+    host = np.zeros((n, 4), dtype=np.int32)
+    has = np.zeros(n, dtype=np.uint8)
+    for i, b in enumerate(boxes):
+        if b is not None:
+            host[i] = [int(v) for v in b]
+            has[i] = 1
+    dev = masks.device
+    boxes_d = torch.from_numpy(host).to(dev)
+    has_d = torch.from_numpy(has).to(dev)
+    area = torch.empty(n, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _native.check(_native.load().ogl_mask_area_boxes(
+            masks.contiguous().data_ptr(), n, hgt, wid, boxes_d.data_ptr(), has_d.data_ptr(),
+            area.data_ptr(), _stream(dev)))
+    return area
+
+
+def letterbox_geometry(hgt: int, wid: int, size: int = 256):
+    """``(pad_top, pad_left, content_h, content_w)`` of ``letterbox_with_info``
+    (/root/reference/openglottal/utils.py:119-126; Python ``round`` = half to even)."""
+    scale = size / max(hgt, wid)
+    new_h, new_w = int(round(hgt * scale)), int(round(wid * scale))
+    return (size - new_h) // 2, (size - new_w) // 2, new_h, new_w
+
+
+def _crop_geometry(boxes, hgt: int, wid: int, size: int) -> np.ndarray:
+    """8 int32 per frame {x1, y1, x2, y2, pad_top, pad_left, content_h, content_w}; all zero for
+    frames without a usable crop (box None or empty slice, scripts/infer.py:228-231)."""
+    geom = np.zeros((len(boxes), 8), dtype=np.int32)
+    for i, b in enumerate(boxes):
+        if b is None:
+            continue
+        x1, y1, x2, y2 = (int(v) for v in b)
+        ys, xs = slice(y1, y2).indices(hgt), slice(x1, x2).indices(wid)
+        ch, cw = max(0, ys[1] - ys[0]), max(0, xs[1] - xs[0])
+        if ch == 0 or cw == 0:
+            continue
+        pt, pl, nh, nw = letterbox_geometry(ch, cw, size)
+        if nh <= 0 or nw <= 0:
+            raise ValueError(f"crop {cw}x{ch} collapses under letterboxing (cv2.resize would fail)")
+        geom[i] = [xs[0], ys[0], xs[1], ys[1], pt, pl, nh, nw]
+    return geom
+
+
+def letterbox_crops(frames_gray: torch.Tensor, boxes, size: int = 256):
+    """Batched ``letterbox_with_info(gray[y1:y2, x1:x2], size)`` for gray frames
+    (/root/reference/scripts/infer.py:229-236). Returns ``(boxed uint8 CUDA (N,size,size),
+    geometry int32 numpy (N,8))``; frames without a usable box give all-zero images."""
+    from . import _native
+
+    if frames_gray.device.type != "cuda" or frames_gray.dtype != torch.uint8 or frames_gray.dim() != 3:
+        raise ValueError("expected (N, H, W) uint8 CUDA frames")
+    n, hgt, wid = frames_gray.shape
+    if len(boxes) != n:
+        raise ValueError(f"{len(boxes)} boxes for {n} frames")
+    geom = _crop_geometry(boxes, hgt, wid, size)
+    dev = frames_gray.device
+    geom_d = torch.from_numpy(geom).to(dev)
+    out = torch.empty((n, size, size), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _native.check(_native.load().ogl_letterbox_crops(
+            frames_gray.contiguous().data_ptr(), n, hgt, wid, geom_d.data_ptr(), size,
+            out.data_ptr(), _stream(dev)))
+    return out, geom
+
+
+def unletterbox_area(masks_cs: torch.Tensor, geom: np.ndarray, hgt: int, wid: int,
+                     want_full: bool = False):
+    """``unletterbox`` (/root/reference/openglottal/utils.py:170-186) of every crop-space mask back
+    to its crop size, its area, and optionally the full-size mask with the crop pasted in
+    (scripts/infer.py:237-244). Returns ``(area int32 CUDA (N,), full uint8 CUDA (N,H,W) | None)``."""
+    from . import _native
+
+    if masks_cs.device.type != "cuda" or masks_cs.dtype != torch.uint8 or masks_cs.dim() != 3:
+        raise ValueError("expected (N, size, size) uint8 CUDA masks")
+    n, size, size2 = masks_cs.shape
+    if size != size2 or geom.shape != (n, 8):
+        raise ValueError("geometry does not match the masks")
+    dev = masks_cs.device
+    geom_d = torch.from_numpy(np.ascontiguousarray(geom, dtype=np.int32)).to(dev)
+    area = torch.empty(n, dtype=torch.int32, device=dev)
+    full = torch.empty((n, hgt, wid), dtype=torch.uint8, device=dev) if want_full else None
+    with torch.cuda.device(dev):
+        _native.check(_native.load().ogl_unletterbox_area(
+            masks_cs.contiguous().data_ptr(), n, size, geom_d.data_ptr(), hgt, wid,
+            full.data_ptr() if want_full else None, area.data_ptr(), _stream(dev)))
+    return area, full
+
+
+def segment_crops(frames_gray, boxes, model, size: int = 256, threshold: float = 0.5,
+                  want_full: bool = False, batch: int = 512):
+    """The ``yolo-crop+unet`` stage (/root/reference/scripts/infer.py:222-248) for a batch: crop
+    each frame at its box, letterbox to ``size`` x ``size``, segment with the (crop-trained)
+    U-Net, un-letterbox, count. Boxes come from the caller (the reference's TemporalDetector).
+    Returns ``(area int32 CUDA (N,), full-size masks uint8 CUDA (N,H,W) | None)``."""
+    model = _require_native(model)
+    dev = model._device()
+    if isinstance(frames_gray, np.ndarray):
+        frames_gray = torch.from_numpy(np.ascontiguousarray(frames_gray))
+    frames_gray = frames_gray.to(dev, non_blocking=True)
+    n, hgt, wid = frames_gray.shape
+    areas, fulls = [], []
+    for i0 in range(0, n, batch):
+        sl = slice(i0, min(n, i0 + batch))
+        boxed, geom = letterbox_crops(frames_gray[sl], boxes[sl], size)
+        _, mask_cs, _ = model.run(boxed, threshold=threshold, want_area=False)
+        a, f = unletterbox_area(mask_cs, geom, hgt, wid, want_full=want_full)
+        areas.append(a)
+        fulls.append(f)
+    return torch.cat(areas), (torch.cat(fulls) if want_full else None)
+
+
+def overlap_counts(pred: torch.Tensor, gt: torch.Tensor) -> torch.Tensor:
+    """Per-frame ``{|pred & gt|, |pred|, |gt|}`` over ``value > 0`` as int32 CUDA ``(N, 3)``."""
+    from . import _native
+
+    if pred.shape != gt.shape or pred.dim() < 2:
+        raise ValueError("pred and gt must have the same (N, ...) shape")
+    if pred.device.type != "cuda" or gt.device != pred.device:
+        raise ValueError("pred and gt must be CUDA tensors on the same device")
+    if pred.dtype != torch.uint8 or gt.dtype != torch.uint8:
+        raise TypeError("masks must be uint8")
+    n = pred.shape[0]
+    pixels = pred[0].numel()
+    dev = pred.device
+    counts = torch.empty((n, 3), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _native.check(_native.load().ogl_mask_overlap_counts(
+            pred.contiguous().data_ptr(), gt.contiguous().data_ptr(), n, pixels,
+            counts.data_ptr(), _stream(dev)))
+    return counts
+
+
+def dice_iou_batch(pred: torch.Tensor, gt: torch.Tensor):
+    """Batched ``dice`` / ``iou`` (/root/reference/openglottal/utils.py:191-206) for ``(N, H, W)``
+    uint8 CUDA masks: the counts come from one kernel, the ratios are formed exactly as the
+    reference forms them (float32 sums, 1.0 when the denominator is 0). Returns two float64
+    numpy arrays of length N."""
+    c = overlap_counts(pred, gt).cpu().numpy().astype(np.float32)
+    inter, p, g = c[:, 0], c[:, 1], c[:, 2]
+    denom = p + g
+    union = p + g - inter
+    with np.errstate(divide="ignore", invalid="ignore"):
+        d = np.where(denom > 0, (np.float32(2) * inter) / denom, np.float32(1.0))
+        j = np.where(union > 0, inter / union, np.float32(1.0))
+    return d.astype(np.float64), j.astype(np.float64)
+
+
+def iou(pred: np.ndarray, gt: np.ndarray) -> float:
+    """Intersection-over-union of two binary masks, 1.0 when both are empty
+    (/root/reference/openglottal/utils.py:200-206)."""
+    p = pred > 0
+    g = gt > 0
+    inter = int(np.logical_and(p, g).sum())
+    union = int(p.sum()) + int(g.sum()) - inter
+    return inter / union if union > 0 else 1.0
+
+
 def dice(pred: np.ndarray, gt: np.ndarray) -> float:
     """Dice of two binary masks, 1.0 when both are empty -- the parity metric
     (same definition as /root/reference/openglottal/utils.py:191-197)."""

@@ -10,6 +10,10 @@ Outputs (all small, committed):
                            96x128 frame through both cv2 resizes), bit-packed
   pipeline_clip.avi        30-frame 64x64 lossless (FFV1) synthetic clip
   pipeline.json            reference `extract_features_unet(clip, None, model, cpu)` output
+  crops.npz                reference `letterbox_with_info` / `unletterbox` on seeded gray crops
+  metrics.json             reference `dice` / `iou` on seeded mask pairs (incl. empty ones)
+  gated.json               reference `extract_features_unet(clip, detector, model, cpu)` with a
+                           scripted detector (boxes listed in the file)
 
 The state dict is regenerated from its seed at test time (oracle.synth.calibrated_state uses only
 a CPU torch.Generator), so no weights are committed.
@@ -33,7 +37,8 @@ sys.path.insert(0, "/root/reference")
 import cv2  # noqa: E402
 from openglottal.features import _kinematic_features, extract_features_unet  # noqa: E402
 from openglottal.models.unet import UNet  # noqa: E402
-from openglottal.utils import unet_segment_frame  # noqa: E402
+from openglottal.utils import (  # noqa: E402
+    dice, iou, letterbox_with_info, unet_segment_frame, unletterbox)
 
 from oracle import synth  # noqa: E402
 
@@ -71,8 +76,66 @@ def features_kat():
     (HERE / "features_kat.json").write_text(json.dumps(out))
 
 
+class ScriptedDetector:
+    """Stands in for TemporalDetector (Ultralytics is absent): replays a list of boxes."""
+
+    def __init__(self, boxes):
+        self.boxes, self.i = boxes, 0
+
+    def reset(self):
+        self.i = 0
+
+    def detect(self, frame_bgr):
+        b = self.boxes[self.i]
+        self.i += 1
+        return b
+
+
+def scripted_boxes(n, hgt, wid, seed):
+    rng = np.random.default_rng(seed)
+    boxes = []
+    for i in range(n):
+        if i % 7 == 3:
+            boxes.append(None)
+            continue
+        x1, y1 = int(rng.integers(0, wid - 8)), int(rng.integers(0, hgt - 8))
+        x2, y2 = int(rng.integers(x1 + 1, wid + 1)), int(rng.integers(y1 + 1, hgt + 1))
+        boxes.append((x1, y1, x2, y2))
+    return boxes
+
+
+def crops_and_metrics():
+    rng = np.random.default_rng(77)
+    out = {}
+    sizes = [(256, 256), (40, 57), (300, 123), (17, 301), (255, 256), (1, 9), (128, 64), (333, 334)]
+    for k, (h, w) in enumerate(sizes):
+        crop = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        boxed, pt, pl, ch, cw = letterbox_with_info(crop, 256, value=0)
+        mask_cs = (rng.random((256, 256)) > 0.6).astype(np.uint8) * 255
+        back = unletterbox(mask_cs, pt, pl, ch, cw, h, w, interp=cv2.INTER_NEAREST)
+        out[f"crop{k}"] = crop
+        out[f"boxed{k}"] = boxed
+        out[f"geom{k}"] = np.array([pt, pl, ch, cw], dtype=np.int32)
+        out[f"maskcs{k}"] = np.packbits(mask_cs > 0)
+        out[f"back{k}"] = np.packbits(back > 0)
+    np.savez_compressed(HERE / "crops.npz", **out)
+    cases = []
+    for k in range(6):
+        a = (rng.random((48, 64)) > (0.3 + 0.1 * k)).astype(np.uint8) * 255
+        b = (rng.random((48, 64)) > 0.5).astype(np.uint8) * (k + 1)
+        if k == 4:
+            a[:] = 0
+            b[:] = 0
+        if k == 5:
+            b[:] = 0
+        cases.append({"seed_index": k, "a": np.packbits(a > 0).tolist(), "b": np.packbits(b > 0).tolist(),
+                      "dice": dice(a, b), "iou": iou(a, b)})
+    (HERE / "metrics.json").write_text(json.dumps(cases))
+
+
 def main():
     features_kat()
+    crops_and_metrics()
     sd = synth.calibrated_state(0)
     model = UNet(1, 1, (32, 64, 128, 256))
     model.load_state_dict(sd)
@@ -107,6 +170,9 @@ def main():
     assert len(back) == 30 and np.array_equal(np.stack(back), clip), "codec is not lossless here"
     feats = extract_features_unet(str(path), None, model, torch.device("cpu"))
     (HERE / "pipeline.json").write_text(json.dumps(jsonable(feats)))
+    boxes = scripted_boxes(30, 64, 64, seed=15)
+    gated = extract_features_unet(str(path), ScriptedDetector(boxes), model, torch.device("cpu"))
+    (HERE / "gated.json").write_text(json.dumps({"boxes": boxes, "features": jsonable(gated)}))
     print("golden written:", sorted(p.name for p in HERE.iterdir() if p.is_file()))
 
 

@@ -1,0 +1,217 @@
+"""GPU parity of the callers around the U-Net against the
+oracle (oracle/pipeline_oracle.py, pinned by tests/golden/crops.npz, metrics.json, gated.json):
+detection-gated area, the yolo-crop+unet letterbox / un-letterbox geometry, batched Dice / IoU.
+All integer / byte work: bit-exact."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLDEN = Path(__file__).parent / "golden"
+
+
+def _boxes(n, hgt, wid, seed, none_every=5):
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n):
+        if none_every and i % none_every == 2:
+            out.append(None)
+            continue
+        x1, y1 = int(rng.integers(0, wid - 2)), int(rng.integers(0, hgt - 2))
+        x2, y2 = int(rng.integers(x1 + 1, wid + 1)), int(rng.integers(y1 + 1, hgt + 1))
+        out.append((x1, y1, x2, y2))
+    return out
+
+
+def test_gated_area_bit_exact(lib):
+    import openglottal_b200 as ogl
+    from oracle import pipeline_oracle as po
+
+    rng = np.random.default_rng(3)
+    masks = (rng.random((37, 96, 128)) > 0.7).astype(np.uint8) * 255
+    boxes = _boxes(37, 96, 128, seed=4)
+    # Python slice semantics: negative, reversed, out-of-range and empty boxes
+    boxes[0] = (-20, -10, 128, 96)
+    boxes[1] = (5, 5, 5, 50)
+    boxes[3] = (100, 90, 400, 300)
+    boxes[4] = (60, 40, 30, 20)
+    boxes[5] = (0, 0, -1, -1)
+    got = ogl.gated_area(torch.from_numpy(masks).cuda(), boxes).cpu().numpy()
+    want = np.array(po.gated_area_wave(masks, boxes))
+    assert np.array_equal(got, want.astype(np.int64))
+    full = ogl.gated_area(torch.from_numpy(masks).cuda(), [(0, 0, 128, 96)] * 37).cpu().numpy()
+    assert np.array_equal(full, (masks > 0).reshape(37, -1).sum(1))
+
+
+def test_letterbox_and_unletterbox_match_golden(lib):
+    """The reference's own letterbox_with_info / unletterbox outputs (crops.npz)."""
+    import openglottal_b200 as ogl
+
+    g = np.load(GOLDEN / "crops.npz")
+    for k in range(8):
+        crop = g[f"crop{k}"]
+        h, w = crop.shape
+        hgt, wid = 352, 352
+        frame = np.random.default_rng(k).integers(0, 256, (hgt, wid), dtype=np.uint8)
+        y1, x1 = 7 + k, 3 + 2 * k
+        frame[y1:y1 + h, x1:x1 + w] = crop
+        box = (x1, y1, x1 + w, y1 + h)
+        boxed, geom = ogl.letterbox_crops(torch.from_numpy(frame[None]).cuda(), [box], 256)
+        assert geom[0, 4:].tolist() == g[f"geom{k}"].tolist()
+        assert np.array_equal(boxed[0].cpu().numpy(), g[f"boxed{k}"]), k
+        mask_cs = np.unpackbits(g[f"maskcs{k}"])[:256 * 256].reshape(256, 256).astype(np.uint8) * 255
+        area, full = ogl.unletterbox_area(torch.from_numpy(mask_cs[None]).cuda(), geom, hgt, wid,
+                                          want_full=True)
+        back = np.unpackbits(g[f"back{k}"])[:h * w].reshape(h, w).astype(np.uint8) * 255
+        want_full = np.zeros((hgt, wid), np.uint8)
+        want_full[y1:y1 + h, x1:x1 + w] = back
+        assert np.array_equal(full[0].cpu().numpy(), want_full), k
+        assert int(area[0]) == int((back > 0).sum())
+
+
+def test_letterbox_random_boxes_match_oracle(lib):
+    import openglottal_b200 as ogl
+    from oracle import pipeline_oracle as po
+
+    rng = np.random.default_rng(9)
+    n, hgt, wid = 24, 200, 312
+    frames = rng.integers(0, 256, (n, hgt, wid), dtype=np.uint8)
+    boxes = _boxes(n, hgt, wid, seed=10)
+    boxes[0] = (10, 10, 10, 80)          # empty crop -> treated like no box
+    boxed, geom = ogl.letterbox_crops(torch.from_numpy(frames).cuda(), boxes, 256)
+    boxed = boxed.cpu().numpy()
+    masks_cs = (rng.random((n, 256, 256)) > 0.5).astype(np.uint8) * 255
+    area, full = ogl.unletterbox_area(torch.from_numpy(masks_cs).cuda(), geom, hgt, wid, want_full=True)
+    area, full = area.cpu().numpy(), full.cpu().numpy()
+    for i, b in enumerate(boxes):
+        it = iter([masks_cs[i]])
+        want_area, want_full = po.crop_unet_frame(frames[i], b, lambda boxed_ref: next(it))
+        if want_full is None:
+            assert not boxed[i].any() and area[i] == 0 and not full[i].any()
+            continue
+        x1, y1, x2, y2 = b
+        ref_boxed = po.letterbox_with_info(frames[i][y1:y2, x1:x2], 256, 0)[0]
+        assert np.array_equal(boxed[i], ref_boxed), i
+        assert area[i] == want_area and np.array_equal(full[i], want_full), i
+
+
+def test_dice_iou_batch_matches_reference_metrics(lib):
+    import openglottal_b200 as ogl
+    from oracle import pipeline_oracle as po
+
+    cases = json.loads((GOLDEN / "metrics.json").read_text())
+    a = np.stack([np.unpackbits(np.array(c["a"], np.uint8))[:48 * 64].reshape(48, 64) for c in cases]).astype(np.uint8) * 255
+    b = np.stack([np.unpackbits(np.array(c["b"], np.uint8))[:48 * 64].reshape(48, 64) for c in cases]).astype(np.uint8) * 7
+    d, j = ogl.dice_iou_batch(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda())
+    for k, c in enumerate(cases):
+        assert d[k] == c["dice"] and j[k] == c["iou"], k
+    rng = np.random.default_rng(1)
+    p = (rng.random((40, 256, 256)) > 0.8).astype(np.uint8) * 255
+    q = (rng.random((40, 256, 256)) > 0.8).astype(np.uint8)
+    d, j = ogl.dice_iou_batch(torch.from_numpy(p).cuda(), torch.from_numpy(q).cuda())
+    for k in range(40):
+        assert d[k] == po.dice(p[k], q[k]) and j[k] == po.iou(p[k], q[k])
+
+
+class ScriptedDetector:
+    def __init__(self, boxes):
+        self.boxes, self.i, self.resets = boxes, 0, 0
+
+    def reset(self):
+        self.i = 0
+        self.resets += 1
+
+    def detect(self, frame_bgr):
+        b = self.boxes[self.i]
+        self.i += 1
+        return b
+
+
+def test_gated_pipeline_matches_reference_golden(lib, calibrated_sd):
+    """extract_features_unet(clip, detector, ...) against the reference's own output (gated.json);
+    64x64 clip -> the reference-resize path. The golden was made with the variance-calibrated
+    RANDOM weights, which amplify bf16 rounding, so the network runs in
+    the fp32 validation mode here: this test is about the pipeline semantics around it."""
+    import openglottal_b200 as ogl
+
+    ref = json.loads((GOLDEN / "gated.json").read_text())
+    boxes = [None if b is None else tuple(b) for b in ref["boxes"]]
+    m = ogl.UNet().to("cuda")
+    m.load_state_dict(calibrated_sd)
+    m.eval()
+    m.precision = "fp32"
+    det = ScriptedDetector(boxes)
+    got = ogl.extract_features_unet(str(GOLDEN / "pipeline_clip.avi"), det, m, torch.device("cuda"))
+    assert det.resets == 1 and det.i == len(boxes)
+    want = ref["features"]
+    area = np.array(want["_area"])
+    err = np.abs(got["_area"] - area)
+    print("gated area max abs err", err.max(), "max area", area.max())
+    assert err.max() <= 2.0
+    assert all(g == 0 for g, b in zip(got["_area"], boxes) if b is None)
+    for k in ("area_mean", "area_std", "open_quotient", "periodicity"):
+        assert got[k] == pytest.approx(want[k], rel=5e-3, abs=1e-3), k
+
+
+def test_gated_pipeline_native_size(lib, native_model, trained_sd, tmp_path):
+    """256x256 clip: masks never leave the GPU; compare with the oracle's gated wave."""
+    import cv2
+    import openglottal_b200 as ogl
+    from oracle import pipeline_oracle as po, synth, unet_oracle as uo
+
+    clip, _ = synth.glottis_clip(20, 256, 256, seed=31, period=7.0)
+    path = tmp_path / "clip.avi"
+    vw = cv2.VideoWriter(str(path), cv2.VideoWriter_fourcc(*"FFV1"), 25.0, (256, 256))
+    for f in clip:
+        vw.write(cv2.cvtColor(f, cv2.COLOR_GRAY2BGR))
+    vw.release()
+    boxes = _boxes(20, 256, 256, seed=32, none_every=6)
+    got = ogl.extract_features_unet(str(path), ScriptedDetector(boxes), native_model, None)
+    _, ref_masks, _ = uo.batch_masks(trained_sd, clip)
+    want = np.array(po.gated_area_wave(ref_masks, boxes))
+    rel = np.abs(got["_area"] - want) / np.maximum(want, 1)
+    print("gated native: max rel area err", rel.max())
+    assert rel.max() <= 0.005 or np.abs(got["_area"] - want).max() <= 2
+
+
+def test_yolo_crop_unet_pipeline(lib, native_model, trained_sd, tmp_path):
+    """scripts/infer.py:222-248 end to end: GPU crop/letterbox/segment/un-letterbox/count vs the
+    oracle loop with the fp32 reference forward (area within 0.5 % or 4 boundary pixels -- the
+    crops are out of distribution for the full-frame-trained test weights, so a few logits sit
+    at the threshold --, Dice >= 0.99 on the pasted masks)."""
+    import cv2
+    import openglottal_b200 as ogl
+    from oracle import pipeline_oracle as po, synth, unet_oracle as uo
+
+    clip, _ = synth.glottis_clip(12, 256, 256, seed=41, period=6.0)
+    path = tmp_path / "clip.avi"
+    vw = cv2.VideoWriter(str(path), cv2.VideoWriter_fourcc(*"FFV1"), 25.0, (256, 256))
+    for f in clip:
+        vw.write(cv2.cvtColor(f, cv2.COLOR_GRAY2BGR))
+    vw.release()
+    rng = np.random.default_rng(42)
+    boxes = []
+    for i in range(12):
+        if i == 5:
+            boxes.append(None)
+            continue
+        x1, y1 = int(rng.integers(20, 90)), int(rng.integers(20, 90))
+        boxes.append((x1, y1, x1 + int(rng.integers(90, 150)), y1 + int(rng.integers(90, 150))))
+    got = ogl.extract_features_yolo_crop_unet(str(path), ScriptedDetector(boxes), native_model)
+    seg = lambda boxed: uo.segment_frame(trained_sd, boxed)
+    want = [po.crop_unet_frame(f, b, seg) for f, b in zip(clip, boxes)]
+    want_area = np.array([w[0] for w in want])
+    err = np.abs(got["_area"] - want_area)
+    print("crop pipeline area", got["_area"][:6], want_area[:6])
+    assert (err <= np.maximum(4.0, 0.005 * want_area)).all()
+    area, full = ogl.segment_crops(torch.from_numpy(clip).cuda(), boxes, native_model, want_full=True)
+    full = full.cpu().numpy()
+    for i, (a, fm) in enumerate(want):
+        if fm is None:
+            assert not full[i].any() and int(area[i]) == 0
+        else:
+            assert ogl.dice(full[i], fm) >= 0.99, i
+    assert np.array_equal(area.cpu().numpy(), (full > 0).reshape(12, -1).sum(1))

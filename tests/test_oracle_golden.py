@@ -115,3 +115,70 @@ def test_synthetic_fixtures_are_reproducible():
     f1, m1 = synth.glottis_clip(3, 64, 64, seed=5)
     f2, _ = synth.glottis_clip(3, 64, 64, seed=5)
     assert np.array_equal(f1, f2) and set(np.unique(m1)) <= {0, 255}
+
+
+# ------------------------------------------------------------------ callers around the U-Net
+def _unpack(bits, shape):
+    return np.unpackbits(bits)[: shape[0] * shape[1]].reshape(shape).astype(np.uint8) * 255
+
+
+def test_letterbox_oracle_matches_reference():
+    from oracle import pipeline_oracle as po
+
+    g = np.load(GOLDEN / "crops.npz")
+    n = sum(1 for k in g.files if k.startswith("crop"))
+    assert n >= 8
+    for k in range(n):
+        crop = g[f"crop{k}"]
+        boxed, pt, pl, ch, cw = po.letterbox_with_info(crop, 256, 0)
+        assert [pt, pl, ch, cw] == g[f"geom{k}"].tolist()
+        assert np.array_equal(boxed, g[f"boxed{k}"])
+        mask_cs = _unpack(g[f"maskcs{k}"], (256, 256))
+        back = po.unletterbox(mask_cs, pt, pl, ch, cw, *crop.shape)
+        assert np.array_equal(back > 0, _unpack(g[f"back{k}"], crop.shape) > 0)
+
+
+def test_letterbox_geometry_matches_reference():
+    import openglottal_b200 as ogl
+
+    g = np.load(GOLDEN / "crops.npz")
+    for k in range(8):
+        h, w = g[f"crop{k}"].shape
+        assert list(ogl.letterbox_geometry(h, w, 256)) == g[f"geom{k}"].tolist()
+
+
+def test_metric_oracle_matches_reference():
+    from oracle import pipeline_oracle as po
+    import openglottal_b200 as ogl
+
+    for case in json.loads((GOLDEN / "metrics.json").read_text()):
+        a = _unpack(np.array(case["a"], dtype=np.uint8), (48, 64))
+        b = _unpack(np.array(case["b"], dtype=np.uint8), (48, 64))
+        assert po.dice(a, b) == case["dice"] and po.iou(a, b) == case["iou"]
+        assert ogl.dice(a, b) == pytest.approx(case["dice"], rel=1e-6)
+        assert ogl.iou(a, b) == pytest.approx(case["iou"], rel=1e-6)
+
+
+def test_gated_oracle_matches_reference_features(calibrated_sd):
+    import cv2
+    from oracle import pipeline_oracle as po, unet_oracle as uo
+    from oracle.features_oracle import kinematic_features
+
+    ref = json.loads((GOLDEN / "gated.json").read_text())
+    boxes = [None if b is None else tuple(b) for b in ref["boxes"]]
+    cap = cv2.VideoCapture(str(GOLDEN / "pipeline_clip.avi"))
+    frames = []
+    while True:
+        ok, frm = cap.read()
+        if not ok:
+            break
+        frames.append(cv2.cvtColor(frm, cv2.COLOR_BGR2GRAY))
+    cap.release()
+    masks = [uo.segment_frame(calibrated_sd, f) for f in frames]
+    wave = po.gated_area_wave(masks, boxes)
+    want = ref["features"]["_area"]
+    assert np.abs(np.array(wave) - np.array(want)).max() <= 2
+    assert all(w == 0.0 for w, b in zip(want, boxes) if b is None)
+    feats = kinematic_features(want)
+    for k in ("area_mean", "area_std", "open_quotient", "periodicity"):
+        assert feats[k] == pytest.approx(ref["features"][k], rel=1e-12, abs=1e-12), k
