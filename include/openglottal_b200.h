@@ -103,6 +103,12 @@ const char* ogl_unet_launch_name(const ogl_unet* h, int index);
  * per-tap form used at the other levels (22 launches). Same results within bf16 rounding. */
 int ogl_unet_set_schedule(ogl_unet* h, int s2d_level0);
 
+/* CTA pairs for the conv3x3 layers with Cout >= 64: 1 = one CTA per tile; 2 = two CTAs of a
+ * cluster share one 256-row tcgen05.mma.cta_group::2 and each stages half of the weights
+ * (used when a launch has at least one tile per SM); 3 = pairs whenever a launch has two
+ * tiles (unit tests). Same results bit for bit. */
+int ogl_unet_set_cta_pairs(ogl_unet* h, int mode);
+
 /* Kinematic features of an area waveform of n >= 2 samples.
  * out8_dev: {area_mean, area_std, area_range, open_quotient, f0, periodicity, cv, peak_bin};
  * flags2_dev: {is_silent (reference returns None), f0_is_none (peak in first bin)}. */

@@ -56,6 +56,7 @@ EXPORTS = [
     "ogl_unet_launch_count",
     "ogl_unet_launch_name",
     "ogl_unet_set_schedule",
+    "ogl_unet_set_cta_pairs",
     "ogl_features_workspace_bytes",
     "ogl_features",
     "ogl_features_f64",
@@ -111,6 +112,8 @@ def load() -> C.CDLL:
     lib.ogl_unet_launch_count.argtypes = [vp]
     lib.ogl_unet_launch_name.restype = C.c_char_p
     lib.ogl_unet_launch_name.argtypes = [vp, i32]
+    lib.ogl_unet_set_cta_pairs.restype = i32
+    lib.ogl_unet_set_cta_pairs.argtypes = [vp, i32]
     lib.ogl_unet_set_schedule.restype = i32
     lib.ogl_unet_set_schedule.argtypes = [vp, i32]
     lib.ogl_features_workspace_bytes.restype = sz

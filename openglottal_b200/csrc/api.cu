@@ -73,6 +73,7 @@ struct ogl_unet {
     // ups.6 (convT) composed into ups.7.net.0, ups.7.net.3 (+head)
     S2dLayer s2d_down, s2d_up0, s2d_up1;
     bool use_s2d = true;
+    int cta_group = 2;  // 2: conv3x3 layers with N >= 64 run on CTA pairs (tcgen05 cta_group::2)
     // fp32 validation path
     F32Conv f_down[4][2], f_bott[2], f_up[4][2];
     F32ConvT f_upt[4];
@@ -141,6 +142,26 @@ std::vector<__nv_bfloat16> pack_conv(const std::vector<float>& w, int cout, int 
     return out;
 }
 
+// The same weights for a CTA pair (cta_group::2): rank r of the pair stages output channels
+// [r*N/2, (r+1)*N/2) of every pass -- [pass][cin/32][rank][tap][4][N/2][8] bf16.
+std::vector<__nv_bfloat16> pack_conv_pair(const std::vector<float>& w, int cout, int cin, int N) {
+    const int npass = cout / N, kb = cin / 32, nh = N / 2;
+    std::vector<__nv_bfloat16> out(static_cast<size_t>(cout) * cin * 9);
+    for (int pass = 0; pass < npass; ++pass)
+        for (int b = 0; b < kb; ++b)
+            for (int r = 0; r < 2; ++r)
+                for (int tap = 0; tap < 9; ++tap)
+                    for (int c = 0; c < 4; ++c)
+                        for (int n = 0; n < nh; ++n)
+                            for (int e = 0; e < 8; ++e) {
+                                const int co = pass * N + r * nh + n, ci = b * 32 + c * 8 + e;
+                                const size_t dst =
+                                    ((((((static_cast<size_t>(pass) * kb + b) * 2 + r) * 9 + tap) * 4 + c) * nh + n) * 8) + e;
+                                out[dst] = to_bf16(w[(static_cast<size_t>(co) * cin + ci) * 9 + tap]);
+                            }
+    return out;
+}
+
 // ConvTranspose2d weights [cin][cout][2][2]: pass = (dy, block of cb = N/2 output channels),
 // GEMM column n of a pass = dx * cb + (co - blk*cb); layout [pass][cin/32][4][N][8] bf16.
 int convt_n(int cout) { return 2 * (cout < 64 ? cout : 64); }
@@ -171,6 +192,9 @@ int build_tc_conv(ogl_unet* h, const std::vector<float>& w, const std::vector<fl
     L->npass = cout / L->N;
     L->epi = epi;
     if (dev_upload(h, pack_conv(w, cout, cin0 + cin1, L->N), &L->wpack)) return 1;
+    if (L->N >= 64 && (epi == EPI_RELU || epi == EPI_RELU_POOL) &&
+        dev_upload(h, pack_conv_pair(w, cout, cin0 + cin1, L->N), &L->wpack2))
+        return 1;
     return dev_upload(h, b, &L->bias);
 }
 
@@ -271,6 +295,7 @@ int ogl_unet_create(ogl_unet** out, int device) {
     if (conv_tc_init() || s2d_tc_init()) return 1;
     ogl_unet* h = new ogl_unet();
     if (const char* e = getenv("OGL_S2D")) h->use_s2d = atoi(e) != 0;
+    if (const char* e = getenv("OGL_CG")) h->cta_group = atoi(e);
     h->device = device;
     h->num_sms = prop.multiProcessorCount;
     *out = h;
@@ -426,7 +451,7 @@ int ogl_unet_forward(ogl_unet* h, const void* frames_dev, int in_dtype, int n, i
             const int hh = H >> l, ww = W >> l;
             if (l > 0) {
                 if (launch_conv_tc(h->down_c1[l], P[l - 1], nullptr, n, hh, ww, B(p.T[l]), nullptr,
-                                   nullptr, h->num_sms, stream))
+                                   nullptr, h->num_sms, stream, h->cta_group))
                     return 1;
                 mark(h, stream, kDownC1[l]);
             }
@@ -435,17 +460,17 @@ int ogl_unet_forward(ogl_unet* h, const void* frames_dev, int in_dtype, int n, i
                                   nullptr, h->num_sms, stream))
                     return 1;
             } else if (launch_conv_tc(h->down_c2[l], B(p.T[l]), nullptr, n, hh, ww, B(p.S[l]),
-                                      P[l], nullptr, h->num_sms, stream)) {
+                                      P[l], nullptr, h->num_sms, stream, h->cta_group)) {
                 return 1;
             }
             mark(h, stream, kDownC2[l]);
         }
         if (launch_conv_tc(h->bott[0], P[3], nullptr, n, H >> 4, W >> 4, B(p.T[4]), nullptr,
-                           nullptr, h->num_sms, stream))
+                           nullptr, h->num_sms, stream, h->cta_group))
             return 1;
         mark(h, stream, "bottleneck.net.0");
         if (launch_conv_tc(h->bott[1], B(p.T[4]), nullptr, n, H >> 4, W >> 4, B(p.B4), nullptr,
-                           nullptr, h->num_sms, stream))
+                           nullptr, h->num_sms, stream, h->cta_group))
             return 1;
         mark(h, stream, "bottleneck.net.3");
         const __nv_bfloat16* below = B(p.B4);
@@ -473,15 +498,15 @@ int ogl_unet_forward(ogl_unet* h, const void* frames_dev, int in_dtype, int n, i
                 break;
             }
             if (launch_conv_tc(h->up_t[k], below, nullptr, n, hh / 2, ww / 2, B(p.U[l]), nullptr,
-                               nullptr, h->num_sms, stream))
+                               nullptr, h->num_sms, stream, h->cta_group))
                 return 1;
             mark(h, stream, kUpT[k]);
             if (launch_conv_tc(h->up_c[k][0], B(p.S[l]), B(p.U[l]), n, hh, ww, B(p.T[l]), nullptr,
-                               nullptr, h->num_sms, stream))
+                               nullptr, h->num_sms, stream, h->cta_group))
                 return 1;
             mark(h, stream, kUpC1[k]);
             if (launch_conv_tc(h->up_c[k][1], B(p.T[l]), nullptr, n, hh, ww, B(p.U[l]), nullptr,
-                               k == 3 ? &hp : nullptr, h->num_sms, stream))
+                               k == 3 ? &hp : nullptr, h->num_sms, stream, h->cta_group))
                 return 1;
             mark(h, stream, kUpC2[k]);
             below = B(p.U[l]);
@@ -571,6 +596,13 @@ const char* ogl_unet_launch_name(const ogl_unet* h, int index) {
 int ogl_unet_set_schedule(ogl_unet* h, int s2d_level0) {
     if (!h) return fail("ogl_unet_set_schedule: NULL handle");
     h->use_s2d = s2d_level0 != 0;
+    return 0;
+}
+
+int ogl_unet_set_cta_pairs(ogl_unet* h, int mode) {
+    if (!h) return fail("ogl_unet_set_cta_pairs: NULL handle");
+    if (mode < 1 || mode > 3) return fail("ogl_unet_set_cta_pairs: mode must be 1, 2 or 3");
+    h->cta_group = mode;
     return 0;
 }
 
@@ -685,7 +717,7 @@ int ogl_debug_tc_layer(ogl_unet* h, int kind, const float* src0_dev, int c0, con
     L.cout = cout;
     L.N = kind == EPI_CONVT ? convt_n(cout) : (cout < 128 ? cout : 128);
     L.epi = kind;
-    std::vector<__nv_bfloat16> pk;
+    std::vector<__nv_bfloat16> pk, pk2;
     if (kind == EPI_CONVT) {
         L.taps = 1;
         L.npass = 4 * cout / L.N;
@@ -695,28 +727,34 @@ int ogl_debug_tc_layer(ogl_unet* h, int kind, const float* src0_dev, int c0, con
         L.npass = cout / L.N;
         std::vector<float> w(weight_host, weight_host + static_cast<size_t>(cout) * cin * 9);
         pk = pack_conv(w, cout, cin, L.N);
+        if (L.N >= 64) pk2 = pack_conv_pair(w, cout, cin, L.N);
     }
     const size_t hw = static_cast<size_t>(height) * width;
     const int oh = kind == EPI_CONVT ? 2 * height : height;
     const int ow = kind == EPI_CONVT ? 2 * width : width;
-    __nv_bfloat16 *d_w = nullptr, *d_s0 = nullptr, *d_s1 = nullptr, *d_o = nullptr, *d_p = nullptr;
+    __nv_bfloat16 *d_w = nullptr, *d_w2 = nullptr, *d_s0 = nullptr, *d_s1 = nullptr, *d_o = nullptr,
+                  *d_p = nullptr;
     float* d_b = nullptr;
     int rc = 1;
     do {
         if (cudaMalloc(&d_w, pk.size() * 2) != cudaSuccess) break;
+        if (!pk2.empty() && cudaMalloc(&d_w2, pk2.size() * 2) != cudaSuccess) break;
         if (cudaMalloc(&d_b, cout * 4) != cudaSuccess) break;
         if (cudaMalloc(&d_s0, n * c0 * hw * 2) != cudaSuccess) break;
         if (c1 && cudaMalloc(&d_s1, n * c1 * hw * 2) != cudaSuccess) break;
         if (cudaMalloc(&d_o, static_cast<size_t>(n) * cout * oh * ow * 2) != cudaSuccess) break;
         if (kind == EPI_RELU_POOL && cudaMalloc(&d_p, n * cout * hw / 4 * 2) != cudaSuccess) break;
         cudaMemcpyAsync(d_w, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice, stream);
+        if (d_w2) cudaMemcpyAsync(d_w2, pk2.data(), pk2.size() * 2, cudaMemcpyHostToDevice, stream);
         cudaMemcpyAsync(d_b, bias_host, cout * 4, cudaMemcpyHostToDevice, stream);
         cudaStreamSynchronize(stream);
         L.wpack = d_w;
+        L.wpack2 = d_w2;
         L.bias = d_b;
         if (launch_nchw_to_c8(src0_dev, d_s0, n, c0, height, width, stream)) break;
         if (c1 && launch_nchw_to_c8(src1_dev, d_s1, n, c1, height, width, stream)) break;
-        if (launch_conv_tc(L, d_s0, d_s1, n, height, width, d_o, d_p, nullptr, h->num_sms, stream))
+        if (launch_conv_tc(L, d_s0, d_s1, n, height, width, d_o, d_p, nullptr, h->num_sms, stream,
+                           h->cta_group))
             break;
         if (launch_c8_to_nchw(d_o, out_dev, n, cout, oh, ow, stream)) break;
         if (kind == EPI_RELU_POOL && out_pool_dev &&
@@ -731,6 +769,7 @@ int ogl_debug_tc_layer(ogl_unet* h, int kind, const float* src0_dev, int c0, con
     } while (0);
     if (rc && g_err.empty()) fail("ogl_debug_tc_layer: allocation or launch failed");
     cudaFree(d_w);
+    cudaFree(d_w2);
     cudaFree(d_b);
     cudaFree(d_s0);
     cudaFree(d_s1);

@@ -94,15 +94,21 @@ __device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
     return *reinterpret_cast<uint32_t*>(&r);
 }
 
-template <int EPI, int TPS, int S>
+// CG = 1: one CTA per tile. CG = 2: the two CTAs of a cluster (one TPC) take two neighbouring
+// tiles of the same pass and run their MMAs as ONE 256-row tcgen05.mma.cta_group::2: each CTA
+// stages its own activations but only HALF of the weight columns, so the weight traffic
+// (L2 -> shared memory) and the B-operand shared-memory reads per SM are halved.
+template <int EPI, int TPS, int S, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-               const ConvParams p) {
+               const __grid_constant__ CUtensorMap tmW, const ConvParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
+    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
 
     constexpr uint32_t a_stage_bytes = static_cast<uint32_t>(S) * kSubBytes;
-    const uint32_t w_tap_bytes = 64u * static_cast<uint32_t>(p.N);
+    const uint32_t nb = static_cast<uint32_t>(p.N) / CG;          // weight columns staged per CTA
+    const uint32_t w_tap_bytes = 64u * nb;
     const uint32_t w_stage_bytes = TPS * w_tap_bytes;
     const uint32_t a_ring = smem_base;
     const uint32_t w_ring = a_ring + p.na * a_stage_bytes;
@@ -130,7 +136,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int kb_total = p.kb0 + p.kb1;
-    const int items = p.npass * p.num_tiles;
+    // work items: (pass, tile) for CG = 1, (pass, pair of tiles) for CG = 2
+    const int num_units = CG == 2 ? (p.num_tiles + 1) >> 1 : p.num_tiles;
+    const int items = p.npass * num_units;
+    const int item0 = CG == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int item_step = CG == 2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+    auto tile_of = [&](int item) {
+        const int unit = p.pass_fast ? item / p.npass : item % num_units;
+        return CG == 2 ? 2 * unit + static_cast<int>(rank) : unit;   // may be >= num_tiles (tail)
+    };
+    auto pass_of = [&](int item) { return p.pass_fast ? item % p.npass : item / num_units; };
 
     // ---------------------------------------------------------------- setup
     for (int i = threadIdx.x; i < p.cout; i += kThreads) bias_sp[i] = p.bias[i];
@@ -140,6 +155,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA0);
         tma_prefetch_desc(&tmA1);
+        if (CG == 2) tma_prefetch_desc(&tmW);
         for (int i = 0; i < p.na; ++i) {
             mbar_init(a_full + 8u * i, 1);
             mbar_init(a_empty + 8u * i, 1);
@@ -150,13 +166,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
         for (int i = 0; i < 4; ++i) {
             mbar_init(acc_full + 8u * i, 1);
-            mbar_init(acc_empty + 8u * i, kEpiThreads);
+            mbar_init(acc_empty + 8u * i, kEpiThreads * CG);  // CG = 2: both CTAs' epilogues
         }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+    if (warp == 2) {
+        if (CG == 2) tmem_alloc_pair(tmem_slot, kTmemCols);
+        else tmem_alloc(tmem_slot, kTmemCols);
+    }
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();  // the peer's barriers exist before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_p;
 
@@ -164,25 +184,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         // ================================================ activation producer
         if (lane == 0) {
             uint32_t it = 0;
-            for (int item = blockIdx.x; item < items; item += gridDim.x) {
-                const int tile = p.pass_fast ? item / p.npass : item % p.num_tiles;
+            for (int item = item0; item < items; item += item_step) {
+                const int tile = tile_of(item);
                 for (int kb = 0; kb < kb_total; ++kb, ++it) {
                     const uint32_t s = it % p.na;
                     const uint32_t ph = (it / p.na) & 1u;
                     mbar_wait(a_empty + 8u * s, ph ^ 1u);
-                    if (p.dbg & 8) {
+                    if (CG == 1 && (p.dbg & 8)) {
                         mbar_arrive(a_full + 8u * s);
                         continue;
                     }
-                    mbar_arrive_expect_tx(a_full + 8u * s, a_stage_bytes);
+                    // CG = 2: the leader's barrier counts the bytes of both CTAs
+                    uint32_t full = a_full + 8u * s;
+                    if (CG == 1) {
+                        mbar_arrive_expect_tx(full, a_stage_bytes);
+                    } else {
+                        if (rank == 0) mbar_arrive_expect_tx(full, 2u * a_stage_bytes);
+                        full = map_to_cta(full, 0);
+                    }
                     const CUtensorMap* tm = kb < p.kb0 ? &tmA0 : &tmA1;
                     const int plane0 = (kb < p.kb0 ? kb : kb - p.kb0) * 4;
                     for (int sub = 0; sub < S; ++sub) {
                         int st = tile * S + sub;
                         if (st >= p.total_sub) st = p.total_sub - 1;  // tail: load a duplicate
                         const SubTile t = decode_sub(p, st);
-                        tma_load_4d(a_ring + s * a_stage_bytes + sub * kSubBytes, tm,
-                                    a_full + 8u * s, (t.x0 - 1) * 8, t.y0 - 1, plane0, t.n);
+                        const uint32_t dst = a_ring + s * a_stage_bytes + sub * kSubBytes;
+                        if (CG == 1)
+                            tma_load_4d(dst, tm, full, (t.x0 - 1) * 8, t.y0 - 1, plane0, t.n);
+                        else
+                            tma_load_4d_pair(dst, tm, full, (t.x0 - 1) * 8, t.y0 - 1, plane0, t.n);
                     }
                 }
             }
@@ -192,44 +222,70 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (lane == 0) {
             uint32_t it = 0;
             const uint8_t* wbytes = reinterpret_cast<const uint8_t*>(p.wpack);
-            for (int item = blockIdx.x; item < items; item += gridDim.x) {
-                const int pass = p.pass_fast ? item % p.npass : item / p.num_tiles;
+            for (int item = item0; item < items; item += item_step) {
+                const int pass = pass_of(item);
                 for (int kb = 0; kb < kb_total; ++kb) {
                     for (int tg = 0; tg < p.taps / TPS; ++tg, ++it) {
                         const uint32_t s = it % p.nw;
                         const uint32_t ph = (it / p.nw) & 1u;
                         mbar_wait(w_empty + 8u * s, ph ^ 1u);
-                        if (p.dbg & 16) {
+                        if (CG == 1 && (p.dbg & 16)) {
                             mbar_arrive(w_full + 8u * s);
                             continue;
                         }
-                        mbar_arrive_expect_tx(w_full + 8u * s, w_stage_bytes);
-                        const size_t off =
-                            (static_cast<size_t>(pass * kb_total + kb) * p.taps + tg * TPS) *
-                            w_tap_bytes;
-                        bulk_load(w_ring + s * w_stage_bytes, wbytes + off, w_stage_bytes,
-                                  w_full + 8u * s);
+                        if (CG == 1) {
+                            mbar_arrive_expect_tx(w_full + 8u * s, w_stage_bytes);
+                            const size_t off =
+                                (static_cast<size_t>(pass * kb_total + kb) * p.taps + tg * TPS) *
+                                w_tap_bytes;
+                            bulk_load(w_ring + s * w_stage_bytes, wbytes + off, w_stage_bytes,
+                                      w_full + 8u * s);
+                        } else {
+                            // pair layout [pass][kb][rank][tap][4][N/2][8], seen by TMA as rows
+                            // of 256 bytes; this CTA's half of the stage is one box
+                            if (rank == 0) mbar_arrive_expect_tx(w_full + 8u * s, 2u * w_stage_bytes);
+                            const uint32_t rows_per_tap = w_tap_bytes >> 8;
+                            const int row0 = static_cast<int>(
+                                ((static_cast<uint32_t>(pass * kb_total + kb) * 2u + rank) * p.taps +
+                                 tg * TPS) * rows_per_tap);
+                            tma_load_2d_pair(w_ring + s * w_stage_bytes, &tmW,
+                                             map_to_cta(w_full + 8u * s, 0), 0, row0);
+                        }
                     }
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 1 && rank == 0) {
         // ========================================================= MMA issuer
         // The whole warp walks the loops (all values warp-uniform); one elected lane issues.
         // Descriptors differ only in their start-address field, so each MMA is one 32-bit add.
-        const uint32_t idesc = make_idesc_bf16(p.N);
+        // CG = 2: only the leader CTA issues; shared-memory offsets are the same in both CTAs.
+        const uint32_t idesc = CG == 2 ? make_idesc_bf16_pair(p.N) : make_idesc_bf16(p.N);
         constexpr uint32_t lbo_a = kPlaneBytes, sbo_a = kHalo * 16;
-        const uint32_t lbo_b = 16u * p.N, sbo_b = 128u;
+        const uint32_t lbo_b = 16u * nb, sbo_b = 128u;
         const uint64_t adesc0 = make_smem_desc(0, lbo_a, sbo_a);
         const uint64_t bdesc0 = make_smem_desc(0, lbo_b, sbo_b);
         const uint32_t acc_cols = static_cast<uint32_t>(2 * S * p.N);
         const uint32_t bstep = (2u * lbo_b) >> 4;   // second K=16 half of a 32-channel block
+        const uint32_t btap = 4u * nb;              // one tap of B, in 16-byte units
+        auto mma = [](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
+            if (CG == 2) umma_bf16_pair(d, a, b, id, acc);
+            else umma_bf16(d, a, b, id, acc);
+        };
+        auto commit = [](uint32_t bar) {
+            if (CG == 2) umma_commit_pair(bar);
+            else umma_commit(bar);
+        };
+        auto wait_acc_empty = [](uint32_t bar, uint32_t parity) {
+            if (CG == 2) mbar_wait_cluster(bar, parity);   // the peer's epilogue arrives remotely
+            else mbar_wait(bar, parity);
+        };
         uint32_t ita = 0, itw = 0, li = 0;
-        for (int item = blockIdx.x; item < items; item += gridDim.x, ++li) {
+        for (int item = item0; item < items; item += item_step, ++li) {
             const uint32_t buf = kSplit ? 0u : li % p.acc_bufs;
             const uint32_t aph = kSplit ? (li & 1u) : (li / p.acc_bufs) & 1u;
             if (!kSplit) {
-                mbar_wait(acc_empty + 8u * buf, aph ^ 1u);
+                wait_acc_empty(acc_empty + 8u * buf, aph ^ 1u);
                 tc_fence_after();
             }
             const uint32_t d0 = tmem_base + buf * acc_cols;
@@ -249,7 +305,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     tc_fence_after();
                     for (int mt = 0; mt < 4; ++mt) {
                         if (kb == 0) {
-                            mbar_wait(acc_empty + 8u * mt, aph ^ 1u);
+                            wait_acc_empty(acc_empty + 8u * mt, aph ^ 1u);
                             tc_fence_after();
                         }
                         if (elect_one()) {
@@ -266,20 +322,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                                         constexpr uint32_t kSubStep = kSubBytes >> 4;
                                         const uint32_t aoff = t + (mt >> 1) * kSubStep +
                                                               j * ((2u * lbo_a) >> 4) + (mt & 1) * 8u;
-                                        umma_bf16(d0 + mt * p.N, ad + aoff,
-                                                  bd + (t * 4u * p.N + j * bstep), idesc,
-                                                  (kb | tg | t | j) ? 1u : 0u);
+                                        mma(d0 + mt * p.N, ad + aoff, bd + (t * btap + j * bstep),
+                                            idesc, (kb | tg | t | j) ? 1u : 0u);
                                     }
                                 }
                             }
-                            if (kb == kb_total - 1) umma_commit(acc_full + 8u * mt);
+                            if (kb == kb_total - 1) commit(acc_full + 8u * mt);
                         }
                         __syncwarp();
                     }
                     if (elect_one()) {
 #pragma unroll
-                        for (int tg = 0; tg < 3; ++tg) umma_commit(w_empty + 8u * wst[tg]);
-                        umma_commit(a_empty + 8u * sa);
+                        for (int tg = 0; tg < 3; ++tg) commit(w_empty + 8u * wst[tg]);
+                        commit(a_empty + 8u * sa);
                     }
                     __syncwarp();
                     itw += 3;
@@ -312,16 +367,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                                     constexpr uint32_t kSubStep = kSubBytes >> 4;
                                     const uint32_t aoff = toff + (mt >> 1) * kSubStep +
                                                           j * ((2u * lbo_a) >> 4) + (mt & 1) * 8u;
-                                    umma_bf16(d0 + mt * p.N, ad + aoff,
-                                              bd + (t * 4u * p.N + j * bstep), idesc,
-                                              (t | j) ? 1u : first);
+                                    mma(d0 + mt * p.N, ad + aoff, bd + (t * btap + j * bstep),
+                                        idesc, (t | j) ? 1u : first);
                                 }
                             }
                         }
-                        umma_commit(w_empty + 8u * sw);
-                        if (last_tg) umma_commit(a_empty + 8u * sa);
-                        if (!kSplit && last_tg && kb == kb_total - 1)
-                            umma_commit(acc_full + 8u * buf);
+                        commit(w_empty + 8u * sw);
+                        if (last_tg) commit(a_empty + 8u * sa);
+                        if (!kSplit && last_tg && kb == kb_total - 1) commit(acc_full + 8u * buf);
                     }
                     __syncwarp();
                 }
@@ -339,9 +392,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int OH = EPI == EPI_CONVT ? 2 * p.H : p.H;
         const int OW = EPI == EPI_CONVT ? 2 * p.W : p.W;
         uint32_t li = 0;
-        for (int item = blockIdx.x; item < items; item += gridDim.x, ++li) {
-            const int tile = p.pass_fast ? item / p.npass : item % p.num_tiles;
-            const int pass = p.pass_fast ? item % p.npass : item / p.num_tiles;
+        auto release_acc = [](uint32_t bar) {
+            if (CG == 2) mbar_arrive_cluster(map_to_cta(bar, 0));  // the leader's barrier
+            else mbar_arrive(bar);
+        };
+        for (int item = item0; item < items; item += item_step, ++li) {
+            const int tile = tile_of(item);
+            const int pass = pass_of(item);
             const uint32_t buf = kSplit ? 0u : li % p.acc_bufs;
             const uint32_t aph = kSplit ? (li & 1u) : (li / p.acc_bufs) & 1u;
             if (!kSplit) {
@@ -477,12 +534,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 }
                 if (kSplit) {
                     tc_fence_before();
-                    mbar_arrive(acc_empty + 8u * mt);
+                    release_acc(acc_empty + 8u * mt);
                 }
             }
             if (!kSplit) {
                 tc_fence_before();
-                mbar_arrive(acc_empty + 8u * buf);
+                release_acc(acc_empty + 8u * buf);
             }
         }
     }
@@ -490,9 +547,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // ------------------------------------------------------------- teardown
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();  // neither CTA leaves while the pair may still touch it
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
+        if (CG == 2) tmem_dealloc_pair(tmem_base, kTmemCols);
+        else tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
@@ -531,17 +590,42 @@ template <int EPI, int TPS>
 int launch_epi(const CUtensorMap& tm0, const CUtensorMap& tm1, const ConvParams& p, int grid,
                size_t smem, cudaStream_t stream) {
     if (p.S == 1)
-        conv_tc_kernel<EPI, TPS, 1><<<grid, kThreads, smem, stream>>>(tm0, tm1, p);
+        conv_tc_kernel<EPI, TPS, 1, 1><<<grid, kThreads, smem, stream>>>(tm0, tm1, tm0, p);
     else
-        conv_tc_kernel<EPI, TPS, 2><<<grid, kThreads, smem, stream>>>(tm0, tm1, p);
+        conv_tc_kernel<EPI, TPS, 2, 1><<<grid, kThreads, smem, stream>>>(tm0, tm1, tm0, p);
     OGL_CUDA(cudaGetLastError());
+    return 0;
+}
+// CTA-pair form (cta_group::2): clusters of 2 CTAs, 2 sub-tiles per CTA
+template <int EPI, int TPS>
+int launch_epi_pair(const CUtensorMap& tm0, const CUtensorMap& tm1, const CUtensorMap& tmw,
+                    const ConvParams& p, int grid, size_t smem, cudaStream_t stream) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    OGL_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<EPI, TPS, 2, 2>, tm0, tm1, tmw, p));
     return 0;
 }
 template <int EPI, int TPS>
 int set_smem_attr() {
-    OGL_CUDA(cudaFuncSetAttribute(conv_tc_kernel<EPI, TPS, 1>,
+    OGL_CUDA(cudaFuncSetAttribute(conv_tc_kernel<EPI, TPS, 1, 1>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    OGL_CUDA(cudaFuncSetAttribute(conv_tc_kernel<EPI, TPS, 2>,
+    OGL_CUDA(cudaFuncSetAttribute(conv_tc_kernel<EPI, TPS, 2, 1>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    return 0;
+}
+template <int EPI, int TPS>
+int set_smem_attr_pair() {
+    OGL_CUDA(cudaFuncSetAttribute(conv_tc_kernel<EPI, TPS, 2, 2>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     return 0;
 }
@@ -584,14 +668,16 @@ int conv_tc_init() {
     }
     if (set_smem_attr<EPI_RELU, 9>() || set_smem_attr<EPI_RELU, 3>() ||
         set_smem_attr<EPI_RELU_POOL, 9>() || set_smem_attr<EPI_RELU_POOL, 3>() ||
-        set_smem_attr<EPI_HEAD, 9>() || set_smem_attr<EPI_CONVT, 1>())
+        set_smem_attr<EPI_HEAD, 9>() || set_smem_attr<EPI_CONVT, 1>() ||
+        set_smem_attr_pair<EPI_RELU, 9>() || set_smem_attr_pair<EPI_RELU, 3>() ||
+        set_smem_attr_pair<EPI_RELU_POOL, 9>() || set_smem_attr_pair<EPI_RELU_POOL, 3>())
         return 1;
     return 0;
 }
 
 int launch_conv_tc(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloat16* src1, int B,
                    int H, int W, __nv_bfloat16* out, __nv_bfloat16* out_pool,
-                   const HeadParams* head, int num_sms, cudaStream_t stream) {
+                   const HeadParams* head, int num_sms, cudaStream_t stream, int cta_group) {
     if (!g_encode) return fail("conv_tc_init() was not called");
     if (H < 1 || W < 1) return fail("tensor-core conv needs a non-empty feature map");
     if (L.epi == EPI_RELU_POOL && (H % 2 || W % 2))
@@ -647,7 +733,16 @@ int launch_conv_tc(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloa
     static const int dbg_env = getenv("OGL_DBG") ? atoi(getenv("OGL_DBG")) : 0;
     p.dbg = dbg_env;
     const int tps = taps_per_stage(L);
-    const size_t w_stage = static_cast<size_t>(tps) * 64u * p.N;
+    // CTA pairs (cta_group::2) for the conv3x3 layers with N >= 64 when there is enough work
+    // (cta_group 2), or whenever possible (cta_group 3: unit tests on small inputs)
+    // Layers with a single 32-channel K block (downs.1.net.0) are faster unpaired (measured):
+    // the pair's per-tile hand-shakes are not amortised over so short a K loop.
+    static const int minkb_env = getenv("OGL_CG_MINKB") ? atoi(getenv("OGL_CG_MINKB")) : 2;
+    const bool pair = cta_group >= 2 && L.wpack2 && L.taps == 9 && (L.N == 64 || L.N == 128) &&
+                      (L.epi == EPI_RELU || L.epi == EPI_RELU_POOL) && p.S == 2 &&
+                      num_sms >= 2 && p.num_tiles >= (cta_group == 3 ? 2 : num_sms) &&
+                      (cta_group == 3 || p.kb0 + p.kb1 >= minkb_env);
+    const size_t w_stage = static_cast<size_t>(tps) * 64u * p.N / (pair ? 2 : 1);
     const size_t tables = sizeof(float) * (L.cout + 32);
     auto smem_need = [&](int na, int nw) {
         return static_cast<size_t>(128 /*align slack*/ + na * p.S * kSubBytes + nw * w_stage +
@@ -678,6 +773,22 @@ int launch_conv_tc(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloa
         if (make_act_map(&tm1, src1, B, L.cin1, H, W)) return 1;
     } else {
         tm1 = tm0;
+    }
+    if (pair) {
+        // weights as rows of 256 bytes; one box = this CTA's half of a stage
+        CUtensorMap tmw;
+        const uint64_t rows = static_cast<uint64_t>(L.cout) * (L.cin0 + L.cin1) * 9 * 2 / 256;
+        const uint64_t dims[2] = {128, rows};
+        const uint64_t str[1] = {256};
+        const uint32_t box[2] = {128, static_cast<uint32_t>(w_stage / 256)};
+        if (encode_bf16_map(&tmw, L.wpack2, 2, dims, str, box)) return 1;
+        p.pass_fast = 0;
+        const int grid2 = num_sms & ~1;
+        if (L.epi == EPI_RELU)
+            return tps == 9 ? launch_epi_pair<EPI_RELU, 9>(tm0, tm1, tmw, p, grid2, smem, stream)
+                            : launch_epi_pair<EPI_RELU, 3>(tm0, tm1, tmw, p, grid2, smem, stream);
+        return tps == 9 ? launch_epi_pair<EPI_RELU_POOL, 9>(tm0, tm1, tmw, p, grid2, smem, stream)
+                        : launch_epi_pair<EPI_RELU_POOL, 3>(tm0, tm1, tmw, p, grid2, smem, stream);
     }
     const int items = p.npass * p.num_tiles;
     const int grid = items < num_sms ? items : num_sms;

@@ -35,6 +35,7 @@ enum Epilogue : int {
 
 struct TcLayer {
     __nv_bfloat16* wpack = nullptr;  // [npass][Cin/32][taps][4][N][8] bf16 (device)
+    __nv_bfloat16* wpack2 = nullptr; // CTA-pair form [npass][Cin/32][rank 2][taps][4][N/2][8], or null
     float* bias = nullptr;           // [cout] fp32 (device)
     int cin0 = 0, cin1 = 0;          // channels of source 0 (skip / only) and source 1 (up)
     int cout = 0;                    // channels of the output tensor
@@ -57,7 +58,7 @@ struct HeadParams {
 int conv_tc_init();  // resolves cuTensorMapEncodeTiled, sets smem attributes
 int launch_conv_tc(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloat16* src1, int B,
                    int H, int W, __nv_bfloat16* out, __nv_bfloat16* out_pool,
-                   const HeadParams* head, int num_sms, cudaStream_t stream);
+                   const HeadParams* head, int num_sms, cudaStream_t stream, int cta_group = 1);
 
 // ------------------------------------------------------------------ full-resolution level
 // The tensor-core convs at full resolution (Cout = 32) run on tensors stored "space-to-depth"

@@ -11,6 +11,7 @@ There is no CPU path and no training path.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import math
 
 import torch
@@ -67,6 +68,9 @@ class UNet(nn.Module):
         self.max_batch = 512         # frames per native call; larger inputs are chunked
         self.schedule = "s2d"        # full-resolution level: "s2d" (space-to-depth GEMMs, the
                                      # default) or "direct" (per-tap form of the other levels)
+        self.cta_pairs = int(os.environ.get("OGL_CG", "2"))   # 1: one CTA per tile; 2: CTA pairs
+                                     # (tcgen05 cta_group::2) for the Cout >= 64 conv layers when
+                                     # a launch has a tile per SM; 3: pairs whenever possible
         self._handle = None
         self._handle_device = None
         self._packed_sig = None
@@ -195,6 +199,7 @@ class UNet(nn.Module):
         self._pack_if_needed()
         lib = _native.load()
         _native.check(lib.ogl_unet_set_schedule(self._handle, 1 if self.schedule == "s2d" else 0))
+        _native.check(lib.ogl_unet_set_cta_pairs(self._handle, int(self.cta_pairs)))
         frames = frames.contiguous()
         logits = torch.empty((n, hgt, wid), dtype=torch.float32, device=dev) if want_logits else None
         mask = torch.empty((n, hgt, wid), dtype=torch.uint8, device=dev) if want_mask else None

@@ -163,3 +163,34 @@ def test_s2d_conv3x3_with_composed_convt(lib, handle, n, hgt, wid):
     edge = torch.ones_like(err, dtype=torch.bool)
     edge[:, :, 1:-1, 1:-1] = False
     assert err[edge].max() <= 2e-2 * max(1.0, ref.abs().max().item() / 2), msg
+
+
+# ------------------------------------------------------------------ CTA pairs (cta_group::2)
+@pytest.mark.parametrize("kind,c0,c1,cout,n,hgt,wid", [c for c in CONV_CASES if c[3] >= 64] + [
+    (0, 64, 0, 64, 9, 64, 64), (1, 128, 0, 128, 7, 48, 32), (0, 64, 64, 64, 5, 32, 32),
+    (0, 512, 0, 256, 3, 32, 32)])
+def test_conv3x3_cta_pairs_bit_identical(lib, handle, kind, c0, c1, cout, n, hgt, wid):
+    """The CTA-pair form issues the same MMAs on the same operands (256 rows at a time), so its
+    output must equal the one-CTA form bit for bit; and both match the fp64 reference."""
+    from openglottal_b200 import _native
+
+    g = torch.Generator().manual_seed(c0 * 5 + cout + wid)
+    cin = c0 + c1
+    x = _bf(torch.randn(n, cin, hgt, wid, generator=g))
+    w = _bf(torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (cin * 9)) ** 0.5)
+    b = torch.randn(cout, generator=g) * 0.1
+    xc = x.cuda()
+    x0 = xc[:, :c0].contiguous()
+    x1 = xc[:, c0:].contiguous() if c1 else None
+    try:
+        _native.check(lib.ogl_unet_set_cta_pairs(handle, 1))
+        out1, pool1 = _run_layer(lib, handle, kind, x0, x1, w, b, cout)
+        _native.check(lib.ogl_unet_set_cta_pairs(handle, 3))
+        out2, pool2 = _run_layer(lib, handle, kind, x0, x1, w, b, cout)
+    finally:
+        _native.check(lib.ogl_unet_set_cta_pairs(handle, 2))
+    ref = F.relu(F.conv2d(x.double(), w.double(), b.double(), padding=1)).float()
+    _report(f"pair conv {c0}+{c1}->{cout} {n}x{hgt}x{wid}", out2.cpu(), ref)
+    assert torch.equal(out1, out2)
+    if kind == 1:
+        assert torch.equal(pool1, pool2)

@@ -101,6 +101,26 @@ def test_direct_schedule_matches_bitmodel_and_s2d(native_model, trained_sd):
     assert np.array_equal(a.cpu().numpy(), (m.cpu().numpy() > 0).reshape(3, -1).sum(1))
 
 
+def test_cta_pairs_bit_identical(native_model):
+    """tcgen05 cta_group::2 for the Cout >= 64 conv layers: same logits, masks and areas, bit for
+    bit, on a small batch (pairs forced) and on a batch with a tile per SM (the default rule)."""
+    frames = torch.from_numpy(_clip(5)).cuda()
+    big = torch.from_numpy(np.concatenate([_clip(64, seed=s) for s in (71, 72, 73, 74, 75)])).cuda()
+    default = native_model.cta_pairs
+    try:
+        native_model.cta_pairs = 1
+        ref = native_model.run(frames, want_logits=True)
+        ref_big = native_model.run(big)
+        native_model.cta_pairs = 3
+        got = native_model.run(frames, want_logits=True)
+        native_model.cta_pairs = 2
+        got_big = native_model.run(big)
+    finally:
+        native_model.cta_pairs = default
+    assert all(torch.equal(a, b) for a, b in zip(ref, got))
+    assert torch.equal(ref_big[1], got_big[1]) and torch.equal(ref_big[2], got_big[2])
+
+
 def test_bf16_matches_reference_within_north_star(native_model, trained_sd):
     from oracle import unet_oracle as uo
     from openglottal_b200 import dice
