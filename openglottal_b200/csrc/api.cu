@@ -214,6 +214,7 @@ int build_s2d_layer(ogl_unet* h, const std::vector<float>& w3, const std::vector
     L->epi = epi;
     for (int i = 0; i < 32; ++i) L->bias_host[i] = hs.btab[4 * 32 + i];
     if (dev_upload(h, hs.wblob, &L->wblob)) return 1;
+    if (dev_upload(h, hs.wblob_pair, &L->wblob2)) return 1;
     return dev_upload(h, hs.btab, &L->btab);
 }
 
@@ -457,7 +458,7 @@ int ogl_unet_forward(ogl_unet* h, const void* frames_dev, int in_dtype, int n, i
             }
             if (l == 0 && s2d) {
                 if (launch_s2d_tc(h->s2d_down, B(p.T[0]), nullptr, n, H, W, B(p.S[0]), P[0],
-                                  nullptr, h->num_sms, stream))
+                                  nullptr, h->num_sms, stream, h->cta_group))
                     return 1;
             } else if (launch_conv_tc(h->down_c2[l], B(p.T[l]), nullptr, n, hh, ww, B(p.S[l]),
                                       P[l], nullptr, h->num_sms, stream, h->cta_group)) {
@@ -488,11 +489,11 @@ int ogl_unet_forward(ogl_unet* h, const void* frames_dev, int in_dtype, int n, i
             if (l == 0 && s2d) {
                 // ups.6 is composed into ups.7.net.0: reads the skip (S2D) and the level-1 tensor
                 if (launch_s2d_tc(h->s2d_up0, B(p.S[0]), below, n, H, W, B(p.T[0]), nullptr,
-                                  nullptr, h->num_sms, stream))
+                                  nullptr, h->num_sms, stream, h->cta_group))
                     return 1;
                 mark(h, stream, "ups.6(convT)+ups.7.net.0(cat)");
                 if (launch_s2d_tc(h->s2d_up1, B(p.T[0]), nullptr, n, H, W, nullptr, nullptr, &hp,
-                                  h->num_sms, stream))
+                                  h->num_sms, stream, h->cta_group))
                     return 1;
                 mark(h, stream, kUpC2[k]);
                 break;
@@ -830,22 +831,26 @@ int ogl_debug_s2d_layer(ogl_unet* h, int kind, const float* src_dev, int cin_s,
     S2dHost hs;
     if (build_s2d_host(w3.data(), b3.data(), cin_s, wt_host, bt_host, cin_b, &hs)) return 1;
     const size_t hw = static_cast<size_t>(height) * width;
-    uint8_t* d_w = nullptr;
+    uint8_t *d_w = nullptr, *d_w2 = nullptr;
     float* d_bt = nullptr;
     __nv_bfloat16 *d_s = nullptr, *d_b = nullptr, *d_o = nullptr, *d_p = nullptr;
     int rc = 1;
     do {
         if (cudaMalloc(&d_w, hs.wblob.size()) != cudaSuccess) break;
+        if (cudaMalloc(&d_w2, hs.wblob_pair.size()) != cudaSuccess) break;
         if (cudaMalloc(&d_bt, hs.btab.size() * 4) != cudaSuccess) break;
         if (cudaMalloc(&d_s, n * cin_s * hw * 2) != cudaSuccess) break;
         if (cin_b && cudaMalloc(&d_b, n * cin_b * hw / 4 * 2) != cudaSuccess) break;
         if (cudaMalloc(&d_o, n * 32 * hw * 2) != cudaSuccess) break;
         if (kind == EPI_RELU_POOL && cudaMalloc(&d_p, n * 32 * hw / 4 * 2) != cudaSuccess) break;
         cudaMemcpyAsync(d_w, hs.wblob.data(), hs.wblob.size(), cudaMemcpyHostToDevice, stream);
+        cudaMemcpyAsync(d_w2, hs.wblob_pair.data(), hs.wblob_pair.size(), cudaMemcpyHostToDevice,
+                        stream);
         cudaMemcpyAsync(d_bt, hs.btab.data(), hs.btab.size() * 4, cudaMemcpyHostToDevice, stream);
         cudaStreamSynchronize(stream);
         S2dLayer L;
         L.wblob = d_w;
+        L.wblob2 = d_w2;
         L.wbytes = static_cast<uint32_t>(hs.wblob.size());
         L.n_stages = hs.n_stages;
         for (int i = 0; i < kS2dMaxStages; ++i) {
@@ -860,7 +865,8 @@ int ogl_debug_s2d_layer(ogl_unet* h, int kind, const float* src_dev, int cin_s,
         if (launch_nchw_to_c8(src_dev, d_s, n, cin_s, height, width, stream, true)) break;
         if (cin_b && launch_nchw_to_c8(below_dev, d_b, n, cin_b, height / 2, width / 2, stream))
             break;
-        if (launch_s2d_tc(L, d_s, d_b, n, height, width, d_o, d_p, nullptr, h->num_sms, stream))
+        if (launch_s2d_tc(L, d_s, d_b, n, height, width, d_o, d_p, nullptr, h->num_sms, stream,
+                          h->cta_group))
             break;
         if (launch_c8_to_nchw(d_o, out_dev, n, 32, height, width, stream, true)) break;
         if (kind == EPI_RELU_POOL && out_pool_dev &&
@@ -875,6 +881,7 @@ int ogl_debug_s2d_layer(ogl_unet* h, int kind, const float* src_dev, int cin_s,
     } while (0);
     if (rc && g_err.empty()) fail("ogl_debug_s2d_layer: allocation or launch failed");
     cudaFree(d_w);
+    cudaFree(d_w2);
     cudaFree(d_bt);
     cudaFree(d_s);
     cudaFree(d_b);

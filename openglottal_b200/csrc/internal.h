@@ -80,6 +80,7 @@ struct S2dOp {        // one tcgen05.mma of the per-tile program, as the host pa
 constexpr int kS2dMaxStages = 8;
 struct S2dLayer {
     uint8_t* wblob = nullptr;  // device: B tiles in op order
+    uint8_t* wblob2 = nullptr; // device: the same for a CTA pair (rank 0's column halves, then rank 1's)
     uint32_t wbytes = 0;
     int n_stages = 0;          // activation stages (TMA boxes) per tile
     int stage_src[kS2dMaxStages] = {0};     // 0: S2D source, 1: plain half-resolution source
@@ -90,7 +91,7 @@ struct S2dLayer {
     int epi = EPI_RELU;        // EPI_RELU / EPI_RELU_POOL / EPI_HEAD
 };
 struct S2dHost {               // host-side result of build_s2d_host, uploaded by the caller
-    std::vector<uint8_t> wblob;
+    std::vector<uint8_t> wblob, wblob_pair;
     std::vector<S2dOp> ops;
     int n_stages = 0;
     int stage_src[kS2dMaxStages] = {0}, stage_plane0[kS2dMaxStages] = {0},
@@ -105,7 +106,7 @@ int s2d_tc_init();
 // src_s2d: [B][cin_s/8][4][H/2][W/2][8]; below: [B][cin_b/8][H/2][W/2][8] or null. H, W = full res.
 int launch_s2d_tc(const S2dLayer& L, const __nv_bfloat16* src_s2d, const __nv_bfloat16* below,
                   int B, int H, int W, __nv_bfloat16* out_s2d, __nv_bfloat16* out_pool,
-                  const HeadParams* head, int num_sms, cudaStream_t stream);
+                  const HeadParams* head, int num_sms, cudaStream_t stream, int cta_group = 1);
 // cuTensorMapEncodeTiled for a bf16 tensor (conv_tc.cu owns the driver entry point)
 int encode_bf16_map(void* tensor_map, const void* base, int rank, const uint64_t* dims,
                     const uint64_t* strides_bytes, const uint32_t* box);

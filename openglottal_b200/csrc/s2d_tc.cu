@@ -158,15 +158,22 @@ __device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
     return *reinterpret_cast<uint32_t*>(&r);
 }
 
-template <int EPI>
+// CG = 2: the two CTAs of a cluster take neighbouring tiles and run every MMA as one 256-row
+// tcgen05.mma.cta_group::2; each CTA keeps only HALF of every weight block resident (columns
+// [r N/2, (r+1) N/2) of each op for cluster rank r), which frees shared memory for a deeper
+// activation ring (6 instead of 3 stages beside the composed transposed conv) and halves the
+// B-operand shared-memory reads.
+template <int EPI, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmB,
               const S2dParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t smem_base = (raw + 127u) & ~127u;
+    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+    const uint32_t wbytes = p.wbytes / CG;                            // resident in this CTA
     const uint32_t w_s = smem_base;                                   // resident weights
-    const uint32_t a_ring = w_s + ((p.wbytes + 127u) & ~127u);        // activation stages
+    const uint32_t a_ring = w_s + ((wbytes + 127u) & ~127u);          // activation stages
     const uint32_t btab_s = a_ring + static_cast<uint32_t>(p.nslots) * kSlot;
     const uint32_t bar_base = btab_s + 9u * 32u * 4u;
     const uint32_t w_full = bar_base;
@@ -175,12 +182,19 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
     const uint32_t acc_full = a_empty + 8u * p.nslots;
     const uint32_t acc_empty = acc_full + 8u * kAccBufs;
     const uint32_t tmem_slot = acc_empty + 8u * kAccBufs;
+    const uint32_t w_peer = tmem_slot + 16u;   // leader: the peer's weights are resident (CG = 2)
     uint8_t* gen = smem_raw - raw;  // generic pointer = gen + shared address
     float* btab_sp = reinterpret_cast<float*>(gen + btab_s);
     volatile uint32_t* tmem_slot_p = reinterpret_cast<volatile uint32_t*>(gen + tmem_slot);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    // tiles of this CTA: CG = 1: blockIdx.x, + gridDim.x, ...; CG = 2: cluster c takes the tile
+    // pairs c, c + clusters, ... and rank r the r-th tile of each pair (the last pair may lack one)
+    const int unit0 = CG == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int unit_step = CG == 2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+    const int num_units = CG == 2 ? (p.num_tiles + 1) >> 1 : p.num_tiles;
+    auto tile_of = [&](int unit) { return CG == 2 ? 2 * unit + static_cast<int>(rank) : unit; };
 
     // ---------------------------------------------------------------- setup
     for (int i = threadIdx.x; i < 9 * 32; i += kThreads) btab_sp[i] = p.btab[i];
@@ -188,19 +202,24 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
         tma_prefetch_desc(&tmS);
         tma_prefetch_desc(&tmB);
         mbar_init(w_full, 1);
+        mbar_init(w_peer, 1);
         for (int i = 0; i < p.nslots; ++i) {
             mbar_init(a_full + 8u * i, 1);
             mbar_init(a_empty + 8u * i, 1);
         }
         for (int i = 0; i < kAccBufs; ++i) {
             mbar_init(acc_full + 8u * i, 1);
-            mbar_init(acc_empty + 8u * i, 128);
+            mbar_init(acc_empty + 8u * i, 128 * CG);   // CG = 2: the epilogues of both CTAs
         }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    if (warp == 2) {
+        if (CG == 2) tmem_alloc_pair(tmem_slot, 512);
+        else tmem_alloc(tmem_slot, 512);
+    }
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();  // the peer's barriers exist before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_p;
 
@@ -208,33 +227,55 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
         // ================================================ activation producer
         if (lane == 0) {
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (int unit = unit0; unit < num_units; unit += unit_step) {
+                int tile = tile_of(unit);
+                if (tile >= p.num_tiles) tile = p.num_tiles - 1;   // tail of the last pair: a duplicate
                 const Tile t = decode_tile(p, tile);
                 for (int s = 0; s < p.n_stages; ++s, ++it) {
                     const uint32_t slot = it % p.nslots;
                     const uint32_t ph = (it / p.nslots) & 1u;
                     mbar_wait(a_empty + 8u * slot, ph ^ 1u);
-                    mbar_arrive_expect_tx(a_full + 8u * slot, kSlot);
                     const uint32_t dst = a_ring + slot * kSlot;
-                    if (p.stage_src[s] == 0)
-                        tma_load_5d(dst, &tmS, a_full + 8u * slot, (t.x0 - 1) * 8, t.y0 - 1, 0,
-                                    p.stage_plane0[s], t.n);
-                    else
-                        tma_load_4d(dst, &tmB, a_full + 8u * slot, (t.x0 - 1) * 8, t.y0 - 1,
-                                    p.stage_plane0[s], t.n);
+                    if (CG == 1) {
+                        const uint32_t full = a_full + 8u * slot;
+                        mbar_arrive_expect_tx(full, kSlot);
+                        if (p.stage_src[s] == 0)
+                            tma_load_5d(dst, &tmS, full, (t.x0 - 1) * 8, t.y0 - 1, 0,
+                                        p.stage_plane0[s], t.n);
+                        else
+                            tma_load_4d(dst, &tmB, full, (t.x0 - 1) * 8, t.y0 - 1,
+                                        p.stage_plane0[s], t.n);
+                    } else {
+                        // the leader's barrier counts the bytes of both CTAs
+                        if (rank == 0) mbar_arrive_expect_tx(a_full + 8u * slot, 2u * kSlot);
+                        const uint32_t full = map_to_cta(a_full + 8u * slot, 0);
+                        if (p.stage_src[s] == 0)
+                            tma_load_5d_pair(dst, &tmS, full, (t.x0 - 1) * 8, t.y0 - 1, 0,
+                                             p.stage_plane0[s], t.n);
+                        else
+                            tma_load_4d_pair(dst, &tmB, full, (t.x0 - 1) * 8, t.y0 - 1,
+                                             p.stage_plane0[s], t.n);
+                    }
                 }
             }
         }
     } else if (warp == 3) {
         // ================================================== weights, once per CTA
+        // (CG = 2: the blob holds rank 0's halves, then rank 1's)
         if (lane == 0) {
-            mbar_arrive_expect_tx(w_full, p.wbytes);
-            for (uint32_t off = 0; off < p.wbytes; off += kWChunk) {
-                const uint32_t n = p.wbytes - off < kWChunk ? p.wbytes - off : kWChunk;
-                bulk_load(w_s + off, p.wblob + off, n, w_full);
+            const uint8_t* src = p.wblob + static_cast<size_t>(rank) * wbytes;
+            mbar_arrive_expect_tx(w_full, wbytes);
+            for (uint32_t off = 0; off < wbytes; off += kWChunk) {
+                const uint32_t n = wbytes - off < kWChunk ? wbytes - off : kWChunk;
+                bulk_load(w_s + off, src + off, n, w_full);
+            }
+            if (CG == 2 && rank == 1) {
+                // tell the leader that this CTA's weights are resident too
+                mbar_wait(w_full, 0);
+                mbar_arrive_cluster(map_to_cta(w_peer, 0));
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 1 && rank == 0) {
         // ========================================================= MMA issuer
         // The whole warp walks the loops (all values warp-uniform); one elected lane issues.
         // descriptor halves that never change: A (two LBOs: S2D stage / plain stage), B
@@ -243,12 +284,23 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
         constexpr uint32_t a_lbo_plain = (static_cast<uint32_t>(kPlane) >> 4) << 16;
         constexpr uint64_t b_hi = static_cast<uint64_t>((128u >> 4) | (1u << 14)) << 32;
         const uint32_t w_lo = w_s >> 4;
+        // CG = 2: every B block is half as wide in this CTA, so offsets, slab sizes and LBO halve
+        auto mma = [](uint32_t d, uint64_t a, uint64_t b, int n, uint32_t acc) {
+            if (CG == 2) umma_bf16_pair(d, a, b, make_idesc_bf16_pair(n), acc);
+            else umma_bf16(d, a, b, make_idesc_bf16(n), acc);
+        };
+        auto commit = [](uint32_t bar) {
+            if (CG == 2) umma_commit_pair(bar);
+            else umma_commit(bar);
+        };
         mbar_wait(w_full, 0);
+        if (CG == 2) mbar_wait_cluster(w_peer, 0);
         uint32_t ita = 0, li = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++li) {
+        for (int unit = unit0; unit < num_units; unit += unit_step, ++li) {
             const uint32_t buf = li % kAccBufs;
             const uint32_t aph = (li / kAccBufs) & 1u;
-            mbar_wait(acc_empty + 8u * buf, aph ^ 1u);
+            if (CG == 2) mbar_wait_cluster(acc_empty + 8u * buf, aph ^ 1u);
+            else mbar_wait(acc_empty + 8u * buf, aph ^ 1u);
             tc_fence_after();
             const uint32_t d0 = tmem_base + buf * 128u;
             for (int s = 0; s < p.n_s2d; ++s, ++ita) {
@@ -257,7 +309,7 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
                 tc_fence_after();
                 const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) |
                                     (((a_ring + slot * kSlot) >> 4) | a_lbo_s2d);
-                const uint64_t bd = b_hi | (w_lo + static_cast<uint32_t>(s) * kS2dSlabUnits);
+                const uint64_t bd = b_hi | (w_lo + static_cast<uint32_t>(s) * (kS2dSlabUnits / CG));
                 const uint32_t first = s != 0 ? 1u : 0u;
                 const bool last = (s == p.n_s2d - 1) && !p.has_below;
                 if (elect_one()) {
@@ -266,12 +318,12 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
                         if (p.dbg & 1) break;
                         const OpShape sh = s2d_shape(c);
                         // LBO of B = 16 * N bytes -> (N) in the descriptor's bits 16..29
-                        umma_bf16(d0 + sh.dcol, ad + sh.a_off,
-                                  bd + (s2d_boff(c) + (static_cast<uint32_t>(sh.n) << 16)),
-                                  make_idesc_bf16(sh.n), c ? 1u : first);
+                        mma(d0 + sh.dcol, ad + sh.a_off,
+                            bd + (s2d_boff(c) / CG + (static_cast<uint32_t>(sh.n / CG) << 16)), sh.n,
+                            c ? 1u : first);
                     }
-                    umma_commit(a_empty + 8u * slot);
-                    if (last) umma_commit(acc_full + 8u * buf);
+                    commit(a_empty + 8u * slot);
+                    if (last) commit(acc_full + 8u * buf);
                 }
                 __syncwarp();
             }
@@ -282,7 +334,7 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
                 const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) |
                                     (((a_ring + slot * kSlot) >> 4) | a_lbo_plain);
                 const uint64_t bd =
-                    b_hi | (w_lo + static_cast<uint32_t>(p.n_s2d) * kS2dSlabUnits);
+                    b_hi | (w_lo + static_cast<uint32_t>(p.n_s2d) * (kS2dSlabUnits / CG));
                 if (elect_one()) {
 #pragma unroll
                     for (int k16 = 0; k16 < 4; ++k16) {
@@ -290,14 +342,14 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
                         for (int i = 0; i < 9; ++i) {
                             if (p.dbg & 1) break;
                             const OpShape sh = below_shape(i);
-                            umma_bf16(d0 + sh.dcol, ad + (2 * k16 * (kPlane / 16) + sh.a_off),
-                                      bd + (k16 * kBelowSlabUnits + below_boff(i) +
-                                            (static_cast<uint32_t>(sh.n) << 16)),
-                                      make_idesc_bf16(sh.n), 1u);
+                            mma(d0 + sh.dcol, ad + (2 * k16 * (kPlane / 16) + sh.a_off),
+                                bd + ((k16 * kBelowSlabUnits + below_boff(i)) / CG +
+                                      (static_cast<uint32_t>(sh.n / CG) << 16)),
+                                sh.n, 1u);
                         }
                     }
-                    umma_commit(a_empty + 8u * slot);
-                    umma_commit(acc_full + 8u * buf);
+                    commit(a_empty + 8u * slot);
+                    commit(acc_full + 8u * buf);
                 }
                 __syncwarp();
                 ++ita;
@@ -312,13 +364,15 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
         const int H = 2 * p.H2, W = 2 * p.W2;
         const size_t plane = static_cast<size_t>(p.H2) * p.W2 * 8;  // one phase of one 8-ch group
         uint32_t li = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++li) {
+        for (int unit = unit0; unit < num_units; unit += unit_step, ++li) {
             if (static_cast<int>(li & 1u) != grp) continue;
             const uint32_t buf = li % kAccBufs;
             const uint32_t aph = (li / kAccBufs) & 1u;
-            const Tile t = decode_tile(p, tile);
+            const int tile = tile_of(unit);
+            const bool in_range = tile < p.num_tiles;   // false only for the tail of the last pair
+            const Tile t = decode_tile(p, in_range ? tile : p.num_tiles - 1);
             const int Y = t.y0 + py, X = t.x0 + px;
-            const bool valid = Y < p.H2 && X < p.W2 && !(p.dbg & 2);
+            const bool valid = in_range && Y < p.H2 && X < p.W2 && !(p.dbg & 2);
             mbar_wait(acc_full + 8u * buf, aph);
             tc_fence_after();
             const uint32_t tcol = tmem_base + lane_sel + buf * 128u;
@@ -410,16 +464,19 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
                 if (lane == 0 && p.area && cnt) atomicAdd(p.area + t.n, cnt);
             }
             tc_fence_before();
-            mbar_arrive(acc_empty + 8u * buf);
+            if (CG == 2) mbar_arrive_cluster(map_to_cta(acc_empty + 8u * buf, 0));
+            else mbar_arrive(acc_empty + 8u * buf);
         }
     }
 
     // ------------------------------------------------------------- teardown
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();  // neither CTA leaves while the pair may still touch it
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        if (CG == 2) tmem_dealloc_pair(tmem_base, 512);
+        else tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -443,6 +500,7 @@ int build_s2d_host(const float* w3, const float* b3, int cin_s, const float* wt,
     out->wblob.clear();
     out->ops.clear();
     int n_stages = 0;
+    std::vector<uint8_t> pair_half[2];
 
     // One MMA: its shape comes from the table the kernel unrolls (s2d_shape / below_shape); the
     // B block [2][N][8] holds, for column n = (phase - first phase) * 32 + cout, the weight
@@ -463,6 +521,22 @@ int build_s2d_host(const float* w3, const float* b3, int cin_s, const float* wt,
                         v = weight(kh * 8 + e, pp >> 1, pp & 1, c);
                     B[(static_cast<size_t>(kh) * N + n) * 8 + e] = bf16_bits(v);
                 }
+        // CTA-pair form: rank r keeps columns [r N/2, (r+1) N/2) of this op as [2][N/2][8], at half
+        // the offset inside its own half of the blob
+        {
+            const int nh = N / 2;
+            for (int r = 0; r < 2; ++r) {
+                std::vector<uint8_t>& dstv = pair_half[r];
+                const size_t o = dstv.size();
+                dstv.resize(o + static_cast<size_t>(nh) * 32);
+                uint16_t* P = reinterpret_cast<uint16_t*>(dstv.data() + o);
+                for (int kh = 0; kh < 2; ++kh)
+                    for (int n = 0; n < nh; ++n)
+                        for (int e = 0; e < 8; ++e)
+                            P[(static_cast<size_t>(kh) * nh + n) * 8 + e] =
+                                B[(static_cast<size_t>(kh) * N + r * nh + n) * 8 + e];
+            }
+        }
         S2dOp op;
         op.w0 = (static_cast<uint32_t>(sh.a_off) + a_extra) | (static_cast<uint32_t>(sh.dcol) << 16) |
                 (static_cast<uint32_t>(src) << 24) | ((out->ops.empty() ? 0u : 1u) << 25);
@@ -528,6 +602,8 @@ int build_s2d_host(const float* w3, const float* b3, int cin_s, const float* wt,
         ++n_stages;
     }
     out->n_stages = n_stages;
+    out->wblob_pair = pair_half[0];
+    out->wblob_pair.insert(out->wblob_pair.end(), pair_half[1].begin(), pair_half[1].end());
     // ---- bias per (row class, column class): the transposed conv's bias reaches an output
     // pixel only through the taps that fall inside the image (zero padding of `up`)
     out->btab.assign(9 * 32, 0.f);
@@ -548,19 +624,47 @@ int build_s2d_host(const float* w3, const float* b3, int cin_s, const float* wt,
     return 0;
 }
 
-int s2d_tc_init() {
-    OGL_CUDA(cudaFuncSetAttribute(s2d_tc_kernel<EPI_RELU>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    OGL_CUDA(cudaFuncSetAttribute(s2d_tc_kernel<EPI_RELU_POOL>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    OGL_CUDA(cudaFuncSetAttribute(s2d_tc_kernel<EPI_HEAD>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+namespace {
+template <int EPI>
+int set_attr() {
+    OGL_CUDA(cudaFuncSetAttribute(s2d_tc_kernel<EPI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  kMaxSmem));
+    OGL_CUDA(cudaFuncSetAttribute(s2d_tc_kernel<EPI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  kMaxSmem));
     return 0;
+}
+template <int EPI>
+int launch_kernel(bool pair, int grid, size_t smem, cudaStream_t stream, const CUtensorMap& tmS,
+                  const CUtensorMap& tmB, const S2dParams& p) {
+    if (!pair) {
+        s2d_tc_kernel<EPI, 1><<<grid, kThreads, smem, stream>>>(tmS, tmB, p);
+        OGL_CUDA(cudaGetLastError());
+        return 0;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    OGL_CUDA(cudaLaunchKernelEx(&cfg, s2d_tc_kernel<EPI, 2>, tmS, tmB, p));
+    return 0;
+}
+}  // namespace
+
+int s2d_tc_init() {
+    return set_attr<EPI_RELU>() || set_attr<EPI_RELU_POOL>() || set_attr<EPI_HEAD>();
 }
 
 int launch_s2d_tc(const S2dLayer& L, const __nv_bfloat16* src_s2d, const __nv_bfloat16* below,
                   int B, int H, int W, __nv_bfloat16* out_s2d, __nv_bfloat16* out_pool,
-                  const HeadParams* head, int num_sms, cudaStream_t stream) {
+                  const HeadParams* head, int num_sms, cudaStream_t stream, int cta_group) {
     if (H < 2 || W < 2 || H % 2 || W % 2) return fail("s2d layer needs even, non-empty H and W");
     if ((W / 2) % 8) return fail("s2d layer needs W to be a multiple of 16");
     if (!src_s2d || L.n_stages < 1 || !L.wblob || !L.btab)
@@ -572,7 +676,6 @@ int launch_s2d_tc(const S2dLayer& L, const __nv_bfloat16* src_s2d, const __nv_bf
 
     S2dParams p;
     memset(&p, 0, sizeof p);
-    p.wblob = L.wblob;
     p.wbytes = L.wbytes;
     p.n_stages = L.n_stages;
     p.has_below = L.stage_src[L.n_stages - 1] == 1 ? 1 : 0;
@@ -613,8 +716,16 @@ int launch_s2d_tc(const S2dLayer& L, const __nv_bfloat16* src_s2d, const __nv_bf
     static const int dbg_env = getenv("OGL_DBG") ? atoi(getenv("OGL_DBG")) : 0;
     p.dbg = dbg_env;
 
-    const size_t fixed = 128 + ((L.wbytes + 127u) & ~127u) + 9 * 32 * 4 + 8 +
-                         16 * kAccBufs + 16 + 64;
+    // CTA pairs. cta_group 2: for the layer with the composed transposed conv, whose 152 KB of
+    // weights leave one CTA only 3 activation stages (measured 1.57 -> 1.12 ms; the HBM-bound
+    // downs.0.net.3 is slower paired, 0.85 -> 1.05 ms, and ups.7.net.3 unchanged), when there
+    // is a tile per SM. cta_group 3 (unit tests): whenever there are two tiles.
+    const bool pair = cta_group >= 2 && L.wblob2 && num_sms >= 2 &&
+                      (cta_group == 3 ? p.num_tiles >= 2 : (p.num_tiles >= num_sms && L.cin_b > 0));
+    p.wblob = pair ? L.wblob2 : L.wblob;
+    const size_t wres = L.wbytes / (pair ? 2 : 1);
+    const size_t fixed = 128 + ((wres + 127u) & ~static_cast<size_t>(127)) + 9 * 32 * 4 + 8 +
+                         16 * kAccBufs + 16 + 8 + 64;
     int nslots = 6;
     static const int ns_env = getenv("OGL_S2D_SLOTS") ? atoi(getenv("OGL_S2D_SLOTS")) : 0;
     if (ns_env > 0) nslots = ns_env;
@@ -643,17 +754,12 @@ int launch_s2d_tc(const S2dLayer& L, const __nv_bfloat16* src_s2d, const __nv_bf
     } else {
         tmB = tmS;
     }
-    const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-    if (L.epi == EPI_RELU)
-        s2d_tc_kernel<EPI_RELU><<<grid, kThreads, smem, stream>>>(tmS, tmB, p);
-    else if (L.epi == EPI_RELU_POOL)
-        s2d_tc_kernel<EPI_RELU_POOL><<<grid, kThreads, smem, stream>>>(tmS, tmB, p);
-    else if (L.epi == EPI_HEAD)
-        s2d_tc_kernel<EPI_HEAD><<<grid, kThreads, smem, stream>>>(tmS, tmB, p);
-    else
-        return fail("s2d layer: unknown epilogue");
-    OGL_CUDA(cudaGetLastError());
-    return 0;
+    const int grid = pair ? (num_sms & ~1) : (p.num_tiles < num_sms ? p.num_tiles : num_sms);
+    if (L.epi == EPI_RELU) return launch_kernel<EPI_RELU>(pair, grid, smem, stream, tmS, tmB, p);
+    if (L.epi == EPI_RELU_POOL)
+        return launch_kernel<EPI_RELU_POOL>(pair, grid, smem, stream, tmS, tmB, p);
+    if (L.epi == EPI_HEAD) return launch_kernel<EPI_HEAD>(pair, grid, smem, stream, tmS, tmB, p);
+    return fail("s2d layer: unknown epilogue");
 }
 
 }  // namespace ogl

@@ -194,3 +194,34 @@ def test_conv3x3_cta_pairs_bit_identical(lib, handle, kind, c0, c1, cout, n, hgt
     assert torch.equal(out1, out2)
     if kind == 1:
         assert torch.equal(pool1, pool2)
+
+
+@pytest.mark.parametrize("kind,composed,n,hgt,wid", [(0, False, 3, 32, 48), (1, False, 5, 64, 64),
+                                                     (0, True, 3, 48, 80), (1, False, 2, 256, 256),
+                                                     (0, True, 2, 256, 256), (0, False, 1, 16, 16)])
+def test_s2d_cta_pairs_bit_identical(lib, handle, kind, composed, n, hgt, wid):
+    """Space-to-depth layers on CTA pairs (each CTA keeps half of every weight block): same bits
+    as the one-CTA form, odd tile counts included (the last pair lacks a tile)."""
+    from openglottal_b200 import _native
+
+    g = torch.Generator().manual_seed(hgt * 3 + wid + n)
+    x = _bf(torch.randn(n, 32, hgt, wid, generator=g))
+    cin3 = 64 if composed else 32
+    w3 = _bf(torch.randn(32, cin3, 3, 3, generator=g) * (2.0 / (cin3 * 9)) ** 0.5)
+    b3 = torch.randn(32, generator=g) * 0.1
+    below = wt = bt = None
+    if composed:
+        below = _bf(torch.randn(n, 64, hgt // 2, wid // 2, generator=g))
+        wt = _bf(torch.randn(64, 32, 2, 2, generator=g) * (1.0 / 64) ** 0.5)
+        bt = torch.randn(32, generator=g) * 0.5
+    try:
+        _native.check(lib.ogl_unet_set_cta_pairs(handle, 1))
+        out1, pool1 = _run_s2d(lib, handle, kind, x, below, w3, b3, wt, bt)
+        _native.check(lib.ogl_unet_set_cta_pairs(handle, 3))
+        out2, pool2 = _run_s2d(lib, handle, kind, x, below, w3, b3, wt, bt)
+    finally:
+        _native.check(lib.ogl_unet_set_cta_pairs(handle, 2))
+    assert not torch.isnan(out2).any()
+    assert torch.equal(out1, out2)
+    if kind == 1:
+        assert torch.equal(pool1, pool2)
