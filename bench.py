@@ -89,6 +89,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index = index
         self.samples: list[int] = []
+        self.power: list[float] = []
         self.reasons: set[str] = set()
         self.max_mhz = None
         self._halt = threading.Event()
@@ -118,6 +119,7 @@ class ClockSampler(threading.Thread):
         while not self._halt.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
                 mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
                 for bit, name in names.items():
                     if mask & bit:
@@ -133,7 +135,9 @@ class ClockSampler(threading.Thread):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
         s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz,
+        pw = sorted(self.power)
+        return {"sm_mhz": s[len(s) // 2], "sm_mhz_min": s[0], "sm_max_mhz": self.max_mhz,
+                "power_w": round(pw[len(pw) // 2], 1) if pw else None,
                 "reasons": sorted(self.reasons), "samples": len(s)}
 
 
@@ -324,10 +328,14 @@ def run_native(args) -> None:
         which = "measured"
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))   # kernels timed inside a long step
     achieved_tf = tc_flops / (tc_ms * 1e-3) / 1e12
+    # DRAM bytes per launch (read + write) of the same 20 launches from the newest committed
+    # `ncu --set full` capture (scripts/ncu_summary.py), scaled to this batch
     traffic = None
-    tr = ROOT / "profiles" / "traffic_r01.json"
-    if tr.exists():
-        traffic = json.loads(tr.read_text()).get("dram_bytes_per_launch_avg")
+    captures = sorted((ROOT / "profiles").glob("traffic_*.json"))
+    if captures:
+        traffic = json.loads(captures[-1].read_text()).get("dram_bytes_per_launch_avg_batch512")
+        if traffic is not None:
+            traffic *= BATCH / 512
     roofline = {
         "bound": "tensor",
         "kernel": f"conv_tc_kernel + s2d_tc_kernel ({nl - 1} tcgen05 launches/step: every conv3x3, "

@@ -33,13 +33,16 @@ frames = torch.randint(0, 256, (4 * batch, hgt, wid), dtype=torch.uint8, generat
 for i in range(3):
     model.run(frames[(i % 4) * batch:(i % 4 + 1) * batch])
 torch.cuda.synchronize()
+sampler = bench.ClockSampler(0)
+sampler.start()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
-for i in range(steps):
+for i in range(steps * 8):
     model.run(frames[(i % 4) * batch:(i % 4 + 1) * batch])
 e1.record()
 torch.cuda.synchronize()
-total = e0.elapsed_time(e1) / steps
+clocks = sampler.stop()
+total = e0.elapsed_time(e1) / (steps * 8)
 _native.check(lib.ogl_unet_set_profiling(model._handle, 1))
 buf = (C.c_float * 64)()
 cnt = C.c_int(0)
@@ -52,5 +55,5 @@ for i in range(steps):
 acc /= steps
 names = [lib.ogl_unet_launch_name(model._handle, i).decode() for i in range(cnt.value)]
 print(json.dumps({"tag": tag, "env": {k: v for k, v in os.environ.items() if k.startswith("OGL_")},
-                  "batch": batch, "ms_step": total, "fps": batch / total * 1e3,
+                  "batch": batch, "clocks": clocks, "ms_step": total, "fps": batch / total * 1e3,
                   "layers": dict(zip(names, [round(float(x), 4) for x in acc]))}))
