@@ -318,8 +318,10 @@ def run_native(args) -> None:
     mfl = module_flops(HGT, WID)
     fl = np.array([launch_flops(n_, mfl) for n_ in names]) * BATCH
     assert abs(fl.sum() / BATCH - sum(mfl.values())) < 1.0, "launch names do not cover the path"
-    tc_ms = float(layer_ms[1:].sum())
-    tc_flops = float(fl[1:].sum())
+    is_tc = np.array([n_ != "stem" for n_ in names])     # every launch but the CUDA-core stem
+    n_tc = int(is_tc.sum())
+    tc_ms = float(layer_ms[is_tc].sum())
+    tc_flops = float(fl[is_tc].sum())
     peaks = {}
     pk = ROOT / "MEASURED_PEAKS.json"
     which = "fallback"
@@ -338,11 +340,11 @@ def run_native(args) -> None:
             traffic *= BATCH / 512
     roofline = {
         "bound": "tensor",
-        "kernel": f"conv_tc_kernel + s2d_tc_kernel ({nl - 1} tcgen05 launches/step: every conv3x3, "
+        "kernel": f"conv_tc_kernel + s2d_tc_kernel ({n_tc} timed tcgen05 groups/step: every conv3x3, "
                   "ConvTranspose2d and the head; the Cin=1 stem is CUDA-core)",
         "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
         "peak_source": f"{which} bf16_tflops_sustained", "traffic": traffic,
-        "flops_per_launch_avg": tc_flops / (nl - 1), "ms_per_launch_avg": tc_ms / (nl - 1),
+        "flops_per_launch_avg": tc_flops / n_tc, "ms_per_launch_avg": tc_ms / n_tc,
         "tc_share_of_step": tc_ms / float(layer_ms.sum()),
     }
     layers = [{"layer": n_, "ms": float(m), "tflops": float(f / (m * 1e-3) / 1e12) if m > 0 else None}
