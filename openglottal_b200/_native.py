@@ -57,6 +57,7 @@ EXPORTS = [
     "ogl_unet_launch_name",
     "ogl_unet_set_schedule",
     "ogl_unet_set_cta_pairs",
+    "ogl_unet_set_fused_stem",
     "ogl_features_workspace_bytes",
     "ogl_features",
     "ogl_features_f64",
@@ -112,6 +113,8 @@ def load() -> C.CDLL:
     lib.ogl_unet_launch_count.argtypes = [vp]
     lib.ogl_unet_launch_name.restype = C.c_char_p
     lib.ogl_unet_launch_name.argtypes = [vp, i32]
+    lib.ogl_unet_set_fused_stem.restype = i32
+    lib.ogl_unet_set_fused_stem.argtypes = [vp, i32]
     lib.ogl_unet_set_cta_pairs.restype = i32
     lib.ogl_unet_set_cta_pairs.argtypes = [vp, i32]
     lib.ogl_unet_set_schedule.restype = i32

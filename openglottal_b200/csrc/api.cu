@@ -73,6 +73,10 @@ struct ogl_unet {
     // ups.6 (convT) composed into ups.7.net.0, ups.7.net.3 (+head)
     S2dLayer s2d_down, s2d_up0, s2d_up1;
     bool use_s2d = true;
+    // u8 input: compute the stem inside the downs.0.net.3 kernel (its output never touches HBM).
+    // Bit-identical; measured neutral (8 CUDA-core warps per SM cannot hide the FFMA latency the
+    // stand-alone stem kernel hides with 48), so the separate stem kernel stays the default.
+    bool fuse_stem = false;
     int cta_group = 2;  // 2: conv3x3 layers with N >= 64 run on CTA pairs (tcgen05 cta_group::2)
     // fp32 validation path
     F32Conv f_down[4][2], f_bott[2], f_up[4][2];
@@ -297,6 +301,7 @@ int ogl_unet_create(ogl_unet** out, int device) {
     ogl_unet* h = new ogl_unet();
     if (const char* e = getenv("OGL_S2D")) h->use_s2d = atoi(e) != 0;
     if (const char* e = getenv("OGL_CG")) h->cta_group = atoi(e);
+    if (const char* e = getenv("OGL_FUSE_STEM")) h->fuse_stem = atoi(e) != 0;
     h->device = device;
     h->num_sms = prop.multiProcessorCount;
     *out = h;
@@ -445,9 +450,12 @@ int ogl_unet_forward(ogl_unet* h, const void* frames_dev, int in_dtype, int n, i
         h->launch_names.clear();
         const bool s2d = h->use_s2d;
         mark(h, stream, nullptr);
-        if (launch_stem(frames_dev, in_dtype, h->stem, n, H, W, B(p.T[0]), s2d, stream))
-            return 1;
-        mark(h, stream, kDownC1[0]);
+        const bool fused_stem = s2d && h->fuse_stem && in_dtype == OGL_DTYPE_U8;
+        if (!fused_stem) {
+            if (launch_stem(frames_dev, in_dtype, h->stem, n, H, W, B(p.T[0]), s2d, stream))
+                return 1;
+            mark(h, stream, kDownC1[0]);
+        }
         for (int l = 0; l < 4; ++l) {
             const int hh = H >> l, ww = W >> l;
             if (l > 0) {
@@ -455,6 +463,14 @@ int ogl_unet_forward(ogl_unet* h, const void* frames_dev, int in_dtype, int n, i
                                    nullptr, h->num_sms, stream, h->cta_group))
                     return 1;
                 mark(h, stream, kDownC1[l]);
+            }
+            if (l == 0 && fused_stem) {
+                if (launch_s2d_tc(h->s2d_down, nullptr, nullptr, n, H, W, B(p.S[0]), P[0], nullptr,
+                                  h->num_sms, stream, h->cta_group,
+                                  static_cast<const uint8_t*>(frames_dev), &h->stem))
+                    return 1;
+                mark(h, stream, "stem+downs.0.net.3+pool");
+                continue;
             }
             if (l == 0 && s2d) {
                 if (launch_s2d_tc(h->s2d_down, B(p.T[0]), nullptr, n, H, W, B(p.S[0]), P[0],
@@ -597,6 +613,12 @@ const char* ogl_unet_launch_name(const ogl_unet* h, int index) {
 int ogl_unet_set_schedule(ogl_unet* h, int s2d_level0) {
     if (!h) return fail("ogl_unet_set_schedule: NULL handle");
     h->use_s2d = s2d_level0 != 0;
+    return 0;
+}
+
+int ogl_unet_set_fused_stem(ogl_unet* h, int enable) {
+    if (!h) return fail("ogl_unet_set_fused_stem: NULL handle");
+    h->fuse_stem = enable != 0;
     return 0;
 }
 

@@ -635,6 +635,11 @@ inline int taps_per_stage(const TcLayer& L) { return L.taps == 1 ? 1 : (L.N <= 6
 
 int encode_bf16_map(void* tensor_map, const void* base, int rank, const uint64_t* dims,
                     const uint64_t* strides_bytes, const uint32_t* box) {
+    return encode_map(tensor_map, base, rank, dims, strides_bytes, box, false);
+}
+
+int encode_map(void* tensor_map, const void* base, int rank, const uint64_t* dims,
+               const uint64_t* strides_bytes, const uint32_t* box, bool u8) {
     if (!g_encode) return fail("conv_tc_init() was not called");
     cuuint64_t d[5], st[4];
     cuuint32_t bx[5], es[5];
@@ -644,7 +649,8 @@ int encode_bf16_map(void* tensor_map, const void* base, int rank, const uint64_t
         es[i] = 1;
         if (i < rank - 1) st[i] = strides_bytes[i];
     }
-    CUresult r = g_encode(static_cast<CUtensorMap*>(tensor_map), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+    CUresult r = g_encode(static_cast<CUtensorMap*>(tensor_map),
+                          u8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
                           static_cast<cuuint32_t>(rank), const_cast<void*>(base), d, st, bx, es,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

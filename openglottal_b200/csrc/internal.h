@@ -60,6 +60,11 @@ int launch_conv_tc(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloa
                    int H, int W, __nv_bfloat16* out, __nv_bfloat16* out_pool,
                    const HeadParams* head, int num_sms, cudaStream_t stream, int cta_group = 1);
 
+// stem: u8 / f32 gray -> conv3x3(1->32)+bias+ReLU in fp32 -> C8-planar bf16
+struct StemWeights {  // passed by value: lives in the kernel-parameter constant bank
+    float w[32 * 9];
+    float b[32];
+};
 // ------------------------------------------------------------------ full-resolution level
 // The tensor-core convs at full resolution (Cout = 32) run on tensors stored "space-to-depth"
 // (S2D): [frame][C/8][phase = (y&1)*2 + (x&1)][H/2][W/2][8]. A GEMM row is a half-resolution
@@ -106,16 +111,16 @@ int s2d_tc_init();
 // src_s2d: [B][cin_s/8][4][H/2][W/2][8]; below: [B][cin_b/8][H/2][W/2][8] or null. H, W = full res.
 int launch_s2d_tc(const S2dLayer& L, const __nv_bfloat16* src_s2d, const __nv_bfloat16* below,
                   int B, int H, int W, __nv_bfloat16* out_s2d, __nv_bfloat16* out_pool,
-                  const HeadParams* head, int num_sms, cudaStream_t stream, int cta_group = 1);
+                  const HeadParams* head, int num_sms, cudaStream_t stream, int cta_group = 1,
+                  const uint8_t* stem_frames = nullptr, const StemWeights* stem = nullptr);
+// (stem_frames != null: downs.0.net.3 with the stem fused in -- the A operand is computed from
+//  the u8 frames [B][H][W] inside the kernel and src_s2d is not read)
 // cuTensorMapEncodeTiled for a bf16 tensor (conv_tc.cu owns the driver entry point)
 int encode_bf16_map(void* tensor_map, const void* base, int rank, const uint64_t* dims,
                     const uint64_t* strides_bytes, const uint32_t* box);
+int encode_map(void* tensor_map, const void* base, int rank, const uint64_t* dims,
+               const uint64_t* strides_bytes, const uint32_t* box, bool u8);
 
-// stem: u8 / f32 gray -> conv3x3(1->32)+bias+ReLU in fp32 -> C8-planar bf16
-struct StemWeights {  // passed by value: lives in the kernel-parameter constant bank
-    float w[32 * 9];
-    float b[32];
-};
 int launch_stem(const void* frames, int in_dtype, const StemWeights& sw, int B, int H, int W,
                 __nv_bfloat16* out, bool s2d, cudaStream_t stream);
 

@@ -109,7 +109,21 @@ constexpr int kBelowSlabUnits = below_boff(9);   // 1152 (18 KB)
 static_assert(kS2dSlabUnits == 2560 && kBelowSlabUnits == 1152, "weight block sizes");
 static_assert(s2d_shape(0).n == 128 && s2d_shape(0).dcol == 0, "op 0 must initialise all columns");
 
+constexpr int kStemThreads = 256;   // 8 warps computing the Cin = 1 stem into the A stages (STEM = 1)
+constexpr int kStagePxH = 2 * kHH + 2;                // u8 region of a tile: 38 rows x 22 bytes
+// ... loaded as a TMA box of 48 x 38 bytes starting 16 bytes left of the tile (TMA needs the
+// innermost coordinate to give a 16-byte aligned address: measured, scripts/microbench/
+// tma_u8_test.cu), so the region's first column sits at byte kU8Off of each row
+constexpr int kU8Row = 48;
+constexpr int kU8Off = 13;                            // (2 X0 - 3) - (2 X0 - 16)
+static_assert(kU8Off + 2 * kHW + 2 <= kU8Row, "u8 box too narrow");
+constexpr int kU8Bytes = kU8Row * kStagePxH;          // 1824
+constexpr int kU8Slot = 1920;                         // 128-byte aligned slots
+constexpr int kU8Slots = 4;
+
 struct S2dParams {
+    const uint8_t* frames;   // STEM = 1: u8 gray frames [B][2 H2][2 W2]
+    StemWeights stem;        // STEM = 1: folded stem weights already divided by 255, and bias
     const uint8_t* wblob;
     const float* btab;     // [3][3][32]: bias per (row class, column class), border pixels only
     float bias[32];        // bias of interior pixels (= btab[1][1]); constant-bank operands
@@ -163,8 +177,12 @@ __device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
 // [r N/2, (r+1) N/2) of each op for cluster rank r), which frees shared memory for a deeper
 // activation ring (6 instead of 3 stages beside the composed transposed conv) and halves the
 // B-operand shared-memory reads.
-template <int EPI, int CG>
-__global__ void __launch_bounds__(kThreads, 1)
+// STEM = 1 (downs.0.net.3): the A stages are not loaded by TMA but COMPUTED in place by four extra
+// warps from the u8 frame -- utils.py:235 (/255) + downs.0.net.0 (conv3x3 1->32, BN, ReLU) in fp32
+// on the CUDA cores, rounded to bf16 straight into the UMMA operand layout -- so the stem's
+// 4.19 MB-per-frame output tensor is never written to or read from HBM.
+template <int EPI, int CG, int STEM>
+__global__ void __launch_bounds__(kThreads + STEM * kStemThreads, 1)
 s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmB,
               const S2dParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -183,6 +201,10 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
     const uint32_t acc_empty = acc_full + 8u * kAccBufs;
     const uint32_t tmem_slot = acc_empty + 8u * kAccBufs;
     const uint32_t w_peer = tmem_slot + 16u;   // leader: the peer's weights are resident (CG = 2)
+    // STEM = 1: ring of u8 regions (one per tile, loaded by TMA ahead of the stem warps)
+    const uint32_t u8_full = w_peer + 16u;
+    const uint32_t u8_empty = u8_full + 8u * kU8Slots;
+    const uint32_t u8_s = (u8_empty + 8u * kU8Slots + 127u) & ~127u;
     uint8_t* gen = smem_raw - raw;  // generic pointer = gen + shared address
     float* btab_sp = reinterpret_cast<float*>(gen + btab_s);
     volatile uint32_t* tmem_slot_p = reinterpret_cast<volatile uint32_t*>(gen + tmem_slot);
@@ -197,14 +219,19 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
     auto tile_of = [&](int unit) { return CG == 2 ? 2 * unit + static_cast<int>(rank) : unit; };
 
     // ---------------------------------------------------------------- setup
-    for (int i = threadIdx.x; i < 9 * 32; i += kThreads) btab_sp[i] = p.btab[i];
+    for (int i = threadIdx.x; i < 9 * 32; i += kThreads + STEM * kStemThreads) btab_sp[i] = p.btab[i];
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmS);
         tma_prefetch_desc(&tmB);
         mbar_init(w_full, 1);
         mbar_init(w_peer, 1);
+        if (STEM)
+            for (int i = 0; i < kU8Slots; ++i) {
+                mbar_init(u8_full + 8u * i, 1);
+                mbar_init(u8_empty + 8u * i, kStemThreads);
+            }
         for (int i = 0; i < p.nslots; ++i) {
-            mbar_init(a_full + 8u * i, 1);
+            mbar_init(a_full + 8u * i, STEM ? kStemThreads : 1);
             mbar_init(a_empty + 8u * i, 1);
         }
         for (int i = 0; i < kAccBufs; ++i) {
@@ -223,7 +250,104 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_p;
 
-    if (warp == 0) {
+    if (STEM && warp >= kThreads / 32) {
+        // ====================================== stem: compute the A stages from the u8 frame
+        // A tile needs the stem output on 10 x 18 half-resolution positions x 4 phases, of which
+        // the outermost ring is read through one phase only: 34 x 18 full-resolution pixels.
+        // Per pixel and stage 16 channels = 144 FFMAs with constant-bank weights, bias, ReLU,
+        // bf16, two 16-byte stores into the operand layout.
+        const int st = threadIdx.x - kThreads;
+        const int W = 2 * p.W2, H = 2 * p.H2;
+        constexpr int kNeedH = 2 * kHH - 2, kNeedW = 2 * kHW - 2;   // 34 x 18
+        uint32_t it = 0, iu = 0;
+        for (int unit = unit0; unit < num_units; unit += unit_step, ++iu) {
+            const Tile t = decode_tile(p, unit);
+            const int gy0 = 2 * t.y0 - 3, gx0 = 2 * t.x0 - 3;   // frame coordinates of u8p[0][0]
+            const uint32_t us = iu % kU8Slots;
+            const uint8_t* u8p = gen + u8_s + us * kU8Slot;      // rows of kU8Row bytes (TMA box)
+            mbar_wait(u8_full + 8u * us, (iu / kU8Slots) & 1u);
+            // One work item = 3 horizontally adjacent pixels of one row (34 rows x 6 triples = 204
+            // items per tile, thread st takes item st): every weight fetched from the constant
+            // bank feeds 3 FFMAs, the 3x5 input window is read once.
+            constexpr int kItems = kNeedH * (kNeedW / 3);
+            static_assert(kNeedW % 3 == 0 && kItems <= kStemThreads, "stem work split");
+            const bool active = st < kItems;
+            const int ly = 1 + st / (kNeedW / 3), lx0 = 1 + 3 * (st % (kNeedW / 3));
+            const int gy = gy0 + 1 + ly;
+            float in[3][5];
+            uint32_t inside[3];   // all-ones inside the image, 0 outside (a mask, not a branch:
+                                  // the six accumulator chains of an item stay interleaved)
+            if (active) {
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                    for (int dx = 0; dx < 5; ++dx)
+                        in[dy][dx] = static_cast<float>(u8p[(ly + dy) * kU8Row + kU8Off + lx0 + dx]);
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const int gx = gx0 + 1 + lx0 + q;
+                    inside[q] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? 0xffffffffu : 0u;
+                }
+            }
+#pragma unroll   // `half` must be a compile-time constant: weights are constant-bank operands
+            for (int half = 0; half < 2; ++half, ++it) {
+                const uint32_t slot = it % p.nslots;
+                mbar_wait(a_empty + 8u * slot, ((it / p.nslots) & 1u) ^ 1u);
+                uint8_t* stage = gen + a_ring + slot * kSlot;
+                if (active && !(p.dbg & 64)) {
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {
+                        uint32_t pk[3][4];
+#pragma unroll
+                        for (int c2 = 0; c2 < 4; ++c2) {
+                            float a[3][2];
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int co = half * 16 + g * 8 + c2 * 2 + e;
+#pragma unroll
+                                for (int q = 0; q < 3; ++q) a[q][e] = p.stem.b[co];
+#pragma unroll
+                                for (int k = 0; k < 9; ++k) {
+                                    const float w = p.stem.w[co * 9 + k];
+#pragma unroll
+                                    for (int q = 0; q < 3; ++q)
+                                        a[q][e] = fmaf(in[k / 3][k % 3 + q], w, a[q][e]);
+                                }
+                            }
+#pragma unroll
+                            for (int q = 0; q < 3; ++q)   // zero outside the image: conv2's padding
+                                pk[q][c2] = pack_bf16x2(fmaxf(a[q][0], 0.f), fmaxf(a[q][1], 0.f)) & inside[q];
+                        }
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) {
+                            const int lx = lx0 + q;
+                            uint8_t* dst = stage + ((ly & 1) * 2 + (lx & 1)) * kPlane +
+                                           ((ly >> 1) * kHW + (lx >> 1)) * 16 + g * 4 * kPlane;
+                            *reinterpret_cast<uint4*>(dst) =
+                                make_uint4(pk[q][0], pk[q][1], pk[q][2], pk[q][3]);
+                        }
+                    }
+                }
+                if (!(p.dbg & 128)) fence_proxy_async();   // stores visible to the tensor core's reads
+                mbar_arrive(a_full + 8u * slot);
+            }
+            mbar_arrive(u8_empty + 8u * us);
+        }
+    } else if (warp == 0 && STEM) {
+        // ================================ u8 regions of the tiles, by TMA, ahead of the stem warps
+        // box = 48 x 38 bytes at (2 X0 - 16, 2 Y0 - 3): conv1's zero padding is the OOB fill
+        if (lane == 0) {
+            uint32_t iu = 0;
+            for (int unit = unit0; unit < num_units; unit += unit_step, ++iu) {
+                const Tile t = decode_tile(p, unit);
+                const uint32_t us = iu % kU8Slots;
+                mbar_wait(u8_empty + 8u * us, ((iu / kU8Slots) & 1u) ^ 1u);
+                mbar_arrive_expect_tx(u8_full + 8u * us, kU8Bytes);
+                tma_load_3d(u8_s + us * kU8Slot, &tmS, u8_full + 8u * us, 2 * t.x0 - 16, 2 * t.y0 - 3,
+                            t.n);
+            }
+        }
+    } else if (warp == 0 && !STEM) {
         // ================================================ activation producer
         if (lane == 0) {
             uint32_t it = 0;
@@ -627,17 +751,17 @@ int build_s2d_host(const float* w3, const float* b3, int cin_s, const float* wt,
 namespace {
 template <int EPI>
 int set_attr() {
-    OGL_CUDA(cudaFuncSetAttribute(s2d_tc_kernel<EPI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  kMaxSmem));
-    OGL_CUDA(cudaFuncSetAttribute(s2d_tc_kernel<EPI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  kMaxSmem));
+    OGL_CUDA(cudaFuncSetAttribute(s2d_tc_kernel<EPI, 1, 0>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    OGL_CUDA(cudaFuncSetAttribute(s2d_tc_kernel<EPI, 2, 0>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     return 0;
 }
 template <int EPI>
 int launch_kernel(bool pair, int grid, size_t smem, cudaStream_t stream, const CUtensorMap& tmS,
                   const CUtensorMap& tmB, const S2dParams& p) {
     if (!pair) {
-        s2d_tc_kernel<EPI, 1><<<grid, kThreads, smem, stream>>>(tmS, tmB, p);
+        s2d_tc_kernel<EPI, 1, 0><<<grid, kThreads, smem, stream>>>(tmS, tmB, p);
         OGL_CUDA(cudaGetLastError());
         return 0;
     }
@@ -653,21 +777,27 @@ int launch_kernel(bool pair, int grid, size_t smem, cudaStream_t stream, const C
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    OGL_CUDA(cudaLaunchKernelEx(&cfg, s2d_tc_kernel<EPI, 2>, tmS, tmB, p));
+    OGL_CUDA(cudaLaunchKernelEx(&cfg, s2d_tc_kernel<EPI, 2, 0>, tmS, tmB, p));
     return 0;
 }
 }  // namespace
 
 int s2d_tc_init() {
+    OGL_CUDA(cudaFuncSetAttribute(s2d_tc_kernel<EPI_RELU_POOL, 1, 1>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     return set_attr<EPI_RELU>() || set_attr<EPI_RELU_POOL>() || set_attr<EPI_HEAD>();
 }
 
 int launch_s2d_tc(const S2dLayer& L, const __nv_bfloat16* src_s2d, const __nv_bfloat16* below,
                   int B, int H, int W, __nv_bfloat16* out_s2d, __nv_bfloat16* out_pool,
-                  const HeadParams* head, int num_sms, cudaStream_t stream, int cta_group) {
+                  const HeadParams* head, int num_sms, cudaStream_t stream, int cta_group,
+                  const uint8_t* stem_frames, const StemWeights* stem) {
     if (H < 2 || W < 2 || H % 2 || W % 2) return fail("s2d layer needs even, non-empty H and W");
     if ((W / 2) % 8) return fail("s2d layer needs W to be a multiple of 16");
-    if (!src_s2d || L.n_stages < 1 || !L.wblob || !L.btab)
+    const bool fused_stem = stem_frames != nullptr;
+    if (fused_stem && (!stem || L.cin_s != 32 || L.cin_b != 0 || L.epi != EPI_RELU_POOL))
+        return fail("the fused stem feeds downs.0.net.3 only");
+    if ((!src_s2d && !fused_stem) || L.n_stages < 1 || !L.wblob || !L.btab)
         return fail("s2d layer is not built");
     if (L.cin_b > 0 && !below) return fail("s2d layer: the tensor below is missing");
     if (L.epi == EPI_RELU_POOL && !out_pool) return fail("pool epilogue needs out_pool");
@@ -688,6 +818,14 @@ int launch_s2d_tc(const S2dLayer& L, const __nv_bfloat16* src_s2d, const __nv_bf
         L.wbytes != (static_cast<uint32_t>(p.n_s2d) * kS2dSlabUnits +
                      (p.has_below ? 4u * kBelowSlabUnits : 0u)) * 16u)
         return fail("s2d layer: program does not match the kernel's compile-time tables");
+    if (fused_stem) {
+        // weights pre-scaled by 1/255 (in fp64, rounded once) so that the u8 values are used as
+        // they are: utils.py:235 folded into downs.0.net.0
+        p.frames = stem_frames;
+        for (int i = 0; i < 32 * 9; ++i)
+            p.stem.w[i] = static_cast<float>(static_cast<double>(stem->w[i]) / 255.0);
+        for (int i = 0; i < 32; ++i) p.stem.b[i] = stem->b[i];
+    }
     p.btab = L.btab;
     p.border_bias = L.cin_b > 0 ? 1 : 0;
     for (int i = 0; i < 32; ++i) p.bias[i] = L.bias_host[i];
@@ -720,12 +858,12 @@ int launch_s2d_tc(const S2dLayer& L, const __nv_bfloat16* src_s2d, const __nv_bf
     // weights leave one CTA only 3 activation stages (measured 1.57 -> 1.12 ms; the HBM-bound
     // downs.0.net.3 is slower paired, 0.85 -> 1.05 ms, and ups.7.net.3 unchanged), when there
     // is a tile per SM. cta_group 3 (unit tests): whenever there are two tiles.
-    const bool pair = cta_group >= 2 && L.wblob2 && num_sms >= 2 &&
+    const bool pair = !fused_stem && cta_group >= 2 && L.wblob2 && num_sms >= 2 &&
                       (cta_group == 3 ? p.num_tiles >= 2 : (p.num_tiles >= num_sms && L.cin_b > 0));
     p.wblob = pair ? L.wblob2 : L.wblob;
     const size_t wres = L.wbytes / (pair ? 2 : 1);
     const size_t fixed = 128 + ((wres + 127u) & ~static_cast<size_t>(127)) + 9 * 32 * 4 + 8 +
-                         16 * kAccBufs + 16 + 8 + 64;
+                         16 * kAccBufs + 16 + 16 + 16 * kU8Slots + 128 + kU8Slots * kU8Slot + 64;
     int nslots = 6;
     static const int ns_env = getenv("OGL_S2D_SLOTS") ? atoi(getenv("OGL_S2D_SLOTS")) : 0;
     if (ns_env > 0) nslots = ns_env;
@@ -735,6 +873,20 @@ int launch_s2d_tc(const S2dLayer& L, const __nv_bfloat16* src_s2d, const __nv_bf
     p.nslots = nslots;
 
     CUtensorMap tmS, tmB;
+    if (fused_stem) {
+        // u8 frames [B][H][W] as a 3-D tensor; box = the 38 rows x 48 bytes around a tile
+        const uint64_t dims[3] = {static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                                  static_cast<uint64_t>(B)};
+        const uint64_t str[2] = {static_cast<uint64_t>(W), static_cast<uint64_t>(W) * H};
+        const uint32_t box[3] = {kU8Row, kStagePxH, 1};
+        if (encode_map(&tmS, stem_frames, 3, dims, str, box, true)) return 1;
+        memset(&tmB, 0, sizeof tmB);
+        const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+        s2d_tc_kernel<EPI_RELU_POOL, 1, 1>
+            <<<grid, kThreads + kStemThreads, smem, stream>>>(tmS, tmB, p);
+        OGL_CUDA(cudaGetLastError());
+        return 0;
+    }
     {
         const uint64_t W2 = p.W2, H2 = p.H2;
         const uint64_t dims[5] = {W2 * 8, H2, 4, static_cast<uint64_t>(L.cin_s / 8),

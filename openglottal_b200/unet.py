@@ -71,6 +71,7 @@ class UNet(nn.Module):
         self.cta_pairs = int(os.environ.get("OGL_CG", "2"))   # 1: one CTA per tile; 2: CTA pairs
                                      # (tcgen05 cta_group::2) for the Cout >= 64 conv layers when
                                      # a launch has a tile per SM; 3: pairs whenever possible
+        self.fuse_stem = os.environ.get("OGL_FUSE_STEM", "0") != "0"   # stem inside downs.0.net.3 (neutral)
         self._handle = None
         self._handle_device = None
         self._packed_sig = None
@@ -200,6 +201,7 @@ class UNet(nn.Module):
         lib = _native.load()
         _native.check(lib.ogl_unet_set_schedule(self._handle, 1 if self.schedule == "s2d" else 0))
         _native.check(lib.ogl_unet_set_cta_pairs(self._handle, int(self.cta_pairs)))
+        _native.check(lib.ogl_unet_set_fused_stem(self._handle, 1 if self.fuse_stem else 0))
         frames = frames.contiguous()
         logits = torch.empty((n, hgt, wid), dtype=torch.float32, device=dev) if want_logits else None
         mask = torch.empty((n, hgt, wid), dtype=torch.uint8, device=dev) if want_mask else None

@@ -121,6 +121,21 @@ def test_cta_pairs_bit_identical(native_model):
     assert torch.equal(ref_big[1], got_big[1]) and torch.equal(ref_big[2], got_big[2])
 
 
+def test_fused_stem_bit_identical(native_model):
+    """The stem computed inside the downs.0.net.3 kernel (u8 input) equals the separate stem
+    kernel bit for bit -- same fp32 FMA order, same rounding point -- incl. partial tiles."""
+    for shape in ((5, 256, 256), (3, 48, 80), (2, 512, 256), (1, 16, 16)):
+        frames = torch.from_numpy(_clip(*shape)).cuda()
+        try:
+            native_model.fuse_stem = False
+            ref = native_model.run(frames, want_logits=True)
+            native_model.fuse_stem = True
+            got = native_model.run(frames, want_logits=True)
+        finally:
+            native_model.fuse_stem = False
+        assert all(torch.equal(a, b) for a, b in zip(ref, got)), shape
+
+
 def test_bf16_matches_reference_within_north_star(native_model, trained_sd):
     from oracle import unet_oracle as uo
     from openglottal_b200 import dice
