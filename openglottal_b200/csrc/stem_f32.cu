@@ -91,6 +91,29 @@ stem_kernel(const void* __restrict__ frames, int in_dtype, const __grid_constant
     }
 }
 
+// Weights of the u8 stem as channel pairs: wp[co/2][tap] = (w[co][tap], w[co+1][tap]) / 255 and
+// bp[co/2] = (b[co], b[co+1]), so that one packed FFMA2 (fma.rn.f32x2, two IEEE FMAs per
+// instruction with the pair taken from uniform registers) advances two output channels of a pixel
+// and its 64-bit result is exactly the bf16x2 the store packs. Bit-identical to scalar fmaf.
+struct StemPairs {
+    float2 wp[16 * 9];
+    float2 bp[16];
+};
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b,
+                                                   unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned long long dup2(float v) {
+    const unsigned long long u = __float_as_uint(v);
+    return u | (u << 32);
+}
+__device__ __forceinline__ unsigned long long as_u64(float2 v) {
+    return static_cast<unsigned long long>(__float_as_uint(v.x)) |
+           (static_cast<unsigned long long>(__float_as_uint(v.y)) << 32);
+}
+
 // u8 form (the hot path): one warp per image row, one thread per 4 consecutive pixels.
 // The three input rows arrive as one aligned 32-bit load each; the left/right neighbour bytes
 // come from the adjacent lanes by shuffle (warp-edge lanes load them). sw.w holds the folded
@@ -98,7 +121,7 @@ stem_kernel(const void* __restrict__ frames, int in_dtype, const __grid_constant
 // 1152 FFMAs (constant-bank weights) per 4 pixels; bias rides in as the first addend; ReLU is a
 // packed bf16x2 max after rounding; each channel group stores 64 contiguous bytes per thread.
 __global__ void __launch_bounds__(256)
-stem_u8_kernel(const uint8_t* __restrict__ frames, const __grid_constant__ StemWeights sw,
+stem_u8_kernel(const uint8_t* __restrict__ frames, const __grid_constant__ StemPairs sw,
                int rows_total, int H, int W, __nv_bfloat16* __restrict__ out, int s2d) {
     const int lane = threadIdx.x & 31;
     const int warps_per_grid = gridDim.x * (blockDim.x >> 5);
@@ -112,7 +135,7 @@ stem_u8_kernel(const uint8_t* __restrict__ frames, const __grid_constant__ StemW
         for (int q0 = 0; q0 < Q; q0 += 32) {
             const int xq = q0 + lane;
             const bool act = xq < Q;
-            float in[3][6];
+            unsigned long long in[3][6];   // every input value in both halves of a register pair
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy) {
                 const int yy = y + dy - 1;
@@ -125,12 +148,12 @@ stem_u8_kernel(const uint8_t* __restrict__ frames, const __grid_constant__ StemW
                 uint32_t lb = lw >> 24, rb = rw & 0xffu;
                 if (lane == 0) lb = (rowok && act && xq > 0) ? rp[4 * xq - 1] : 0u;
                 if (lane == 31 || xq + 1 >= Q) rb = (rowok && act && xq + 1 < Q) ? rp[4 * xq + 4] : 0u;
-                in[dy][0] = static_cast<float>(lb);
-                in[dy][1] = static_cast<float>(w & 0xffu);
-                in[dy][2] = static_cast<float>((w >> 8) & 0xffu);
-                in[dy][3] = static_cast<float>((w >> 16) & 0xffu);
-                in[dy][4] = static_cast<float>(w >> 24);
-                in[dy][5] = static_cast<float>(rb);
+                in[dy][0] = dup2(static_cast<float>(lb));
+                in[dy][1] = dup2(static_cast<float>(w & 0xffu));
+                in[dy][2] = dup2(static_cast<float>((w >> 8) & 0xffu));
+                in[dy][3] = dup2(static_cast<float>((w >> 16) & 0xffu));
+                in[dy][4] = dup2(static_cast<float>(w >> 24));
+                in[dy][5] = dup2(static_cast<float>(rb));
             }
             if (!act) continue;
             // s2d: even pixels (4xq, 4xq+2) are neighbours in phase (y&1, 0), odd ones in (y&1, 1)
@@ -141,25 +164,19 @@ stem_u8_kernel(const uint8_t* __restrict__ frames, const __grid_constant__ StemW
                 uint32_t pk[4][4];  // [pixel][channel pair]
 #pragma unroll
                 for (int c2 = 0; c2 < 4; ++c2) {
-                    float acc[2][4];
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int co = g * 8 + c2 * 2 + e;
-#pragma unroll
-                        for (int px = 0; px < 4; ++px) {
-                            float a = sw.b[co];
-#pragma unroll
-                            for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-                                for (int dx = 0; dx < 3; ++dx)
-                                    a = fmaf(in[dy][px + dx], sw.w[co * 9 + dy * 3 + dx], a);
-                            acc[e][px] = a;
-                        }
-                    }
+                    const int cp = g * 4 + c2;   // channel pair (2 cp, 2 cp + 1)
                     const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
                     for (int px = 0; px < 4; ++px) {
-                        __nv_bfloat162 h = __hmax2(__floats2bfloat162_rn(acc[0][px], acc[1][px]), zero);
+                        unsigned long long a = as_u64(sw.bp[cp]);
+#pragma unroll
+                        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                            for (int dx = 0; dx < 3; ++dx)
+                                a = fma2(in[dy][px + dx], as_u64(sw.wp[cp * 9 + dy * 3 + dx]), a);
+                        const float lo = __uint_as_float(static_cast<uint32_t>(a));
+                        const float hi = __uint_as_float(static_cast<uint32_t>(a >> 32));
+                        __nv_bfloat162 h = __hmax2(__floats2bfloat162_rn(lo, hi), zero);
                         pk[px][c2] = *reinterpret_cast<uint32_t*>(&h);
                     }
                 }
@@ -347,9 +364,14 @@ int launch_stem(const void* frames, int in_dtype, const StemWeights& sw, int B, 
     if (in_dtype == 0 && W % 4 == 0) {
         // hot path: weights pre-scaled by 1/255 (in fp64, rounded once) so the u8 values are
         // used directly; differs from fl(v/255)*w by ~1 ulp of fp32, far below bf16 rounding
-        StemWeights scaled = sw;
-        for (int i = 0; i < 32 * 9; ++i)
-            scaled.w[i] = static_cast<float>(static_cast<double>(sw.w[i]) / 255.0);
+        StemPairs scaled;
+        for (int cp = 0; cp < 16; ++cp) {
+            for (int k = 0; k < 9; ++k) {
+                scaled.wp[cp * 9 + k].x = static_cast<float>(static_cast<double>(sw.w[(2 * cp) * 9 + k]) / 255.0);
+                scaled.wp[cp * 9 + k].y = static_cast<float>(static_cast<double>(sw.w[(2 * cp + 1) * 9 + k]) / 255.0);
+            }
+            scaled.bp[cp] = make_float2(sw.b[2 * cp], sw.b[2 * cp + 1]);
+        }
         const int rows = B * H;
         int grid = (rows + 7) / 8;
         if (grid > 148 * 6) grid = 148 * 6;
