@@ -12,6 +12,7 @@ Outputs (all small, committed):
   pipeline.json            reference `extract_features_unet(clip, None, model, cpu)` output
   crops.npz                reference `letterbox_with_info` / `unletterbox` on seeded gray crops
   metrics.json             reference `dice` / `iou` on seeded mask pairs (incl. empty ones)
+  overlay.npz              reference `_draw_overlay` (scripts/infer.py) on a seeded frame and mask
   gated.json               reference `extract_features_unet(clip, detector, model, cpu)` with a
                            scripted detector (boxes listed in the file)
 
@@ -133,9 +134,28 @@ def crops_and_metrics():
     (HERE / "metrics.json").write_text(json.dumps(cases))
 
 
+def overlay_golden():
+    """The reference's own _draw_overlay (scripts/infer.py:91-124) on seeded inputs."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("ref_infer", "/root/reference/scripts/infer.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rng = np.random.default_rng(91)
+    frame = rng.integers(0, 256, (96, 128, 3), dtype=np.uint8)
+    mask = np.zeros((96, 128), np.uint8)
+    cv2.ellipse(mask, (60, 50), (25, 12), 20, 0, 360, 255, -1)
+    out = {"frame": frame, "mask": mask}
+    for style in ("fill", "contour", "none"):
+        out[f"out_{style}"] = mod._draw_overlay(frame, mask, (30, 20, 100, 80), 1234.0, style)
+    out["out_nomask"] = mod._draw_overlay(frame, None, None, 0.0, "fill")
+    np.savez_compressed(HERE / "overlay.npz", **out)
+
+
 def main():
     features_kat()
     crops_and_metrics()
+    overlay_golden()
     sd = synth.calibrated_state(0)
     model = UNet(1, 1, (32, 64, 128, 256))
     model.load_state_dict(sd)

@@ -215,3 +215,32 @@ def test_yolo_crop_unet_pipeline(lib, native_model, trained_sd, tmp_path):
         else:
             assert ogl.dice(full[i], fm) >= 0.99, i
     assert np.array_equal(area.cpu().numpy(), (full > 0).reshape(12, -1).sum(1))
+
+
+def test_gaw_features_and_annotation(lib, native_model, trained_sd, tmp_path):
+    """scripts/analyze_gaw.py:75-100 (gated waveform, f0 in Hz) and the unet-only branch of
+    scripts/infer.py:212-219 (overlay frames + area), against the oracle."""
+    import cv2
+    from openglottal_b200.analysis import annotate_unet_only, extract_gaw_features, write_avi
+    from oracle import pipeline_oracle as po, synth, unet_oracle as uo
+    from oracle.features_oracle import kinematic_features
+
+    clip, _ = synth.glottis_clip(24, 256, 256, seed=81, period=8.0)
+    frames_bgr = [cv2.cvtColor(f, cv2.COLOR_GRAY2BGR) for f in clip]
+    boxes = _boxes(24, 256, 256, seed=82, none_every=7)
+    got = extract_gaw_features(frames_bgr, 4000.0, ScriptedDetector(boxes), native_model)
+    _, ref_masks, _ = uo.batch_masks(trained_sd, clip)
+    want = kinematic_features(po.gated_area_wave(ref_masks, boxes))
+    if want["f0"] is not None:
+        assert got["f0"] == pytest.approx(want["f0"] * 4000.0, rel=1e-9)
+    assert got["area_mean"] == pytest.approx(want["area_mean"], rel=5e-3)
+    annotated, wave = annotate_unet_only(frames_bgr, native_model)
+    assert len(annotated) == 24 and annotated[0].shape == (256, 256, 3)
+    ref_area = (ref_masks > 0).reshape(24, -1).sum(1)
+    assert np.abs(np.array(wave) - ref_area).max() <= np.maximum(2, 0.005 * ref_area).max()
+    out = tmp_path / "annotated.avi"
+    write_avi(out, annotated, fps=25.0)
+    cap = cv2.VideoCapture(str(out))
+    ok, frm = cap.read()
+    cap.release()
+    assert ok and frm.shape == (256, 256, 3)

@@ -182,3 +182,17 @@ def test_gated_oracle_matches_reference_features(calibrated_sd):
     feats = kinematic_features(want)
     for k in ("area_mean", "area_std", "open_quotient", "periodicity"):
         assert feats[k] == pytest.approx(ref["features"][k], rel=1e-12, abs=1e-12), k
+
+
+def test_draw_overlay_matches_reference():
+    """openglottal_b200.analysis.draw_overlay vs the reference's _draw_overlay (overlay.npz)."""
+    from openglottal_b200.analysis import draw_overlay, features_row, FEATURE_COLS
+
+    g = np.load(GOLDEN / "overlay.npz")
+    for style in ("fill", "contour", "none"):
+        got = draw_overlay(g["frame"], g["mask"], (30, 20, 100, 80), 1234.0, style)
+        assert np.array_equal(got, g[f"out_{style}"]), style
+    assert np.array_equal(draw_overlay(g["frame"], None, None, 0.0, "fill"), g["out_nomask"])
+    row = features_row("clip", {"area_mean": 1.0, "f0": None, "cv": 2.0})
+    assert len(row) == 1 + len(FEATURE_COLS) and row[0] == "clip" and row[5] == ""
+    assert features_row("x", None) == ["x"] + [""] * 7
