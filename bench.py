@@ -280,9 +280,12 @@ def run_native(args) -> None:
     finish(area_all)
     barrier()
 
-    # ---- device-resident timed region (value)
+    # ---- device-resident timed region (value). Events between the launches are recorded INSIDE
+    # this region (ogl_unet_set_profiling keeps the last 16 forwards), so the per-launch times
+    # behind `roofline` come from the same steps, at the same clocks, as `value`.
     sampler = ClockSampler(local_rank)
     sampler.start()
+    _native.check(lib.ogl_unet_set_profiling(model._handle, 1))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -299,21 +302,13 @@ def run_native(args) -> None:
     ms = float(t.item())
     value = world * steps * BATCH / (ms * 1e-3)
 
-    # ---- per-launch timing (roofline of the dominant kernel), same workload, events between
-    # launches on the launching stream
-    _native.check(lib.ogl_unet_set_profiling(model._handle, 1))
-    prof_steps = min(steps, 10)
+    # ---- per-launch times of the last min(K, 16) timed steps (CUDA events on the launching stream)
     buf = (C.c_float * 64)()
     cnt = C.c_int(0)
-    acc = None
-    for i in range(prof_steps):
-        step_dev(i, None)
-        _native.check(lib.ogl_unet_layer_times(model._handle, buf, 64, C.byref(cnt)))
-        v = np.array(buf[:cnt.value])
-        acc = v if acc is None else acc + v
+    _native.check(lib.ogl_unet_layer_times(model._handle, buf, 64, C.byref(cnt)))
     _native.check(lib.ogl_unet_set_profiling(model._handle, 0))
     nl = cnt.value
-    layer_ms = acc / prof_steps
+    layer_ms = np.array(buf[:nl])
     names = [lib.ogl_unet_launch_name(model._handle, i).decode() for i in range(nl)]
     mfl = module_flops(HGT, WID)
     fl = np.array([launch_flops(n_, mfl) for n_ in names]) * BATCH

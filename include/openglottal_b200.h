@@ -89,8 +89,9 @@ int ogl_unet_forward(ogl_unet* h, const void* frames_dev, int in_dtype, int n, i
                      void* stream);
 
 /* Optional per-launch timing of the bf16 path (CUDA events on the caller's stream between the
- * launches of one forward; used by bench.py for the roofline numbers).
- * ogl_unet_layer_times synchronises on the last event of the most recent profiled forward.
+ * launches of every forward while enabled; used by bench.py for the roofline numbers).
+ * ogl_unet_layer_times synchronises on and averages the (up to 16) most recent profiled forwards,
+ * so a caller can time its own steady-state loop and read the per-launch times afterwards.
  * ogl_unet_launch_count / _name describe the launches of the most recent bf16 forward, each
  * named after the reference modules (openglottal/models/unet.py:50-72) it computes. */
 int ogl_unet_set_profiling(ogl_unet* h, int enable);

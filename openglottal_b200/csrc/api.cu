@@ -83,9 +83,14 @@ struct ogl_unet {
     F32ConvT f_upt[4];
     std::vector<void*> allocs;
     // optional per-launch timing (ogl_unet_set_profiling)
+    // Events between the launches of the most recent kProfSets profiled forwards, so that a
+    // caller can time its own steady-state loop and read the per-launch averages afterwards.
     bool profile = false;
-    std::vector<cudaEvent_t> events;
-    int n_events = 0;
+    std::vector<cudaEvent_t> events;   // kProfSets x kMaxLaunches
+    int n_events = 0;                  // events recorded by the forward in progress
+    int prof_set = 0;                  // set the forward in progress writes
+    int prof_forwards = 0;             // profiled forwards since profiling was enabled
+    int prof_count[16] = {0};          // events recorded in each set
     std::vector<const char*> launch_names;  // of the most recent bf16 forward
 };
 
@@ -262,6 +267,7 @@ Plan make_plan(int n, int H, int W, size_t elem) {
 }
 
 constexpr int kMaxLaunches = 40;
+constexpr int kProfSets = 16;
 const char* const kDownC1[4] = {"stem", "downs.1.net.0", "downs.2.net.0", "downs.3.net.0"};
 const char* const kDownC2[4] = {"downs.0.net.3+pool", "downs.1.net.3+pool", "downs.2.net.3+pool",
                                 "downs.3.net.3+pool"};
@@ -273,8 +279,10 @@ const char* const kUpC2[4] = {"ups.1.net.3", "ups.3.net.3", "ups.5.net.3", "ups.
 // closes the launch that was just enqueued: its name, and (when profiling) an event after it
 inline void mark(ogl_unet* h, cudaStream_t stream, const char* name) {
     if (name) h->launch_names.push_back(name);
-    if (h->profile && h->n_events < static_cast<int>(h->events.size()))
-        cudaEventRecord(h->events[h->n_events++], stream);
+    if (h->profile && h->n_events < kMaxLaunches) {
+        cudaEventRecord(h->events[h->prof_set * kMaxLaunches + h->n_events++], stream);
+        h->prof_count[h->prof_set] = h->n_events;
+    }
 }
 
 }  // namespace
@@ -447,6 +455,10 @@ int ogl_unet_forward(ogl_unet* h, const void* frames_dev, int in_dtype, int n, i
         auto B = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(ws + off); };
         __nv_bfloat16* P[4] = {B(p.U[1]), B(p.U[2]), B(p.U[3]), B(p.P3)};
         h->n_events = 0;
+        if (h->profile) {
+            h->prof_set = h->prof_forwards % kProfSets;
+            ++h->prof_forwards;
+        }
         h->launch_names.clear();
         const bool s2d = h->use_s2d;
         mark(h, stream, nullptr);
@@ -581,22 +593,39 @@ int ogl_unet_set_profiling(ogl_unet* h, int enable) {
     if (!h) return fail("ogl_unet_set_profiling: NULL handle");
     OGL_CUDA(cudaSetDevice(h->device));
     if (enable && h->events.empty()) {
-        h->events.resize(kMaxLaunches);
+        h->events.resize(static_cast<size_t>(kProfSets) * kMaxLaunches);
         for (auto& e : h->events) OGL_CUDA(cudaEventCreate(&e));
     }
     h->profile = enable != 0;
     h->n_events = 0;
+    h->prof_forwards = 0;
+    for (int& c : h->prof_count) c = 0;
     return 0;
 }
 
 int ogl_unet_layer_times(ogl_unet* h, float* ms_out, int capacity, int* count_out) {
     if (!h || !ms_out || !count_out) return fail("ogl_unet_layer_times: NULL argument");
     *count_out = 0;
-    if (!h->profile || h->n_events < 2) return fail("ogl_unet_layer_times: no profiled forward");
-    OGL_CUDA(cudaEventSynchronize(h->events[h->n_events - 1]));
+    if (!h->profile || h->prof_forwards < 1 || h->n_events < 2)
+        return fail("ogl_unet_layer_times: no profiled forward");
+    // average over the (up to kProfSets) most recent profiled forwards with the same launch list
     const int n = h->n_events - 1;
-    for (int i = 0; i < n && i < capacity; ++i)
-        OGL_CUDA(cudaEventElapsedTime(ms_out + i, h->events[i], h->events[i + 1]));
+    const int sets = h->prof_forwards < kProfSets ? h->prof_forwards : kProfSets;
+    for (int i = 0; i < n && i < capacity; ++i) ms_out[i] = 0.f;
+    int used = 0;
+    for (int sidx = 0; sidx < sets; ++sidx) {
+        if (h->prof_count[sidx] != h->n_events) continue;
+        cudaEvent_t* ev = h->events.data() + static_cast<size_t>(sidx) * kMaxLaunches;
+        OGL_CUDA(cudaEventSynchronize(ev[n]));
+        for (int i = 0; i < n && i < capacity; ++i) {
+            float ms = 0.f;
+            OGL_CUDA(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+            ms_out[i] += ms;
+        }
+        ++used;
+    }
+    if (used == 0) return fail("ogl_unet_layer_times: no complete profiled forward");
+    for (int i = 0; i < n && i < capacity; ++i) ms_out[i] /= static_cast<float>(used);
     *count_out = n < capacity ? n : capacity;
     return 0;
 }

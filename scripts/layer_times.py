@@ -35,6 +35,7 @@ for i in range(3):
 torch.cuda.synchronize()
 sampler = bench.ClockSampler(0)
 sampler.start()
+_native.check(lib.ogl_unet_set_profiling(model._handle, 1))
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for i in range(steps * 8):
@@ -43,16 +44,11 @@ e1.record()
 torch.cuda.synchronize()
 clocks = sampler.stop()
 total = e0.elapsed_time(e1) / (steps * 8)
-_native.check(lib.ogl_unet_set_profiling(model._handle, 1))
 buf = (C.c_float * 64)()
 cnt = C.c_int(0)
-acc = None
-for i in range(steps):
-    model.run(frames[(i % 4) * batch:(i % 4 + 1) * batch])
-    _native.check(lib.ogl_unet_layer_times(model._handle, buf, 64, C.byref(cnt)))
-    v = np.array(buf[:cnt.value])
-    acc = v if acc is None else acc + v
-acc /= steps
+_native.check(lib.ogl_unet_layer_times(model._handle, buf, 64, C.byref(cnt)))   # last 16 steps
+_native.check(lib.ogl_unet_set_profiling(model._handle, 0))
+acc = np.array(buf[:cnt.value])
 names = [lib.ogl_unet_launch_name(model._handle, i).decode() for i in range(cnt.value)]
 print(json.dumps({"tag": tag, "env": {k: v for k, v in os.environ.items() if k.startswith("OGL_")},
                   "batch": batch, "clocks": clocks, "ms_step": total, "fps": batch / total * 1e3,
