@@ -104,9 +104,9 @@ const char* ogl_unet_launch_name(const ogl_unet* h, int index);
  * per-tap form used at the other levels (22 launches). Same results within bf16 rounding. */
 int ogl_unet_set_schedule(ogl_unet* h, int s2d_level0);
 
-/* 1: with u8 frames and the space-to-depth schedule, downs.0.net.0 (the Cin = 1 stem) is computed
- * inside the downs.0.net.3 kernel, so its output never touches HBM; 0 (default): separate stem
- * kernel. Same results bit for bit; measured equally fast. */
+/* 1 (default): with u8 frames and the space-to-depth schedule, downs.0.net.0 (the Cin = 1 stem) is
+ * computed inside the downs.0.net.3 kernel, so its output never touches HBM; 0: separate stem
+ * kernel. Same results bit for bit. */
 int ogl_unet_set_fused_stem(ogl_unet* h, int enable);
 
 /* CTA pairs for the conv3x3 layers with Cout >= 64: 1 = one CTA per tile; 2 = two CTAs of a

@@ -65,6 +65,44 @@ struct StemWeights {  // passed by value: lives in the kernel-parameter constant
     float w[32 * 9];
     float b[32];
 };
+// Weights of the u8 stem as channel pairs: wp[co/2][tap] = (w[co][tap], w[co+1][tap]) / 255 and
+// bp[co/2] = (b[co], b[co+1]), so that one packed FFMA2 (fma.rn.f32x2, two IEEE FMAs per
+// instruction with the pair taken from uniform registers) advances two output channels of a pixel
+// and its 64-bit result is exactly the bf16x2 the store packs. Bit-identical to scalar fmaf.
+// The 1/255 of utils.py:235 is folded into the weights in fp64 and rounded once.
+struct StemPairs {
+    float2 wp[16 * 9];
+    float2 bp[16];
+};
+inline StemPairs make_stem_pairs(const StemWeights& sw) {
+    StemPairs sp;
+    for (int cp = 0; cp < 16; ++cp) {
+        for (int k = 0; k < 9; ++k) {
+            sp.wp[cp * 9 + k].x = static_cast<float>(static_cast<double>(sw.w[(2 * cp) * 9 + k]) / 255.0);
+            sp.wp[cp * 9 + k].y = static_cast<float>(static_cast<double>(sw.w[(2 * cp + 1) * 9 + k]) / 255.0);
+        }
+        sp.bp[cp].x = sw.b[2 * cp];
+        sp.bp[cp].y = sw.b[2 * cp + 1];
+    }
+    return sp;
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b,
+                                                   unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned long long dup2(float v) {
+    const unsigned long long u = __float_as_uint(v);
+    return u | (u << 32);
+}
+__device__ __forceinline__ unsigned long long as_u64(float2 v) {
+    return static_cast<unsigned long long>(__float_as_uint(v.x)) |
+           (static_cast<unsigned long long>(__float_as_uint(v.y)) << 32);
+}
+#endif
+
 // ------------------------------------------------------------------ full-resolution level
 // The tensor-core convs at full resolution (Cout = 32) run on tensors stored "space-to-depth"
 // (S2D): [frame][C/8][phase = (y&1)*2 + (x&1)][H/2][W/2][8]. A GEMM row is a half-resolution

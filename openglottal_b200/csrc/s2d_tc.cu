@@ -123,7 +123,7 @@ constexpr int kU8Slots = 4;
 
 struct S2dParams {
     const uint8_t* frames;   // STEM = 1: u8 gray frames [B][2 H2][2 W2]
-    StemWeights stem;        // STEM = 1: folded stem weights already divided by 255, and bias
+    StemPairs stem;          // STEM = 1: folded stem weights / 255 and bias, as channel pairs
     const uint8_t* wblob;
     const float* btab;     // [3][3][32]: bias per (row class, column class), border pixels only
     float bias[32];        // bias of interior pixels (= btab[1][1]); constant-bank operands
@@ -274,7 +274,7 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
             const bool active = st < kItems;
             const int ly = 1 + st / (kNeedW / 3), lx0 = 1 + 3 * (st % (kNeedW / 3));
             const int gy = gy0 + 1 + ly;
-            float in[3][5];
+            unsigned long long in[3][5];   // each input value in both halves of a register pair
             uint32_t inside[3];   // all-ones inside the image, 0 outside (a mask, not a branch:
                                   // the six accumulator chains of an item stay interleaved)
             if (active) {
@@ -282,7 +282,8 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
                 for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
                     for (int dx = 0; dx < 5; ++dx)
-                        in[dy][dx] = static_cast<float>(u8p[(ly + dy) * kU8Row + kU8Off + lx0 + dx]);
+                        in[dy][dx] =
+                            dup2(static_cast<float>(u8p[(ly + dy) * kU8Row + kU8Off + lx0 + dx]));
 #pragma unroll
                 for (int q = 0; q < 3; ++q) {
                     const int gx = gx0 + 1 + lx0 + q;
@@ -300,23 +301,23 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
                         uint32_t pk[3][4];
 #pragma unroll
                         for (int c2 = 0; c2 < 4; ++c2) {
-                            float a[3][2];
+                            // channel pair (2 cp, 2 cp + 1) of the 3 pixels: packed FFMA2s
+                            const int cp = half * 8 + g * 4 + c2;
+                            unsigned long long a[3];
 #pragma unroll
-                            for (int e = 0; e < 2; ++e) {
-                                const int co = half * 16 + g * 8 + c2 * 2 + e;
+                            for (int q = 0; q < 3; ++q) a[q] = as_u64(p.stem.bp[cp]);
 #pragma unroll
-                                for (int q = 0; q < 3; ++q) a[q][e] = p.stem.b[co];
+                            for (int k = 0; k < 9; ++k) {
+                                const unsigned long long w = as_u64(p.stem.wp[cp * 9 + k]);
 #pragma unroll
-                                for (int k = 0; k < 9; ++k) {
-                                    const float w = p.stem.w[co * 9 + k];
-#pragma unroll
-                                    for (int q = 0; q < 3; ++q)
-                                        a[q][e] = fmaf(in[k / 3][k % 3 + q], w, a[q][e]);
-                                }
+                                for (int q = 0; q < 3; ++q) a[q] = fma2(in[k / 3][k % 3 + q], w, a[q]);
                             }
 #pragma unroll
-                            for (int q = 0; q < 3; ++q)   // zero outside the image: conv2's padding
-                                pk[q][c2] = pack_bf16x2(fmaxf(a[q][0], 0.f), fmaxf(a[q][1], 0.f)) & inside[q];
+                            for (int q = 0; q < 3; ++q) {   // zero outside the image: conv2's padding
+                                const float lo = __uint_as_float(static_cast<uint32_t>(a[q]));
+                                const float hi = __uint_as_float(static_cast<uint32_t>(a[q] >> 32));
+                                pk[q][c2] = pack_bf16x2(fmaxf(lo, 0.f), fmaxf(hi, 0.f)) & inside[q];
+                            }
                         }
 #pragma unroll
                         for (int q = 0; q < 3; ++q) {
@@ -822,9 +823,7 @@ int launch_s2d_tc(const S2dLayer& L, const __nv_bfloat16* src_s2d, const __nv_bf
         // weights pre-scaled by 1/255 (in fp64, rounded once) so that the u8 values are used as
         // they are: utils.py:235 folded into downs.0.net.0
         p.frames = stem_frames;
-        for (int i = 0; i < 32 * 9; ++i)
-            p.stem.w[i] = static_cast<float>(static_cast<double>(stem->w[i]) / 255.0);
-        for (int i = 0; i < 32; ++i) p.stem.b[i] = stem->b[i];
+        p.stem = make_stem_pairs(*stem);
     }
     p.btab = L.btab;
     p.border_bias = L.cin_b > 0 ? 1 : 0;

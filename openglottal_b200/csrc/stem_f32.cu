@@ -91,29 +91,6 @@ stem_kernel(const void* __restrict__ frames, int in_dtype, const __grid_constant
     }
 }
 
-// Weights of the u8 stem as channel pairs: wp[co/2][tap] = (w[co][tap], w[co+1][tap]) / 255 and
-// bp[co/2] = (b[co], b[co+1]), so that one packed FFMA2 (fma.rn.f32x2, two IEEE FMAs per
-// instruction with the pair taken from uniform registers) advances two output channels of a pixel
-// and its 64-bit result is exactly the bf16x2 the store packs. Bit-identical to scalar fmaf.
-struct StemPairs {
-    float2 wp[16 * 9];
-    float2 bp[16];
-};
-__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b,
-                                                   unsigned long long c) {
-    unsigned long long d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-__device__ __forceinline__ unsigned long long dup2(float v) {
-    const unsigned long long u = __float_as_uint(v);
-    return u | (u << 32);
-}
-__device__ __forceinline__ unsigned long long as_u64(float2 v) {
-    return static_cast<unsigned long long>(__float_as_uint(v.x)) |
-           (static_cast<unsigned long long>(__float_as_uint(v.y)) << 32);
-}
-
 // u8 form (the hot path): one warp per image row, one thread per 4 consecutive pixels.
 // The three input rows arrive as one aligned 32-bit load each; the left/right neighbour bytes
 // come from the adjacent lanes by shuffle (warp-edge lanes load them). sw.w holds the folded
@@ -364,14 +341,7 @@ int launch_stem(const void* frames, int in_dtype, const StemWeights& sw, int B, 
     if (in_dtype == 0 && W % 4 == 0) {
         // hot path: weights pre-scaled by 1/255 (in fp64, rounded once) so the u8 values are
         // used directly; differs from fl(v/255)*w by ~1 ulp of fp32, far below bf16 rounding
-        StemPairs scaled;
-        for (int cp = 0; cp < 16; ++cp) {
-            for (int k = 0; k < 9; ++k) {
-                scaled.wp[cp * 9 + k].x = static_cast<float>(static_cast<double>(sw.w[(2 * cp) * 9 + k]) / 255.0);
-                scaled.wp[cp * 9 + k].y = static_cast<float>(static_cast<double>(sw.w[(2 * cp + 1) * 9 + k]) / 255.0);
-            }
-            scaled.bp[cp] = make_float2(sw.b[2 * cp], sw.b[2 * cp + 1]);
-        }
+        const StemPairs scaled = make_stem_pairs(sw);
         const int rows = B * H;
         int grid = (rows + 7) / 8;
         if (grid > 148 * 6) grid = 148 * 6;

@@ -71,7 +71,7 @@ class UNet(nn.Module):
         self.cta_pairs = int(os.environ.get("OGL_CG", "2"))   # 1: one CTA per tile; 2: CTA pairs
                                      # (tcgen05 cta_group::2) for the Cout >= 64 conv layers when
                                      # a launch has a tile per SM; 3: pairs whenever possible
-        self.fuse_stem = os.environ.get("OGL_FUSE_STEM", "0") != "0"   # stem inside downs.0.net.3 (neutral)
+        self.fuse_stem = os.environ.get("OGL_FUSE_STEM", "1") != "0"   # stem inside downs.0.net.3
         self._handle = None
         self._handle_device = None
         self._packed_sig = None

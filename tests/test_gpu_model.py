@@ -132,7 +132,7 @@ def test_fused_stem_bit_identical(native_model):
             native_model.fuse_stem = True
             got = native_model.run(frames, want_logits=True)
         finally:
-            native_model.fuse_stem = False
+            native_model.fuse_stem = True
         assert all(torch.equal(a, b) for a, b in zip(ref, got)), shape
 
 
