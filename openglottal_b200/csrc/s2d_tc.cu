@@ -228,10 +228,10 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
         if (STEM)
             for (int i = 0; i < kU8Slots; ++i) {
                 mbar_init(u8_full + 8u * i, 1);
-                mbar_init(u8_empty + 8u * i, kStemThreads);
+                mbar_init(u8_empty + 8u * i, kStemThreads / 32);
             }
         for (int i = 0; i < p.nslots; ++i) {
-            mbar_init(a_full + 8u * i, STEM ? kStemThreads : 1);
+            mbar_init(a_full + 8u * i, STEM ? kStemThreads / 32 : 1);   // one arrival per stem warp
             mbar_init(a_empty + 8u * i, 1);
         }
         for (int i = 0; i < kAccBufs; ++i) {
@@ -329,10 +329,12 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
                         }
                     }
                 }
-                if (!(p.dbg & 128)) fence_proxy_async();   // stores visible to the tensor core's reads
-                mbar_arrive(a_full + 8u * slot);
+                fence_proxy_async();   // this thread's stores visible to the tensor core's reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_full + 8u * slot);
             }
-            mbar_arrive(u8_empty + 8u * us);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(u8_empty + 8u * us);
         }
     } else if (warp == 0 && STEM) {
         // ================================ u8 regions of the tiles, by TMA, ahead of the stem warps
