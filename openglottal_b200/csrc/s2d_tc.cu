@@ -143,7 +143,8 @@ struct S2dParams {
     int tiles_x, tiles_y, num_tiles;
     unsigned long long magic_tx, magic_tpf;
     int nslots;
-    int dbg;  // 1 no MMA, 2 no stores, 4 no epilogue work
+    int dual;   // two MMA issuer warps on alternate tiles (needs nslots >= 2 * n_stages)
+    int dbg;  // 1 no MMA, 2 no stores, 4 no epilogue work, 8 no activation loads (1-CTA form)
 };
 
 struct Tile {
@@ -363,6 +364,10 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
                     const uint32_t ph = (it / p.nslots) & 1u;
                     mbar_wait(a_empty + 8u * slot, ph ^ 1u);
                     const uint32_t dst = a_ring + slot * kSlot;
+                    if (CG == 1 && (p.dbg & 8)) {   // experiment: no activation loads
+                        mbar_arrive(a_full + 8u * slot);
+                        continue;
+                    }
                     if (CG == 1) {
                         const uint32_t full = a_full + 8u * slot;
                         mbar_arrive_expect_tx(full, kSlot);
@@ -402,9 +407,20 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
                 mbar_arrive_cluster(map_to_cta(w_peer, 0));
             }
         }
-    } else if (warp == 1 && rank == 0) {
-        // ========================================================= MMA issuer
+    } else if ((warp == 1 || warp == 2) && rank == 0) {
+        // ================================================= MMA issuers (two warps)
+        // The tensor pipe accepts an MMA only when the previous one is (nearly) done, and a wait
+        // on an mbarrier costs the issuing warp ~120 cycles even when the phase completed long
+        // ago, so with ONE issuer every barrier wait between two groups of MMAs is a bubble in the
+        // pipe (measured: 82 instead of 48 cycles per N = 64 MMA with a wait every 4 MMAs;
+        // profiles/microbench_mma_issuer_bubbles_r01.txt). Two warps issue alternate tiles (into
+        // different accumulator buffers, so the summation order inside a tile is unchanged):
+        // while one waits, the other's MMAs keep the pipe full -- 48.0 cycles in the same test.
+        // An issuer may then wait for a ring slot's NEXT use while the other issuer has not yet
+        // seen its current one; mbarrier parities tell phases apart only one step, so this needs
+        // a ring of at least two tiles (p.dual is 0 otherwise and warp 2 idles).
         // The whole warp walks the loops (all values warp-uniform); one elected lane issues.
+        const uint32_t me = static_cast<uint32_t>(warp - 1);
         // descriptor halves that never change: A (two LBOs: S2D stage / plain stage), B
         constexpr uint32_t a_hi = ((kHW * 16u) >> 4) | (1u << 14);           // SBO = one halo row
         constexpr uint32_t a_lbo_s2d = ((4u * kPlane) >> 4) << 16;          // plane pair of a phase
@@ -424,6 +440,8 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
         if (CG == 2) mbar_wait_cluster(w_peer, 0);
         uint32_t ita = 0, li = 0;
         for (int unit = unit0; unit < num_units; unit += unit_step, ++li) {
+            if (p.dual ? (li & 1u) != me : me != 0u) continue;   // the other issuer's tile
+            ita = li * static_cast<uint32_t>(p.n_stages);       // its stages in the ring
             const uint32_t buf = li % kAccBufs;
             const uint32_t aph = (li / kAccBufs) & 1u;
             if (CG == 2) mbar_wait_cluster(acc_empty + 8u * buf, aph ^ 1u);
@@ -872,6 +890,8 @@ int launch_s2d_tc(const S2dLayer& L, const __nv_bfloat16* src_s2d, const __nv_bf
     const size_t smem = fixed + static_cast<size_t>(nslots) * (kSlot + 16);
     if (smem > static_cast<size_t>(kMaxSmem)) return fail("s2d layer: shared memory budget exceeded");
     p.nslots = nslots;
+    static const int dual_env = getenv("OGL_DUAL") ? atoi(getenv("OGL_DUAL")) : 1;
+    p.dual = (dual_env && nslots >= 2 * p.n_stages) ? 1 : 0;
 
     CUtensorMap tmS, tmB;
     if (fused_stem) {
