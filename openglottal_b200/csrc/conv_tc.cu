@@ -158,11 +158,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (CG == 2) tma_prefetch_desc(&tmW);
         for (int i = 0; i < p.na; ++i) {
             mbar_init(a_full + 8u * i, 1);
-            mbar_init(a_empty + 8u * i, 1);
+            mbar_init(a_empty + 8u * i, 2);   // both MMA issuers commit every stage
         }
         for (int i = 0; i < p.nw; ++i) {
             mbar_init(w_full + 8u * i, 1);
-            mbar_init(w_empty + 8u * i, 1);
+            mbar_init(w_empty + 8u * i, 2);
         }
         for (int i = 0; i < 4; ++i) {
             mbar_init(acc_full + 8u * i, 1);
@@ -255,8 +255,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 }
             }
         }
-    } else if (warp == 1 && rank == 0) {
-        // ========================================================= MMA issuer
+    } else if ((warp == 1 || warp == 2) && rank == 0) {
+        // ================================================= MMA issuers (two warps)
+        // The tensor pipe accepts an MMA only when the previous one is (nearly) done and a wait on
+        // an mbarrier costs ~120 cycles even on a long-completed phase, so a single issuer's
+        // barrier waits are bubbles in the pipe (profiles/microbench_mma_issuer_bubbles_r01.txt).
+        // Two warps walk the SAME sequence of stages; warp 1 issues the MMAs of the tile's first
+        // half of the accumulators (sub-tile 0), warp 2 those of the second half, each commits
+        // every stage it has read (the empty barriers count two arrivals). While one waits, the
+        // other's MMAs keep the pipe busy; per-accumulator summation order is unchanged.
+        const uint32_t me = static_cast<uint32_t>(warp - 1);
         // The whole warp walks the loops (all values warp-uniform); one elected lane issues.
         // Descriptors differ only in their start-address field, so each MMA is one 32-bit add.
         // CG = 2: only the leader CTA issues; shared-memory offsets are the same in both CTAs.
@@ -268,6 +276,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const uint32_t acc_cols = static_cast<uint32_t>(2 * S * p.N);
         const uint32_t bstep = (2u * lbo_b) >> 4;   // second K=16 half of a 32-channel block
         const uint32_t btap = 4u * nb;              // one tap of B, in 16-byte units
+        // this issuer's accumulators: mt = me * S + m (S == 2: sub-tile me; S == 1: x-half me)
+        const uint32_t a_me = S == 2 ? me * (kSubBytes >> 4) : me * 8u;
+        const uint32_t d_me = me * S * static_cast<uint32_t>(p.N);
         auto mma = [](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
             if (CG == 2) umma_bf16_pair(d, a, b, id, acc);
             else umma_bf16(d, a, b, id, acc);
@@ -303,7 +314,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                         mbar_wait(w_full + 8u * wst[tg], ((itw + tg) / p.nw) & 1u);
                     }
                     tc_fence_after();
-                    for (int mt = 0; mt < 4; ++mt) {
+                    for (int m = 0; m < 2; ++m) {
+                        const uint32_t mt = me * 2u + m;
                         if (kb == 0) {
                             wait_acc_empty(acc_empty + 8u * mt, aph ^ 1u);
                             tc_fence_after();
@@ -319,9 +331,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                                     if (p.dbg & 1) break;
 #pragma unroll
                                     for (int j = 0; j < 2; ++j) {
-                                        constexpr uint32_t kSubStep = kSubBytes >> 4;
-                                        const uint32_t aoff = t + (mt >> 1) * kSubStep +
-                                                              j * ((2u * lbo_a) >> 4) + (mt & 1) * 8u;
+                                        const uint32_t aoff =
+                                            t + a_me + j * ((2u * lbo_a) >> 4) + m * 8u;
                                         mma(d0 + mt * p.N, ad + aoff, bd + (t * btap + j * bstep),
                                             idesc, (kb | tg | t | j) ? 1u : 0u);
                                     }
@@ -363,18 +374,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
                             for (int j = 0; j < 2; ++j) {
 #pragma unroll
-                                for (int mt = 0; mt < 2 * S; ++mt) {
-                                    constexpr uint32_t kSubStep = kSubBytes >> 4;
-                                    const uint32_t aoff = toff + (mt >> 1) * kSubStep +
-                                                          j * ((2u * lbo_a) >> 4) + (mt & 1) * 8u;
-                                    mma(d0 + mt * p.N, ad + aoff, bd + (t * btap + j * bstep),
+                                for (int m = 0; m < S; ++m) {
+                                    const uint32_t aoff =
+                                        toff + a_me + j * ((2u * lbo_a) >> 4) + m * 8u;
+                                    mma(d0 + d_me + m * p.N, ad + aoff, bd + (t * btap + j * bstep),
                                         idesc, (t | j) ? 1u : first);
                                 }
                             }
                         }
                         commit(w_empty + 8u * sw);
                         if (last_tg) commit(a_empty + 8u * sa);
-                        if (!kSplit && last_tg && kb == kb_total - 1) commit(acc_full + 8u * buf);
+                        if (!kSplit && last_tg && kb == kb_total - 1)
+                            commit(acc_full + 8u * (buf * 2u + me));   // this issuer's half
                     }
                     __syncwarp();
                 }
@@ -402,7 +413,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const uint32_t buf = kSplit ? 0u : li % p.acc_bufs;
             const uint32_t aph = kSplit ? (li & 1u) : (li / p.acc_bufs) & 1u;
             if (!kSplit) {
-                mbar_wait(acc_full + 8u * buf, aph);
+                mbar_wait(acc_full + 8u * (buf * 2u + egrp), aph);   // the issuer of this half
                 tc_fence_after();
             }
 #pragma unroll 1
