@@ -83,12 +83,15 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
+    import os
+
+    lib_path = Path(os.environ.get("OGL_LIB", str(LIB_PATH)))   # experiment builds
+    if not lib_path.exists():
         raise RuntimeError(
-            f"{LIB_PATH} is missing: run `python -m openglottal_b200.build` (needs nvcc). "
+            f"{lib_path} is missing: run `python -m openglottal_b200.build` (needs nvcc). "
             "openglottal_b200 has no CPU or PyTorch fallback."
         )
-    lib = C.CDLL(str(LIB_PATH))
+    lib = C.CDLL(str(lib_path))
     vp, i32, i64, sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
     lib.ogl_version.restype = i32
     lib.ogl_version.argtypes = []

@@ -189,7 +189,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 for (int kb = 0; kb < kb_total; ++kb, ++it) {
                     const uint32_t s = it % p.na;
                     const uint32_t ph = (it / p.na) & 1u;
-                    mbar_wait(a_empty + 8u * s, ph ^ 1u);
+                    mbar_wait_relaxed(a_empty + 8u * s, ph ^ 1u);
                     if (CG == 1 && (p.dbg & 8)) {
                         mbar_arrive(a_full + 8u * s);
                         continue;
@@ -228,7 +228,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     for (int tg = 0; tg < p.taps / TPS; ++tg, ++it) {
                         const uint32_t s = it % p.nw;
                         const uint32_t ph = (it / p.nw) & 1u;
-                        mbar_wait(w_empty + 8u * s, ph ^ 1u);
+                        mbar_wait_relaxed(w_empty + 8u * s, ph ^ 1u);
                         if (CG == 1 && (p.dbg & 16)) {
                             mbar_arrive(w_full + 8u * s);
                             continue;
@@ -413,7 +413,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const uint32_t buf = kSplit ? 0u : li % p.acc_bufs;
             const uint32_t aph = kSplit ? (li & 1u) : (li / p.acc_bufs) & 1u;
             if (!kSplit) {
-                mbar_wait(acc_full + 8u * (buf * 2u + egrp), aph);   // the issuer of this half
+                mbar_wait_relaxed(acc_full + 8u * (buf * 2u + egrp), aph);   // the issuer of this half
                 tc_fence_after();
             }
 #pragma unroll 1
@@ -427,7 +427,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 const bool in_range = st < p.total_sub;  // warp-uniform
                 const SubTile t = decode_sub(p, in_range ? st : p.total_sub - 1);
                 if (kSplit) {
-                    mbar_wait(acc_full + 8u * mt, aph);
+                    mbar_wait_relaxed(acc_full + 8u * mt, aph);
                     tc_fence_after();
                 }
                 const int c_begin = kSplit ? egrp * 64 : 0;

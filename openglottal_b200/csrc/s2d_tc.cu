@@ -266,7 +266,7 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
             const int gy0 = 2 * t.y0 - 3, gx0 = 2 * t.x0 - 3;   // frame coordinates of u8p[0][0]
             const uint32_t us = iu % kU8Slots;
             const uint8_t* u8p = gen + u8_s + us * kU8Slot;      // rows of kU8Row bytes (TMA box)
-            mbar_wait(u8_full + 8u * us, (iu / kU8Slots) & 1u);
+            mbar_wait_relaxed(u8_full + 8u * us, (iu / kU8Slots) & 1u);
             // One work item = 3 horizontally adjacent pixels of one row (34 rows x 6 triples = 204
             // items per tile, thread st takes item st): every weight fetched from the constant
             // bank feeds 3 FFMAs, the 3x5 input window is read once.
@@ -294,7 +294,7 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
 #pragma unroll   // `half` must be a compile-time constant: weights are constant-bank operands
             for (int half = 0; half < 2; ++half, ++it) {
                 const uint32_t slot = it % p.nslots;
-                mbar_wait(a_empty + 8u * slot, ((it / p.nslots) & 1u) ^ 1u);
+                mbar_wait_relaxed(a_empty + 8u * slot, ((it / p.nslots) & 1u) ^ 1u);
                 uint8_t* stage = gen + a_ring + slot * kSlot;
                 if (active && !(p.dbg & 64)) {
 #pragma unroll
@@ -345,7 +345,7 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
             for (int unit = unit0; unit < num_units; unit += unit_step, ++iu) {
                 const Tile t = decode_tile(p, unit);
                 const uint32_t us = iu % kU8Slots;
-                mbar_wait(u8_empty + 8u * us, ((iu / kU8Slots) & 1u) ^ 1u);
+                mbar_wait_relaxed(u8_empty + 8u * us, ((iu / kU8Slots) & 1u) ^ 1u);
                 mbar_arrive_expect_tx(u8_full + 8u * us, kU8Bytes);
                 tma_load_3d(u8_s + us * kU8Slot, &tmS, u8_full + 8u * us, 2 * t.x0 - 16, 2 * t.y0 - 3,
                             t.n);
@@ -362,7 +362,7 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
                 for (int s = 0; s < p.n_stages; ++s, ++it) {
                     const uint32_t slot = it % p.nslots;
                     const uint32_t ph = (it / p.nslots) & 1u;
-                    mbar_wait(a_empty + 8u * slot, ph ^ 1u);
+                    mbar_wait_relaxed(a_empty + 8u * slot, ph ^ 1u);
                     const uint32_t dst = a_ring + slot * kSlot;
                     if (CG == 1 && (p.dbg & 8)) {   // experiment: no activation loads
                         mbar_arrive(a_full + 8u * slot);
@@ -518,7 +518,7 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
             const Tile t = decode_tile(p, in_range ? tile : p.num_tiles - 1);
             const int Y = t.y0 + py, X = t.x0 + px;
             const bool valid = in_range && Y < p.H2 && X < p.W2 && !(p.dbg & 2);
-            mbar_wait(acc_full + 8u * buf, aph);
+            mbar_wait_relaxed(acc_full + 8u * buf, aph);
             tc_fence_after();
             const uint32_t tcol = tmem_base + lane_sel + buf * 128u;
             uint32_t mx[16];
