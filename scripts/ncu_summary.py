@@ -13,7 +13,7 @@ rep, batch, tag = sys.argv[1], int(sys.argv[2]), sys.argv[3]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, data = rows[0], rows[1], rows[2:]
-names = ["downs.0.net.3+pool", "downs.1.net.0", "downs.1.net.3+pool", "downs.2.net.0",
+names = ["stem+downs.0.net.3+pool", "downs.1.net.0", "downs.1.net.3+pool", "downs.2.net.0",
          "downs.2.net.3+pool", "downs.3.net.0", "downs.3.net.3+pool", "bottleneck.net.0",
          "bottleneck.net.3", "ups.0(convT)", "ups.1.net.0(cat)", "ups.1.net.3", "ups.2(convT)",
          "ups.3.net.0(cat)", "ups.3.net.3", "ups.4(convT)", "ups.5.net.0(cat)", "ups.5.net.3",
