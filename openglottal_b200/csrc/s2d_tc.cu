@@ -877,8 +877,10 @@ int launch_s2d_tc(const S2dLayer& L, const __nv_bfloat16* src_s2d, const __nv_bf
     // weights leave one CTA only 3 activation stages (measured 1.57 -> 1.12 ms; the HBM-bound
     // downs.0.net.3 is slower paired, 0.85 -> 1.05 ms, and ups.7.net.3 unchanged), when there
     // is a tile per SM. cta_group 3 (unit tests): whenever there are two tiles.
+    static const int pair_all_env = getenv("OGL_S2D_PAIR_ALL") ? atoi(getenv("OGL_S2D_PAIR_ALL")) : 0;
     const bool pair = !fused_stem && cta_group >= 2 && L.wblob2 && num_sms >= 2 &&
-                      (cta_group == 3 ? p.num_tiles >= 2 : (p.num_tiles >= num_sms && L.cin_b > 0));
+                      (cta_group == 3 ? p.num_tiles >= 2
+                                      : (p.num_tiles >= num_sms && (L.cin_b > 0 || pair_all_env)));
     p.wblob = pair ? L.wblob2 : L.wblob;
     const size_t wres = L.wbytes / (pair ? 2 : 1);
     const size_t fixed = 128 + ((wres + 127u) & ~static_cast<size_t>(127)) + 9 * 32 * 4 + 8 +
