@@ -217,8 +217,9 @@ def run_reference(args) -> None:
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "unet-only 256x256 clip, reference per-frame loop (batch 1, fp32, CPU)",
-                   "frames_per_step": per_step, "weights": wname},
+        "config": {"workload": "unet-only 256x256 GIRAFE-shaped clip (BASELINE.json configs[1]); the "
+                               "reference's own per-frame loop: batch 1, fp32, CPU",
+                   "frames_per_step": per_step, "height": HGT, "width": WID, "weights": wname},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                          "sample": f"{args.steps * per_step} frames of the synthetic 256x256 clip, "
                                    f"{per_step} per step, torch CPU fp32 batch-1 loop"},

@@ -145,3 +145,19 @@ def test_dice_matches_reference_definition():
     b = a.copy(); b[0, :2] = 255
     c = a.copy(); c[0, 1:3] = 255
     assert dice(b, c) == pytest.approx(0.5)
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the reference's CPU loop restated in oracle/) runs without a
+    GPU and prints one JSON line with the keys the driver reads."""
+    import json
+
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "3"], capture_output=True, text=True, timeout=600, cwd=str(ROOT))
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["value"] > 0
+    assert line["metric"] == "unet_only_frames_per_sec_256x256_bf16" and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["e2e"]["value"] == line["value"]
