@@ -125,22 +125,39 @@ def segment_clip(frames_gray, model: UNet, batch: int = 512, threshold: float = 
                 masks[i0:i0 + batch] = m
         return area, masks
 
-    host = frames_gray if frames_gray.is_pinned() else frames_gray.pin_memory()
+    # Pinned input is copied from in place. Pageable input is staged through two pinned batch
+    # buffers (pinning a whole 10^6-frame clip would lock 65 GB of host memory): the CPU copy of
+    # batch k+1 into its staging buffer overlaps the GPU work of batch k.
+    pinned_in = frames_gray.is_pinned()
+    stage = None if pinned_in else [
+        torch.empty((min(batch, n), hgt, wid), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
     compute = torch.cuda.current_stream(dev)
     copy = torch.cuda.Stream(device=dev)
     bufs = [torch.empty((min(batch, n), hgt, wid), dtype=torch.uint8, device=dev) for _ in range(2)]
+    # `bufs` come from the caching allocator and may be the blocks an earlier, still queued call on
+    # the compute stream reads from: the side stream must not write them before that work is done
+    copy.wait_stream(compute)
     ready = [torch.cuda.Event() for _ in range(2)]
     freed = [torch.cuda.Event() for _ in range(2)]
+    copied = [torch.cuda.Event() for _ in range(2)]   # H2D of a staging buffer has finished
     starts = list(range(0, n, batch))
 
     def issue_copy(k: int) -> None:
         i0 = starts[k]
         m = min(batch, n - i0)
+        if pinned_in:
+            src = frames_gray[i0:i0 + m]
+        else:
+            if k >= 2:
+                copied[k % 2].synchronize()        # the staging buffer is free again
+            stage[k % 2][:m].copy_(frames_gray[i0:i0 + m])
+            src = stage[k % 2][:m]
         with torch.cuda.stream(copy):
             if k >= 2:
                 copy.wait_event(freed[k % 2])
-            bufs[k % 2][:m].copy_(host[i0:i0 + m], non_blocking=True)
+            bufs[k % 2][:m].copy_(src, non_blocking=True)
             ready[k % 2].record(copy)
+            copied[k % 2].record(copy)
 
     issue_copy(0)
     for k, i0 in enumerate(starts):

@@ -222,3 +222,16 @@ def test_errors_are_loud(native_model):
     cpu_model = ogl.UNet()
     with pytest.raises(RuntimeError):
         cpu_model.eval()(torch.zeros(1, 1, 32, 32))
+
+
+def test_segment_clip_host_paths_agree(native_model):
+    """Pinned input (copied from in place), pageable input (staged through two pinned buffers) and
+    device input give identical areas and masks; ragged last batch included."""
+    import openglottal_b200 as ogl
+
+    frames = torch.from_numpy(_clip(11))
+    a_dev, m_dev = ogl.segment_clip(frames.cuda(), native_model, batch=4, want_masks=True)
+    a_page, m_page = ogl.segment_clip(frames, native_model, batch=4, want_masks=True)
+    a_pin, m_pin = ogl.segment_clip(frames.pin_memory(), native_model, batch=4, want_masks=True)
+    assert torch.equal(a_dev, a_page) and torch.equal(a_dev, a_pin)
+    assert torch.equal(m_dev, m_page) and torch.equal(m_dev, m_pin)
