@@ -16,8 +16,8 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from .features import kinematic_features_device, segment_clip
-from .utils import _require_native, bgr_to_gray, gated_area
+from .features import gray_clip_from_bgr, kinematic_features_device, segment_clip
+from .utils import _require_native, gated_area
 
 FEATURE_COLS = ["area_mean", "area_std", "area_range", "open_quotient", "f0", "periodicity", "cv"]
 GIRAFE_CAPTURE_FPS = 4000.0
@@ -49,8 +49,7 @@ def annotate_unet_only(frames_bgr: list, model, overlay_style: str = "fill", bat
     area waveform as a list of floats)`` for frames whose size the network takes natively."""
     model = _require_native(model)
     dev = model._device()
-    bgr = torch.from_numpy(np.stack(frames_bgr)).to(dev)
-    area, masks = segment_clip(bgr_to_gray(bgr), model, batch=batch, want_masks=True)
+    area, masks = segment_clip(gray_clip_from_bgr(frames_bgr, dev), model, batch=batch, want_masks=True)
     area_h = area.cpu().numpy()
     masks_h = masks.cpu().numpy()
     annotated = [draw_overlay(f, m, None, float(a), overlay_style)
@@ -78,8 +77,7 @@ def extract_gaw_features(frames: list, capture_fps: float, detector, unet_model,
     dev = model._device()
     detector.reset()
     boxes = [detector.detect(frm) for frm in frames]
-    bgr = torch.from_numpy(np.stack(frames)).to(dev)
-    _, masks = segment_clip(bgr_to_gray(bgr), model, want_masks=True)
+    _, masks = segment_clip(gray_clip_from_bgr(frames, dev), model, want_masks=True)
     feats = kinematic_features_device(gated_area(masks, boxes))
     if feats is not None and feats.get("f0") is not None:
         feats["f0"] = feats["f0"] * capture_fps

@@ -173,6 +173,19 @@ def segment_clip(frames_gray, model: UNet, batch: int = 512, threshold: float = 
     return area, masks
 
 
+def gray_clip_from_bgr(frames_bgr: list, dev: torch.device, chunk: int = 2048) -> torch.Tensor:
+    """List of ``(H, W, 3)`` uint8 BGR frames -> ``(N, H, W)`` uint8 gray CUDA tensor, converted on
+    the GPU (bit-exact with ``cv2.COLOR_BGR2GRAY``, features.py:235) ``chunk`` frames at a time so
+    that neither the 3-channel clip nor a pinned copy of it has to exist as a whole."""
+    n = len(frames_bgr)
+    hgt, wid = frames_bgr[0].shape[:2]
+    gray = torch.empty((n, hgt, wid), dtype=torch.uint8, device=dev)
+    for i0 in range(0, n, chunk):
+        part = torch.from_numpy(np.stack(frames_bgr[i0:i0 + chunk])).to(dev)
+        gray[i0:i0 + part.shape[0]] = bgr_to_gray(part)
+    return gray
+
+
 def extract_features_unet_frames(frames_gray, model: UNet, batch: int = 512,
                                  threshold: float = 0.5, group=None) -> dict | None:
     """unet-only pipeline on raw gray frames ``(N, H, W)`` uint8 (H, W multiples of 16).
@@ -242,8 +255,8 @@ def extract_features_unet(avi_path: str, detector, model, device=None) -> dict |
         boxes = [detector.detect(frm) for frm in frames_bgr]
 
     if native_size:
-        bgr = torch.from_numpy(np.stack(frames_bgr)).pin_memory().to(dev, non_blocking=True)
-        area, masks = segment_clip(bgr_to_gray(bgr), model, want_masks=boxes is not None)
+        area, masks = segment_clip(gray_clip_from_bgr(frames_bgr, dev), model,
+                                   want_masks=boxes is not None)
         if boxes is not None:
             area = gated_area(masks, boxes)
         return kinematic_features_device(area)
@@ -273,6 +286,5 @@ def extract_features_yolo_crop_unet(avi_path: str, detector, model, device=None,
         return None
     detector.reset()
     boxes = [detector.detect(frm) for frm in frames_bgr]
-    bgr = torch.from_numpy(np.stack(frames_bgr)).pin_memory().to(dev, non_blocking=True)
-    area, _ = segment_crops(bgr_to_gray(bgr), boxes, model, size=crop_size)
+    area, _ = segment_crops(gray_clip_from_bgr(frames_bgr, dev), boxes, model, size=crop_size)
     return kinematic_features_device(area)
