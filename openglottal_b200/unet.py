@@ -179,12 +179,14 @@ class UNet(nn.Module):
                                "(training stays with the reference implementation)")
         if frames.dim() != 3:
             raise ValueError(f"expected (N, H, W) frames, got shape {tuple(frames.shape)}")
+        if frames.dtype in (torch.bfloat16, torch.float16):
+            frames = frames.float()      # exact widening; the stem computes in fp32 anyway
         if frames.dtype == torch.uint8:
             in_dtype = _native.DTYPE_U8
         elif frames.dtype == torch.float32:
             in_dtype = _native.DTYPE_F32
         else:
-            raise TypeError(f"frames must be uint8 or float32, got {frames.dtype}")
+            raise TypeError(f"frames must be uint8, float32, bfloat16 or float16, got {frames.dtype}")
         dev = self._device()
         if frames.device != dev:
             raise RuntimeError(f"frames are on {frames.device} but the model is on {dev}")

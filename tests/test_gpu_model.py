@@ -173,6 +173,17 @@ def test_forward_signature_matches_reference(native_model, trained_sd):
     assert (y.cpu() - ref).abs().max() <= 5e-2
 
 
+def test_half_precision_input_is_widened(native_model):
+    x = torch.from_numpy(_clip(2, 64, 96)).cuda().float() / 255.0
+    xb = x.to(torch.bfloat16)
+    with torch.no_grad():
+        y16 = native_model(xb.unsqueeze(1))
+        y32 = native_model(xb.float().unsqueeze(1))
+    assert y16.dtype == torch.float32 and torch.equal(y16, y32)
+    with pytest.raises(TypeError):
+        native_model.run(torch.zeros((1, 32, 32), dtype=torch.int32, device="cuda"))
+
+
 def test_batch_chunking_and_ragged_tail(native_model):
     """Odd batch sizes (tail tiles) and chunked calls give identical results."""
     frames = torch.from_numpy(_clip(7)).cuda()
