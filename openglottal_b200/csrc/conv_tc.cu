@@ -17,9 +17,12 @@
 //     copies, TPS taps per stage (9 for N <= 64, 3 for N = 128, 1 for convT) so the issuer
 //     pays one barrier wait per 8*TPS MMAs.
 //   * torch.cat([skip, up]) is two tensor maps walked back to back in the K loop.
-//   * Warp roles: w0 = activation TMA producer, w1 = MMA issuer, w2 = TMEM allocator,
-//     w3 = weight producer, w4..11 = epilogue (TMEM -> regs -> bias/ReLU/pool/head -> HBM);
-//     epilogue warp w reads TMEM lanes 32*(w%4).. and handles sub-tile (w-4)/4 of each tile.
+//   * Warp roles: w0 = activation TMA producer, w1 and w2 = MMA issuers (each issues half of the
+//     tile's accumulators; w2 also allocates TMEM), w3 = weight producer, w4..11 = epilogue
+//     (TMEM -> regs -> bias/ReLU/pool/head -> HBM); epilogue warp w reads TMEM lanes 32*(w%4)..
+//     and handles sub-tile (w-4)/4 of each tile.
+//   * CG = 2 (conv3x3, N >= 64): the two CTAs of a cluster run one 256-row tcgen05.mma.cta_group::2
+//     per MMA and each stages half of the weight columns (see the kernel's comment).
 #include "internal.h"
 #include "ptx.cuh"
 
