@@ -109,3 +109,26 @@ def test_million_frame_feature_step(lib):
     assert float(got["area_mean"]) == pytest.approx(wave.astype(np.float64).mean(), rel=1e-12)
     assert float(got["area_range"]) == float(wave.max() - wave.min())
     assert got["periodicity"] > 0.99
+
+
+def test_config1_pipeline_batch32_vs_oracle(native_model, trained_sd):
+    """BASELINE.json configs[0] in miniature: the unet-only pipeline at batch 32 on a 256x256
+    clip (240 frames, 12 periods) against the fp32 oracle run on the host cores: masks
+    (Dice >= 0.999), area waveform (0.5 %), kinematic features (1e-3 relative; f0 exact)."""
+    import openglottal_b200 as ogl
+    from oracle import unet_oracle as uo
+    from oracle.features_oracle import kinematic_features
+
+    frames = _clip(240, seed=91, period=20.0)
+    _, ref_mask, ref_area = uo.batch_masks(trained_sd, frames, chunk=16)
+    area, masks = ogl.segment_clip(torch.from_numpy(frames), native_model, batch=32, want_masks=True)
+    got_area = area.cpu().numpy()
+    assert ogl.dice(masks.cpu().numpy(), ref_mask) >= 0.999
+    rel = np.abs(got_area - ref_area) / np.maximum(ref_area, 1)
+    assert rel.max() <= 0.005
+    got = ogl.kinematic_features_device(area)
+    want = kinematic_features(ref_area.astype(np.float64))
+    print({k: (got[k], want[k]) for k in ("area_mean", "open_quotient", "f0", "periodicity")})
+    for k in ("area_mean", "area_std", "area_range", "open_quotient", "periodicity", "cv"):
+        assert abs(float(got[k]) - float(want[k])) <= 1e-3 * max(abs(float(want[k])), 1e-9) + 1e-9, k
+    assert got["f0"] == want["f0"] == 0.05

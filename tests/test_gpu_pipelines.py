@@ -244,3 +244,24 @@ def test_gaw_features_and_annotation(lib, native_model, trained_sd, tmp_path):
     ok, frm = cap.read()
     cap.release()
     assert ok and frm.shape == (256, 256, 3)
+
+
+def test_unet_only_pipeline_on_512x256_video_reference_resize(lib, native_model, trained_sd, tmp_path):
+    """BASELINE.json configs[2] through the pipeline: BAGLS-shaped 512(H) x 256(W) frames take the
+    reference's resize path (utils.py:234-241: squash to 256x256, upsample the probability), here
+    batched; areas against the oracle's per-frame loop."""
+    import cv2
+    import openglottal_b200 as ogl
+    from oracle import synth, unet_oracle as uo
+
+    clip, _ = synth.glottis_clip(6, 512, 256, seed=71, period=5.0)
+    path = tmp_path / "bagls.avi"
+    vw = cv2.VideoWriter(str(path), cv2.VideoWriter_fourcc(*"FFV1"), 25.0, (256, 512))
+    for f in clip:
+        vw.write(cv2.cvtColor(f, cv2.COLOR_GRAY2BGR))
+    vw.release()
+    got = ogl.extract_features_unet(str(path), None, native_model, torch.device("cuda"))
+    want = np.array(uo.area_wave(trained_sd, list(clip)))
+    err = np.abs(got["_area"] - want)
+    print("512x256 reference-resize areas", got["_area"], want)
+    assert (err <= np.maximum(4.0, 0.005 * want)).all()
