@@ -115,6 +115,13 @@ int ogl_unet_set_fused_stem(ogl_unet* h, int enable);
  * tiles (unit tests). Same results bit for bit. */
 int ogl_unet_set_cta_pairs(ogl_unet* h, int mode);
 
+/* Measurement aid: launch `launch_index` (0-based position in ogl_unet_launch_name's list) of the
+ * bf16 forward is enqueued `times` times (1..64) instead of once, with the same inputs and
+ * outputs; launch_index -1 (default) repeats nothing. Used by scripts/layer_energy.py to take the
+ * energy of one launch from the board's energy counter. The area vector is garbage when the
+ * repeated launch is the head's (its atomics accumulate). */
+int ogl_unet_set_repeat(ogl_unet* h, int launch_index, int times);
+
 /* Kinematic features of an area waveform of n >= 2 samples.
  * out8_dev: {area_mean, area_std, area_range, open_quotient, f0, periodicity, cv, peak_bin};
  * flags2_dev: {is_silent (reference returns None), f0_is_none (peak in first bin)}. */

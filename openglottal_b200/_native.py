@@ -57,6 +57,7 @@ EXPORTS = [
     "ogl_unet_launch_name",
     "ogl_unet_set_schedule",
     "ogl_unet_set_cta_pairs",
+    "ogl_unet_set_repeat",
     "ogl_unet_set_fused_stem",
     "ogl_features_workspace_bytes",
     "ogl_features",
@@ -120,6 +121,8 @@ def load() -> C.CDLL:
     lib.ogl_unet_set_fused_stem.argtypes = [vp, i32]
     lib.ogl_unet_set_cta_pairs.restype = i32
     lib.ogl_unet_set_cta_pairs.argtypes = [vp, i32]
+    lib.ogl_unet_set_repeat.restype = i32
+    lib.ogl_unet_set_repeat.argtypes = [vp, i32, i32]
     lib.ogl_unet_set_schedule.restype = i32
     lib.ogl_unet_set_schedule.argtypes = [vp, i32]
     lib.ogl_features_workspace_bytes.restype = sz

@@ -92,6 +92,8 @@ struct ogl_unet {
     int prof_forwards = 0;             // profiled forwards since profiling was enabled
     int prof_count[16] = {0};          // events recorded in each set
     std::vector<const char*> launch_names;  // of the most recent bf16 forward
+    // measurement aid (ogl_unet_set_repeat): launch `rep_launch` of the bf16 forward runs rep_n times
+    int rep_launch = -1, rep_n = 1;
 };
 
 namespace {
@@ -462,46 +464,64 @@ int ogl_unet_forward(ogl_unet* h, const void* frames_dev, int in_dtype, int n, i
         h->launch_names.clear();
         const bool s2d = h->use_s2d;
         mark(h, stream, nullptr);
+        // one launch of the schedule: enqueued once (or rep_n times when it is the launch picked by
+        // ogl_unet_set_repeat for an energy / time measurement), then named and time-stamped
+        // OGL_PINGPONG=1: launches alternate their tile order (rev) so that each starts with the
+        // frames the previous one wrote last, which are still in L2. Measured (batch 512,
+        // gpurun_out/exp_pp.jsonl -> DESIGN.md section 6): 10.58 -> 10.67 ms, no gain; off.
+        static const bool pingpong = getenv("OGL_PINGPONG") && atoi(getenv("OGL_PINGPONG")) != 0;
+        int launch_idx = 0;
+        bool rev = false;
+        auto step = [&](const char* name, auto&& launch) {
+            const int idx = launch_idx++;
+            rev = pingpong && (idx & 1);
+            for (int r = idx == h->rep_launch ? h->rep_n : 1; r > 0; --r)
+                if (launch()) return 1;
+            mark(h, stream, name);
+            return 0;
+        };
+        const int sms = h->num_sms, cg = h->cta_group;
         const bool fused_stem = s2d && h->fuse_stem && in_dtype == OGL_DTYPE_U8;
-        if (!fused_stem) {
-            if (launch_stem(frames_dev, in_dtype, h->stem, n, H, W, B(p.T[0]), s2d, stream))
-                return 1;
-            mark(h, stream, kDownC1[0]);
-        }
+        if (!fused_stem &&
+            step(kDownC1[0], [&] {
+                return launch_stem(frames_dev, in_dtype, h->stem, n, H, W, B(p.T[0]), s2d, stream);
+            }))
+            return 1;
         for (int l = 0; l < 4; ++l) {
             const int hh = H >> l, ww = W >> l;
-            if (l > 0) {
-                if (launch_conv_tc(h->down_c1[l], P[l - 1], nullptr, n, hh, ww, B(p.T[l]), nullptr,
-                                   nullptr, h->num_sms, stream, h->cta_group))
-                    return 1;
-                mark(h, stream, kDownC1[l]);
-            }
+            if (l > 0 && step(kDownC1[l], [&] {
+                    return launch_conv_tc(h->down_c1[l], P[l - 1], nullptr, n, hh, ww, B(p.T[l]),
+                                          nullptr, nullptr, sms, stream, cg, rev);
+                }))
+                return 1;
             if (l == 0 && fused_stem) {
-                if (launch_s2d_tc(h->s2d_down, nullptr, nullptr, n, H, W, B(p.S[0]), P[0], nullptr,
-                                  h->num_sms, stream, h->cta_group,
-                                  static_cast<const uint8_t*>(frames_dev), &h->stem))
+                if (step("stem+downs.0.net.3+pool", [&] {
+                        return launch_s2d_tc(h->s2d_down, nullptr, nullptr, n, H, W, B(p.S[0]), P[0],
+                                             nullptr, sms, stream, cg,
+                                             static_cast<const uint8_t*>(frames_dev), &h->stem, rev);
+                    }))
                     return 1;
-                mark(h, stream, "stem+downs.0.net.3+pool");
                 continue;
             }
-            if (l == 0 && s2d) {
-                if (launch_s2d_tc(h->s2d_down, B(p.T[0]), nullptr, n, H, W, B(p.S[0]), P[0],
-                                  nullptr, h->num_sms, stream, h->cta_group))
-                    return 1;
-            } else if (launch_conv_tc(h->down_c2[l], B(p.T[l]), nullptr, n, hh, ww, B(p.S[l]),
-                                      P[l], nullptr, h->num_sms, stream, h->cta_group)) {
+            if (step(kDownC2[l], [&] {
+                    if (l == 0 && s2d)
+                        return launch_s2d_tc(h->s2d_down, B(p.T[0]), nullptr, n, H, W, B(p.S[0]), P[0],
+                                             nullptr, sms, stream, cg, nullptr, nullptr, rev);
+                    return launch_conv_tc(h->down_c2[l], B(p.T[l]), nullptr, n, hh, ww, B(p.S[l]),
+                                          P[l], nullptr, sms, stream, cg, rev);
+                }))
                 return 1;
-            }
-            mark(h, stream, kDownC2[l]);
         }
-        if (launch_conv_tc(h->bott[0], P[3], nullptr, n, H >> 4, W >> 4, B(p.T[4]), nullptr,
-                           nullptr, h->num_sms, stream, h->cta_group))
+        if (step("bottleneck.net.0", [&] {
+                return launch_conv_tc(h->bott[0], P[3], nullptr, n, H >> 4, W >> 4, B(p.T[4]), nullptr,
+                                      nullptr, sms, stream, cg, rev);
+            }))
             return 1;
-        mark(h, stream, "bottleneck.net.0");
-        if (launch_conv_tc(h->bott[1], B(p.T[4]), nullptr, n, H >> 4, W >> 4, B(p.B4), nullptr,
-                           nullptr, h->num_sms, stream, h->cta_group))
+        if (step("bottleneck.net.3", [&] {
+                return launch_conv_tc(h->bott[1], B(p.T[4]), nullptr, n, H >> 4, W >> 4, B(p.B4),
+                                      nullptr, nullptr, sms, stream, cg, rev);
+            }))
             return 1;
-        mark(h, stream, "bottleneck.net.3");
         const __nv_bfloat16* below = B(p.B4);
         HeadParams hp;
         hp.w = h->head_w;
@@ -516,28 +536,33 @@ int ogl_unet_forward(ogl_unet* h, const void* frames_dev, int in_dtype, int n, i
             const int hh = H >> l, ww = W >> l;
             if (l == 0 && s2d) {
                 // ups.6 is composed into ups.7.net.0: reads the skip (S2D) and the level-1 tensor
-                if (launch_s2d_tc(h->s2d_up0, B(p.S[0]), below, n, H, W, B(p.T[0]), nullptr,
-                                  nullptr, h->num_sms, stream, h->cta_group))
+                if (step("ups.6(convT)+ups.7.net.0(cat)", [&] {
+                        return launch_s2d_tc(h->s2d_up0, B(p.S[0]), below, n, H, W, B(p.T[0]), nullptr,
+                                             nullptr, sms, stream, cg, nullptr, nullptr, rev);
+                    }))
                     return 1;
-                mark(h, stream, "ups.6(convT)+ups.7.net.0(cat)");
-                if (launch_s2d_tc(h->s2d_up1, B(p.T[0]), nullptr, n, H, W, nullptr, nullptr, &hp,
-                                  h->num_sms, stream, h->cta_group))
+                if (step(kUpC2[k], [&] {
+                        return launch_s2d_tc(h->s2d_up1, B(p.T[0]), nullptr, n, H, W, nullptr, nullptr,
+                                             &hp, sms, stream, cg, nullptr, nullptr, rev);
+                    }))
                     return 1;
-                mark(h, stream, kUpC2[k]);
                 break;
             }
-            if (launch_conv_tc(h->up_t[k], below, nullptr, n, hh / 2, ww / 2, B(p.U[l]), nullptr,
-                               nullptr, h->num_sms, stream, h->cta_group))
+            if (step(kUpT[k], [&] {
+                    return launch_conv_tc(h->up_t[k], below, nullptr, n, hh / 2, ww / 2, B(p.U[l]),
+                                          nullptr, nullptr, sms, stream, cg, rev);
+                }))
                 return 1;
-            mark(h, stream, kUpT[k]);
-            if (launch_conv_tc(h->up_c[k][0], B(p.S[l]), B(p.U[l]), n, hh, ww, B(p.T[l]), nullptr,
-                               nullptr, h->num_sms, stream, h->cta_group))
+            if (step(kUpC1[k], [&] {
+                    return launch_conv_tc(h->up_c[k][0], B(p.S[l]), B(p.U[l]), n, hh, ww, B(p.T[l]),
+                                          nullptr, nullptr, sms, stream, cg, rev);
+                }))
                 return 1;
-            mark(h, stream, kUpC1[k]);
-            if (launch_conv_tc(h->up_c[k][1], B(p.T[l]), nullptr, n, hh, ww, B(p.U[l]), nullptr,
-                               k == 3 ? &hp : nullptr, h->num_sms, stream, h->cta_group))
+            if (step(kUpC2[k], [&] {
+                    return launch_conv_tc(h->up_c[k][1], B(p.T[l]), nullptr, n, hh, ww, B(p.U[l]),
+                                          nullptr, k == 3 ? &hp : nullptr, sms, stream, cg, rev);
+                }))
                 return 1;
-            mark(h, stream, kUpC2[k]);
             below = B(p.U[l]);
         }
         return 0;
@@ -655,6 +680,14 @@ int ogl_unet_set_cta_pairs(ogl_unet* h, int mode) {
     if (!h) return fail("ogl_unet_set_cta_pairs: NULL handle");
     if (mode < 1 || mode > 3) return fail("ogl_unet_set_cta_pairs: mode must be 1, 2 or 3");
     h->cta_group = mode;
+    return 0;
+}
+
+int ogl_unet_set_repeat(ogl_unet* h, int launch_index, int times) {
+    if (!h) return fail("ogl_unet_set_repeat: NULL handle");
+    if (times < 1 || times > 64) return fail("ogl_unet_set_repeat: times must be in 1..64");
+    h->rep_launch = launch_index;
+    h->rep_n = times;
     return 0;
 }
 

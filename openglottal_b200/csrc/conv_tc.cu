@@ -36,8 +36,7 @@ namespace ogl {
 namespace {
 
 constexpr int kHalo = 18;                          // 16 + 2
-constexpr int kPlaneBytes = kHalo * kHalo * 16;    // one 8-channel plane of a halo tile
-constexpr int kSubBytes = 4 * kPlaneBytes;         // 32 channels of one 16x16 sub-tile (20736 B)
+// one 8-channel plane of a halo tile = 18 * 18 * 16 B; 32 channels of a sub-tile = 20736 B
 constexpr int kThreads = 384;       // 4 control warps + 8 epilogue warps
 constexpr int kEpiThreads = 256;
 constexpr int kTmemCols = 512;
@@ -65,6 +64,7 @@ struct ConvParams {
     int pass_fast;   // items ordered (tile, pass) with the pass fastest: the CTAs that re-read a
                      // tile for its other passes run at the same time, so the re-reads hit L2;
                      // with gridDim % npass == 0 each CTA still keeps one pass (its weights)
+    int reverse;     // walk the tiles from the last frame to the first (see launch_conv_tc)
     int split;       // N = 128, S = 2: per-accumulator barriers (see kSplit in the kernel)
     int dbg;         // experiment switches (OGL_DBG): 1 no MMA, 2 no stores, 4 no epilogue math,
                      // 8 no activation TMA, 16 no weight copies. Results are garbage when set.
@@ -108,8 +108,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
     const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+    // activation tile of a sub-tile: 18x18 with the conv's halo; the transposed conv reads the
+    // 16x16 pixels only (21 % fewer bytes L2 -> shared memory per K block)
+    constexpr int kEdge = EPI == EPI_CONVT ? 16 : kHalo;
+    constexpr int kPlaneB = kEdge * kEdge * 16;
+    constexpr int kSubB = 4 * kPlaneB;
 
-    constexpr uint32_t a_stage_bytes = static_cast<uint32_t>(S) * kSubBytes;
+    constexpr uint32_t a_stage_bytes = static_cast<uint32_t>(S) * kSubB;
     const uint32_t nb = static_cast<uint32_t>(p.N) / CG;          // weight columns staged per CTA
     const uint32_t w_tap_bytes = 64u * nb;
     const uint32_t w_stage_bytes = TPS * w_tap_bytes;
@@ -145,7 +150,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const int item0 = CG == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
     const int item_step = CG == 2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
     auto tile_of = [&](int item) {
-        const int unit = p.pass_fast ? item / p.npass : item % num_units;
+        int unit = p.pass_fast ? item / p.npass : item % num_units;
+        if (p.reverse) unit = num_units - 1 - unit;
         return CG == 2 ? 2 * unit + static_cast<int>(rank) : unit;   // may be >= num_tiles (tail)
     };
     auto pass_of = [&](int item) { return p.pass_fast ? item % p.npass : item / num_units; };
@@ -211,11 +217,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                         int st = tile * S + sub;
                         if (st >= p.total_sub) st = p.total_sub - 1;  // tail: load a duplicate
                         const SubTile t = decode_sub(p, st);
-                        const uint32_t dst = a_ring + s * a_stage_bytes + sub * kSubBytes;
+                        const uint32_t dst = a_ring + s * a_stage_bytes + sub * kSubB;
+                        constexpr int kPad = EPI == EPI_CONVT ? 0 : 1;
                         if (CG == 1)
-                            tma_load_4d(dst, tm, full, (t.x0 - 1) * 8, t.y0 - 1, plane0, t.n);
+                            tma_load_4d(dst, tm, full, (t.x0 - kPad) * 8, t.y0 - kPad, plane0, t.n);
                         else
-                            tma_load_4d_pair(dst, tm, full, (t.x0 - 1) * 8, t.y0 - 1, plane0, t.n);
+                            tma_load_4d_pair(dst, tm, full, (t.x0 - kPad) * 8, t.y0 - kPad, plane0, t.n);
                     }
                 }
             }
@@ -272,7 +279,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         // Descriptors differ only in their start-address field, so each MMA is one 32-bit add.
         // CG = 2: only the leader CTA issues; shared-memory offsets are the same in both CTAs.
         const uint32_t idesc = CG == 2 ? make_idesc_bf16_pair(p.N) : make_idesc_bf16(p.N);
-        constexpr uint32_t lbo_a = kPlaneBytes, sbo_a = kHalo * 16;
+        constexpr uint32_t lbo_a = kPlaneB, sbo_a = kEdge * 16;
         const uint32_t lbo_b = 16u * nb, sbo_b = 128u;
         const uint64_t adesc0 = make_smem_desc(0, lbo_a, sbo_a);
         const uint64_t bdesc0 = make_smem_desc(0, lbo_b, sbo_b);
@@ -280,7 +287,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const uint32_t bstep = (2u * lbo_b) >> 4;   // second K=16 half of a 32-channel block
         const uint32_t btap = 4u * nb;              // one tap of B, in 16-byte units
         // this issuer's accumulators: mt = me * S + m (S == 2: sub-tile me; S == 1: x-half me)
-        const uint32_t a_me = S == 2 ? me * (kSubBytes >> 4) : me * 8u;
+        const uint32_t a_me = S == 2 ? me * (kSubB >> 4) : me * 8u;
         const uint32_t d_me = me * S * static_cast<uint32_t>(p.N);
         auto mma = [](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
             if (CG == 2) umma_bf16_pair(d, a, b, id, acc);
@@ -370,7 +377,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                         for (int t = 0; t < TPS; ++t) {
                             if (p.dbg & 1) break;
                             // tap offset inside the halo tile, in 16-byte units
-                            constexpr int kCenter = kHalo + 1;
+                            constexpr int kCenter = EPI == EPI_CONVT ? 0 : kHalo + 1;
                             const uint32_t toff = TPS == 9   ? (t / 3) * kHalo + (t % 3)
                                                   : TPS == 3 ? t
                                                              : kCenter;
@@ -480,14 +487,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     tmem_ld32(tcol + c0, r);
                     tmem_ld_wait();
                     const int co0 = pass * p.N + c0;  // first output channel of these columns
-                    float v[32];
+                    float v[32];   // + bias; ReLU in fp32 for the head only, else in the conversion
 #pragma unroll
                     for (int c4 = 0; c4 < 8; ++c4) {
                         const float4 b4 = *reinterpret_cast<const float4*>(bias_sp + co0 + 4 * c4);
-                        v[4 * c4 + 0] = fmaxf(__uint_as_float(r[4 * c4 + 0]) + b4.x, 0.f);
-                        v[4 * c4 + 1] = fmaxf(__uint_as_float(r[4 * c4 + 1]) + b4.y, 0.f);
-                        v[4 * c4 + 2] = fmaxf(__uint_as_float(r[4 * c4 + 2]) + b4.z, 0.f);
-                        v[4 * c4 + 3] = fmaxf(__uint_as_float(r[4 * c4 + 3]) + b4.w, 0.f);
+                        v[4 * c4 + 0] = __uint_as_float(r[4 * c4 + 0]) + b4.x;
+                        v[4 * c4 + 1] = __uint_as_float(r[4 * c4 + 1]) + b4.y;
+                        v[4 * c4 + 2] = __uint_as_float(r[4 * c4 + 2]) + b4.z;
+                        v[4 * c4 + 3] = __uint_as_float(r[4 * c4 + 3]) + b4.w;
+                        if (EPI == EPI_HEAD) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) v[4 * c4 + e] = fmaxf(v[4 * c4 + e], 0.f);
+                        }
                     }
                     if (EPI == EPI_HEAD) {
 #pragma unroll
@@ -507,10 +518,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
                             uint4 q4;
-                            q4.x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]);
-                            q4.y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
-                            q4.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]);
-                            q4.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
+                            q4.x = pack_relu_bf16x2(v[g * 8 + 0], v[g * 8 + 1]);
+                            q4.y = pack_relu_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
+                            q4.z = pack_relu_bf16x2(v[g * 8 + 4], v[g * 8 + 5]);
+                            q4.w = pack_relu_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
                             if (valid) *reinterpret_cast<uint4*>(optr + g * plane) = q4;
                             if (EPI == EPI_RELU_POOL) {
                                 // 2x2 max over (x^1, y^1): lanes ^1 and ^8 of this warp
@@ -578,14 +589,16 @@ EncodeTiledFn g_encode = nullptr;
 constexpr int kMaxSmem = 227 * 1024;
 
 // Tensor map over a C8-planar activation tensor [B][C/8][H][W][8] bf16:
-// dims (innermost first) = (W*8, H, C/8, B); box = (18*8, 18, 4, 1).
-int make_act_map(CUtensorMap* tm, const __nv_bfloat16* base, int B, int C, int H, int W) {
+// dims (innermost first) = (W*8, H, C/8, B); box = (edge*8, edge, 4, 1), edge = 18 (conv3x3 with
+// its halo) or 16 (transposed conv).
+int make_act_map(CUtensorMap* tm, const __nv_bfloat16* base, int B, int C, int H, int W,
+                 int edge = kHalo) {
     cuuint64_t dims[4] = {static_cast<cuuint64_t>(W) * 8, static_cast<cuuint64_t>(H),
                           static_cast<cuuint64_t>(C / 8), static_cast<cuuint64_t>(B)};
     cuuint64_t strides[3] = {static_cast<cuuint64_t>(W) * 16,
                              static_cast<cuuint64_t>(W) * 16 * H,
                              static_cast<cuuint64_t>(W) * 16 * H * (C / 8)};
-    cuuint32_t box[4] = {kHalo * 8, kHalo, 4, 1};
+    cuuint32_t box[4] = {static_cast<cuuint32_t>(edge) * 8, static_cast<cuuint32_t>(edge), 4, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
                           const_cast<__nv_bfloat16*>(base), dims, strides, box, estr,
@@ -686,6 +699,7 @@ int conv_tc_init() {
             return fail("cuTensorMapEncodeTiled entry point not available");
         g_encode = reinterpret_cast<EncodeTiledFn>(fn);
     }
+    OGL_CUDA(set_wait_cfg());
     if (set_smem_attr<EPI_RELU, 9>() || set_smem_attr<EPI_RELU, 3>() ||
         set_smem_attr<EPI_RELU_POOL, 9>() || set_smem_attr<EPI_RELU_POOL, 3>() ||
         set_smem_attr<EPI_HEAD, 9>() || set_smem_attr<EPI_CONVT, 1>() ||
@@ -697,7 +711,8 @@ int conv_tc_init() {
 
 int launch_conv_tc(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloat16* src1, int B,
                    int H, int W, __nv_bfloat16* out, __nv_bfloat16* out_pool,
-                   const HeadParams* head, int num_sms, cudaStream_t stream, int cta_group) {
+                   const HeadParams* head, int num_sms, cudaStream_t stream, int cta_group,
+                   bool reverse) {
     if (!g_encode) return fail("conv_tc_init() was not called");
     if (H < 1 || W < 1) return fail("tensor-core conv needs a non-empty feature map");
     if (L.epi == EPI_RELU_POOL && (H % 2 || W % 2))
@@ -733,6 +748,9 @@ int launch_conv_tc(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloa
     p.H = H;
     p.W = W;
     p.B = B;
+    // Tile order (experiment, api.cu OGL_PINGPONG): a launch that starts with the frames its
+    // producer wrote last could find them still in the 126 MB L2; measured, no gain at batch 512.
+    p.reverse = reverse ? 1 : 0;
     // 2 sub-tiles (4 accumulators) per tile. Measured alternatives (experiment switches):
     // 1 sub-tile for N = 128 (OGL_S128=1) or for the transposed conv (OGL_ST=1) doubles the
     // weight traffic per pixel and is slower although TMEM could then be double-buffered.
@@ -764,8 +782,10 @@ int launch_conv_tc(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloa
                       (cta_group == 3 || p.kb0 + p.kb1 >= minkb_env);
     const size_t w_stage = static_cast<size_t>(tps) * 64u * p.N / (pair ? 2 : 1);
     const size_t tables = sizeof(float) * (L.cout + 32);
+    const int edge = L.epi == EPI_CONVT ? 16 : kHalo;
+    const int sub_bytes = 4 * edge * edge * 16;
     auto smem_need = [&](int na, int nw) {
-        return static_cast<size_t>(128 /*align slack*/ + na * p.S * kSubBytes + nw * w_stage +
+        return static_cast<size_t>(128 /*align slack*/ + na * p.S * sub_bytes + nw * w_stage +
                                    16 * (na + nw) + 80 + tables + 64);
     };
     // ring depths: as many weight stages as fit beside 3 activation stages (2 when the
@@ -788,9 +808,9 @@ int launch_conv_tc(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloa
         return fail("N = 128 layers hold three weight stages at once: nw must be >= 3");
 
     CUtensorMap tm0, tm1;
-    if (make_act_map(&tm0, src0, B, L.cin0, H, W)) return 1;
+    if (make_act_map(&tm0, src0, B, L.cin0, H, W, edge)) return 1;
     if (L.cin1 > 0) {
-        if (make_act_map(&tm1, src1, B, L.cin1, H, W)) return 1;
+        if (make_act_map(&tm1, src1, B, L.cin1, H, W, edge)) return 1;
     } else {
         tm1 = tm0;
     }

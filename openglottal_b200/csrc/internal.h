@@ -58,7 +58,8 @@ struct HeadParams {
 int conv_tc_init();  // resolves cuTensorMapEncodeTiled, sets smem attributes
 int launch_conv_tc(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloat16* src1, int B,
                    int H, int W, __nv_bfloat16* out, __nv_bfloat16* out_pool,
-                   const HeadParams* head, int num_sms, cudaStream_t stream, int cta_group = 1);
+                   const HeadParams* head, int num_sms, cudaStream_t stream, int cta_group = 1,
+                   bool reverse = false);  // reverse: tiles from the last frame to the first
 
 // stem: u8 / f32 gray -> conv3x3(1->32)+bias+ReLU in fp32 -> C8-planar bf16
 struct StemWeights {  // passed by value: lives in the kernel-parameter constant bank
@@ -150,7 +151,8 @@ int s2d_tc_init();
 int launch_s2d_tc(const S2dLayer& L, const __nv_bfloat16* src_s2d, const __nv_bfloat16* below,
                   int B, int H, int W, __nv_bfloat16* out_s2d, __nv_bfloat16* out_pool,
                   const HeadParams* head, int num_sms, cudaStream_t stream, int cta_group = 1,
-                  const uint8_t* stem_frames = nullptr, const StemWeights* stem = nullptr);
+                  const uint8_t* stem_frames = nullptr, const StemWeights* stem = nullptr,
+                  bool reverse = false);
 // (stem_frames != null: downs.0.net.3 with the stem fused in -- the A operand is computed from
 //  the u8 frames [B][H][W] inside the kernel and src_s2d is not read)
 // cuTensorMapEncodeTiled for a bf16 tensor (conv_tc.cu owns the driver entry point)

@@ -3,7 +3,9 @@
 // Nothing here is generic: every wrapper is the exact form the kernels need.
 #pragma once
 #include <cstdint>
+#include <cstdlib>
 #include <cuda.h>
+#include <cuda_runtime.h>
 
 namespace ogl {
 
@@ -24,6 +26,14 @@ __device__ __forceinline__ bool elect_one() {
         "}\n"
         : "=r"(pred));
     return pred != 0;
+}
+
+// bf16x2 {lo, hi} = round-to-nearest-even of max(x, 0): ReLU folded into the conversion
+// (one F2FP instead of two FMNMX + one F2FP; the values are those of fmaxf then __float2bfloat16_rn).
+__device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
 }
 
 // ---------------------------------------------------------------- mbarrier
@@ -56,21 +66,65 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// How the warps wait (per translation unit, set once from the environment by set_wait_cfg()):
+//   [0] nanosleep between the polls of the non-critical waits (ns; 0 = none)
+//   [1] suspend-time hint of the non-critical waits' mbarrier.try_wait (ns; 0 = the default limit)
+//   [2] suspend-time hint of the critical waits (the MMA issuers)
+//   [3] the issuers of the fused-stem kernel wait like the non-critical warps (0 / 1)
+// With the default time limit a failed try_wait comes back after ~25 cycles, so a waiting warp
+// issues SYNCS + BRA (+ NANOSLEEP) at that rate: 37 % of the instructions of the fused-stem
+// kernel were such polls (profiles/ncu_full_tc_r01_v9_batch128.csv, source page), taking issue
+// slots from its CUDA-core stem warps and energy from everything else.
+static __constant__ uint32_t c_wait_cfg[4];
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(ns)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) {
+    const uint32_t hint = c_wait_cfg[2];
+    if (hint) {
+        while (!mbar_try_wait_hint(bar, parity, hint)) {
+        }
+    } else {
+        while (!mbar_try_wait(bar, parity)) {
+        }
     }
 }
 // For the warps that are NOT on the tensor pipe's critical path (producers waiting for a free
 // slot, epilogue warps waiting for an accumulator): back off between polls, so that their spinning
 // does not take issue slots from the warps that have work (measured: the in-kernel stem of
 // downs.0.net.3 1.48 -> 1.25 ms).
-#ifndef OGL_WAIT_SLEEP
-#define OGL_WAIT_SLEEP 64
-#endif
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) {
-        __nanosleep(OGL_WAIT_SLEEP);
+    const uint32_t ns = c_wait_cfg[0], hint = c_wait_cfg[1];
+    if (hint) {
+        while (!mbar_try_wait_hint(bar, parity, hint)) {
+            if (ns) __nanosleep(ns);
+        }
+    } else {
+        while (!mbar_try_wait(bar, parity)) {
+            if (ns) __nanosleep(ns);
+        }
     }
+}
+// Host side: OGL_WAIT_SLEEP / OGL_WAIT_HINT / OGL_WAIT_HINT_CRIT (ns), OGL_WAIT_STEM_RELAXED
+// -> this unit's c_wait_cfg
+inline cudaError_t set_wait_cfg() {
+    auto env = [](const char* name, uint32_t dflt) {
+        const char* v = getenv(name);
+        return v ? static_cast<uint32_t>(atoi(v)) : dflt;
+    };
+    const uint32_t cfg[4] = {env("OGL_WAIT_SLEEP", 64), env("OGL_WAIT_HINT", 0),
+                             env("OGL_WAIT_HINT_CRIT", 0), env("OGL_WAIT_STEM_RELAXED", 0)};
+    return cudaMemcpyToSymbol(c_wait_cfg, cfg, sizeof cfg);
 }
 
 // --------------------------------------------------------------------- TMA

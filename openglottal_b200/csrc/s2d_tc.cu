@@ -143,6 +143,7 @@ struct S2dParams {
     int tiles_x, tiles_y, num_tiles;
     unsigned long long magic_tx, magic_tpf;
     int nslots;
+    int reverse;  // walk the tiles from the last frame to the first (L2 reuse, see conv_tc.cu)
     int dual;   // two MMA issuer warps on alternate tiles (needs nslots >= 2 * n_stages)
     int dbg;  // 1 no MMA, 2 no stores, 4 no epilogue work, 8 no activation loads (1-CTA form)
 };
@@ -163,10 +164,6 @@ __device__ __forceinline__ Tile decode_tile(const S2dParams& p, int tile) {
     return t;
 }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&v);
-}
 __device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
     __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a),
                                *reinterpret_cast<__nv_bfloat162*>(&b));
@@ -217,7 +214,10 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
     const int unit0 = CG == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
     const int unit_step = CG == 2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
     const int num_units = CG == 2 ? (p.num_tiles + 1) >> 1 : p.num_tiles;
-    auto tile_of = [&](int unit) { return CG == 2 ? 2 * unit + static_cast<int>(rank) : unit; };
+    auto tile_of = [&](int unit) {
+        if (p.reverse) unit = num_units - 1 - unit;
+        return CG == 2 ? 2 * unit + static_cast<int>(rank) : unit;
+    };
 
     // ---------------------------------------------------------------- setup
     for (int i = threadIdx.x; i < 9 * 32; i += kThreads + STEM * kStemThreads) btab_sp[i] = p.btab[i];
@@ -262,7 +262,7 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
         constexpr int kNeedH = 2 * kHH - 2, kNeedW = 2 * kHW - 2;   // 34 x 18
         uint32_t it = 0, iu = 0;
         for (int unit = unit0; unit < num_units; unit += unit_step, ++iu) {
-            const Tile t = decode_tile(p, unit);
+            const Tile t = decode_tile(p, tile_of(unit));
             const int gy0 = 2 * t.y0 - 3, gx0 = 2 * t.x0 - 3;   // frame coordinates of u8p[0][0]
             const uint32_t us = iu % kU8Slots;
             const uint8_t* u8p = gen + u8_s + us * kU8Slot;      // rows of kU8Row bytes (TMA box)
@@ -317,7 +317,7 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
                             for (int q = 0; q < 3; ++q) {   // zero outside the image: conv2's padding
                                 const float lo = __uint_as_float(static_cast<uint32_t>(a[q]));
                                 const float hi = __uint_as_float(static_cast<uint32_t>(a[q] >> 32));
-                                pk[q][c2] = pack_bf16x2(fmaxf(lo, 0.f), fmaxf(hi, 0.f)) & inside[q];
+                                pk[q][c2] = pack_relu_bf16x2(lo, hi) & inside[q];
                             }
                         }
 #pragma unroll
@@ -343,7 +343,7 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
         if (lane == 0) {
             uint32_t iu = 0;
             for (int unit = unit0; unit < num_units; unit += unit_step, ++iu) {
-                const Tile t = decode_tile(p, unit);
+                const Tile t = decode_tile(p, tile_of(unit));
                 const uint32_t us = iu % kU8Slots;
                 mbar_wait_relaxed(u8_empty + 8u * us, ((iu / kU8Slots) & 1u) ^ 1u);
                 mbar_arrive_expect_tx(u8_full + 8u * us, kU8Bytes);
@@ -450,7 +450,9 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
             const uint32_t d0 = tmem_base + buf * 128u;
             for (int s = 0; s < p.n_s2d; ++s, ++ita) {
                 const uint32_t slot = ita % p.nslots;
-                mbar_wait(a_full + 8u * slot, (ita / p.nslots) & 1u);
+                // fused stem: the CUDA-core stem warps are the critical path, not the issuers
+                if (STEM && c_wait_cfg[3]) mbar_wait_relaxed(a_full + 8u * slot, (ita / p.nslots) & 1u);
+                else mbar_wait(a_full + 8u * slot, (ita / p.nslots) & 1u);
                 tc_fence_after();
                 const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) |
                                     (((a_ring + slot * kSlot) >> 4) | a_lbo_s2d);
@@ -535,19 +537,25 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
                 const int ry = y == 0 ? 0 : (y == H - 1 ? 2 : 1);
                 const int rx = x == 0 ? 0 : (x == W - 1 ? 2 : 1);
                 float v[32];
-                // bias + ReLU. Interior pixels (every lane of nearly every warp) take the bias
-                // straight from the constant bank; only warps touching the image border of a
-                // layer with a composed transposed conv read their per-class bias from smem.
+                // bias (+ ReLU for the head, whose dot product runs on the fp32 values; the other
+                // epilogues fold the ReLU into the bf16 conversion). Interior pixels (every lane of
+                // nearly every warp) take the bias straight from the constant bank; only warps
+                // touching the image border of a layer with a composed transposed conv read
+                // their per-class bias from smem.
                 const bool plain = !p.border_bias || (ry == 1 && rx == 1);
                 if (__all_sync(0xffffffffu, plain)) {
 #pragma unroll
-                    for (int k = 0; k < 32; ++k)
-                        v[k] = fmaxf(__uint_as_float(r[k]) + p.bias[k], 0.f);
+                    for (int k = 0; k < 32; ++k) {
+                        v[k] = __uint_as_float(r[k]) + p.bias[k];
+                        if (EPI == EPI_HEAD) v[k] = fmaxf(v[k], 0.f);
+                    }
                 } else {
                     const float* bp = btab_sp + (ry * 3 + rx) * 32;
 #pragma unroll
-                    for (int k = 0; k < 32; ++k)
-                        v[k] = fmaxf(__uint_as_float(r[k]) + bp[k], 0.f);
+                    for (int k = 0; k < 32; ++k) {
+                        v[k] = __uint_as_float(r[k]) + bp[k];
+                        if (EPI == EPI_HEAD) v[k] = fmaxf(v[k], 0.f);
+                    }
                 }
                 if (EPI == EPI_HEAD) {
                     float z = 0.f;
@@ -575,10 +583,10 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         uint4 q4;
-                        q4.x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]);
-                        q4.y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
-                        q4.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]);
-                        q4.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
+                        q4.x = pack_relu_bf16x2(v[g * 8 + 0], v[g * 8 + 1]);
+                        q4.y = pack_relu_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
+                        q4.z = pack_relu_bf16x2(v[g * 8 + 4], v[g * 8 + 5]);
+                        q4.w = pack_relu_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
                         if (valid) *reinterpret_cast<uint4*>(optr + g * 4 * plane) = q4;
                         if (EPI == EPI_RELU_POOL) {
                             if (ph == 0) {
@@ -804,6 +812,7 @@ int launch_kernel(bool pair, int grid, size_t smem, cudaStream_t stream, const C
 }  // namespace
 
 int s2d_tc_init() {
+    OGL_CUDA(set_wait_cfg());
     OGL_CUDA(cudaFuncSetAttribute(s2d_tc_kernel<EPI_RELU_POOL, 1, 1>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     return set_attr<EPI_RELU>() || set_attr<EPI_RELU_POOL>() || set_attr<EPI_HEAD>();
@@ -812,7 +821,7 @@ int s2d_tc_init() {
 int launch_s2d_tc(const S2dLayer& L, const __nv_bfloat16* src_s2d, const __nv_bfloat16* below,
                   int B, int H, int W, __nv_bfloat16* out_s2d, __nv_bfloat16* out_pool,
                   const HeadParams* head, int num_sms, cudaStream_t stream, int cta_group,
-                  const uint8_t* stem_frames, const StemWeights* stem) {
+                  const uint8_t* stem_frames, const StemWeights* stem, bool reverse) {
     if (H < 2 || W < 2 || H % 2 || W % 2) return fail("s2d layer needs even, non-empty H and W");
     if ((W / 2) % 8) return fail("s2d layer needs W to be a multiple of 16");
     const bool fused_stem = stem_frames != nullptr;
@@ -872,6 +881,7 @@ int launch_s2d_tc(const S2dLayer& L, const __nv_bfloat16* src_s2d, const __nv_bf
     p.magic_tpf = ((1ull << 40) / static_cast<unsigned long long>(p.tiles_x * p.tiles_y)) + 1;
     static const int dbg_env = getenv("OGL_DBG") ? atoi(getenv("OGL_DBG")) : 0;
     p.dbg = dbg_env;
+    p.reverse = reverse ? 1 : 0;
 
     // CTA pairs. cta_group 2: for the layer with the composed transposed conv, whose 152 KB of
     // weights leave one CTA only 3 activation stages (measured 1.57 -> 1.12 ms; the HBM-bound
