@@ -76,7 +76,8 @@ struct ogl_unet {
     // u8 input: compute the stem inside the downs.0.net.3 kernel (its output never touches HBM:
     // 8.4 MB per frame less traffic). Bit-identical to the stand-alone stem; as fast or slightly
     // faster under the board's power cap.
-    bool fuse_stem = true;
+    int fuse_stem = 1;                 // 0 separate kernel, 1 in-kernel on CUDA cores, 2 on tensor cores
+    uint8_t* stem_tc = nullptr;        // B operands of the tensor-core stem (device)
     int cta_group = 2;  // 2: conv3x3 layers with N >= 64 run on CTA pairs (tcgen05 cta_group::2)
     // fp32 validation path
     F32Conv f_down[4][2], f_bott[2], f_up[4][2];
@@ -311,7 +312,7 @@ int ogl_unet_create(ogl_unet** out, int device) {
     ogl_unet* h = new ogl_unet();
     if (const char* e = getenv("OGL_S2D")) h->use_s2d = atoi(e) != 0;
     if (const char* e = getenv("OGL_CG")) h->cta_group = atoi(e);
-    if (const char* e = getenv("OGL_FUSE_STEM")) h->fuse_stem = atoi(e) != 0;
+    if (const char* e = getenv("OGL_FUSE_STEM")) h->fuse_stem = atoi(e);
     h->device = device;
     h->num_sms = prop.multiProcessorCount;
     *out = h;
@@ -353,6 +354,8 @@ int ogl_unet_load_state(ogl_unet* h, const ogl_unet_state* st) {
         if (i == 0) {
             memcpy(h->stem.w, w.data(), sizeof h->stem.w);
             memcpy(h->stem.b, b.data(), sizeof h->stem.b);
+            std::vector<uint8_t> blob;
+            if (build_stem_tc_blob(h->stem, &blob) || dev_upload(h, blob, &h->stem_tc)) return 1;
         } else {
             if (build_tc_conv(h, w, b, cin, 0, f, EPI_RELU, &h->down_c1[i])) return 1;
         }
@@ -498,7 +501,8 @@ int ogl_unet_forward(ogl_unet* h, const void* frames_dev, int in_dtype, int n, i
                 if (step("stem+downs.0.net.3+pool", [&] {
                         return launch_s2d_tc(h->s2d_down, nullptr, nullptr, n, H, W, B(p.S[0]), P[0],
                                              nullptr, sms, stream, cg,
-                                             static_cast<const uint8_t*>(frames_dev), &h->stem, rev);
+                                             static_cast<const uint8_t*>(frames_dev), &h->stem, rev,
+                                             h->fuse_stem == 2 ? h->stem_tc : nullptr);
                     }))
                     return 1;
                 continue;
@@ -672,7 +676,8 @@ int ogl_unet_set_schedule(ogl_unet* h, int s2d_level0) {
 
 int ogl_unet_set_fused_stem(ogl_unet* h, int enable) {
     if (!h) return fail("ogl_unet_set_fused_stem: NULL handle");
-    h->fuse_stem = enable != 0;
+    if (enable < 0 || enable > 2) return fail("ogl_unet_set_fused_stem: mode must be 0, 1 or 2");
+    h->fuse_stem = enable;
     return 0;
 }
 

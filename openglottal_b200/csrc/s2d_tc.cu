@@ -31,6 +31,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 namespace ogl {
 
@@ -120,10 +121,20 @@ static_assert(kU8Off + 2 * kHW + 2 <= kU8Row, "u8 box too narrow");
 constexpr int kU8Bytes = kU8Row * kStagePxH;          // 1824
 constexpr int kU8Slot = 1920;                         // 128-byte aligned slots
 constexpr int kU8Slots = 4;
+// STEM = 2: the stem itself is a GEMM on the tensor cores. Rows = the 720 positions of a stage
+// (phase, halo row, halo column: exactly the order of a stage's 16-byte cells), K = 16 = the nine
+// taps as bf16 (u8 values are exact), two ones for the bias and zeros, N = 32 channels.
+constexpr int kStemRows = 4 * kHW * kHH;                 // 720
+constexpr int kStemChunks = (kStemRows + 127) / 128;     // 6 MMAs of 128 rows (the last is partial)
+constexpr int kStemABytes = 2 * kStemRows * 16;          // [K half][row][8 bf16] = 23040 B
+constexpr int kStemBBytes = 2 * 2 * 32 * 16;             // B_hi, B_lo: [K half][32][8 bf16] each
+constexpr int kStemDSlots = 4;                           // 32-column accumulators, TMEM cols 384..511
+constexpr int kStemDCol = 384;
 
 struct S2dParams {
-    const uint8_t* frames;   // STEM = 1: u8 gray frames [B][2 H2][2 W2]
+    const uint8_t* frames;   // STEM: u8 gray frames [B][2 H2][2 W2]
     StemPairs stem;          // STEM = 1: folded stem weights / 255 and bias, as channel pairs
+    const uint8_t* stem_b;   // STEM = 2: B operands of the stem GEMM (build_stem_tc_blob), device
     const uint8_t* wblob;
     const float* btab;     // [3][3][32]: bias per (row class, column class), border pixels only
     float bias[32];        // bias of interior pixels (= btab[1][1]); constant-bank operands
@@ -164,6 +175,10 @@ __device__ __forceinline__ Tile decode_tile(const S2dParams& p, int tile) {
     return t;
 }
 
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
 __device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
     __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a),
                                *reinterpret_cast<__nv_bfloat162*>(&b));
@@ -179,8 +194,13 @@ __device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
 // warps from the u8 frame -- utils.py:235 (/255) + downs.0.net.0 (conv3x3 1->32, BN, ReLU) in fp32
 // on the CUDA cores, rounded to bf16 straight into the UMMA operand layout -- so the stem's
 // 4.19 MB-per-frame output tensor is never written to or read from HBM.
+// STEM = 2: the same, but the stem is computed on the tensor cores: the stem warps only build the
+// 720 x 16 im2col operand of a tile from the u8 region (bf16, exact) and move the GEMM's result
+// from TMEM (ReLU folded into the bf16 conversion) into the A stages; warp 3 issues the stem MMAs.
+// The weights are split w/255 = hi + lo in bf16 (two MMAs per 128 rows, fp32 accumulation), the
+// bias rides on two constant-one K columns the same way: within ~2^-17 relative of the fp32 stem.
 template <int EPI, int CG, int STEM>
-__global__ void __launch_bounds__(kThreads + STEM * kStemThreads, 1)
+__global__ void __launch_bounds__(kThreads + (STEM ? kStemThreads : 0), 1)
 s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmB,
               const S2dParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -202,7 +222,15 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
     // STEM = 1: ring of u8 regions (one per tile, loaded by TMA ahead of the stem warps)
     const uint32_t u8_full = w_peer + 16u;
     const uint32_t u8_empty = u8_full + 8u * kU8Slots;
-    const uint32_t u8_s = (u8_empty + 8u * kU8Slots + 127u) & ~127u;
+    // STEM = 2: im2col buffers (two tiles) and accumulator slots of the stem GEMM
+    const uint32_t sa_full = u8_empty + 8u * kU8Slots;
+    const uint32_t sa_empty = sa_full + 16u;
+    const uint32_t sd_full = sa_empty + 16u;
+    const uint32_t sd_empty = sd_full + 8u * kStemDSlots;
+    const uint32_t u8_s = (sd_empty + 8u * kStemDSlots + 127u) & ~127u;
+    const uint32_t sA = u8_s + kU8Slots * kU8Slot;
+    const uint32_t sB = sA + 2u * kStemABytes;
+    constexpr int kBufs = STEM == 2 ? 3 : kAccBufs;   // main accumulators (128 columns each)
     uint8_t* gen = smem_raw - raw;  // generic pointer = gen + shared address
     float* btab_sp = reinterpret_cast<float*>(gen + btab_s);
     volatile uint32_t* tmem_slot_p = reinterpret_cast<volatile uint32_t*>(gen + tmem_slot);
@@ -220,7 +248,13 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
     };
 
     // ---------------------------------------------------------------- setup
-    for (int i = threadIdx.x; i < 9 * 32; i += kThreads + STEM * kStemThreads) btab_sp[i] = p.btab[i];
+    for (int i = threadIdx.x; i < 9 * 32; i += kThreads + (STEM ? kStemThreads : 0)) btab_sp[i] = p.btab[i];
+    if (STEM == 2) {
+        if (threadIdx.x < kStemBBytes / 16)
+            *reinterpret_cast<uint4*>(gen + sB + 16u * threadIdx.x) =
+                reinterpret_cast<const uint4*>(p.stem_b)[threadIdx.x];
+        fence_proxy_async();
+    }
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmS);
         tma_prefetch_desc(&tmB);
@@ -231,11 +265,21 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
                 mbar_init(u8_full + 8u * i, 1);
                 mbar_init(u8_empty + 8u * i, kStemThreads / 32);
             }
+        if (STEM == 2) {
+            for (int i = 0; i < 2; ++i) {
+                mbar_init(sa_full + 8u * i, kStemThreads / 32);
+                mbar_init(sa_empty + 8u * i, 1);
+            }
+            for (int i = 0; i < kStemDSlots; ++i) {
+                mbar_init(sd_full + 8u * i, 1);
+                mbar_init(sd_empty + 8u * i, 4);   // the four warps of the draining group
+            }
+        }
         for (int i = 0; i < p.nslots; ++i) {
             mbar_init(a_full + 8u * i, STEM ? kStemThreads / 32 : 1);   // one arrival per stem warp
             mbar_init(a_empty + 8u * i, 1);
         }
-        for (int i = 0; i < kAccBufs; ++i) {
+        for (int i = 0; i < kBufs; ++i) {
             mbar_init(acc_full + 8u * i, 1);
             mbar_init(acc_empty + 8u * i, 128 * CG);   // CG = 2: the epilogues of both CTAs
         }
@@ -251,7 +295,103 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_p;
 
-    if (STEM && warp >= kThreads / 32) {
+    if (STEM == 2 && warp >= kThreads / 32) {
+        // ============================ stem on the tensor cores: im2col in, A stages out
+        const int st = threadIdx.x - kThreads;
+        const int sw = st >> 5;            // stem warp 0..7; TMEM lane quarter = sw & 3 (= warp & 3)
+        const int grp = sw >> 2;           // drains the chunks j with (j & 1) == grp
+        const uint32_t lane_sel = static_cast<uint32_t>((sw & 3) * 32) << 16;
+        const int W = 2 * p.W2, H = 2 * p.H2;
+        // im2col of tile number iu of this CTA into buffer iu & 1
+        auto build = [&](uint32_t iu, int unit) {
+            const Tile t = decode_tile(p, tile_of(unit));
+            const int gy0 = 2 * t.y0 - 2, gx0 = 2 * t.x0 - 2;   // frame coordinates of stage pixel (0, 0)
+            const uint32_t us = iu % kU8Slots;
+            const uint8_t* u8p = gen + u8_s + us * kU8Slot;      // rows of kU8Row bytes (TMA box)
+            uint8_t* abuf = gen + sA + (iu & 1u) * kStemABytes;
+            mbar_wait_relaxed(u8_full + 8u * us, (iu / kU8Slots) & 1u);
+            mbar_wait_relaxed(sa_empty + 8u * (iu & 1u), ((iu >> 1) & 1u) ^ 1u);
+#pragma unroll
+            for (int rr = 0; rr < (kStemRows + kStemThreads - 1) / kStemThreads; ++rr) {
+                const int r = st + rr * kStemThreads;
+                if (r < kStemRows) {
+                    const int ph = r / (kHW * kHH), pos = r - ph * (kHW * kHH);
+                    const int hy = pos / kHW, hx = pos - hy * kHW;
+                    const int ly = 2 * hy + (ph >> 1), lx = 2 * hx + (ph & 1);
+                    const int gy = gy0 + ly, gx = gx0 + lx;
+                    // outside the image the stem's OUTPUT is zero (conv2's padding): a zero row,
+                    // bias columns included
+                    const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W && !(p.dbg & 64);
+                    const uint8_t* src = u8p + ly * kU8Row + kU8Off + lx;
+                    float v[9];
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) v[k] = static_cast<float>(src[(k / 3) * kU8Row + (k % 3)]);
+                    uint4 k0 = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                          pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+                    uint4 k1 = make_uint4(pack_bf16x2(v[8], 1.f), pack_bf16x2(1.f, 0.f), 0u, 0u);
+                    if (!in) k0 = k1 = make_uint4(0u, 0u, 0u, 0u);
+                    *reinterpret_cast<uint4*>(abuf + r * 16) = k0;
+                    *reinterpret_cast<uint4*>(abuf + kStemRows * 16 + r * 16) = k1;
+                }
+            }
+            fence_proxy_async();   // visible to the tensor core's reads
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(sa_full + 8u * (iu & 1u));
+                mbar_arrive(u8_empty + 8u * us);
+            }
+        };
+        // result of the stem GEMM of tile iu: TMEM -> ReLU -> bf16 -> the tile's two A stages
+        // (row r of the GEMM is the 16-byte cell r of each 8-channel group of a stage)
+        auto drain = [&](uint32_t iu) {
+            const uint32_t it0 = 2u * iu, it1 = 2u * iu + 1u;
+            const uint32_t s0 = it0 % p.nslots, s1 = it1 % p.nslots;
+            mbar_wait_relaxed(a_empty + 8u * s0, ((it0 / p.nslots) & 1u) ^ 1u);
+            mbar_wait_relaxed(a_empty + 8u * s1, ((it1 / p.nslots) & 1u) ^ 1u);
+            uint8_t* stage0 = gen + a_ring + s0 * kSlot;
+            uint8_t* stage1 = gen + a_ring + s1 * kSlot;
+#pragma unroll 1
+            for (int j = grp; j < kStemChunks; j += 2) {
+                const uint32_t c = static_cast<uint32_t>(kStemChunks) * iu + j;
+                const uint32_t slot = c % kStemDSlots;
+                mbar_wait_relaxed(sd_full + 8u * slot, (c / kStemDSlots) & 1u);
+                tc_fence_after();
+                uint32_t v[32];
+                tmem_ld32(tmem_base + lane_sel + kStemDCol + slot * 32u, v);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(sd_empty + 8u * slot);   // the values are in registers
+                const int r = j * 128 + (sw & 3) * 32 + lane;
+                if (r < kStemRows) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {   // 8-channel groups: (stage, plane group)
+                        const uint4 q = make_uint4(
+                            pack_relu_bf16x2(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1])),
+                            pack_relu_bf16x2(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])),
+                            pack_relu_bf16x2(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])),
+                            pack_relu_bf16x2(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
+                        uint8_t* dst = ((g >> 1) ? stage1 : stage0) + (g & 1) * 4 * kPlane + r * 16;
+                        *reinterpret_cast<uint4*>(dst) = q;
+                    }
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(a_full + 8u * s0);
+                mbar_arrive(a_full + 8u * s1);
+            }
+        };
+        uint32_t iu = 0;
+        int unit = unit0;
+        if (unit < num_units) build(0, unit);
+        for (; unit < num_units; unit += unit_step, ++iu) {
+            // the im2col of the next tile first: the stem MMAs of this one run meanwhile
+            if (unit + unit_step < num_units) build(iu + 1, unit + unit_step);
+            drain(iu);
+        }
+    } else if (STEM == 1 && warp >= kThreads / 32) {
         // ====================================== stem: compute the A stages from the u8 frame
         // A tile needs the stem output on 10 x 18 half-resolution positions x 4 phases, of which
         // the outermost ring is read through one phase only: 34 x 18 full-resolution pixels.
@@ -407,6 +547,42 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
                 mbar_arrive_cluster(map_to_cta(w_peer, 0));
             }
         }
+        if (STEM == 2) {
+            // ============================================== issuer of the stem GEMM
+            // per tile 6 x (A[128 rows x 16] x B_hi, then x B_lo) into a ring of four 32-column
+            // accumulators; the whole warp walks the loop, one elected lane issues
+            __syncwarp();
+            constexpr uint32_t a_hi_s = (128u >> 4) | (1u << 14);                 // SBO = 8 rows
+            constexpr uint32_t a_lbo_s = (static_cast<uint32_t>(kStemRows * 16) >> 4) << 16;
+            constexpr uint64_t b_hi_s = static_cast<uint64_t>((128u >> 4) | (1u << 14)) << 32;
+            const uint64_t bd_hi = b_hi_s | ((sB >> 4) | (32u << 16));            // LBO = 16 N = 512 B
+            const uint64_t bd_lo = bd_hi + (1024u >> 4);
+            uint32_t c = 0, iu = 0;
+            for (int unit = unit0; unit < num_units; unit += unit_step, ++iu) {
+                const uint32_t b = iu & 1u;
+                mbar_wait(sa_full + 8u * b, (iu >> 1) & 1u);
+                tc_fence_after();
+#pragma unroll 1
+                for (int j = 0; j < kStemChunks; ++j, ++c) {
+                    const uint32_t slot = c % kStemDSlots;
+                    mbar_wait(sd_empty + 8u * slot, ((c / kStemDSlots) & 1u) ^ 1u);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t ad =
+                            (static_cast<uint64_t>(a_hi_s) << 32) |
+                            (((sA + b * kStemABytes + static_cast<uint32_t>(j) * 2048u) >> 4) | a_lbo_s);
+                        const uint32_t d = tmem_base + kStemDCol + slot * 32u;
+                        if (!(p.dbg & 1)) {
+                            umma_bf16(d, ad, bd_hi, make_idesc_bf16(32), 0u);
+                            umma_bf16(d, ad, bd_lo, make_idesc_bf16(32), 1u);
+                        }
+                        umma_commit(sd_full + 8u * slot);
+                        if (j == kStemChunks - 1) umma_commit(sa_empty + 8u * b);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
     } else if ((warp == 1 || warp == 2) && rank == 0) {
         // ================================================= MMA issuers (two warps)
         // The tensor pipe accepts an MMA only when the previous one is (nearly) done, and a wait
@@ -442,8 +618,8 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
         for (int unit = unit0; unit < num_units; unit += unit_step, ++li) {
             if (p.dual ? (li & 1u) != me : me != 0u) continue;   // the other issuer's tile
             ita = li * static_cast<uint32_t>(p.n_stages);       // its stages in the ring
-            const uint32_t buf = li % kAccBufs;
-            const uint32_t aph = (li / kAccBufs) & 1u;
+            const uint32_t buf = li % kBufs;
+            const uint32_t aph = (li / kBufs) & 1u;
             if (CG == 2) mbar_wait_cluster(acc_empty + 8u * buf, aph ^ 1u);
             else mbar_wait(acc_empty + 8u * buf, aph ^ 1u);
             tc_fence_after();
@@ -513,8 +689,8 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
         uint32_t li = 0;
         for (int unit = unit0; unit < num_units; unit += unit_step, ++li) {
             if (static_cast<int>(li & 1u) != grp) continue;
-            const uint32_t buf = li % kAccBufs;
-            const uint32_t aph = (li / kAccBufs) & 1u;
+            const uint32_t buf = li % kBufs;
+            const uint32_t aph = (li / kBufs) & 1u;
             const int tile = tile_of(unit);
             const bool in_range = tile < p.num_tiles;   // false only for the tail of the last pair
             const Tile t = decode_tile(p, in_range ? tile : p.num_tiles - 1);
@@ -641,6 +817,32 @@ inline uint16_t bf16_bits(double v) {
 }
 
 }  // namespace
+
+// B operands of the tensor-core stem: [B_hi, B_lo][K half][n = 32 channels][8 K elements] bf16.
+// K rows 0..8 = the taps' weights / 255 (the fp32 value of the CUDA-core stem, split hi + lo),
+// row 9 = bias (hi), row 10 = bias (lo) -- the im2col operand holds ones there -- rows 11..15 zero.
+int build_stem_tc_blob(const StemWeights& sw, std::vector<uint8_t>* out) {
+    out->assign(kStemBBytes, 0);
+    uint16_t* B = reinterpret_cast<uint16_t*>(out->data());
+    auto split = [](float v, uint16_t* hi, uint16_t* lo) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        const float rest = v - __bfloat162float(h);
+        const __nv_bfloat16 l = __float2bfloat16_rn(rest);
+        memcpy(hi, &h, 2);
+        memcpy(lo, &l, 2);
+    };
+    auto at = [&](int part, int k, int n) -> uint16_t& {
+        return B[part * 512 + ((k >> 3) * 32 + n) * 8 + (k & 7)];
+    };
+    for (int n = 0; n < 32; ++n) {
+        for (int k = 0; k < 9; ++k) {
+            const float w = static_cast<float>(static_cast<double>(sw.w[n * 9 + k]) / 255.0);
+            split(w, &at(0, k, n), &at(1, k, n));
+        }
+        split(sw.b[n], &at(0, 9, n), &at(0, 10, n));
+    }
+    return 0;
+}
 
 int build_s2d_host(const float* w3, const float* b3, int cin_s, const float* wt, const float* bt,
                    int cin_b, S2dHost* out) {
@@ -815,13 +1017,16 @@ int s2d_tc_init() {
     OGL_CUDA(set_wait_cfg());
     OGL_CUDA(cudaFuncSetAttribute(s2d_tc_kernel<EPI_RELU_POOL, 1, 1>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    OGL_CUDA(cudaFuncSetAttribute(s2d_tc_kernel<EPI_RELU_POOL, 1, 2>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     return set_attr<EPI_RELU>() || set_attr<EPI_RELU_POOL>() || set_attr<EPI_HEAD>();
 }
 
 int launch_s2d_tc(const S2dLayer& L, const __nv_bfloat16* src_s2d, const __nv_bfloat16* below,
                   int B, int H, int W, __nv_bfloat16* out_s2d, __nv_bfloat16* out_pool,
                   const HeadParams* head, int num_sms, cudaStream_t stream, int cta_group,
-                  const uint8_t* stem_frames, const StemWeights* stem, bool reverse) {
+                  const uint8_t* stem_frames, const StemWeights* stem, bool reverse,
+                  const uint8_t* stem_tc_blob) {
     if (H < 2 || W < 2 || H % 2 || W % 2) return fail("s2d layer needs even, non-empty H and W");
     if ((W / 2) % 8) return fail("s2d layer needs W to be a multiple of 16");
     const bool fused_stem = stem_frames != nullptr;
@@ -853,6 +1058,7 @@ int launch_s2d_tc(const S2dLayer& L, const __nv_bfloat16* src_s2d, const __nv_bf
         // they are: utils.py:235 folded into downs.0.net.0
         p.frames = stem_frames;
         p.stem = make_stem_pairs(*stem);
+        p.stem_b = stem_tc_blob;   // non-null: the stem runs on the tensor cores (STEM = 2)
     }
     p.btab = L.btab;
     p.border_bias = L.cin_b > 0 ? 1 : 0;
@@ -893,8 +1099,10 @@ int launch_s2d_tc(const S2dLayer& L, const __nv_bfloat16* src_s2d, const __nv_bf
                                       : (p.num_tiles >= num_sms && (L.cin_b > 0 || pair_all_env)));
     p.wblob = pair ? L.wblob2 : L.wblob;
     const size_t wres = L.wbytes / (pair ? 2 : 1);
+    const bool tc_stem = fused_stem && stem_tc_blob != nullptr;
     const size_t fixed = 128 + ((wres + 127u) & ~static_cast<size_t>(127)) + 9 * 32 * 4 + 8 +
-                         16 * kAccBufs + 16 + 16 + 16 * kU8Slots + 128 + kU8Slots * kU8Slot + 64;
+                         16 * kAccBufs + 16 + 16 + 16 * kU8Slots + 32 + 16 * kStemDSlots + 128 +
+                         kU8Slots * kU8Slot + (tc_stem ? 2 * kStemABytes + kStemBBytes : 0) + 64;
     int nslots = 6;
     static const int ns_env = getenv("OGL_S2D_SLOTS") ? atoi(getenv("OGL_S2D_SLOTS")) : 0;
     if (ns_env > 0) nslots = ns_env;
@@ -915,8 +1123,14 @@ int launch_s2d_tc(const S2dLayer& L, const __nv_bfloat16* src_s2d, const __nv_bf
         if (encode_map(&tmS, stem_frames, 3, dims, str, box, true)) return 1;
         memset(&tmB, 0, sizeof tmB);
         const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-        s2d_tc_kernel<EPI_RELU_POOL, 1, 1>
-            <<<grid, kThreads + kStemThreads, smem, stream>>>(tmS, tmB, p);
+        if (tc_stem) {
+            if (nslots < 4) return fail("s2d layer: the tensor-core stem needs 4 activation stages");
+            s2d_tc_kernel<EPI_RELU_POOL, 1, 2>
+                <<<grid, kThreads + kStemThreads, smem, stream>>>(tmS, tmB, p);
+        } else {
+            s2d_tc_kernel<EPI_RELU_POOL, 1, 1>
+                <<<grid, kThreads + kStemThreads, smem, stream>>>(tmS, tmB, p);
+        }
         OGL_CUDA(cudaGetLastError());
         return 0;
     }

@@ -71,7 +71,9 @@ class UNet(nn.Module):
         self.cta_pairs = int(os.environ.get("OGL_CG", "2"))   # 1: one CTA per tile; 2: CTA pairs
                                      # (tcgen05 cta_group::2) for the Cout >= 64 conv layers when
                                      # a launch has a tile per SM; 3: pairs whenever possible
-        self.fuse_stem = os.environ.get("OGL_FUSE_STEM", "1") != "0"   # stem inside downs.0.net.3
+        self.fuse_stem = int(os.environ.get("OGL_FUSE_STEM", "1"))   # stem inside downs.0.net.3:
+                                     # 0 separate kernel, 1 in-kernel on the CUDA cores (fp32),
+                                     # 2 in-kernel on the tensor cores (bf16 hi + lo weights)
         self._handle = None
         self._handle_device = None
         self._packed_sig = None
@@ -203,7 +205,7 @@ class UNet(nn.Module):
         lib = _native.load()
         _native.check(lib.ogl_unet_set_schedule(self._handle, 1 if self.schedule == "s2d" else 0))
         _native.check(lib.ogl_unet_set_cta_pairs(self._handle, int(self.cta_pairs)))
-        _native.check(lib.ogl_unet_set_fused_stem(self._handle, 1 if self.fuse_stem else 0))
+        _native.check(lib.ogl_unet_set_fused_stem(self._handle, int(self.fuse_stem)))
         frames = frames.contiguous()
         logits = torch.empty((n, hgt, wid), dtype=torch.float32, device=dev) if want_logits else None
         mask = torch.empty((n, hgt, wid), dtype=torch.uint8, device=dev) if want_mask else None

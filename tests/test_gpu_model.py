@@ -124,16 +124,44 @@ def test_cta_pairs_bit_identical(native_model):
 def test_fused_stem_bit_identical(native_model):
     """The stem computed inside the downs.0.net.3 kernel (u8 input) equals the separate stem
     kernel bit for bit -- same fp32 FMA order, same rounding point -- incl. partial tiles."""
+    default = native_model.fuse_stem
     for shape in ((5, 256, 256), (3, 48, 80), (2, 512, 256), (1, 16, 16)):
         frames = torch.from_numpy(_clip(*shape)).cuda()
         try:
-            native_model.fuse_stem = False
+            native_model.fuse_stem = 0
             ref = native_model.run(frames, want_logits=True)
-            native_model.fuse_stem = True
+            native_model.fuse_stem = 1
             got = native_model.run(frames, want_logits=True)
         finally:
-            native_model.fuse_stem = True
+            native_model.fuse_stem = default
         assert all(torch.equal(a, b) for a, b in zip(ref, got)), shape
+
+
+def test_tensor_core_stem_matches_fp32_stem(native_model):
+    """The stem as a GEMM on the tensor cores (u8 taps exact in bf16, weights and bias split
+    hi + lo in bf16, fp32 accumulation) against the fp32 CUDA-core stem: the stem outputs differ
+    by ~2^-17 relative before their rounding to bf16, so a few of them round the other way and
+    the logits move by a fraction of the bf16 noise; masks and areas almost everywhere equal.
+    Incl. partial tiles, a single 16x16 frame and a batch with several tiles per SM."""
+    default = native_model.fuse_stem
+    shapes = ((5, 256, 256), (3, 48, 80), (2, 512, 256), (1, 16, 16), (40, 256, 256))
+    for shape in shapes:
+        frames = torch.from_numpy(_clip(*shape)).cuda()
+        try:
+            native_model.fuse_stem = 1
+            ref = native_model.run(frames, want_logits=True)
+            native_model.fuse_stem = 2
+            got = native_model.run(frames, want_logits=True)
+            again = native_model.run(frames, want_logits=True)
+        finally:
+            native_model.fuse_stem = default
+        assert all(torch.equal(a, b) for a, b in zip(got, again)), shape     # deterministic
+        d = (ref[0] - got[0]).abs()
+        scale = max(1.0, ref[0].abs().max().item())
+        print(shape, "tc stem vs fp32 stem: max|dz|", d.max().item(), "mean", d.mean().item())
+        assert d.max().item() <= 2e-2 * scale and d.mean().item() <= 1e-3 * scale, shape
+        assert (ref[1] != got[1]).sum().item() <= 1e-4 * ref[1].numel() + 2, shape
+        assert torch.equal(got[2].cpu(), (got[1] > 0).flatten(1).sum(1).to(torch.int32).cpu()), shape
 
 
 def test_bf16_matches_reference_within_north_star(native_model, trained_sd):
