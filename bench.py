@@ -21,6 +21,7 @@ import argparse
 import ctypes as C
 import json
 import os
+import re
 import sys
 import threading
 import time
@@ -116,6 +117,10 @@ class ClockSampler(threading.Thread):
             nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
             nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
         }
+        try:    # board energy counter (mJ): the step runs at the power cap, so J/step is the cost
+            self.e0, self.t0 = nv.nvmlDeviceGetTotalEnergyConsumption(self.h), time.perf_counter()
+        except Exception:
+            self.e0 = None
         while not self._halt.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
@@ -136,9 +141,19 @@ class ClockSampler(threading.Thread):
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
         s = sorted(self.samples)
         pw = sorted(self.power)
-        return {"sm_mhz": s[len(s) // 2], "sm_mhz_min": s[0], "sm_max_mhz": self.max_mhz,
-                "power_w": round(pw[len(pw) // 2], 1) if pw else None,
-                "reasons": sorted(self.reasons), "samples": len(s)}
+        out = {"sm_mhz": s[len(s) // 2], "sm_mhz_min": s[0], "sm_max_mhz": self.max_mhz,
+               "power_w": round(pw[len(pw) // 2], 1) if pw else None,
+               "reasons": sorted(self.reasons), "samples": len(s)}
+        try:    # mean board power over the sampled window from the energy counter (power_w above is
+            # NVML's own ~1 s moving average and lags a 0.2 s timed region)
+            if getattr(self, "e0", None) is not None:
+                e1, t1 = self.nv.nvmlDeviceGetTotalEnergyConsumption(self.h), time.perf_counter()
+                out["window_s"] = round(t1 - self.t0, 4)
+                out["energy_j"] = round((e1 - self.e0) * 1e-3, 3)
+                out["mean_w"] = round((e1 - self.e0) * 1e-3 / max(t1 - self.t0, 1e-6), 1)
+        except Exception:
+            pass
+        return out
 
 
 def bench_state():
@@ -329,7 +344,8 @@ def run_native(args) -> None:
     # DRAM bytes per launch (read + write) of the same 20 launches from the newest committed
     # `ncu --set full` capture (scripts/ncu_summary.py), scaled to this batch
     traffic = None
-    captures = sorted((ROOT / "profiles").glob("traffic_*.json"))
+    captures = sorted((ROOT / "profiles").glob("traffic_*.json"),
+                      key=lambda q: [int(t) if t.isdigit() else t for t in re.split(r"(\d+)", q.name)])
     if captures:
         traffic = json.loads(captures[-1].read_text()).get("dram_bytes_per_launch_avg_batch512")
         if traffic is not None:

@@ -104,9 +104,12 @@ const char* ogl_unet_launch_name(const ogl_unet* h, int index);
  * per-tap form used at the other levels (22 launches). Same results within bf16 rounding. */
 int ogl_unet_set_schedule(ogl_unet* h, int s2d_level0);
 
-/* 1 (default): with u8 frames and the space-to-depth schedule, downs.0.net.0 (the Cin = 1 stem) is
- * computed inside the downs.0.net.3 kernel, so its output never touches HBM; 0: separate stem
- * kernel. Same results bit for bit. */
+/* With u8 frames and the space-to-depth schedule, downs.0.net.0 (the Cin = 1 stem) can be computed
+ * inside the downs.0.net.3 kernel, so that its output never touches HBM. 0: separate stem kernel;
+ * 1 (default): in-kernel on the CUDA cores in fp32 -- same results as 0 bit for bit; 2: in-kernel
+ * as a GEMM on the tensor cores (u8 taps exact in bf16, weights / 255 and bias split hi + lo in
+ * bf16, fp32 accumulation) -- stem outputs within ~2^-17 relative of mode 1 before their rounding
+ * to bf16, logits within the bf16 noise of the path. */
 int ogl_unet_set_fused_stem(ogl_unet* h, int enable);
 
 /* CTA pairs for the conv3x3 layers with Cout >= 64: 1 = one CTA per tile; 2 = two CTAs of a

@@ -7,7 +7,9 @@ forward; (E(R) - E(1)) / (R - 1) is its energy, the same difference of the loop 
 at the clocks of that mix. torch.matmul (8192^3 bf16) and a device-to-device copy are measured
 the same way as yardsticks (pJ/FLOP of a dense GEMM, pJ/byte of HBM traffic).
 
-Usage: layer_energy.py [batch] [seconds per measurement] [repeat]   -> one JSON document on stdout
+Usage: layer_energy.py [batch] [seconds per measurement] [repeat] [launch,launch,...]
+-> one JSON document on stdout (all launches when no list is given; experiment switches such as
+OGL_FUSE_STEM come from the environment)
 """
 import ctypes as C
 import json
@@ -27,6 +29,7 @@ from openglottal_b200 import _native  # noqa: E402
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 seconds = float(sys.argv[2]) if len(sys.argv) > 2 else 1.5
 R = int(sys.argv[3]) if len(sys.argv) > 3 else 9
+only = [int(x) for x in sys.argv[4].split(",")] if len(sys.argv) > 4 else None
 
 pynvml.nvmlInit()
 nv = pynvml.nvmlDeviceGetHandleByIndex(0)
@@ -92,6 +95,8 @@ base_j, base_ms, base_w, base_mhz = measure(forward, 2 * seconds)
 noise_j, noise_ms, noise_w, noise_mhz = measure(lambda: forward(frames), 2 * seconds)
 rows = []
 for i, name in enumerate(names):
+    if only is not None and i not in only:
+        continue
     _native.check(lib.ogl_unet_set_repeat(model._handle, i, R))
     j, ms, w, mhz = measure(forward, seconds)
     lj, lms = (j - base_j) / (R - 1), (ms - base_ms) / (R - 1)
