@@ -164,6 +164,27 @@ def test_tensor_core_stem_matches_fp32_stem(native_model):
         assert torch.equal(got[2].cpu(), (got[1] > 0).flatten(1).sum(1).to(torch.int32).cpu()), shape
 
 
+def test_repeated_launch_is_idempotent(native_model):
+    """ogl_unet_set_repeat (the energy-measurement aid): enqueueing one launch of the schedule
+    several times leaves logits and masks unchanged -- every launch reads and writes distinct
+    tensors -- for each kind of launch (fused stem, conv, transposed conv, composed level-0 conv)."""
+    from openglottal_b200 import _native
+
+    lib = _native.load()
+    frames = torch.from_numpy(_clip(3)).cuda()
+    ref = native_model.run(frames, want_logits=True)
+    n_launch = lib.ogl_unet_launch_count(native_model._handle)
+    try:
+        for idx in (0, 1, 9, 10, n_launch - 2):
+            _native.check(lib.ogl_unet_set_repeat(native_model._handle, idx, 3))
+            got = native_model.run(frames, want_logits=True)
+            assert torch.equal(ref[0], got[0]) and torch.equal(ref[1], got[1]), idx
+            assert torch.equal(ref[2], got[2]), idx
+        assert lib.ogl_unet_set_repeat(native_model._handle, 0, 0) != 0      # times out of range
+    finally:
+        _native.check(lib.ogl_unet_set_repeat(native_model._handle, -1, 1))
+
+
 def test_bf16_matches_reference_within_north_star(native_model, trained_sd):
     from oracle import unet_oracle as uo
     from openglottal_b200 import dice
