@@ -1,7 +1,7 @@
 # Round evidence: bench line (with CPU baseline), ncu launch list of bench.py, full ncu capture
 # of every tcgen05 launch of one forward (batch 128).
 mkdir -p gpurun_out
-timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
+timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
 python - <<'PY'
 import json
 d=json.load(open('gpurun_out/bench.json'))
