@@ -353,8 +353,8 @@ def run_native(args) -> None:
     roofline = {
         "bound": "tensor",
         "kernel": f"conv_tc_kernel + s2d_tc_kernel ({n_tc} tcgen05 launches/step: every conv3x3, "
-                  "ConvTranspose2d and the head; the Cin=1 stem runs on CUDA cores inside the "
-                  "first of them when the frames are u8)",
+                  "ConvTranspose2d and the head; the Cin=1 stem is a K=16 GEMM inside the first "
+                  "of them when the frames are u8)",
         "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
         "peak_source": f"{which} bf16_tflops_sustained", "traffic": traffic,
         "flops_per_launch_avg": tc_flops / n_tc, "ms_per_launch_avg": tc_ms / n_tc,

@@ -106,7 +106,7 @@ int ogl_unet_set_schedule(ogl_unet* h, int s2d_level0);
 
 /* With u8 frames and the space-to-depth schedule, downs.0.net.0 (the Cin = 1 stem) can be computed
  * inside the downs.0.net.3 kernel, so that its output never touches HBM. 0: separate stem kernel;
- * 1 (default): in-kernel on the CUDA cores in fp32 -- same results as 0 bit for bit; 2: in-kernel
+ * 1: in-kernel on the CUDA cores in fp32 -- same results as 0 bit for bit; 2 (default): in-kernel
  * as a GEMM on the tensor cores (u8 taps exact in bf16, weights / 255 and bias split hi + lo in
  * bf16, fp32 accumulation) -- stem outputs within ~2^-17 relative of mode 1 before their rounding
  * to bf16, logits within the bf16 noise of the path. */

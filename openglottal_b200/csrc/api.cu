@@ -76,7 +76,7 @@ struct ogl_unet {
     // u8 input: compute the stem inside the downs.0.net.3 kernel (its output never touches HBM:
     // 8.4 MB per frame less traffic). Bit-identical to the stand-alone stem; as fast or slightly
     // faster under the board's power cap.
-    int fuse_stem = 1;                 // 0 separate kernel, 1 in-kernel on CUDA cores, 2 on tensor cores
+    int fuse_stem = 2;                 // 0 separate kernel, 1 in-kernel on CUDA cores, 2 on tensor cores
     uint8_t* stem_tc = nullptr;        // B operands of the tensor-core stem (device)
     int cta_group = 2;  // 2: conv3x3 layers with N >= 64 run on CTA pairs (tcgen05 cta_group::2)
     // fp32 validation path

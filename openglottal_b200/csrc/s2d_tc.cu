@@ -302,6 +302,20 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
         const int grp = sw >> 2;           // drains the chunks j with (j & 1) == grp
         const uint32_t lane_sel = static_cast<uint32_t>((sw & 3) * 32) << 16;
         const int W = 2 * p.W2, H = 2 * p.H2;
+        // The rows a thread builds (st, st + 256, st + 512) are the same in every tile: their
+        // position inside the u8 region and the stage is computed once. Rows past the end (the
+        // third row of threads >= 208) read row 719 and store nothing.
+        constexpr int kRowsPerThread = (kStemRows + kStemThreads - 1) / kStemThreads;   // 3
+        int row_src[kRowsPerThread], row_ly[kRowsPerThread], row_lx[kRowsPerThread];
+#pragma unroll
+        for (int rr = 0; rr < kRowsPerThread; ++rr) {
+            const int r = min(st + rr * kStemThreads, kStemRows - 1);
+            const int ph = r / (kHW * kHH), pos = r - ph * (kHW * kHH);
+            const int hy = pos / kHW, hx = pos - hy * kHW;
+            row_ly[rr] = 2 * hy + (ph >> 1);
+            row_lx[rr] = 2 * hx + (ph & 1);
+            row_src[rr] = row_ly[rr] * kU8Row + kU8Off + row_lx[rr];
+        }
         // im2col of tile number iu of this CTA into buffer iu & 1
         auto build = [&](uint32_t iu, int unit) {
             const Tile t = decode_tile(p, tile_of(unit));
@@ -311,25 +325,28 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
             uint8_t* abuf = gen + sA + (iu & 1u) * kStemABytes;
             mbar_wait_relaxed(u8_full + 8u * us, (iu / kU8Slots) & 1u);
             mbar_wait_relaxed(sa_empty + 8u * (iu & 1u), ((iu >> 1) & 1u) ^ 1u);
+            // all 27 byte loads first, then the conversions, then the stores: three independent
+            // latency chains per thread instead of one after the other
+            uint32_t b[kRowsPerThread][9];
 #pragma unroll
-            for (int rr = 0; rr < (kStemRows + kStemThreads - 1) / kStemThreads; ++rr) {
+            for (int rr = 0; rr < kRowsPerThread; ++rr)
+#pragma unroll
+                for (int k = 0; k < 9; ++k) b[rr][k] = u8p[row_src[rr] + (k / 3) * kU8Row + (k % 3)];
+#pragma unroll
+            for (int rr = 0; rr < kRowsPerThread; ++rr) {
                 const int r = st + rr * kStemThreads;
-                if (r < kStemRows) {
-                    const int ph = r / (kHW * kHH), pos = r - ph * (kHW * kHH);
-                    const int hy = pos / kHW, hx = pos - hy * kHW;
-                    const int ly = 2 * hy + (ph >> 1), lx = 2 * hx + (ph & 1);
-                    const int gy = gy0 + ly, gx = gx0 + lx;
-                    // outside the image the stem's OUTPUT is zero (conv2's padding): a zero row,
-                    // bias columns included
-                    const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W && !(p.dbg & 64);
-                    const uint8_t* src = u8p + ly * kU8Row + kU8Off + lx;
-                    float v[9];
+                const int gy = gy0 + row_ly[rr], gx = gx0 + row_lx[rr];
+                // outside the image the stem's OUTPUT is zero (conv2's padding): a zero row,
+                // bias columns included
+                const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W && !(p.dbg & 64);
+                float v[9];
 #pragma unroll
-                    for (int k = 0; k < 9; ++k) v[k] = static_cast<float>(src[(k / 3) * kU8Row + (k % 3)]);
-                    uint4 k0 = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
-                                          pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-                    uint4 k1 = make_uint4(pack_bf16x2(v[8], 1.f), pack_bf16x2(1.f, 0.f), 0u, 0u);
-                    if (!in) k0 = k1 = make_uint4(0u, 0u, 0u, 0u);
+                for (int k = 0; k < 9; ++k) v[k] = static_cast<float>(b[rr][k]);
+                const uint32_t keep = in ? 0xffffffffu : 0u;
+                const uint4 k0 = make_uint4(pack_bf16x2(v[0], v[1]) & keep, pack_bf16x2(v[2], v[3]) & keep,
+                                            pack_bf16x2(v[4], v[5]) & keep, pack_bf16x2(v[6], v[7]) & keep);
+                const uint4 k1 = make_uint4(pack_bf16x2(v[8], 1.f) & keep, pack_bf16x2(1.f, 0.f) & keep, 0u, 0u);
+                if (r < kStemRows) {
                     *reinterpret_cast<uint4*>(abuf + r * 16) = k0;
                     *reinterpret_cast<uint4*>(abuf + kStemRows * 16 + r * 16) = k1;
                 }
@@ -341,55 +358,56 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
                 mbar_arrive(u8_empty + 8u * us);
             }
         };
-        // result of the stem GEMM of tile iu: TMEM -> ReLU -> bf16 -> the tile's two A stages
-        // (row r of the GEMM is the 16-byte cell r of each 8-channel group of a stage)
-        auto drain = [&](uint32_t iu) {
+        // result of the stem GEMM: TMEM -> ReLU -> bf16 -> the tile's two A stages (row r of the
+        // GEMM is the 16-byte cell r of each 8-channel group of a stage). One chunk = 128 rows.
+        auto drain_chunk = [&](uint32_t iu, int j, uint8_t* stage0, uint8_t* stage1) {
+            const uint32_t c = static_cast<uint32_t>(kStemChunks) * iu + j;
+            const uint32_t slot = c % kStemDSlots;
+            mbar_wait_relaxed(sd_full + 8u * slot, (c / kStemDSlots) & 1u);
+            tc_fence_after();
+            uint32_t v[32];
+            tmem_ld32(tmem_base + lane_sel + kStemDCol + slot * 32u, v);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(sd_empty + 8u * slot);   // the values are in registers
+            const int r = j * 128 + (sw & 3) * 32 + lane;
+            if (r < kStemRows) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {   // 8-channel groups: (stage, plane group)
+                    const uint4 q = make_uint4(
+                        pack_relu_bf16x2(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1])),
+                        pack_relu_bf16x2(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])),
+                        pack_relu_bf16x2(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])),
+                        pack_relu_bf16x2(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
+                    uint8_t* dst = ((g >> 1) ? stage1 : stage0) + (g & 1) * 4 * kPlane + r * 16;
+                    *reinterpret_cast<uint4*>(dst) = q;
+                }
+            }
+        };
+        // Per tile: first chunk, then the im2col of the NEXT tile, then the other two chunks. The
+        // accumulator ring has 4 slots for 6 chunks, so chunks 2..5 of a tile are issued only when
+        // earlier chunks have been drained: with this order their MMAs run while this warp builds.
+        uint32_t iu = 0;
+        int unit = unit0;
+        if (unit < num_units) build(0, unit);
+        for (; unit < num_units; unit += unit_step, ++iu) {
             const uint32_t it0 = 2u * iu, it1 = 2u * iu + 1u;
             const uint32_t s0 = it0 % p.nslots, s1 = it1 % p.nslots;
             mbar_wait_relaxed(a_empty + 8u * s0, ((it0 / p.nslots) & 1u) ^ 1u);
             mbar_wait_relaxed(a_empty + 8u * s1, ((it1 / p.nslots) & 1u) ^ 1u);
             uint8_t* stage0 = gen + a_ring + s0 * kSlot;
             uint8_t* stage1 = gen + a_ring + s1 * kSlot;
-#pragma unroll 1
-            for (int j = grp; j < kStemChunks; j += 2) {
-                const uint32_t c = static_cast<uint32_t>(kStemChunks) * iu + j;
-                const uint32_t slot = c % kStemDSlots;
-                mbar_wait_relaxed(sd_full + 8u * slot, (c / kStemDSlots) & 1u);
-                tc_fence_after();
-                uint32_t v[32];
-                tmem_ld32(tmem_base + lane_sel + kStemDCol + slot * 32u, v);
-                tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(sd_empty + 8u * slot);   // the values are in registers
-                const int r = j * 128 + (sw & 3) * 32 + lane;
-                if (r < kStemRows) {
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {   // 8-channel groups: (stage, plane group)
-                        const uint4 q = make_uint4(
-                            pack_relu_bf16x2(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1])),
-                            pack_relu_bf16x2(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])),
-                            pack_relu_bf16x2(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])),
-                            pack_relu_bf16x2(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
-                        uint8_t* dst = ((g >> 1) ? stage1 : stage0) + (g & 1) * 4 * kPlane + r * 16;
-                        *reinterpret_cast<uint4*>(dst) = q;
-                    }
-                }
-            }
+            drain_chunk(iu, grp, stage0, stage1);
+            if (unit + unit_step < num_units) build(iu + 1, unit + unit_step);
+            drain_chunk(iu, grp + 2, stage0, stage1);
+            drain_chunk(iu, grp + 4, stage0, stage1);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(a_full + 8u * s0);
                 mbar_arrive(a_full + 8u * s1);
             }
-        };
-        uint32_t iu = 0;
-        int unit = unit0;
-        if (unit < num_units) build(0, unit);
-        for (; unit < num_units; unit += unit_step, ++iu) {
-            // the im2col of the next tile first: the stem MMAs of this one run meanwhile
-            if (unit + unit_step < num_units) build(iu + 1, unit + unit_step);
-            drain(iu);
         }
     } else if (STEM == 1 && warp >= kThreads / 32) {
         // ====================================== stem: compute the A stages from the u8 frame

@@ -71,9 +71,10 @@ class UNet(nn.Module):
         self.cta_pairs = int(os.environ.get("OGL_CG", "2"))   # 1: one CTA per tile; 2: CTA pairs
                                      # (tcgen05 cta_group::2) for the Cout >= 64 conv layers when
                                      # a launch has a tile per SM; 3: pairs whenever possible
-        self.fuse_stem = int(os.environ.get("OGL_FUSE_STEM", "1"))   # stem inside downs.0.net.3:
+        self.fuse_stem = int(os.environ.get("OGL_FUSE_STEM", "2"))   # stem inside downs.0.net.3:
                                      # 0 separate kernel, 1 in-kernel on the CUDA cores (fp32),
-                                     # 2 in-kernel on the tensor cores (bf16 hi + lo weights)
+                                     # 2 (default) in-kernel on the tensor cores (bf16 hi + lo
+                                     # weights, fp32 accumulation)
         self._handle = None
         self._handle_device = None
         self._packed_sig = None

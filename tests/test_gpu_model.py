@@ -145,8 +145,12 @@ def test_tensor_core_stem_matches_fp32_stem(native_model):
     Incl. partial tiles, a single 16x16 frame and a batch with several tiles per SM."""
     default = native_model.fuse_stem
     shapes = ((5, 256, 256), (3, 48, 80), (2, 512, 256), (1, 16, 16), (40, 256, 256))
-    for shape in shapes:
-        frames = torch.from_numpy(_clip(*shape)).cuda()
+    g = torch.Generator().manual_seed(5)
+    for shape in shapes + ("noise",):
+        if shape == "noise":    # uniform random bytes: every tap large, no flat regions
+            frames = torch.randint(0, 256, (4, 256, 256), dtype=torch.uint8, generator=g).cuda()
+        else:
+            frames = torch.from_numpy(_clip(*shape)).cuda()
         try:
             native_model.fuse_stem = 1
             ref = native_model.run(frames, want_logits=True)
