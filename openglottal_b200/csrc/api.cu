@@ -194,6 +194,22 @@ std::vector<__nv_bfloat16> pack_convt(const float* w, int cin, int cout, int N) 
     return out;
 }
 
+// The same for a CTA pair: rank r stages columns [r*N/2, (r+1)*N/2) of every pass (that is dx = r
+// when N = 2 * cb) -- [pass][cin/32][rank][4][N/2][8] bf16.
+std::vector<__nv_bfloat16> pack_convt_pair(const float* w, int cin, int cout, int N) {
+    const std::vector<__nv_bfloat16> flat = pack_convt(w, cin, cout, N);
+    const int nh = N / 2, blocks = static_cast<int>(flat.size() / (static_cast<size_t>(4) * N * 8));
+    std::vector<__nv_bfloat16> out(flat.size());
+    for (int blk = 0; blk < blocks; ++blk)      // one (pass, 32-channel block)
+        for (int r = 0; r < 2; ++r)
+            for (int c = 0; c < 4; ++c)
+                for (int n = 0; n < nh; ++n)
+                    for (int e = 0; e < 8; ++e)
+                        out[((((static_cast<size_t>(blk) * 2 + r) * 4 + c) * nh + n) * 8) + e] =
+                            flat[(((static_cast<size_t>(blk) * 4 + c) * N + r * nh + n) * 8) + e];
+    return out;
+}
+
 int build_tc_conv(ogl_unet* h, const std::vector<float>& w, const std::vector<float>& b, int cin0,
                   int cin1, int cout, int epi, TcLayer* L) {
     L->cin0 = cin0;
@@ -392,6 +408,9 @@ int ogl_unet_load_state(ogl_unet* h, const ogl_unet_state* st) {
             L->npass = 4 * f / L->N;
             L->epi = EPI_CONVT;
             if (dev_upload(h, pack_convt(T.weight, 2 * f, f, L->N), &L->wpack)) return 1;
+            if (L->N == 128 &&
+                dev_upload(h, pack_convt_pair(T.weight, 2 * f, f, L->N), &L->wpack2))
+                return 1;
             if (dev_upload(h, tb, &L->bias)) return 1;
         }
         fold_conv_bn(st->up_c[k][0], f, 2 * f, eps, &w, &b);
@@ -812,6 +831,7 @@ int ogl_debug_tc_layer(ogl_unet* h, int kind, const float* src0_dev, int c0, con
         L.taps = 1;
         L.npass = 4 * cout / L.N;
         pk = pack_convt(weight_host, cin, cout, L.N);
+        if (L.N == 128) pk2 = pack_convt_pair(weight_host, cin, cout, L.N);
     } else {
         L.taps = 9;
         L.npass = cout / L.N;

@@ -623,8 +623,8 @@ int launch_epi(const CUtensorMap& tm0, const CUtensorMap& tm1, const ConvParams&
     OGL_CUDA(cudaGetLastError());
     return 0;
 }
-// CTA-pair form (cta_group::2): clusters of 2 CTAs, 2 sub-tiles per CTA
-template <int EPI, int TPS>
+// CTA-pair form (cta_group::2): clusters of 2 CTAs, S sub-tiles per CTA
+template <int EPI, int TPS, int S = 2>
 int launch_epi_pair(const CUtensorMap& tm0, const CUtensorMap& tm1, const CUtensorMap& tmw,
                     const ConvParams& p, int grid, size_t smem, cudaStream_t stream) {
     cudaLaunchConfig_t cfg = {};
@@ -639,7 +639,7 @@ int launch_epi_pair(const CUtensorMap& tm0, const CUtensorMap& tm1, const CUtens
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    OGL_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<EPI, TPS, 2, 2>, tm0, tm1, tmw, p));
+    OGL_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<EPI, TPS, S, 2>, tm0, tm1, tmw, p));
     return 0;
 }
 template <int EPI, int TPS>
@@ -706,6 +706,8 @@ int conv_tc_init() {
         set_smem_attr_pair<EPI_RELU, 9>() || set_smem_attr_pair<EPI_RELU, 3>() ||
         set_smem_attr_pair<EPI_RELU_POOL, 9>() || set_smem_attr_pair<EPI_RELU_POOL, 3>())
         return 1;
+    OGL_CUDA(cudaFuncSetAttribute(conv_tc_kernel<EPI_CONVT, 1, 1, 2>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     return 0;
 }
 
@@ -760,6 +762,14 @@ int launch_conv_tc(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloa
     p.tiles_x = (W + 15) / 16;
     p.tiles_y = (H + 15) / 16;
     p.total_sub = B * p.tiles_x * p.tiles_y;
+    // Transposed conv on CTA pairs (OGL_CONVT_PAIR=1, experiment): ONE sub-tile per CTA, so that
+    // TMEM holds two accumulator sets and the pixel-shuffle epilogue of a tile overlaps the MMAs
+    // of the next one, while the pair still fetches each weight column once per 512 pixels.
+    static const int convt_pair_env = getenv("OGL_CONVT_PAIR") ? atoi(getenv("OGL_CONVT_PAIR")) : 0;
+    const bool convt_pair = convt_pair_env && L.epi == EPI_CONVT && L.N == 128 && L.wpack2 &&
+                            cta_group >= 2 && num_sms >= 2 &&
+                            p.total_sub >= (cta_group == 3 ? 2 : num_sms);
+    if (convt_pair) p.S = 1;
     p.num_tiles = (p.total_sub + p.S - 1) / p.S;
     p.magic_tx = ((1ull << 40) / static_cast<unsigned long long>(p.tiles_x)) + 1;
     p.magic_tpf = ((1ull << 40) / static_cast<unsigned long long>(p.tiles_x * p.tiles_y)) + 1;
@@ -776,10 +786,11 @@ int launch_conv_tc(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloa
     // Layers with a single 32-channel K block (downs.1.net.0) are faster unpaired (measured):
     // the pair's per-tile hand-shakes are not amortised over so short a K loop.
     static const int minkb_env = getenv("OGL_CG_MINKB") ? atoi(getenv("OGL_CG_MINKB")) : 2;
-    const bool pair = cta_group >= 2 && L.wpack2 && L.taps == 9 && (L.N == 64 || L.N == 128) &&
-                      (L.epi == EPI_RELU || L.epi == EPI_RELU_POOL) && p.S == 2 &&
-                      num_sms >= 2 && p.num_tiles >= (cta_group == 3 ? 2 : num_sms) &&
-                      (cta_group == 3 || p.kb0 + p.kb1 >= minkb_env);
+    const bool pair = convt_pair ||
+                      (cta_group >= 2 && L.wpack2 && L.taps == 9 && (L.N == 64 || L.N == 128) &&
+                       (L.epi == EPI_RELU || L.epi == EPI_RELU_POOL) && p.S == 2 &&
+                       num_sms >= 2 && p.num_tiles >= (cta_group == 3 ? 2 : num_sms) &&
+                       (cta_group == 3 || p.kb0 + p.kb1 >= minkb_env));
     const size_t w_stage = static_cast<size_t>(tps) * 64u * p.N / (pair ? 2 : 1);
     const size_t tables = sizeof(float) * (L.cout + 32);
     const int edge = L.epi == EPI_CONVT ? 16 : kHalo;
@@ -817,13 +828,15 @@ int launch_conv_tc(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloa
     if (pair) {
         // weights as rows of 256 bytes; one box = this CTA's half of a stage
         CUtensorMap tmw;
-        const uint64_t rows = static_cast<uint64_t>(L.cout) * (L.cin0 + L.cin1) * 9 * 2 / 256;
+        const uint64_t rows = static_cast<uint64_t>(L.npass) * (p.kb0 + p.kb1) * L.taps * 64u * p.N / 256;
         const uint64_t dims[2] = {128, rows};
         const uint64_t str[1] = {256};
         const uint32_t box[2] = {128, static_cast<uint32_t>(w_stage / 256)};
         if (encode_bf16_map(&tmw, L.wpack2, 2, dims, str, box)) return 1;
-        p.pass_fast = 0;
+        p.pass_fast = convt_pair ? 1 : 0;   // transposed conv: the passes of a tile back to back,
+                                            // so that their re-reads of the tile hit L2
         const int grid2 = num_sms & ~1;
+        if (convt_pair) return launch_epi_pair<EPI_CONVT, 1, 1>(tm0, tm1, tmw, p, grid2, smem, stream);
         if (L.epi == EPI_RELU)
             return tps == 9 ? launch_epi_pair<EPI_RELU, 9>(tm0, tm1, tmw, p, grid2, smem, stream)
                             : launch_epi_pair<EPI_RELU, 3>(tm0, tm1, tmw, p, grid2, smem, stream);

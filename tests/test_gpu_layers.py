@@ -103,6 +103,31 @@ def test_convt2x2_tc(lib, handle, cin, cout, n, hgt, wid):
     _report(f"convT {cin}->{cout} {n}x{hgt}x{wid}", out.cpu(), ref)
 
 
+@pytest.mark.parametrize("cin,cout,n,hgt,wid", [(128, 64, 3, 32, 48), (512, 256, 5, 16, 16),
+                                                (256, 128, 2, 64, 32), (128, 64, 1, 16, 16)])
+def test_convt_cta_pairs_bit_identical(lib, handle, cin, cout, n, hgt, wid):
+    """Transposed conv on CTA pairs (one sub-tile per CTA, double-buffered accumulators; only
+    with OGL_CONVT_PAIR=1, else this compares the one-CTA form with itself): same MMAs on the
+    same operands, so the same bits, odd tile counts included."""
+    from openglottal_b200 import _native
+
+    g = torch.Generator().manual_seed(cin + cout + hgt)
+    x = _bf(torch.randn(n, cin, hgt, wid, generator=g))
+    w = _bf(torch.randn(cin, cout, 2, 2, generator=g) * (1.0 / cin) ** 0.5)
+    b = torch.randn(cout, generator=g) * 0.1
+    try:
+        _native.check(lib.ogl_unet_set_cta_pairs(handle, 1))
+        out1, _ = _run_layer(lib, handle, 3, x.cuda(), None, w, b, cout)
+        _native.check(lib.ogl_unet_set_cta_pairs(handle, 3))
+        out2, _ = _run_layer(lib, handle, 3, x.cuda(), None, w, b, cout)
+    finally:
+        _native.check(lib.ogl_unet_set_cta_pairs(handle, 2))
+    ref = F.conv_transpose2d(x.double(), w.double(), b.double(), stride=2).float()
+    _report(f"pair convT {cin}->{cout} {n}x{hgt}x{wid}", out2.cpu(), ref)
+    assert not torch.isnan(out2).any()
+    assert torch.equal(out1, out2)
+
+
 # ------------------------------------------------------------------ space-to-depth layers
 def _run_s2d(lib, handle, kind, x, below, w3, b3, wt, bt):
     from openglottal_b200 import _native
