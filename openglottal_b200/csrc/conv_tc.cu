@@ -66,6 +66,7 @@ struct ConvParams {
                      // with gridDim % npass == 0 each CTA still keeps one pass (its weights)
     int reverse;     // walk the tiles from the last frame to the first (see launch_conv_tc)
     int split;       // N = 128, S = 2: per-accumulator barriers (see kSplit in the kernel)
+    int acc_half;    // the other layers: one accumulator-empty barrier per (buffer, issuer half)
     int dbg;         // experiment switches (OGL_DBG): 1 no MMA, 2 no stores, 4 no epilogue math,
                      // 8 no activation TMA, 16 no weight copies. Results are garbage when set.
 };
@@ -175,7 +176,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
         for (int i = 0; i < 4; ++i) {
             mbar_init(acc_full + 8u * i, 1);
-            mbar_init(acc_empty + 8u * i, kEpiThreads * CG);  // CG = 2: both CTAs' epilogues
+            // released by all 8 epilogue warps, or (acc_half) by the warp group that drains the
+            // half of the tile one issuer writes; CG = 2: the epilogues of both CTAs
+            mbar_init(acc_empty + 8u * i, ((kSplit || !p.acc_half) ? kEpiThreads : kEpiThreads / 2) * CG);
         }
         fence_barrier_init();
     }
@@ -306,7 +309,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const uint32_t buf = kSplit ? 0u : li % p.acc_bufs;
             const uint32_t aph = kSplit ? (li & 1u) : (li / p.acc_bufs) & 1u;
             if (!kSplit) {
-                wait_acc_empty(acc_empty + 8u * buf, aph ^ 1u);
+                // acc_half: only this issuer's half of the tile has to be drained, so the two
+                // halves run as independent MMA -> epilogue chains that fall out of phase and keep
+                // the pipe busy where TMEM has no room for a second accumulator set (convT)
+                wait_acc_empty(acc_empty + 8u * (p.acc_half ? buf * 2u + me : buf), aph ^ 1u);
                 tc_fence_after();
             }
             const uint32_t d0 = tmem_base + buf * acc_cols;
@@ -564,7 +570,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             }
             if (!kSplit) {
                 tc_fence_before();
-                release_acc(acc_empty + 8u * buf);
+                release_acc(acc_empty + 8u * (p.acc_half ? buf * 2u + static_cast<uint32_t>(egrp) : buf));
             }
         }
     }
@@ -780,6 +786,8 @@ int launch_conv_tc(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloa
     p.split = split_env;
     static const int dbg_env = getenv("OGL_DBG") ? atoi(getenv("OGL_DBG")) : 0;
     p.dbg = dbg_env;
+    static const int half_env = getenv("OGL_ACC_HALF") ? atoi(getenv("OGL_ACC_HALF")) : 1;
+    p.acc_half = half_env;
     const int tps = taps_per_stage(L);
     // CTA pairs (cta_group::2) for the conv3x3 layers with N >= 64 when there is enough work
     // (cta_group 2), or whenever possible (cta_group 3: unit tests on small inputs)
