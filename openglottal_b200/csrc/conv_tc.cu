@@ -816,6 +816,11 @@ int launch_conv_tc(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloa
         p.na = 2;
         p.nw = 3;
     }
+    // transposed conv: a K block is only 2 x 16 KB and the two halves of a tile drift apart by at
+    // most the ring's depth (acc_half), so its ring may be deeper (OGL_NA_CONVT)
+    // (measured: ups.4 0.39 -> 0.36 ms with 4..6 stages)
+    static const int na_convt_env = getenv("OGL_NA_CONVT") ? atoi(getenv("OGL_NA_CONVT")) : 5;
+    if (L.epi == EPI_CONVT && na_convt_env > 0) p.na = na_convt_env;
     static const int na_env = getenv("OGL_NA") ? atoi(getenv("OGL_NA")) : 0;
     static const int nw_env = getenv("OGL_NW") ? atoi(getenv("OGL_NW")) : 0;
     if (na_env > 0) p.na = na_env;

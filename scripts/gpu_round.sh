@@ -13,5 +13,5 @@ python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain_bench.
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu1.log 2>&1
 echo "launches rc=$?"
 python scripts/profile_forward.py 128 > gpurun_out/plain2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k 'regex:conv_tc_kernel|s2d_tc_kernel' -s 20 -c 20 -o gpurun_out/prof_tc_r01_v11 -f python scripts/profile_forward.py 128 > gpurun_out/ncu2.log 2>&1
+ncu --set full --clock-control none --import-source on -k 'regex:conv_tc_kernel|s2d_tc_kernel' -s 20 -c 20 -o gpurun_out/prof_tc_r01_v12 -f python scripts/profile_forward.py 128 > gpurun_out/ncu2.log 2>&1
 echo "full rc=$?"; tail -2 gpurun_out/ncu2.log
