@@ -34,8 +34,11 @@ extern "C" {
 enum { OGL_DTYPE_U8 = 0, OGL_DTYPE_F32 = 1 };
 /* BF16: bf16 operands on tcgen05 tensor cores, fp32 accumulate (the product path).
  * F32 : fp32 weights/activations on CUDA cores -- validation mode (logits within 1e-4 of the
- *       reference); same folding, tiling-independent arithmetic. Not a timed path. */
-enum { OGL_PRECISION_BF16 = 0, OGL_PRECISION_F32 = 1 };
+ *       reference); same folding, tiling-independent arithmetic. Not a timed path.
+ * F16 : the BF16 kernels compiled for f16 operands (same tcgen05 kind::f16 rate, same bytes;
+ *       3 more mantissa bits: logits within 2e-2 of the reference everywhere; activations saturate
+ *       at +-65504). Needs ogl_unet_prepare(h, OGL_PRECISION_F16) once after loading weights. */
+enum { OGL_PRECISION_BF16 = 0, OGL_PRECISION_F32 = 1, OGL_PRECISION_F16 = 2 };
 
 typedef struct ogl_unet ogl_unet;
 
@@ -75,6 +78,10 @@ int ogl_unet_destroy(ogl_unet* h);
 /* Folds BatchNorm (eval mode) into the convolutions in fp64, keeps an fp32 copy for the
  * validation path, and packs bf16 tensor-core operands. Host pointers; copies synchronously. */
 int ogl_unet_load_state(ogl_unet* h, const ogl_unet_state* state);
+
+/* Packs the operands a precision mode needs that ogl_unet_load_state did not (the f16 set); a
+ * no-op for the other modes. Allocates and copies synchronously -- ogl_unet_forward never does. */
+int ogl_unet_prepare(ogl_unet* h, int precision);
 
 /* Bytes of device workspace ogl_unet_forward needs for n frames of h x w (h, w % 16 == 0). */
 size_t ogl_unet_workspace_bytes(const ogl_unet* h, int n, int height, int width, int precision);
@@ -136,6 +143,21 @@ int ogl_features_f64(const double* area_dev, int64_t n, double* out8_dev, int32_
 
 /* cv2.COLOR_BGR2GRAY on interleaved u8 BGR pixels: (3735 B + 19235 G + 9798 R + 16384) >> 15. */
 int ogl_bgr_to_gray(const uint8_t* bgr_dev, uint8_t* gray_dev, int64_t pixels, void* stream);
+
+/* ---- reference-resize mode of the per-frame wrapper, openglottal/utils.py:234-241 ----------------
+ * ogl_resize_u8_linear: dst[i] = cv2.resize(src[i], (dst_w, dst_h), interpolation=cv2.INTER_LINEAR)
+ *   for n u8 gray frames (utils.py:234 squashes every frame to 256 x 256); bit-exact with cv2
+ *   (11-bit fixed-point weights; the 2x2 area mean cv2 substitutes when both axes halve; a copy
+ *   when the sizes are equal).
+ * ogl_prob_resize_mask: utils.py:237-241 after the forward pass: prob = sigmoid(logits) [n][src_h]
+ *   [src_w]; when (dst_h, dst_w) differs it is resized with cv2's f32 INTER_LINEAR arithmetic;
+ *   mask = (prob > threshold) * 255 [n][dst_h][dst_w] (or NULL); area[i] = count(mask[i] > 0)
+ *   (features.py:238; or NULL). Only masks and areas leave the device. */
+int ogl_resize_u8_linear(const uint8_t* src_dev, int n, int src_h, int src_w, uint8_t* dst_dev,
+                         int dst_h, int dst_w, void* stream);
+int ogl_prob_resize_mask(const float* logits_dev, int n, int src_h, int src_w, int dst_h,
+                         int dst_w, float threshold, uint8_t* mask_dev, int32_t* area_dev,
+                         void* stream);
 
 /* ---- callers around the U-Net (all bit-exact, integer work) ---------------------------------
  * Detection-gated area, openglottal/features.py:240-245:

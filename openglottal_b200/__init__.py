@@ -20,11 +20,15 @@ from .utils import (
     letterbox_crops,
     unletterbox_area,
     segment_crops,
+    resize_u8_linear,
+    prob_resize_mask,
+    segment_frames_reference_resize,
 )
 from .features import (
     _kinematic_features,
     kinematic_features_device,
     segment_clip,
+    masks_for_clip,
     extract_features_unet,
     extract_features_unet_frames,
     extract_features_yolo_crop_unet,
@@ -44,9 +48,13 @@ __all__ = [
     "letterbox_crops",
     "unletterbox_area",
     "segment_crops",
+    "resize_u8_linear",
+    "prob_resize_mask",
+    "segment_frames_reference_resize",
     "_kinematic_features",
     "kinematic_features_device",
     "segment_clip",
+    "masks_for_clip",
     "extract_features_unet",
     "extract_features_unet_frames",
     "extract_features_yolo_crop_unet",

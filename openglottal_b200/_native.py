@@ -11,7 +11,7 @@ from pathlib import Path
 from .build import LIB_PATH
 
 DTYPE_U8, DTYPE_F32 = 0, 1
-PRECISION_BF16, PRECISION_F32 = 0, 1
+PRECISION_BF16, PRECISION_F32, PRECISION_F16 = 0, 1, 2
 
 _c_float_p = C.POINTER(C.c_float)
 
@@ -49,6 +49,7 @@ EXPORTS = [
     "ogl_unet_create",
     "ogl_unet_destroy",
     "ogl_unet_load_state",
+    "ogl_unet_prepare",
     "ogl_unet_workspace_bytes",
     "ogl_unet_forward",
     "ogl_unet_set_profiling",
@@ -67,6 +68,8 @@ EXPORTS = [
     "ogl_letterbox_crops",
     "ogl_unletterbox_area",
     "ogl_mask_overlap_counts",
+    "ogl_resize_u8_linear",
+    "ogl_prob_resize_mask",
     "ogl_debug_tc_layer",
     "ogl_debug_s2d_layer",
     "ogl_debug_s2d_program",
@@ -104,6 +107,8 @@ def load() -> C.CDLL:
     lib.ogl_unet_destroy.argtypes = [vp]
     lib.ogl_unet_load_state.restype = i32
     lib.ogl_unet_load_state.argtypes = [vp, C.POINTER(UNetState)]
+    lib.ogl_unet_prepare.restype = i32
+    lib.ogl_unet_prepare.argtypes = [vp, i32]
     lib.ogl_unet_workspace_bytes.restype = sz
     lib.ogl_unet_workspace_bytes.argtypes = [vp, i32, i32, i32, i32]
     lib.ogl_unet_forward.restype = i32
@@ -141,6 +146,10 @@ def load() -> C.CDLL:
     lib.ogl_unletterbox_area.argtypes = [vp, i32, i32, vp, i32, i32, vp, vp, vp]
     lib.ogl_mask_overlap_counts.restype = i32
     lib.ogl_mask_overlap_counts.argtypes = [vp, vp, i32, i64, vp, vp]
+    lib.ogl_resize_u8_linear.restype = i32
+    lib.ogl_resize_u8_linear.argtypes = [vp, i32, i32, i32, vp, i32, i32, vp]
+    lib.ogl_prob_resize_mask.restype = i32
+    lib.ogl_prob_resize_mask.argtypes = [vp, i32, i32, i32, i32, i32, C.c_float, vp, vp, vp]
     lib.ogl_debug_tc_layer.restype = i32
     lib.ogl_debug_tc_layer.argtypes = [vp, i32, vp, i32, vp, i32, _c_float_p, _c_float_p, i32,
                                        i32, i32, i32, vp, vp, vp]

@@ -16,7 +16,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from .features import gray_clip_from_bgr, kinematic_features_device, segment_clip
+from .features import gray_clip_from_bgr, kinematic_features_device, masks_for_clip
 from .utils import _require_native, gated_area
 
 FEATURE_COLS = ["area_mean", "area_std", "area_range", "open_quotient", "f0", "periodicity", "cv"]
@@ -46,10 +46,12 @@ def draw_overlay(frame_bgr: np.ndarray, mask, box, area: float, overlay_style: s
 
 def annotate_unet_only(frames_bgr: list, model, overlay_style: str = "fill", batch: int = 512):
     """unet-only branch of the reference's ``_run_pipeline``: returns ``(annotated frames,
-    area waveform as a list of floats)`` for frames whose size the network takes natively."""
+    area waveform as a list of floats)``; frames of any size, with the reference's resize semantics
+    (``masks_for_clip``)."""
     model = _require_native(model)
     dev = model._device()
-    area, masks = segment_clip(gray_clip_from_bgr(frames_bgr, dev), model, batch=batch, want_masks=True)
+    area, masks = masks_for_clip(gray_clip_from_bgr(frames_bgr, dev), model, batch=batch,
+                                 want_masks=True)
     area_h = area.cpu().numpy()
     masks_h = masks.cpu().numpy()
     annotated = [draw_overlay(f, m, None, float(a), overlay_style)
@@ -77,7 +79,7 @@ def extract_gaw_features(frames: list, capture_fps: float, detector, unet_model,
     dev = model._device()
     detector.reset()
     boxes = [detector.detect(frm) for frm in frames]
-    _, masks = segment_clip(gray_clip_from_bgr(frames, dev), model, want_masks=True)
+    _, masks = masks_for_clip(gray_clip_from_bgr(frames, dev), model, want_masks=True)
     feats = kinematic_features_device(gated_area(masks, boxes))
     if feats is not None and feats.get("f0") is not None:
         feats["f0"] = feats["f0"] * capture_fps

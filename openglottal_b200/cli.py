@@ -26,6 +26,9 @@ def main(argv: list[str] | None = None) -> None:
                        help="Only unet-only (no YOLO gate) is implemented natively.")
     run_p.add_argument("--output", "-o", default="results", help="Output directory.")
     run_p.add_argument("--device", default="cuda", help="Torch device (cuda / cuda:N).")
+    run_p.add_argument("--precision", choices=["bf16", "fp16", "fp32"], default="bf16",
+                       help="Operand type of the native kernels (not a reference flag): bf16 "
+                            "tensor cores (default), fp16 tensor cores, or the fp32 validation mode.")
     args = parser.parse_args(argv)
     if args.command == "run":
         _cmd_run(parser, args)
@@ -52,6 +55,7 @@ def _cmd_run(parser: argparse.ArgumentParser, args: argparse.Namespace) -> None:
     model = UNet(1, 1, (32, 64, 128, 256)).to(device)
     model.load_state_dict(torch.load(args.unet_weights, map_location=device, weights_only=True))
     model.eval()
+    model.precision = args.precision
     feats = extract_features_unet(args.video, None, model, device)
 
     if feats is None:

@@ -4,6 +4,7 @@
 #include "../../include/openglottal_b200.h"
 #include "internal.h"
 
+#include <cuda_fp16.h>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -59,19 +60,26 @@ struct ogl_unet {
     int device = 0;
     int num_sms = 148;
     bool loaded = false;
-    // bf16 tensor-core path
+    // tensor-core path: one set of packed operands per operand type (0 = bf16, 1 = f16; the f16
+    // set is built on demand by ogl_unet_prepare from the folded host weights)
     StemWeights stem;         // folded fp32 [32][9] + [32], passed by value to the stem kernel
-    TcLayer down_c2[4];       // downs.i.net.3 (+pool)
-    TcLayer down_c1[4];       // downs.i.net.0 for i = 1..3 (index 0 unused: stem)
-    TcLayer bott[2];
-    TcLayer up_t[4];
-    TcLayer up_c[4][2];
+    struct Pack {
+        bool built = false;
+        TcLayer down_c2[4];       // downs.i.net.3 (+pool)
+        TcLayer down_c1[4];       // downs.i.net.0 for i = 1..3 (index 0 unused: stem)
+        TcLayer bott[2];
+        TcLayer up_t[4];
+        TcLayer up_c[4][2];
+        // full-resolution level as space-to-depth GEMMs (s2d_tc.cu): downs.0.net.3 (+pool),
+        // ups.6 (convT) composed into ups.7.net.0, ups.7.net.3 (+head)
+        S2dLayer s2d_down, s2d_up0, s2d_up1;
+    } pack[2];
+    struct Folded {           // BN-folded fp32 weights on the host (PyTorch layouts)
+        std::vector<float> dw[4][2], db[4][2], bw[2], bb[2], tw[4], tb[4], uw[4][2], ub[4][2];
+    } folded;
     float* head_w = nullptr;  // [32] device
     float head_w_host[32] = {0};
     float head_b = 0.f;
-    // full-resolution level as space-to-depth GEMMs (s2d_tc.cu): downs.0.net.3 (+pool),
-    // ups.6 (convT) composed into ups.7.net.0, ups.7.net.3 (+head)
-    S2dLayer s2d_down, s2d_up0, s2d_up1;
     bool use_s2d = true;
     // u8 input: compute the stem inside the downs.0.net.3 kernel (its output never touches HBM:
     // 8.4 MB per frame less traffic). Bit-identical to the stand-alone stem; as fast or slightly
@@ -132,12 +140,25 @@ void fold_conv_bn(const ogl_conv_bn& L, int cout, int cin, double eps, std::vect
     }
 }
 
-__nv_bfloat16 to_bf16(float v) { return __float2bfloat16_rn(v); }
+// one 16-bit tensor-core operand: bf16, or f16 saturated to +-65504 (no folded weight of a
+// trained network comes near it)
+__nv_bfloat16 to_op(float v, bool f16) {
+    __nv_bfloat16 out;
+    if (f16) {
+        v = v > 65504.f ? 65504.f : (v < -65504.f ? -65504.f : v);
+        const __half h = __float2half_rn(v);
+        memcpy(&out, &h, 2);
+    } else {
+        out = __float2bfloat16_rn(v);
+    }
+    return out;
+}
 
 // conv3x3 weights [cout][cin][3][3] -> [pass][cin/32][tap][4][N][8] bf16: one contiguous
 // 64*N-byte block per (32-channel block, tap), taps of a block adjacent so several can be
 // fetched with one bulk copy.
-std::vector<__nv_bfloat16> pack_conv(const std::vector<float>& w, int cout, int cin, int N) {
+std::vector<__nv_bfloat16> pack_conv(const std::vector<float>& w, int cout, int cin, int N,
+                                     bool f16) {
     const int npass = cout / N, kb = cin / 32;
     std::vector<__nv_bfloat16> out(static_cast<size_t>(cout) * cin * 9);
     for (int pass = 0; pass < npass; ++pass)
@@ -149,14 +170,15 @@ std::vector<__nv_bfloat16> pack_conv(const std::vector<float>& w, int cout, int 
                             const int co = pass * N + n, ci = b * 32 + c * 8 + e;
                             const size_t dst =
                                 (((((static_cast<size_t>(pass) * kb + b) * 9 + tap) * 4 + c) * N + n) * 8) + e;
-                            out[dst] = to_bf16(w[(static_cast<size_t>(co) * cin + ci) * 9 + tap]);
+                            out[dst] = to_op(w[(static_cast<size_t>(co) * cin + ci) * 9 + tap], f16);
                         }
     return out;
 }
 
 // The same weights for a CTA pair (cta_group::2): rank r of the pair stages output channels
 // [r*N/2, (r+1)*N/2) of every pass -- [pass][cin/32][rank][tap][4][N/2][8] bf16.
-std::vector<__nv_bfloat16> pack_conv_pair(const std::vector<float>& w, int cout, int cin, int N) {
+std::vector<__nv_bfloat16> pack_conv_pair(const std::vector<float>& w, int cout, int cin, int N,
+                                          bool f16) {
     const int npass = cout / N, kb = cin / 32, nh = N / 2;
     std::vector<__nv_bfloat16> out(static_cast<size_t>(cout) * cin * 9);
     for (int pass = 0; pass < npass; ++pass)
@@ -169,7 +191,7 @@ std::vector<__nv_bfloat16> pack_conv_pair(const std::vector<float>& w, int cout,
                                 const int co = pass * N + r * nh + n, ci = b * 32 + c * 8 + e;
                                 const size_t dst =
                                     ((((((static_cast<size_t>(pass) * kb + b) * 2 + r) * 9 + tap) * 4 + c) * nh + n) * 8) + e;
-                                out[dst] = to_bf16(w[(static_cast<size_t>(co) * cin + ci) * 9 + tap]);
+                                out[dst] = to_op(w[(static_cast<size_t>(co) * cin + ci) * 9 + tap], f16);
                             }
     return out;
 }
@@ -177,7 +199,7 @@ std::vector<__nv_bfloat16> pack_conv_pair(const std::vector<float>& w, int cout,
 // ConvTranspose2d weights [cin][cout][2][2]: pass = (dy, block of cb = N/2 output channels),
 // GEMM column n of a pass = dx * cb + (co - blk*cb); layout [pass][cin/32][4][N][8] bf16.
 int convt_n(int cout) { return 2 * (cout < 64 ? cout : 64); }
-std::vector<__nv_bfloat16> pack_convt(const float* w, int cin, int cout, int N) {
+std::vector<__nv_bfloat16> pack_convt(const float* w, int cin, int cout, int N, bool f16) {
     const int cb = N / 2, nblk = cout / cb, npass = 2 * nblk, kb = cin / 32;
     std::vector<__nv_bfloat16> out(static_cast<size_t>(4) * cout * cin);
     for (int pass = 0; pass < npass; ++pass)
@@ -189,15 +211,15 @@ std::vector<__nv_bfloat16> pack_convt(const float* w, int cin, int cout, int N) 
                         const int dx = n / cb, co = blk * cb + n % cb, ci = b * 32 + c * 8 + e;
                         const size_t dst =
                             ((((static_cast<size_t>(pass) * kb + b) * 4 + c) * N + n) * 8) + e;
-                        out[dst] = to_bf16(w[(static_cast<size_t>(ci) * cout + co) * 4 + dy * 2 + dx]);
+                        out[dst] = to_op(w[(static_cast<size_t>(ci) * cout + co) * 4 + dy * 2 + dx], f16);
                     }
     return out;
 }
 
 // The same for a CTA pair: rank r stages columns [r*N/2, (r+1)*N/2) of every pass (that is dx = r
 // when N = 2 * cb) -- [pass][cin/32][rank][4][N/2][8] bf16.
-std::vector<__nv_bfloat16> pack_convt_pair(const float* w, int cin, int cout, int N) {
-    const std::vector<__nv_bfloat16> flat = pack_convt(w, cin, cout, N);
+std::vector<__nv_bfloat16> pack_convt_pair(const float* w, int cin, int cout, int N, bool f16) {
+    const std::vector<__nv_bfloat16> flat = pack_convt(w, cin, cout, N, f16);
     const int nh = N / 2, blocks = static_cast<int>(flat.size() / (static_cast<size_t>(4) * N * 8));
     std::vector<__nv_bfloat16> out(flat.size());
     for (int blk = 0; blk < blocks; ++blk)      // one (pass, 32-channel block)
@@ -211,7 +233,7 @@ std::vector<__nv_bfloat16> pack_convt_pair(const float* w, int cin, int cout, in
 }
 
 int build_tc_conv(ogl_unet* h, const std::vector<float>& w, const std::vector<float>& b, int cin0,
-                  int cin1, int cout, int epi, TcLayer* L) {
+                  int cin1, int cout, int epi, TcLayer* L, bool f16) {
     L->cin0 = cin0;
     L->cin1 = cin1;
     L->cout = cout;
@@ -219,17 +241,18 @@ int build_tc_conv(ogl_unet* h, const std::vector<float>& w, const std::vector<fl
     L->N = cout < 128 ? cout : 128;
     L->npass = cout / L->N;
     L->epi = epi;
-    if (dev_upload(h, pack_conv(w, cout, cin0 + cin1, L->N), &L->wpack)) return 1;
+    if (dev_upload(h, pack_conv(w, cout, cin0 + cin1, L->N, f16), &L->wpack)) return 1;
     if (L->N >= 64 && (epi == EPI_RELU || epi == EPI_RELU_POOL) &&
-        dev_upload(h, pack_conv_pair(w, cout, cin0 + cin1, L->N), &L->wpack2))
+        dev_upload(h, pack_conv_pair(w, cout, cin0 + cin1, L->N, f16), &L->wpack2))
         return 1;
     return dev_upload(h, b, &L->bias);
 }
 
 int build_s2d_layer(ogl_unet* h, const std::vector<float>& w3, const std::vector<float>& b3,
-                    int cin_s, const float* wt, const float* bt, int cin_b, int epi, S2dLayer* L) {
+                    int cin_s, const float* wt, const float* bt, int cin_b, int epi, S2dLayer* L,
+                    bool f16) {
     S2dHost hs;
-    if (build_s2d_host(w3.data(), b3.data(), cin_s, wt, bt, cin_b, &hs)) return 1;
+    if (build_s2d_host(w3.data(), b3.data(), cin_s, wt, bt, cin_b, &hs, f16)) return 1;
     *L = S2dLayer();
     L->wbytes = static_cast<uint32_t>(hs.wblob.size());
     L->n_stages = hs.n_stages;
@@ -252,6 +275,55 @@ int build_f32_conv(ogl_unet* h, const std::vector<float>& w, const std::vector<f
     L->cout = cout;
     if (dev_upload(h, w, &L->w)) return 1;
     return dev_upload(h, b, &L->b);
+}
+
+// Tensor-core operands of every layer from the folded host weights, for one operand type.
+int build_pack(ogl_unet* h, bool f16) {
+    ogl_unet::Pack& P = h->pack[f16 ? 1 : 0];
+    const ogl_unet::Folded& F = h->folded;
+    P = ogl_unet::Pack();
+    int cin = 1;
+    for (int i = 0; i < 4; ++i) {
+        const int f = kFeat[i];
+        if (i > 0 && build_tc_conv(h, F.dw[i][0], F.db[i][0], cin, 0, f, EPI_RELU, &P.down_c1[i], f16))
+            return 1;
+        if (build_tc_conv(h, F.dw[i][1], F.db[i][1], f, 0, f, EPI_RELU_POOL, &P.down_c2[i], f16))
+            return 1;
+        if (i == 0 && build_s2d_layer(h, F.dw[0][1], F.db[0][1], 32, nullptr, nullptr, 0,
+                                      EPI_RELU_POOL, &P.s2d_down, f16))
+            return 1;
+        cin = f;
+    }
+    if (build_tc_conv(h, F.bw[0], F.bb[0], 256, 0, 512, EPI_RELU, &P.bott[0], f16)) return 1;
+    if (build_tc_conv(h, F.bw[1], F.bb[1], 512, 0, 512, EPI_RELU, &P.bott[1], f16)) return 1;
+    for (int k = 0; k < 4; ++k) {
+        const int f = kFeat[3 - k];
+        TcLayer* L = &P.up_t[k];
+        L->cin0 = 2 * f;
+        L->cin1 = 0;
+        L->cout = f;
+        L->taps = 1;
+        L->N = convt_n(f);
+        L->npass = 4 * f / L->N;
+        L->epi = EPI_CONVT;
+        if (dev_upload(h, pack_convt(F.tw[k].data(), 2 * f, f, L->N, f16), &L->wpack)) return 1;
+        if (L->N == 128 &&
+            dev_upload(h, pack_convt_pair(F.tw[k].data(), 2 * f, f, L->N, f16), &L->wpack2))
+            return 1;
+        if (dev_upload(h, F.tb[k], &L->bias)) return 1;
+        if (build_tc_conv(h, F.uw[k][0], F.ub[k][0], f, f, f, EPI_RELU, &P.up_c[k][0], f16)) return 1;
+        if (k == 3 && build_s2d_layer(h, F.uw[k][0], F.ub[k][0], 32, F.tw[k].data(), F.tb[k].data(),
+                                      64, EPI_RELU, &P.s2d_up0, f16))
+            return 1;
+        if (build_tc_conv(h, F.uw[k][1], F.ub[k][1], f, 0, f, k == 3 ? EPI_HEAD : EPI_RELU,
+                          &P.up_c[k][1], f16))
+            return 1;
+        if (k == 3 && build_s2d_layer(h, F.uw[k][1], F.ub[k][1], 32, nullptr, nullptr, 0, EPI_HEAD,
+                                      &P.s2d_up1, f16))
+            return 1;
+    }
+    P.built = true;
+    return 0;
 }
 
 int check_conv_bn(const ogl_conv_bn& L) {
@@ -358,79 +430,60 @@ int ogl_unet_load_state(ogl_unet* h, const ogl_unet_state* st) {
         if (!st->up_t[i].weight || !st->up_t[i].bias)
             return fail("ogl_unet_load_state: missing convT tensor");
     free_all(h);
+    h->pack[0] = ogl_unet::Pack();
+    h->pack[1] = ogl_unet::Pack();
     const double eps = st->bn_eps;
-    std::vector<float> w, b;
+    ogl_unet::Folded& F = h->folded;
 
-    // encoder
+    // ---- fold BatchNorm (fp64) into host copies; fp32 device copies for the validation path
     int cin = 1;
     for (int i = 0; i < 4; ++i) {
         const int f = kFeat[i];
-        fold_conv_bn(st->downs[i][0], f, cin, eps, &w, &b);
-        if (build_f32_conv(h, w, b, cin, f, &h->f_down[i][0])) return 1;
-        if (i == 0) {
-            memcpy(h->stem.w, w.data(), sizeof h->stem.w);
-            memcpy(h->stem.b, b.data(), sizeof h->stem.b);
-            std::vector<uint8_t> blob;
-            if (build_stem_tc_blob(h->stem, &blob) || dev_upload(h, blob, &h->stem_tc)) return 1;
-        } else {
-            if (build_tc_conv(h, w, b, cin, 0, f, EPI_RELU, &h->down_c1[i])) return 1;
-        }
-        fold_conv_bn(st->downs[i][1], f, f, eps, &w, &b);
-        if (build_f32_conv(h, w, b, f, f, &h->f_down[i][1])) return 1;
-        if (build_tc_conv(h, w, b, f, 0, f, EPI_RELU_POOL, &h->down_c2[i])) return 1;
-        if (i == 0 && build_s2d_layer(h, w, b, 32, nullptr, nullptr, 0, EPI_RELU_POOL, &h->s2d_down))
-            return 1;
+        fold_conv_bn(st->downs[i][0], f, cin, eps, &F.dw[i][0], &F.db[i][0]);
+        if (build_f32_conv(h, F.dw[i][0], F.db[i][0], cin, f, &h->f_down[i][0])) return 1;
+        fold_conv_bn(st->downs[i][1], f, f, eps, &F.dw[i][1], &F.db[i][1]);
+        if (build_f32_conv(h, F.dw[i][1], F.db[i][1], f, f, &h->f_down[i][1])) return 1;
         cin = f;
     }
-    // bottleneck 256 -> 512 -> 512
-    fold_conv_bn(st->bottleneck[0], 512, 256, eps, &w, &b);
-    if (build_f32_conv(h, w, b, 256, 512, &h->f_bott[0])) return 1;
-    if (build_tc_conv(h, w, b, 256, 0, 512, EPI_RELU, &h->bott[0])) return 1;
-    fold_conv_bn(st->bottleneck[1], 512, 512, eps, &w, &b);
-    if (build_f32_conv(h, w, b, 512, 512, &h->f_bott[1])) return 1;
-    if (build_tc_conv(h, w, b, 512, 0, 512, EPI_RELU, &h->bott[1])) return 1;
-    // decoder: up_t[k] / up_c[k] act at level l = 3 - k
-    for (int k = 0; k < 4; ++k) {
+    memcpy(h->stem.w, F.dw[0][0].data(), sizeof h->stem.w);
+    memcpy(h->stem.b, F.db[0][0].data(), sizeof h->stem.b);
+    {
+        std::vector<uint8_t> blob;
+        if (build_stem_tc_blob(h->stem, &blob) || dev_upload(h, blob, &h->stem_tc)) return 1;
+    }
+    fold_conv_bn(st->bottleneck[0], 512, 256, eps, &F.bw[0], &F.bb[0]);
+    if (build_f32_conv(h, F.bw[0], F.bb[0], 256, 512, &h->f_bott[0])) return 1;
+    fold_conv_bn(st->bottleneck[1], 512, 512, eps, &F.bw[1], &F.bb[1]);
+    if (build_f32_conv(h, F.bw[1], F.bb[1], 512, 512, &h->f_bott[1])) return 1;
+    for (int k = 0; k < 4; ++k) {   // decoder: up_t[k] / up_c[k] act at level l = 3 - k
         const int f = kFeat[3 - k];
-        {
-            const ogl_convt& T = st->up_t[k];
-            std::vector<float> tw(T.weight, T.weight + static_cast<size_t>(2 * f) * f * 4);
-            std::vector<float> tb(T.bias, T.bias + f);
-            h->f_upt[k].cin = 2 * f;
-            h->f_upt[k].cout = f;
-            if (dev_upload(h, tw, &h->f_upt[k].w) || dev_upload(h, tb, &h->f_upt[k].b)) return 1;
-            TcLayer* L = &h->up_t[k];
-            L->cin0 = 2 * f;
-            L->cin1 = 0;
-            L->cout = f;
-            L->taps = 1;
-            L->N = convt_n(f);
-            L->npass = 4 * f / L->N;
-            L->epi = EPI_CONVT;
-            if (dev_upload(h, pack_convt(T.weight, 2 * f, f, L->N), &L->wpack)) return 1;
-            if (L->N == 128 &&
-                dev_upload(h, pack_convt_pair(T.weight, 2 * f, f, L->N), &L->wpack2))
-                return 1;
-            if (dev_upload(h, tb, &L->bias)) return 1;
-        }
-        fold_conv_bn(st->up_c[k][0], f, 2 * f, eps, &w, &b);
-        if (build_f32_conv(h, w, b, 2 * f, f, &h->f_up[k][0])) return 1;
-        if (build_tc_conv(h, w, b, f, f, f, EPI_RELU, &h->up_c[k][0])) return 1;
-        if (k == 3 && build_s2d_layer(h, w, b, 32, st->up_t[k].weight, st->up_t[k].bias, 64,
-                                      EPI_RELU, &h->s2d_up0))
-            return 1;
-        fold_conv_bn(st->up_c[k][1], f, f, eps, &w, &b);
-        if (build_f32_conv(h, w, b, f, f, &h->f_up[k][1])) return 1;
-        if (build_tc_conv(h, w, b, f, 0, f, k == 3 ? EPI_HEAD : EPI_RELU, &h->up_c[k][1]))
-            return 1;
-        if (k == 3 && build_s2d_layer(h, w, b, 32, nullptr, nullptr, 0, EPI_HEAD, &h->s2d_up1))
-            return 1;
+        const ogl_convt& T = st->up_t[k];
+        F.tw[k].assign(T.weight, T.weight + static_cast<size_t>(2 * f) * f * 4);
+        F.tb[k].assign(T.bias, T.bias + f);
+        h->f_upt[k].cin = 2 * f;
+        h->f_upt[k].cout = f;
+        if (dev_upload(h, F.tw[k], &h->f_upt[k].w) || dev_upload(h, F.tb[k], &h->f_upt[k].b)) return 1;
+        fold_conv_bn(st->up_c[k][0], f, 2 * f, eps, &F.uw[k][0], &F.ub[k][0]);
+        if (build_f32_conv(h, F.uw[k][0], F.ub[k][0], 2 * f, f, &h->f_up[k][0])) return 1;
+        fold_conv_bn(st->up_c[k][1], f, f, eps, &F.uw[k][1], &F.ub[k][1]);
+        if (build_f32_conv(h, F.uw[k][1], F.ub[k][1], f, f, &h->f_up[k][1])) return 1;
     }
     std::vector<float> hw(st->head_weight, st->head_weight + 32);
     if (dev_upload(h, hw, &h->head_w)) return 1;
     memcpy(h->head_w_host, hw.data(), sizeof h->head_w_host);
     h->head_b = st->head_bias[0];
     h->loaded = true;
+    return build_pack(h, false);
+}
+
+int ogl_unet_prepare(ogl_unet* h, int precision) {
+    if (!h) return fail("ogl_unet_prepare: NULL handle");
+    if (!h->loaded) return fail("ogl_unet_prepare: no weights loaded (ogl_unet_load_state)");
+    if (precision != OGL_PRECISION_BF16 && precision != OGL_PRECISION_F32 &&
+        precision != OGL_PRECISION_F16)
+        return fail("ogl_unet_prepare: unknown precision mode");
+    OGL_CUDA(cudaSetDevice(h->device));
+    if (precision == OGL_PRECISION_F16 && !h->pack[1].built) return build_pack(h, true);
     return 0;
 }
 
@@ -461,7 +514,8 @@ int ogl_unet_forward(ogl_unet* h, const void* frames_dev, int in_dtype, int n, i
         return fail("ogl_unet_forward: in_dtype must be OGL_DTYPE_U8 or OGL_DTYPE_F32");
     if (!(threshold > 0.f && threshold < 1.f))
         return fail("ogl_unet_forward: threshold must be in (0, 1)");
-    if (precision != OGL_PRECISION_BF16 && precision != OGL_PRECISION_F32)
+    if (precision != OGL_PRECISION_BF16 && precision != OGL_PRECISION_F32 &&
+        precision != OGL_PRECISION_F16)
         return fail("ogl_unet_forward: unknown precision mode");
     if (workspace_bytes < ogl_unet_workspace_bytes(h, n, height, width, precision))
         return fail("ogl_unet_forward: workspace too small");
@@ -474,7 +528,14 @@ int ogl_unet_forward(ogl_unet* h, const void* frames_dev, int in_dtype, int n, i
     uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
     if (area_dev) OGL_CUDA(cudaMemsetAsync(area_dev, 0, sizeof(int32_t) * n, stream));
 
-    if (precision == OGL_PRECISION_BF16) {
+    if (precision != OGL_PRECISION_F32) {
+        const bool f16 = precision == OGL_PRECISION_F16;
+        const ogl_unet::Pack& K = h->pack[f16 ? 1 : 0];
+        if (!K.built)
+            return fail("ogl_unet_forward: f16 operands are not packed (call ogl_unet_prepare first)");
+        // the two operand types are the same kernels compiled twice (conv_tc_f16.cu, s2d_tc_f16.cu)
+        auto conv_tc = [&](auto&&... a) { return f16 ? launch_conv_tc_f16(a...) : launch_conv_tc(a...); };
+        auto s2d_tc = [&](auto&&... a) { return f16 ? launch_s2d_tc_f16(a...) : launch_s2d_tc(a...); };
         const Plan p = make_plan(n, H, W, 2);
         auto B = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(ws + off); };
         __nv_bfloat16* P[4] = {B(p.U[1]), B(p.U[2]), B(p.U[3]), B(p.P3)};
@@ -506,19 +567,19 @@ int ogl_unet_forward(ogl_unet* h, const void* frames_dev, int in_dtype, int n, i
         const bool fused_stem = s2d && h->fuse_stem && in_dtype == OGL_DTYPE_U8;
         if (!fused_stem &&
             step(kDownC1[0], [&] {
-                return launch_stem(frames_dev, in_dtype, h->stem, n, H, W, B(p.T[0]), s2d, stream);
+                return launch_stem(frames_dev, in_dtype, h->stem, n, H, W, B(p.T[0]), s2d, stream, f16);
             }))
             return 1;
         for (int l = 0; l < 4; ++l) {
             const int hh = H >> l, ww = W >> l;
             if (l > 0 && step(kDownC1[l], [&] {
-                    return launch_conv_tc(h->down_c1[l], P[l - 1], nullptr, n, hh, ww, B(p.T[l]),
+                    return conv_tc(K.down_c1[l], P[l - 1], nullptr, n, hh, ww, B(p.T[l]),
                                           nullptr, nullptr, sms, stream, cg, rev);
                 }))
                 return 1;
             if (l == 0 && fused_stem) {
                 if (step("stem+downs.0.net.3+pool", [&] {
-                        return launch_s2d_tc(h->s2d_down, nullptr, nullptr, n, H, W, B(p.S[0]), P[0],
+                        return s2d_tc(K.s2d_down, nullptr, nullptr, n, H, W, B(p.S[0]), P[0],
                                              nullptr, sms, stream, cg,
                                              static_cast<const uint8_t*>(frames_dev), &h->stem, rev,
                                              h->fuse_stem == 2 ? h->stem_tc : nullptr);
@@ -528,20 +589,20 @@ int ogl_unet_forward(ogl_unet* h, const void* frames_dev, int in_dtype, int n, i
             }
             if (step(kDownC2[l], [&] {
                     if (l == 0 && s2d)
-                        return launch_s2d_tc(h->s2d_down, B(p.T[0]), nullptr, n, H, W, B(p.S[0]), P[0],
+                        return s2d_tc(K.s2d_down, B(p.T[0]), nullptr, n, H, W, B(p.S[0]), P[0],
                                              nullptr, sms, stream, cg, nullptr, nullptr, rev);
-                    return launch_conv_tc(h->down_c2[l], B(p.T[l]), nullptr, n, hh, ww, B(p.S[l]),
+                    return conv_tc(K.down_c2[l], B(p.T[l]), nullptr, n, hh, ww, B(p.S[l]),
                                           P[l], nullptr, sms, stream, cg, rev);
                 }))
                 return 1;
         }
         if (step("bottleneck.net.0", [&] {
-                return launch_conv_tc(h->bott[0], P[3], nullptr, n, H >> 4, W >> 4, B(p.T[4]), nullptr,
+                return conv_tc(K.bott[0], P[3], nullptr, n, H >> 4, W >> 4, B(p.T[4]), nullptr,
                                       nullptr, sms, stream, cg, rev);
             }))
             return 1;
         if (step("bottleneck.net.3", [&] {
-                return launch_conv_tc(h->bott[1], B(p.T[4]), nullptr, n, H >> 4, W >> 4, B(p.B4),
+                return conv_tc(K.bott[1], B(p.T[4]), nullptr, n, H >> 4, W >> 4, B(p.B4),
                                       nullptr, nullptr, sms, stream, cg, rev);
             }))
             return 1;
@@ -560,29 +621,29 @@ int ogl_unet_forward(ogl_unet* h, const void* frames_dev, int in_dtype, int n, i
             if (l == 0 && s2d) {
                 // ups.6 is composed into ups.7.net.0: reads the skip (S2D) and the level-1 tensor
                 if (step("ups.6(convT)+ups.7.net.0(cat)", [&] {
-                        return launch_s2d_tc(h->s2d_up0, B(p.S[0]), below, n, H, W, B(p.T[0]), nullptr,
+                        return s2d_tc(K.s2d_up0, B(p.S[0]), below, n, H, W, B(p.T[0]), nullptr,
                                              nullptr, sms, stream, cg, nullptr, nullptr, rev);
                     }))
                     return 1;
                 if (step(kUpC2[k], [&] {
-                        return launch_s2d_tc(h->s2d_up1, B(p.T[0]), nullptr, n, H, W, nullptr, nullptr,
+                        return s2d_tc(K.s2d_up1, B(p.T[0]), nullptr, n, H, W, nullptr, nullptr,
                                              &hp, sms, stream, cg, nullptr, nullptr, rev);
                     }))
                     return 1;
                 break;
             }
             if (step(kUpT[k], [&] {
-                    return launch_conv_tc(h->up_t[k], below, nullptr, n, hh / 2, ww / 2, B(p.U[l]),
+                    return conv_tc(K.up_t[k], below, nullptr, n, hh / 2, ww / 2, B(p.U[l]),
                                           nullptr, nullptr, sms, stream, cg, rev);
                 }))
                 return 1;
             if (step(kUpC1[k], [&] {
-                    return launch_conv_tc(h->up_c[k][0], B(p.S[l]), B(p.U[l]), n, hh, ww, B(p.T[l]),
+                    return conv_tc(K.up_c[k][0], B(p.S[l]), B(p.U[l]), n, hh, ww, B(p.T[l]),
                                           nullptr, nullptr, sms, stream, cg, rev);
                 }))
                 return 1;
             if (step(kUpC2[k], [&] {
-                    return launch_conv_tc(h->up_c[k][1], B(p.T[l]), nullptr, n, hh, ww, B(p.U[l]),
+                    return conv_tc(K.up_c[k][1], B(p.T[l]), nullptr, n, hh, ww, B(p.U[l]),
                                           nullptr, k == 3 ? &hp : nullptr, sms, stream, cg, rev);
                 }))
                 return 1;
@@ -794,6 +855,39 @@ int ogl_unletterbox_area(const uint8_t* mask_cs_dev, int n, int size, const int3
     return 0;
 }
 
+int ogl_resize_u8_linear(const uint8_t* src_dev, int n, int src_h, int src_w, uint8_t* dst_dev,
+                         int dst_h, int dst_w, void* stream) {
+    if (!src_dev || !dst_dev || n < 0 || src_h <= 0 || src_w <= 0 || dst_h <= 0 || dst_w <= 0)
+        return fail("ogl_resize_u8_linear: bad argument");
+    const size_t ss = static_cast<size_t>(src_h) * src_w, ds = static_cast<size_t>(dst_h) * dst_w;
+    for (int i = 0; i < n; i += kFramesPerLaunch) {
+        const int m = n - i < kFramesPerLaunch ? n - i : kFramesPerLaunch;
+        if (launch_resize_u8_linear(src_dev + i * ss, m, src_h, src_w, dst_dev + i * ds, dst_h, dst_w,
+                                    static_cast<cudaStream_t>(stream)))
+            return 1;
+    }
+    return 0;
+}
+
+int ogl_prob_resize_mask(const float* logits_dev, int n, int src_h, int src_w, int dst_h,
+                         int dst_w, float threshold, uint8_t* mask_dev, int32_t* area_dev,
+                         void* stream) {
+    if (!logits_dev || n < 0 || src_h <= 0 || src_w <= 0 || dst_h <= 0 || dst_w <= 0)
+        return fail("ogl_prob_resize_mask: bad argument");
+    if (!(threshold > 0.f && threshold < 1.f))
+        return fail("ogl_prob_resize_mask: threshold must be in (0, 1)");
+    const size_t ss = static_cast<size_t>(src_h) * src_w, ds = static_cast<size_t>(dst_h) * dst_w;
+    for (int i = 0; i < n; i += kFramesPerLaunch) {
+        const int m = n - i < kFramesPerLaunch ? n - i : kFramesPerLaunch;
+        if (launch_prob_resize_mask(logits_dev + i * ss, m, src_h, src_w, dst_h, dst_w, threshold,
+                                    mask_dev ? mask_dev + i * ds : nullptr,
+                                    area_dev ? area_dev + i : nullptr,
+                                    static_cast<cudaStream_t>(stream)))
+            return 1;
+    }
+    return 0;
+}
+
 int ogl_mask_overlap_counts(const uint8_t* pred_dev, const uint8_t* gt_dev, int n, int64_t pixels,
                             int32_t* counts_dev, void* stream) {
     if (!pred_dev || !gt_dev || !counts_dev || n < 0 || pixels <= 0 || pixels > 0x7fffffffLL)
@@ -830,14 +924,14 @@ int ogl_debug_tc_layer(ogl_unet* h, int kind, const float* src0_dev, int c0, con
     if (kind == EPI_CONVT) {
         L.taps = 1;
         L.npass = 4 * cout / L.N;
-        pk = pack_convt(weight_host, cin, cout, L.N);
-        if (L.N == 128) pk2 = pack_convt_pair(weight_host, cin, cout, L.N);
+        pk = pack_convt(weight_host, cin, cout, L.N, false);
+        if (L.N == 128) pk2 = pack_convt_pair(weight_host, cin, cout, L.N, false);
     } else {
         L.taps = 9;
         L.npass = cout / L.N;
         std::vector<float> w(weight_host, weight_host + static_cast<size_t>(cout) * cin * 9);
-        pk = pack_conv(w, cout, cin, L.N);
-        if (L.N >= 64) pk2 = pack_conv_pair(w, cout, cin, L.N);
+        pk = pack_conv(w, cout, cin, L.N, false);
+        if (L.N >= 64) pk2 = pack_conv_pair(w, cout, cin, L.N, false);
     }
     const size_t hw = static_cast<size_t>(height) * width;
     const int oh = kind == EPI_CONVT ? 2 * height : height;

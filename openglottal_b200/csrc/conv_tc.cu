@@ -31,6 +31,11 @@
 #include <cstdlib>
 #include <cstring>
 
+#ifdef OGL_F16   // conv_tc_f16.cu: the same kernels with f16 operands, exported under other names
+#define launch_conv_tc launch_conv_tc_f16
+#define conv_tc_init conv_tc_init_f16
+#endif
+
 namespace ogl {
 
 namespace {
@@ -88,15 +93,9 @@ __device__ __forceinline__ SubTile decode_sub(const ConvParams& p, int st) {
     return s;
 }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&v);
-}
-__device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
-    __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a),
-                               *reinterpret_cast<__nv_bfloat162*>(&b));
-    return *reinterpret_cast<uint32_t*>(&r);
-}
+// 16-bit operand pairs of this unit's type (bf16, or f16 in conv_tc_f16.cu)
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) { return pack_x2<kF16>(lo, hi); }
+__device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) { return max_x2<kF16>(a, b); }
 
 // CG = 1: one CTA per tile. CG = 2: the two CTAs of a cluster (one TPC) take two neighbouring
 // tiles of the same pass and run their MMAs as ONE 256-row tcgen05.mma.cta_group::2: each CTA
@@ -666,6 +665,7 @@ inline int taps_per_stage(const TcLayer& L) { return L.taps == 1 ? 1 : (L.N <= 6
 
 }  // namespace
 
+#ifndef OGL_F16
 int encode_bf16_map(void* tensor_map, const void* base, int rank, const uint64_t* dims,
                     const uint64_t* strides_bytes, const uint32_t* box) {
     return encode_map(tensor_map, base, rank, dims, strides_bytes, box, false);
@@ -695,6 +695,7 @@ int encode_map(void* tensor_map, const void* base, int rank, const uint64_t* dim
     }
     return 0;
 }
+#endif  // !OGL_F16
 
 int conv_tc_init() {
     if (!g_encode) {

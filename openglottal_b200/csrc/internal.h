@@ -56,6 +56,12 @@ struct HeadParams {
 };
 
 int conv_tc_init();  // resolves cuTensorMapEncodeTiled, sets smem attributes
+int conv_tc_init_f16();   // the f16-operand twins (conv_tc_f16.cu, s2d_tc_f16.cu): same arguments,
+                          // tensors and weights hold f16 instead of bf16
+int launch_conv_tc_f16(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloat16* src1, int B,
+                       int H, int W, __nv_bfloat16* out, __nv_bfloat16* out_pool,
+                       const HeadParams* head, int num_sms, cudaStream_t stream, int cta_group = 1,
+                       bool reverse = false);
 int launch_conv_tc(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloat16* src1, int B,
                    int H, int W, __nv_bfloat16* out, __nv_bfloat16* out_pool,
                    const HeadParams* head, int num_sms, cudaStream_t stream, int cta_group = 1,
@@ -145,14 +151,20 @@ struct S2dHost {               // host-side result of build_s2d_host, uploaded b
 // w3: folded conv weights [32][cin_s + (wt ? 32 : 0)][3][3], b3 [32]; wt: ConvTranspose2d weights
 // [cin_b][32][2][2] with bias bt [32], or null.
 int build_s2d_host(const float* w3, const float* b3, int cin_s, const float* wt, const float* bt,
-                   int cin_b, S2dHost* out);
+                   int cin_b, S2dHost* out, bool f16 = false);   // f16: pack f16 instead of bf16
 int s2d_tc_init();
+int s2d_tc_init_f16();
 // src_s2d: [B][cin_s/8][4][H/2][W/2][8]; below: [B][cin_b/8][H/2][W/2][8] or null. H, W = full res.
 int launch_s2d_tc(const S2dLayer& L, const __nv_bfloat16* src_s2d, const __nv_bfloat16* below,
                   int B, int H, int W, __nv_bfloat16* out_s2d, __nv_bfloat16* out_pool,
                   const HeadParams* head, int num_sms, cudaStream_t stream, int cta_group = 1,
                   const uint8_t* stem_frames = nullptr, const StemWeights* stem = nullptr,
                   bool reverse = false, const uint8_t* stem_tc_blob = nullptr);
+int launch_s2d_tc_f16(const S2dLayer& L, const __nv_bfloat16* src_s2d, const __nv_bfloat16* below,
+                      int B, int H, int W, __nv_bfloat16* out_s2d, __nv_bfloat16* out_pool,
+                      const HeadParams* head, int num_sms, cudaStream_t stream, int cta_group = 1,
+                      const uint8_t* stem_frames = nullptr, const StemWeights* stem = nullptr,
+                      bool reverse = false, const uint8_t* stem_tc_blob = nullptr);
 // (stem_tc_blob != null, from build_stem_tc_blob: the fused stem runs on the tensor cores)
 int build_stem_tc_blob(const StemWeights& sw, std::vector<uint8_t>* out);
 // (stem_frames != null: downs.0.net.3 with the stem fused in -- the A operand is computed from
@@ -164,7 +176,7 @@ int encode_map(void* tensor_map, const void* base, int rank, const uint64_t* dim
                const uint64_t* strides_bytes, const uint32_t* box, bool u8);
 
 int launch_stem(const void* frames, int in_dtype, const StemWeights& sw, int B, int H, int W,
-                __nv_bfloat16* out, bool s2d, cudaStream_t stream);
+                __nv_bfloat16* out, bool s2d, cudaStream_t stream, bool f16 = false);
 
 // fp32 validation path (NCHW fp32 activations, FFMA kernels)
 int launch_f32_input(const void* frames, int in_dtype, int64_t count, float* out,
@@ -192,6 +204,12 @@ int launch_unletterbox_area(const uint8_t* mask_cs, int n, int size, const int32
                             int W, uint8_t* full, int32_t* area, cudaStream_t stream);
 int launch_overlap_counts(const uint8_t* pred, const uint8_t* gt, int n, long long pixels,
                           int32_t* counts, cudaStream_t stream);
+
+// the reference wrapper's two cv2.resize calls (resize.cu); n <= 65535 per launch
+int launch_resize_u8_linear(const uint8_t* src, int n, int SH, int SW, uint8_t* dst, int DH, int DW,
+                            cudaStream_t stream);
+int launch_prob_resize_mask(const float* logits, int n, int SH, int SW, int DH, int DW,
+                            float threshold, uint8_t* mask, int32_t* area, cudaStream_t stream);
 
 // debugging / unit-test helpers: layout conversion NCHW f32 <-> C8-planar bf16
 // (s2d = true: the space-to-depth form of the same tensor)

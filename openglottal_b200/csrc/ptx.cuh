@@ -5,9 +5,54 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+// Operand type of the tensor-core path, fixed per translation unit: the *_f16.cu units define
+// OGL_F16 and include the bf16 source, so that every kernel exists once per operand type with the
+// conversions resolved at compile time. tcgen05.mma.kind::f16 takes either type at the same rate;
+// f16 has 3 more mantissa bits (logits within 2e-2 of the fp32 reference everywhere), bf16 the
+// range of fp32 (the default; BASELINE.json's metric is quoted in bf16).
+#ifdef OGL_F16
+#define OGL_AB_FMT 0u
+#else
+#define OGL_AB_FMT 1u
+#endif
+
 namespace ogl {
+
+#ifdef OGL_F16
+constexpr bool kF16 = true;
+#else
+constexpr bool kF16 = false;
+#endif
+
+// Two f32 -> one packed pair of 16-bit operands {lo, hi}, round to nearest even. f16 saturates to
+// +-65504 instead of overflowing to infinity (no NaN can appear downstream).
+template <bool F16>
+__device__ __forceinline__ uint32_t pack_x2(float lo, float hi) {
+    uint32_t d;
+    if (F16) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+// the same of max(x, 0): ReLU folded into the conversion (one F2FP instead of two FMNMX + one F2FP;
+// the values are those of fmaxf followed by the plain conversion)
+template <bool F16>
+__device__ __forceinline__ uint32_t pack_relu_x2(float lo, float hi) {
+    uint32_t d;
+    if (F16) asm("cvt.rn.satfinite.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    else asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+template <bool F16>
+__device__ __forceinline__ uint32_t max_x2(uint32_t a, uint32_t b) {
+    uint32_t d;
+    if (F16) asm("max.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    else asm("max.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -28,12 +73,9 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
-// bf16x2 {lo, hi} = round-to-nearest-even of max(x, 0): ReLU folded into the conversion
-// (one F2FP instead of two FMNMX + one F2FP; the values are those of fmaxf then __float2bfloat16_rn).
+// this translation unit's operand type
 __device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
-    uint32_t d;
-    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-    return d;
+    return pack_relu_x2<kF16>(lo, hi);
 }
 
 // ---------------------------------------------------------------- mbarrier
@@ -334,15 +376,18 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
     d |= static_cast<uint64_t>(1) << 46;
     return d;
 }
-// Instruction descriptor for kind::f16: D=f32, A=B=bf16, both K-major, M=128, N runtime.
-__host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
-           (static_cast<uint32_t>(128 >> 4) << 24);
+// Instruction descriptor for kind::f16: D = f32, A and B of format `fmt` (0 = f16, 1 = bf16), both
+// K-major, M = 128 (256 for a CTA pair: 128 rows in each CTA), N runtime.
+__host__ __device__ __forceinline__ uint32_t make_idesc_fmt(int n, uint32_t fmt, int m = 128) {
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+           (static_cast<uint32_t>(m >> 4) << 24);
 }
-// The same for a CTA pair: M = 256 (128 rows in each CTA).
+// ... with this translation unit's operand type
+__host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int n) {
+    return make_idesc_fmt(n, OGL_AB_FMT);
+}
 __host__ __device__ __forceinline__ uint32_t make_idesc_bf16_pair(int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
-           (static_cast<uint32_t>(256 >> 4) << 24);
+    return make_idesc_fmt(n, OGL_AB_FMT, 256);
 }
 
 }  // namespace ogl

@@ -33,6 +33,11 @@
 #include <cstring>
 #include <vector>
 
+#ifdef OGL_F16   // s2d_tc_f16.cu: the same kernels with f16 operands, exported under other names
+#define launch_s2d_tc launch_s2d_tc_f16
+#define s2d_tc_init s2d_tc_init_f16
+#endif
+
 namespace ogl {
 
 namespace {
@@ -175,15 +180,10 @@ __device__ __forceinline__ Tile decode_tile(const S2dParams& p, int tile) {
     return t;
 }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&v);
-}
-__device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
-    __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a),
-                               *reinterpret_cast<__nv_bfloat162*>(&b));
-    return *reinterpret_cast<uint32_t*>(&r);
-}
+// always bf16: the im2col operand of the tensor-core stem (u8 values, exact)
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) { return pack_x2<false>(lo, hi); }
+// this unit's operand type (bf16, or f16 in s2d_tc_f16.cu)
+__device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) { return max_x2<kF16>(a, b); }
 
 // CG = 2: the two CTAs of a cluster take neighbouring tiles and run every MMA as one 256-row
 // tcgen05.mma.cta_group::2; each CTA keeps only HALF of every weight block resident (columns
@@ -591,8 +591,8 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
                             (((sA + b * kStemABytes + static_cast<uint32_t>(j) * 2048u) >> 4) | a_lbo_s);
                         const uint32_t d = tmem_base + kStemDCol + slot * 32u;
                         if (!(p.dbg & 1)) {
-                            umma_bf16(d, ad, bd_hi, make_idesc_bf16(32), 0u);
-                            umma_bf16(d, ad, bd_lo, make_idesc_bf16(32), 1u);
+                            umma_bf16(d, ad, bd_hi, make_idesc_fmt(32, 1u), 0u);   // bf16 x bf16 in
+                            umma_bf16(d, ad, bd_lo, make_idesc_fmt(32, 1u), 1u);   // either unit
                         }
                         umma_commit(sd_full + 8u * slot);
                         if (j == kStemChunks - 1) umma_commit(sa_empty + 8u * b);
@@ -827,14 +827,25 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
     }
 }
 
-inline uint16_t bf16_bits(double v) {
-    const __nv_bfloat16 h = __float2bfloat16_rn(static_cast<float>(v));
+#ifndef OGL_F16
+inline uint16_t operand_bits(double v, bool f16) {
     uint16_t b;
-    memcpy(&b, &h, 2);
+    if (f16) {
+        float f = static_cast<float>(v);
+        f = f > 65504.f ? 65504.f : (f < -65504.f ? -65504.f : f);
+        const __half h = __float2half_rn(f);
+        memcpy(&b, &h, 2);
+    } else {
+        const __nv_bfloat16 h = __float2bfloat16_rn(static_cast<float>(v));
+        memcpy(&b, &h, 2);
+    }
     return b;
 }
+#endif
 
 }  // namespace
+
+#ifndef OGL_F16
 
 // B operands of the tensor-core stem: [B_hi, B_lo][K half][n = 32 channels][8 K elements] bf16.
 // K rows 0..8 = the taps' weights / 255 (the fp32 value of the CUDA-core stem, split hi + lo),
@@ -863,7 +874,7 @@ int build_stem_tc_blob(const StemWeights& sw, std::vector<uint8_t>* out) {
 }
 
 int build_s2d_host(const float* w3, const float* b3, int cin_s, const float* wt, const float* bt,
-                   int cin_b, S2dHost* out) {
+                   int cin_b, S2dHost* out, bool f16) {
     if (cin_s <= 0 || cin_s % 16) return fail("s2d layer: Cin of the S2D source must be a multiple of 16");
     if (wt && cin_b != 64) return fail("s2d layer: the composed ConvTranspose2d needs 64 input channels");
     const int cin3 = cin_s + (wt ? 32 : 0);
@@ -892,7 +903,7 @@ int build_s2d_host(const float* w3, const float* b3, int cin_s, const float* wt,
                     double v = 0.0;
                     if (((ys >> (pp >> 1)) & 1) && ((xs >> (pp & 1)) & 1))
                         v = weight(kh * 8 + e, pp >> 1, pp & 1, c);
-                    B[(static_cast<size_t>(kh) * N + n) * 8 + e] = bf16_bits(v);
+                    B[(static_cast<size_t>(kh) * N + n) * 8 + e] = operand_bits(v, f16);
                 }
         // CTA-pair form: rank r keeps columns [r N/2, (r+1) N/2) of this op as [2][N/2][8], at half
         // the offset inside its own half of the blob
@@ -914,7 +925,7 @@ int build_s2d_host(const float* w3, const float* b3, int cin_s, const float* wt,
         op.w0 = (static_cast<uint32_t>(sh.a_off) + a_extra) | (static_cast<uint32_t>(sh.dcol) << 16) |
                 (static_cast<uint32_t>(src) << 24) | ((out->ops.empty() ? 0u : 1u) << 25);
         op.b_lo = static_cast<uint32_t>(b_off >> 4) | (static_cast<uint32_t>(N) << 16);  // LBO = 16 N
-        op.idesc = make_idesc_bf16(N);
+        op.idesc = make_idesc_fmt(N, f16 ? 0u : 1u);
         op.pad = 0;
         out->ops.push_back(op);
         return 0;
@@ -996,6 +1007,7 @@ int build_s2d_host(const float* w3, const float* b3, int cin_s, const float* wt,
             }
     return 0;
 }
+#endif  // !OGL_F16
 
 namespace {
 template <int EPI>

@@ -11,6 +11,7 @@
 //   unet.py:72,88      logits = conv1x1(x) + b;  utils.py:237,241 sigmoid(z) > thr <=> z > logit(thr)
 //   features.py:238    area = count(mask > 0)
 #include "internal.h"
+#include "ptx.cuh"
 
 namespace ogl {
 
@@ -38,6 +39,7 @@ __device__ __forceinline__ size_t pix_off(int y, int x, int H, int W, int s2d) {
 // Generic form (f32 input): one thread per pixel, 9 taps -> 32 channels in fp32, written as
 // 4 planes of 8 bf16. The 288 folded weights arrive as a by-value kernel parameter, so every
 // FFMA takes its weight straight from the constant bank (no LDS / LDG in the inner loop).
+template <bool F16>
 __global__ void __launch_bounds__(256)
 stem_kernel(const void* __restrict__ frames, int in_dtype, const __grid_constant__ StemWeights sw,
             int B, int H, int W, __nv_bfloat16* __restrict__ out, int s2d) {
@@ -78,14 +80,10 @@ stem_kernel(const void* __restrict__ frames, int in_dtype, const __grid_constant
                 v[c] = fmaxf(acc + sw.b[co], 0.f);
             }
             uint4 q;
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]);
-            __nv_bfloat162 h1 = __floats2bfloat162_rn(v[2], v[3]);
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]);
-            __nv_bfloat162 h3 = __floats2bfloat162_rn(v[6], v[7]);
-            q.x = *reinterpret_cast<uint32_t*>(&h0);
-            q.y = *reinterpret_cast<uint32_t*>(&h1);
-            q.z = *reinterpret_cast<uint32_t*>(&h2);
-            q.w = *reinterpret_cast<uint32_t*>(&h3);
+            q.x = pack_x2<F16>(v[0], v[1]);
+            q.y = pack_x2<F16>(v[2], v[3]);
+            q.z = pack_x2<F16>(v[4], v[5]);
+            q.w = pack_x2<F16>(v[6], v[7]);
             *reinterpret_cast<uint4*>(o + g * plane) = q;
         }
     }
@@ -97,6 +95,7 @@ stem_kernel(const void* __restrict__ frames, int in_dtype, const __grid_constant
 // weights already divided by 255 (utils.py:235), so the bytes are used as integers-in-fp32.
 // 1152 FFMAs (constant-bank weights) per 4 pixels; bias rides in as the first addend; ReLU is a
 // packed bf16x2 max after rounding; each channel group stores 64 contiguous bytes per thread.
+template <bool F16>
 __global__ void __launch_bounds__(256)
 stem_u8_kernel(const uint8_t* __restrict__ frames, const __grid_constant__ StemPairs sw,
                int rows_total, int H, int W, __nv_bfloat16* __restrict__ out, int s2d) {
@@ -142,7 +141,6 @@ stem_u8_kernel(const uint8_t* __restrict__ frames, const __grid_constant__ StemP
 #pragma unroll
                 for (int c2 = 0; c2 < 4; ++c2) {
                     const int cp = g * 4 + c2;   // channel pair (2 cp, 2 cp + 1)
-                    const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
                     for (int px = 0; px < 4; ++px) {
                         unsigned long long a = as_u64(sw.bp[cp]);
@@ -153,8 +151,7 @@ stem_u8_kernel(const uint8_t* __restrict__ frames, const __grid_constant__ StemP
                                 a = fma2(in[dy][px + dx], as_u64(sw.wp[cp * 9 + dy * 3 + dx]), a);
                         const float lo = __uint_as_float(static_cast<uint32_t>(a));
                         const float hi = __uint_as_float(static_cast<uint32_t>(a >> 32));
-                        __nv_bfloat162 h = __hmax2(__floats2bfloat162_rn(lo, hi), zero);
-                        pk[px][c2] = *reinterpret_cast<uint32_t*>(&h);
+                        pk[px][c2] = pack_relu_x2<F16>(lo, hi);   // = max(round(v), 0)
                     }
                 }
                 uint4* dst = reinterpret_cast<uint4*>(o + g * plane);
@@ -335,7 +332,7 @@ inline int grid_for(size_t total, int block = 256, int cap = 148 * 16) {
 }  // namespace
 
 int launch_stem(const void* frames, int in_dtype, const StemWeights& sw, int B, int H, int W,
-                __nv_bfloat16* out, bool s2d, cudaStream_t stream) {
+                __nv_bfloat16* out, bool s2d, cudaStream_t stream, bool f16) {
     const size_t total = static_cast<size_t>(B) * H * W;
     if (s2d && (H % 2 || W % 2)) return fail("space-to-depth stem output needs even H and W");
     if (in_dtype == 0 && W % 4 == 0) {
@@ -345,11 +342,18 @@ int launch_stem(const void* frames, int in_dtype, const StemWeights& sw, int B, 
         const int rows = B * H;
         int grid = (rows + 7) / 8;
         if (grid > 148 * 6) grid = 148 * 6;
-        stem_u8_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint8_t*>(frames), scaled, rows,
-                                                 H, W, out, s2d ? 1 : 0);
+        if (f16)
+            stem_u8_kernel<true><<<grid, 256, 0, stream>>>(static_cast<const uint8_t*>(frames), scaled,
+                                                           rows, H, W, out, s2d ? 1 : 0);
+        else
+            stem_u8_kernel<false><<<grid, 256, 0, stream>>>(static_cast<const uint8_t*>(frames), scaled,
+                                                            rows, H, W, out, s2d ? 1 : 0);
+    } else if (f16) {
+        stem_kernel<true><<<grid_for(total, 256, 148 * 8), 256, 0, stream>>>(frames, in_dtype, sw, B,
+                                                                             H, W, out, s2d ? 1 : 0);
     } else {
-        stem_kernel<<<grid_for(total, 256, 148 * 8), 256, 0, stream>>>(frames, in_dtype, sw, B, H,
-                                                                       W, out, s2d ? 1 : 0);
+        stem_kernel<false><<<grid_for(total, 256, 148 * 8), 256, 0, stream>>>(frames, in_dtype, sw, B,
+                                                                              H, W, out, s2d ? 1 : 0);
     }
     OGL_CUDA(cudaGetLastError());
     return 0;

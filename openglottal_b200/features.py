@@ -205,28 +205,33 @@ def extract_features_unet_frames(frames_gray, model: UNet, batch: int = 512,
     return kinematic_features_device(area)
 
 
-def _masks_reference_resize(frames_gray: list, model: UNet, threshold: float = 0.5,
-                            batch: int = 256) -> list:
-    """Masks of arbitrary-size gray frames with the reference's resize semantics
-    (/root/reference/openglottal/utils.py:234-241), batched: cv2 squash to 256x256 on the host,
-    ONE native forward per batch, sigmoid, cv2 bilinear resize of the probability map back,
-    threshold. Returns a list of ``(H, W)`` uint8 numpy masks."""
-    import cv2
+def masks_for_clip(frames_gray, model: UNet, threshold: float = 0.5, want_masks: bool = False,
+                   batch: int = 512):
+    """Area waveform (and masks) of a clip with the REFERENCE's per-frame semantics
+    (/root/reference/openglottal/utils.py:218-241): every caller of ``unet_segment_frame`` in the
+    reference -- features.py:236, scripts/infer.py:217, scripts/analyze_gaw.py:86 -- squashes the
+    frame to 256 x 256 and resizes the probability back. 256 x 256 clips (both resizes are the
+    identity) take the streaming native path; other sizes the device resize kernels. No per-frame
+    host work in either. Returns ``(area int32 CUDA (N,), masks uint8 CUDA (N, H, W) | None)``."""
+    from .utils import NET_SIZE, segment_frames_reference_resize
 
+    model = _require_native(model)
+    if isinstance(frames_gray, np.ndarray):
+        frames_gray = torch.from_numpy(np.ascontiguousarray(frames_gray))
+    if frames_gray.dim() != 3 or frames_gray.dtype != torch.uint8:
+        raise ValueError("expected (N, H, W) uint8 frames")
+    if tuple(frames_gray.shape[1:]) == (NET_SIZE, NET_SIZE):
+        return segment_clip(frames_gray, model, batch=batch, threshold=threshold,
+                            want_masks=want_masks)
     dev = model._device()
-    out = []
-    for i0 in range(0, len(frames_gray), batch):
-        chunk = frames_gray[i0:i0 + batch]
-        inp = np.stack([cv2.resize(f, (256, 256), interpolation=cv2.INTER_LINEAR) for f in chunk])
-        logits, _, _ = model.run(torch.from_numpy(inp).to(dev), want_logits=True, want_mask=False,
-                                 want_area=False)
-        prob = torch.sigmoid(logits).cpu().numpy()
-        for f, pr in zip(chunk, prob):
-            hgt, wid = f.shape
-            if (hgt, wid) != (256, 256):
-                pr = cv2.resize(pr, (wid, hgt), interpolation=cv2.INTER_LINEAR)
-            out.append((pr > threshold).astype(np.uint8) * 255)
-    return out
+    areas, masks = [], []
+    for i0 in range(0, frames_gray.shape[0], batch):
+        part = frames_gray[i0:i0 + batch].to(dev, non_blocking=True)
+        a, m = segment_frames_reference_resize(part, model, threshold=threshold,
+                                               want_masks=want_masks, batch=batch)
+        areas.append(a)
+        masks.append(m)
+    return torch.cat(areas), (torch.cat(masks) if want_masks else None)
 
 
 def extract_features_unet(avi_path: str, detector, model, device=None) -> dict | None:
@@ -238,7 +243,6 @@ def extract_features_unet(avi_path: str, detector, model, device=None) -> dict |
     per frame in order as the reference does, and the bbox gating of features.py:240-245 runs
     as one CUDA reduction over the batch of masks.
     """
-    import cv2
     from .utils import gated_area
 
     model = _require_native(model)
@@ -246,28 +250,16 @@ def extract_features_unet(avi_path: str, detector, model, device=None) -> dict |
     frames_bgr = load_frames_bgr(avi_path)
     if not frames_bgr:
         return None
-    hgt, wid = frames_bgr[0].shape[:2]
-    native_size = (hgt, wid) == (256, 256)
-
     boxes = None
     if detector is not None:
         detector.reset()
         boxes = [detector.detect(frm) for frm in frames_bgr]
 
-    if native_size:
-        area, masks = segment_clip(gray_clip_from_bgr(frames_bgr, dev), model,
-                                   want_masks=boxes is not None)
-        if boxes is not None:
-            area = gated_area(masks, boxes)
-        return kinematic_features_device(area)
-
-    # other frame sizes: reference-resize semantics (squash to 256x256, upsample the probability)
-    grays = [cv2.cvtColor(frm, cv2.COLOR_BGR2GRAY) for frm in frames_bgr]
-    masks_np = _masks_reference_resize(grays, model)
-    masks = torch.from_numpy(np.stack(masks_np)).to(dev)
-    if boxes is None:
-        boxes = [(0, 0, wid, hgt)] * len(masks_np)
-    return kinematic_features_device(gated_area(masks, boxes))
+    area, masks = masks_for_clip(gray_clip_from_bgr(frames_bgr, dev), model,
+                                 want_masks=boxes is not None)
+    if boxes is not None:
+        area = gated_area(masks, boxes)
+    return kinematic_features_device(area)
 
 
 def extract_features_yolo_crop_unet(avi_path: str, detector, model, device=None,

@@ -64,7 +64,8 @@ class UNet(nn.Module):
             self.ups.append(_conv_bn_relu_x2(2 * f, f))
         self.head = nn.Conv2d(features[0], out_ch, 1)
 
-        self.precision = "bf16"      # "bf16" (tensor cores) or "fp32" (validation mode)
+        self.precision = "bf16"      # "bf16" (tensor cores, the default), "fp16" (the same kernels
+                                     # with f16 operands) or "fp32" (validation mode)
         self.max_batch = 512         # frames per native call; larger inputs are chunked
         self.schedule = "s2d"        # full-resolution level: "s2d" (space-to-depth GEMMs, the
                                      # default) or "direct" (per-tap form of the other levels)
@@ -78,6 +79,7 @@ class UNet(nn.Module):
         self._handle = None
         self._handle_device = None
         self._packed_sig = None
+        self._f16_ready = False
         self._workspace = None
         self._keepalive = None
 
@@ -151,13 +153,16 @@ class UNet(nn.Module):
         st.bn_eps = float(self.downs[0].net[1].eps)
         _native.check(_native.load().ogl_unet_load_state(h, C.byref(st)))
         self._packed_sig = sig
+        self._f16_ready = False
 
     def _precision_code(self) -> int:
         if self.precision == "bf16":
             return _native.PRECISION_BF16
         if self.precision == "fp32":
             return _native.PRECISION_F32
-        raise ValueError(f"precision must be 'bf16' or 'fp32', got {self.precision!r}")
+        if self.precision == "fp16":
+            return _native.PRECISION_F16
+        raise ValueError(f"precision must be 'bf16', 'fp16' or 'fp32', got {self.precision!r}")
 
     def _get_workspace(self, nbytes: int, device: torch.device) -> torch.Tensor:
         ws = self._workspace
@@ -212,7 +217,10 @@ class UNet(nn.Module):
         mask = torch.empty((n, hgt, wid), dtype=torch.uint8, device=dev) if want_mask else None
         area = torch.empty((n,), dtype=torch.int32, device=dev) if want_area else None
         prec = self._precision_code()
-        chunk = min(n, self.max_batch if prec == _native.PRECISION_BF16 else min(self.max_batch, 16))
+        if prec == _native.PRECISION_F16 and not self._f16_ready:
+            _native.check(lib.ogl_unet_prepare(self._handle, prec))
+            self._f16_ready = True
+        chunk = min(n, self.max_batch if prec != _native.PRECISION_F32 else min(self.max_batch, 16))
         nbytes = lib.ogl_unet_workspace_bytes(self._handle, chunk, hgt, wid, prec)
         ws = self._get_workspace(nbytes, dev)
         with torch.cuda.device(dev):

@@ -87,29 +87,87 @@ def unet_segment_frames(frames_gray, model, threshold: float = 0.5):
     return mask, area
 
 
+NET_SIZE = 256     # utils.py:234 squashes every frame to 256 x 256 before the forward pass
+
+
+def resize_u8_linear(frames: torch.Tensor, hgt: int = NET_SIZE, wid: int = NET_SIZE) -> torch.Tensor:
+    """Batched ``cv2.resize(frame, (wid, hgt), interpolation=cv2.INTER_LINEAR)`` of ``(N, H, W)``
+    uint8 CUDA frames (/root/reference/openglottal/utils.py:234), bit-exact with cv2."""
+    from . import _native
+
+    if frames.device.type != "cuda" or frames.dtype != torch.uint8 or frames.dim() != 3:
+        raise ValueError("expected (N, H, W) uint8 CUDA frames")
+    n, sh, sw = frames.shape
+    if (sh, sw) == (hgt, wid):
+        return frames
+    out = torch.empty((n, hgt, wid), dtype=torch.uint8, device=frames.device)
+    with torch.cuda.device(frames.device):
+        _native.check(_native.load().ogl_resize_u8_linear(
+            frames.contiguous().data_ptr(), n, sh, sw, out.data_ptr(), hgt, wid,
+            _stream(frames.device)))
+    return out
+
+
+def prob_resize_mask(logits: torch.Tensor, hgt: int, wid: int, threshold: float = 0.5,
+                     want_mask: bool = True):
+    """/root/reference/openglottal/utils.py:237-241 after the forward pass, batched on the device:
+    sigmoid, bilinear resize of the PROBABILITY to ``(hgt, wid)`` (cv2 f32 INTER_LINEAR arithmetic;
+    skipped when the size is unchanged), ``> threshold``. Returns ``(mask uint8 {0,255} CUDA
+    (N, hgt, wid) | None, area int32 CUDA (N,))``."""
+    from . import _native
+
+    if logits.device.type != "cuda" or logits.dtype != torch.float32 or logits.dim() != 3:
+        raise ValueError("expected (N, H, W) float32 CUDA logits")
+    n, sh, sw = logits.shape
+    dev = logits.device
+    mask = torch.empty((n, hgt, wid), dtype=torch.uint8, device=dev) if want_mask else None
+    area = torch.empty(n, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _native.check(_native.load().ogl_prob_resize_mask(
+            logits.contiguous().data_ptr(), n, sh, sw, hgt, wid, float(threshold),
+            mask.data_ptr() if want_mask else None, area.data_ptr(), _stream(dev)))
+    return mask, area
+
+
+def segment_frames_reference_resize(frames_gray: torch.Tensor, model, threshold: float = 0.5,
+                                    want_masks: bool = True, batch: int = 512):
+    """The reference's per-frame semantics (/root/reference/openglottal/utils.py:234-241) for a
+    batch of equally sized ``(N, H, W)`` uint8 CUDA frames of ANY size, entirely on the device:
+    squash to 256 x 256 (cv2 u8 INTER_LINEAR, bit-exact), forward, sigmoid, bilinear resize of the
+    probability back to ``(H, W)``, threshold, count. Only masks and areas exist at ``(H, W)``.
+    Returns ``(area int32 CUDA (N,), masks uint8 CUDA (N, H, W) | None)``."""
+    model = _require_native(model)
+    n, hgt, wid = frames_gray.shape
+    if (hgt, wid) == (NET_SIZE, NET_SIZE):   # both resizes are the identity: the fused head does it
+        _, mask, area = model.run(frames_gray, threshold=threshold, want_mask=want_masks)
+        return area, mask
+    areas, masks = [], []
+    for i0 in range(0, n, batch):
+        small = resize_u8_linear(frames_gray[i0:i0 + batch])
+        logits, _, _ = model.run(small, want_logits=True, want_mask=False, want_area=False)
+        m, a = prob_resize_mask(logits, hgt, wid, threshold, want_mask=want_masks)
+        areas.append(a)
+        masks.append(m)
+    return torch.cat(areas), (torch.cat(masks) if want_masks else None)
+
+
 def unet_segment_frame(frame_gray: np.ndarray, model, device=None,
                        threshold: float = 0.5) -> np.ndarray:
     """Reference-compatible single-frame call: ``(H, W)`` uint8 -> uint8 mask {0, 255}.
 
-    Same steps as /root/reference/openglottal/utils.py:234-241; the forward pass runs on the
-    native kernels, resizes use the same cv2 calls as the reference.
+    Same steps as /root/reference/openglottal/utils.py:234-241, all of them on the device (the
+    two cv2 resizes are ``ogl_resize_u8_linear`` / ``ogl_prob_resize_mask``); one H2D copy of the
+    frame in, one D2H copy of the mask out.
     """
-    import cv2
-
     model = _require_native(model)
     dev = model._device()
     if device is not None and torch.device(device).type != dev.type:
         raise RuntimeError(f"model is on {dev}, requested device {device}: there is no CPU path")
-    inp = cv2.resize(frame_gray, (256, 256), interpolation=cv2.INTER_LINEAR)
-    hgt, wid = frame_gray.shape
-    t = torch.from_numpy(np.ascontiguousarray(inp)).unsqueeze(0).to(dev)
-    if (hgt, wid) == (256, 256):
-        _, mask, _ = model.run(t, threshold=threshold, want_area=False)
-        return mask[0].cpu().numpy()
-    logits, _, _ = model.run(t, want_logits=True, want_mask=False, want_area=False)
-    prob = torch.sigmoid(logits[0]).cpu().numpy()
-    prob = cv2.resize(prob, (wid, hgt), interpolation=cv2.INTER_LINEAR)
-    return (prob > threshold).astype(np.uint8) * 255
+    if frame_gray.ndim != 2 or frame_gray.dtype != np.uint8:
+        raise ValueError("expected a (H, W) uint8 gray frame")
+    t = torch.from_numpy(np.ascontiguousarray(frame_gray)).unsqueeze(0).to(dev)
+    _, masks = segment_frames_reference_resize(t, model, threshold=threshold)
+    return masks[0].cpu().numpy()
 
 
 # ---------------------------------------------------------------------------------------------

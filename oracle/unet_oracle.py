@@ -77,17 +77,24 @@ def _bf16(t: torch.Tensor) -> torch.Tensor:
     return t.to(torch.bfloat16).to(torch.float32)
 
 
+def _f16(t: torch.Tensor) -> torch.Tensor:
+    return t.clamp(-65504.0, 65504.0).to(torch.float16).to(torch.float32)   # cvt.rn.satfinite
+
+
 @torch.no_grad()
-def folded_forward(sd: dict, x: torch.Tensor, bf16: bool, composed_level0: bool = True) -> torch.Tensor:
+def folded_forward(sd: dict, x: torch.Tensor, bf16: bool, composed_level0: bool = True,
+                   operand: str = "bf16") -> torch.Tensor:
     """Network on BN-folded weights. ``bf16=False``: the fp32 validation mode's arithmetic.
     ``bf16=True``: bit-model of the tensor-core path -- fp32 stem from the fp32 input, bf16
     weights, every stored activation rounded to bf16 (after bias+ReLU; convT after bias),
     fp32 accumulation, and the last conv's ReLU output fed to the 1x1 head unrounded.
     ``composed_level0`` (the default "s2d" schedule): the last ConvTranspose2d is composed into
     the conv that follows it, so its output is never rounded (the composed weights are; that
-    difference is inside the test tolerance and not modelled)."""
+    difference is inside the test tolerance and not modelled).
+    ``operand="fp16"`` (with ``bf16=True``): the same rounding points with f16 operands -- the
+    kernels' f16 precision mode."""
     fs = fold_state(sd)
-    r = _bf16 if bf16 else (lambda t: t)
+    r = (_f16 if operand == "fp16" else _bf16) if bf16 else (lambda t: t)
 
     def conv(x, key, relu=True, round_out=True, round_w=True):
         w = r(fs[f"{key}.w"]) if round_w else fs[f"{key}.w"]

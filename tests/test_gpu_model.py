@@ -190,20 +190,29 @@ def test_repeated_launch_is_idempotent(native_model):
 
 
 def test_bf16_matches_reference_within_north_star(native_model, trained_sd):
+    """north_star: logits max-abs <= 2e-2 in bf16. bf16 operands carry 8 mantissa bits, and IDEAL
+    bf16 arithmetic (the CPU bit-model: fp32 accumulation, every stored activation and weight
+    rounded once) already misses 2e-2 at large |z| on these weights (0.025 on this clip, 0.012 for
+    |z| < 1), so the overall bound is tied to that floor, measured on the same frames: the kernel
+    may not be worse than 1.05 x the bit-model's own distance from the fp32 reference (or 2e-2,
+    whichever is larger). Near the decision boundary (|z| < 1) the 2e-2 bar holds as stated; the
+    f16-operand mode (next test) meets it everywhere."""
     from oracle import unet_oracle as uo
     from openglottal_b200 import dice
 
     frames = _clip(16)
     ref_lg, ref_mask, ref_area = uo.batch_masks(trained_sd, frames)
+    bit = uo.folded_forward(trained_sd, uo.frames_to_input(frames), bf16=True)[:, 0].numpy()
     lg, mask, area = native_model.run(torch.from_numpy(frames).cuda(), want_logits=True)
     lg, mask, area = lg.cpu().numpy(), mask.cpu().numpy(), area.cpu().numpy()
     err = np.abs(lg - ref_lg)
+    floor = np.abs(bit - ref_lg).max()
     near = np.abs(ref_lg) < 1.0
     print(f"bf16 vs fp32 oracle: max|err|={err.max():.4g} (|z|<1: {err[near].max() if near.any() else 0:.4g}) "
-          f"mean={err.mean():.3g} logit std={ref_lg.std():.3g}")
-    # north_star bar 2e-2 is stated for logits near the decision boundary; overall bound scaled
+          f"mean={err.mean():.3g}; ideal-bf16 bit-model vs fp32 oracle: max={floor:.4g}; "
+          f"kernel vs bit-model: max={np.abs(lg - bit).max():.4g}; logit std={ref_lg.std():.3g}")
     assert err[near].max() <= 2e-2 if near.any() else True
-    assert err.max() <= 2e-2 * max(1.0, np.abs(ref_lg).max() / 2)
+    assert err.max() <= max(2e-2, 1.05 * floor)
     d = dice(mask, ref_mask)
     print("dice", d, "areas", area[:6], ref_area[:6])
     assert d >= 0.999
@@ -212,6 +221,52 @@ def test_bf16_matches_reference_within_north_star(native_model, trained_sd):
     assert np.array_equal(area, (mask > 0).reshape(len(mask), -1).sum(1))
     rel = np.abs(area - ref_area) / np.maximum(ref_area, 1)
     assert rel.max() <= 0.005
+
+
+def test_fp16_operand_mode_meets_2e2_everywhere(lib, trained_sd):
+    """The same kernels compiled for f16 operands (precision "fp16": tcgen05 kind::f16 with f16
+    A/B, satfinite conversions): logits within 2e-2 of the fp32 reference OVERALL (north_star's bar
+    as stated), tight against the f16 bit-model, and the bf16 mask / area bars."""
+    import openglottal_b200 as ogl
+    from oracle import unet_oracle as uo
+
+    m = ogl.UNet().to("cuda")
+    m.load_state_dict(trained_sd)
+    m.eval()
+    m.precision = "fp16"
+    frames = _clip(16)
+    ref_lg, ref_mask, ref_area = uo.batch_masks(trained_sd, frames)
+    bit = uo.folded_forward(trained_sd, uo.frames_to_input(frames), bf16=True, operand="fp16")[:, 0].numpy()
+    lg, mask, area = m.run(torch.from_numpy(frames).cuda(), want_logits=True)
+    lg, mask, area = lg.cpu().numpy(), mask.cpu().numpy(), area.cpu().numpy()
+    err = np.abs(lg - ref_lg)
+    print(f"f16 operands vs fp32 oracle: max|err|={err.max():.4g} mean={err.mean():.3g}; "
+          f"kernel vs f16 bit-model: max={np.abs(lg - bit).max():.4g}")
+    assert err.max() <= 2e-2
+    assert np.abs(lg - bit).max() <= 1e-2
+    assert ogl.dice(mask, ref_mask) >= 0.999
+    assert np.array_equal(area, (mask > 0).reshape(len(mask), -1).sum(1))
+    assert (np.abs(area - ref_area) / np.maximum(ref_area, 1)).max() <= 0.005
+    # every schedule variant of the f16 twins: fp32 input (separate stem), CUDA-core fused stem,
+    # direct full-resolution level, forced CTA pairs -- all within the same bar
+    dev = torch.from_numpy(frames[:4]).cuda()
+    base = m.run(dev, want_logits=True)[0]
+    variants = []
+    variants.append(m.run(dev.float() / 255.0, want_logits=True)[0])
+    for attr, val in (("fuse_stem", 1), ("fuse_stem", 0), ("schedule", "direct"), ("cta_pairs", 3)):
+        old = getattr(m, attr)
+        setattr(m, attr, val)
+        try:
+            variants.append(m.run(dev, want_logits=True)[0])
+        finally:
+            setattr(m, attr, old)
+    for v in variants:
+        assert (v - base).abs().max().item() <= 1e-2
+        assert np.abs(v.cpu().numpy() - ref_lg[:4]).max() <= 2e-2
+    # bf16 stays the default of a fresh model and is unaffected by the f16 pack
+    m.precision = "bf16"
+    lg_b = m.run(dev, want_logits=True)[0]
+    assert (lg_b.cpu() - torch.from_numpy(ref_lg[:4])).abs().max().item() <= 5e-2
 
 
 def test_forward_signature_matches_reference(native_model, trained_sd):
@@ -265,7 +320,9 @@ def test_unet_segment_frame_reference_semantics(native_model, trained_sd):
     got = ogl.unet_segment_frame(f512, native_model, torch.device("cuda"))
     ref = uo.segment_frame(trained_sd, f512)
     assert got.shape == (512, 256)
-    assert ogl.dice(got, ref) >= 0.995
+    d512 = ogl.dice(got, ref)
+    print('512x256 single frame dice', d512, 'differing pixels', int((got != ref).sum()))
+    assert d512 >= 0.999 or (got != ref).sum() <= 4    # one frame: 4 boundary pixels of ~1600
 
 
 def test_errors_are_loud(native_model):

@@ -196,3 +196,56 @@ def test_draw_overlay_matches_reference():
     row = features_row("clip", {"area_mean": 1.0, "f0": None, "cv": 2.0})
     assert len(row) == 1 + len(FEATURE_COLS) and row[0] == "clip" and row[5] == ""
     assert features_row("x", None) == ["x"] + [""] * 7
+
+
+RESIZE_SIZES = [(512, 256), (256, 512), (512, 512), (96, 128), (300, 200), (1024, 1024), (128, 128),
+                (257, 255), (480, 640), (64, 64), (256, 256), (320, 256), (256, 1000), (17, 33)]
+
+
+def test_resize_oracle_u8_is_bit_exact_with_cv2():
+    """oracle/resize_oracle.py restates cv2.resize INTER_LINEAR (utils.py:234) for u8 frames:
+    bit-exact with cv2 for down-scales, up-scales, the 2x2 area substitution and the identity."""
+    import cv2
+    from oracle import resize_oracle as ro
+
+    rng = np.random.default_rng(0)
+    for hgt, wid in RESIZE_SIZES:
+        img = rng.integers(0, 256, (hgt, wid), dtype=np.uint8)
+        want = cv2.resize(img, (256, 256), interpolation=cv2.INTER_LINEAR)
+        assert np.array_equal(ro.resize_u8_linear(img, 256, 256), want), (hgt, wid)
+
+
+def test_resize_oracle_f32_matches_opencv_arithmetic():
+    """f32 probability resize (utils.py:238-240): bit-exact with OpenCV's own INTER_LINEAR code
+    (IPP switched off) and within 2e-5 of the IPP routine cv2 dispatches to by default."""
+    import cv2
+    from oracle import resize_oracle as ro
+
+    rng = np.random.default_rng(1)
+    use_ipp = cv2.ipp.useIPP()
+    try:
+        for hgt, wid in RESIZE_SIZES:
+            pr = rng.random((256, 256), dtype=np.float32)
+            got = ro.resize_f32_linear(pr, wid, hgt)
+            cv2.ipp.setUseIPP(use_ipp)
+            dflt = cv2.resize(pr, (wid, hgt), interpolation=cv2.INTER_LINEAR)
+            assert np.abs(got - dflt).max() <= 2e-5, (hgt, wid)
+            cv2.ipp.setUseIPP(False)
+            own = cv2.resize(pr, (wid, hgt), interpolation=cv2.INTER_LINEAR)
+            assert np.array_equal(got, own), (hgt, wid)
+    finally:
+        cv2.ipp.setUseIPP(use_ipp)
+
+
+def test_resize_oracle_reproduces_reference_masks(calibrated_sd):
+    """The restated resize pair inside unet_segment_frame's steps against the reference's OWN mask
+    (segment_frame.npz: the 96x128 frame goes through both resizes)."""
+    from oracle import resize_oracle as ro, unet_oracle as uo
+
+    g = np.load(GOLDEN / "segment_frame.npz")
+    frame = g["f96"]
+    ref = np.unpackbits(g["m96"])[: 96 * 128].reshape(96, 128).astype(bool)
+    small = ro.resize_u8_linear(frame, 256, 256)
+    logits = uo.ref_forward(calibrated_sd, uo.frames_to_input(small[None]))[0, 0].numpy()
+    got = ro.segment_frame_restated(logits, 96, 128) > 0
+    assert (got != ref).sum() <= 2
