@@ -396,7 +396,7 @@ int ogl_unet_create(ogl_unet** out, int device) {
     OGL_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10)
         return fail(std::string("openglottal_b200 is built for sm_100a (B200); found ") + prop.name);
-    if (conv_tc_init() || s2d_tc_init()) return 1;
+    if (conv_tc_init() || s2d_tc_init() || conv_tc_init_f16() || s2d_tc_init_f16()) return 1;
     ogl_unet* h = new ogl_unet();
     if (const char* e = getenv("OGL_S2D")) h->use_s2d = atoi(e) != 0;
     if (const char* e = getenv("OGL_CG")) h->cta_group = atoi(e);
@@ -521,6 +521,12 @@ int ogl_unet_forward(ogl_unet* h, const void* frames_dev, int in_dtype, int n, i
         return fail("ogl_unet_forward: workspace too small");
     if (reinterpret_cast<uintptr_t>(workspace_dev) & 255)
         return fail("ogl_unet_forward: workspace must be 256-byte aligned");
+    {   // the handle's tensors, weights and kernels live on ONE device: it must be the current one
+        int cur = -1;
+        OGL_CUDA(cudaGetDevice(&cur));
+        if (cur != h->device)
+            return fail("ogl_unet_forward: the handle's device is not the current device");
+    }
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
     const float thr = static_cast<float>(
         std::log(static_cast<double>(threshold) / (1.0 - static_cast<double>(threshold))));

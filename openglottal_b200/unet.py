@@ -76,10 +76,15 @@ class UNet(nn.Module):
                                      # 0 separate kernel, 1 in-kernel on the CUDA cores (fp32),
                                      # 2 (default) in-kernel on the tensor cores (bf16 hi + lo
                                      # weights, fp32 accumulation)
+        self.use_graphs = True       # small batches: replay the forward's launches as one CUDA graph
+        self.graph_max_batch = 128   # (a forward is ~20 launches; at batch 32 they take ~1 ms of
+                                     # GPU time, the same order as enqueueing them one by one)
         self._handle = None
         self._handle_device = None
         self._packed_sig = None
+        self._sig_tensors = None
         self._f16_ready = False
+        self._graphs = {}            # key -> [calls seen, graph, static input, static outputs]
         self._workspace = None
         self._keepalive = None
 
@@ -116,7 +121,19 @@ class UNet(nn.Module):
             pass
 
     def _signature(self):
-        return tuple((t.data_ptr(), t._version) for t in self.state_dict(keep_vars=True).values())
+        # the tensor list is cached (building a state dict costs more than a small forward); it is
+        # dropped whenever the module tree can have changed (_apply: .to() / .cuda() / .half();
+        # load_state_dict copies in place and shows up in _version)
+        ts = self._sig_tensors
+        if ts is None:
+            ts = self._sig_tensors = list(self.state_dict(keep_vars=True).values())
+        return tuple((t.data_ptr(), t._version) for t in ts)
+
+    def _apply(self, fn, *args, **kwargs):
+        self._sig_tensors = None
+        self._packed_sig = None
+        self._graphs = {}
+        return super()._apply(fn, *args, **kwargs)
 
     def _pack_if_needed(self) -> None:
         h = self._ensure_handle()
@@ -154,6 +171,7 @@ class UNet(nn.Module):
         _native.check(_native.load().ogl_unet_load_state(h, C.byref(st)))
         self._packed_sig = sig
         self._f16_ready = False
+        self._graphs = {}
 
     def _precision_code(self) -> int:
         if self.precision == "bf16":
@@ -168,6 +186,7 @@ class UNet(nn.Module):
         ws = self._workspace
         if ws is None or ws.numel() < nbytes or ws.device != device:
             self._workspace = None
+            self._graphs = {}        # captured launches hold the old workspace's addresses
             ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
             self._workspace = ws
         return ws
@@ -213,9 +232,6 @@ class UNet(nn.Module):
         _native.check(lib.ogl_unet_set_cta_pairs(self._handle, int(self.cta_pairs)))
         _native.check(lib.ogl_unet_set_fused_stem(self._handle, int(self.fuse_stem)))
         frames = frames.contiguous()
-        logits = torch.empty((n, hgt, wid), dtype=torch.float32, device=dev) if want_logits else None
-        mask = torch.empty((n, hgt, wid), dtype=torch.uint8, device=dev) if want_mask else None
-        area = torch.empty((n,), dtype=torch.int32, device=dev) if want_area else None
         prec = self._precision_code()
         if prec == _native.PRECISION_F16 and not self._f16_ready:
             _native.check(lib.ogl_unet_prepare(self._handle, prec))
@@ -223,17 +239,48 @@ class UNet(nn.Module):
         chunk = min(n, self.max_batch if prec != _native.PRECISION_F32 else min(self.max_batch, 16))
         nbytes = lib.ogl_unet_workspace_bytes(self._handle, chunk, hgt, wid, prec)
         ws = self._get_workspace(nbytes, dev)
+
+        def enqueue(src, logits, mask, area, i0, m):
+            _native.check(lib.ogl_unet_forward(
+                self._handle, src[i0:i0 + m].data_ptr(), in_dtype, m, hgt, wid,
+                ws.data_ptr(), ws.numel(),
+                logits[i0:i0 + m].data_ptr() if want_logits else None,
+                mask[i0:i0 + m].data_ptr() if want_mask else None,
+                area[i0:i0 + m].data_ptr() if want_area else None,
+                float(threshold), prec, torch.cuda.current_stream().cuda_stream))
+
+        def outputs():
+            return (torch.empty((n, hgt, wid), dtype=torch.float32, device=dev) if want_logits else None,
+                    torch.empty((n, hgt, wid), dtype=torch.uint8, device=dev) if want_mask else None,
+                    torch.empty((n,), dtype=torch.int32, device=dev) if want_area else None)
+
         with torch.cuda.device(dev):
-            stream = torch.cuda.current_stream().cuda_stream
+            if (self.use_graphs and n <= min(self.graph_max_batch, chunk)
+                    and prec != _native.PRECISION_F32 and not torch.cuda.is_current_stream_capturing()):
+                # Small batch: the ~20 launches of a forward (each with its tensor maps built on the
+                # host) are captured once per call signature and replayed; inputs and outputs of the
+                # captured launches are static buffers, copied from / into fresh tensors.
+                key = (n, hgt, wid, in_dtype, float(threshold), want_logits, want_mask, want_area, prec,
+                       self.schedule, int(self.cta_pairs), int(self.fuse_stem), ws.data_ptr())
+                ent = self._graphs.get(key)
+                if ent is None:
+                    ent = self._graphs[key] = [0, None, None, None]
+                ent[0] += 1
+                if ent[0] == 2:          # second call with this signature: capture
+                    ent[2] = torch.empty_like(frames)
+                    ent[3] = outputs()
+                    ent[2].copy_(frames)
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        enqueue(ent[2], *ent[3], 0, n)
+                    ent[1] = graph
+                if ent[1] is not None:
+                    ent[2].copy_(frames)
+                    ent[1].replay()
+                    return tuple(None if t is None else t.clone() for t in ent[3])
+            logits, mask, area = outputs()
             for i0 in range(0, n, chunk):
-                m = min(chunk, n - i0)
-                _native.check(lib.ogl_unet_forward(
-                    self._handle, frames[i0:i0 + m].data_ptr(), in_dtype, m, hgt, wid,
-                    ws.data_ptr(), ws.numel(),
-                    logits[i0:i0 + m].data_ptr() if want_logits else None,
-                    mask[i0:i0 + m].data_ptr() if want_mask else None,
-                    area[i0:i0 + m].data_ptr() if want_area else None,
-                    float(threshold), prec, stream))
+                enqueue(frames, logits, mask, area, i0, min(chunk, n - i0))
         return logits, mask, area
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
