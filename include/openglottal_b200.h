@@ -107,9 +107,16 @@ int ogl_unet_launch_count(const ogl_unet* h);
 const char* ogl_unet_launch_name(const ogl_unet* h, int index);
 
 /* Kernel schedule of the full-resolution level of the bf16 path. 1 (default): space-to-depth
- * GEMMs with ConvTranspose2d ups.6 composed into ups.7.net.0 (20 launches); 0: the direct
- * per-tap form used at the other levels (22 launches). Same results within bf16 rounding. */
+ * GEMMs with ConvTranspose2d ups.6 composed into ups.7.net.0 (17 launches with the composed
+ * decoder, else 20); 0: the direct per-tap form used at the other levels (2 more launches). Same
+ * results within bf16 rounding. */
 int ogl_unet_set_schedule(ogl_unet* h, int s2d_level0);
+
+/* Decoder levels 1-3. 1 (default): every ConvTranspose2d (ups.0, ups.2, ups.4; unet.py:82) is
+ * composed into the conv that follows it (ups.{1,3,5}.net.0), as the space-to-depth schedule does
+ * for ups.6 -- 17 launches, no `up` tensor is ever written; 0: separate transposed-conv launches
+ * and two-source convs (20 launches). Same results within bf16 rounding. */
+int ogl_unet_set_compose(ogl_unet* h, int enable);
 
 /* With u8 frames and the space-to-depth schedule, downs.0.net.0 (the Cin = 1 stem) can be computed
  * inside the downs.0.net.3 kernel, so that its output never touches HBM. 0: separate stem kernel;
@@ -205,6 +212,23 @@ int ogl_debug_s2d_layer(ogl_unet* h, int kind, const float* src_dev, int cin_s,
                         const float* wt_host, const float* bt_host, int n, int height, int width,
                         float* out_dev, float* out_pool_dev, void* stream);
 
+
+/* Unit-test hook for the composed decoder layer of levels 1-3 (upcat_tc.cu): out = relu(conv3x3(
+ * cat([skip, conv_transpose2d(below, wt, bt, stride 2)]), w3) + b3) for skip_dev [n][f][H][W] f32,
+ * below_dev [n][2f][H/2][W/2] f32, w3_host [f][2f][3][3], b3_host [f], wt_host [2f][f][2][2],
+ * bt_host [f]; f in {64, 128, 256}; out_dev [n][f][H][W] f32. */
+int ogl_debug_upcat_layer(ogl_unet* h, const float* skip_dev, const float* below_dev,
+                          const float* w3_host, const float* b3_host, const float* wt_host,
+                          const float* bt_host, int f, int n, int height, int width, float* out_dev,
+                          void* stream);
+
+/* Host-only (no device needed): the bf16 operands build_upcat_host packs for that layer, for CPU
+ * emulation in the tests. wskip_out [f/N][f/32][9][4][N][8] and wbelow_out [f/N][2f/32][16][4][N][8]
+ * (N = min(f, 128); pair index = (px * 2 + py) * 4 + oyi * 2 + oxi), their CTA-pair forms
+ * [..][rank][..][N/2][8], btab_out [3][3][f]. Any output pointer may be NULL. */
+int ogl_debug_upcat_program(const float* w3_host, const float* b3_host, const float* wt_host,
+                            const float* bt_host, int f, uint16_t* wskip_out, uint16_t* wskip_pair_out,
+                            uint16_t* wbelow_out, uint16_t* wbelow_pair_out, float* btab_out);
 
 /* Host-only (no device needed): the MMA program build_s2d_host makes for a space-to-depth
  * layer, for CPU emulation in the tests. ops_out: 4 x uint32 per op {a_off | dcol << 16 |

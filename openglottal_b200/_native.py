@@ -60,6 +60,7 @@ EXPORTS = [
     "ogl_unet_set_cta_pairs",
     "ogl_unet_set_repeat",
     "ogl_unet_set_fused_stem",
+    "ogl_unet_set_compose",
     "ogl_features_workspace_bytes",
     "ogl_features",
     "ogl_features_f64",
@@ -72,6 +73,8 @@ EXPORTS = [
     "ogl_prob_resize_mask",
     "ogl_debug_tc_layer",
     "ogl_debug_s2d_layer",
+    "ogl_debug_upcat_layer",
+    "ogl_debug_upcat_program",
     "ogl_debug_s2d_program",
 ]
 
@@ -124,6 +127,8 @@ def load() -> C.CDLL:
     lib.ogl_unet_launch_name.argtypes = [vp, i32]
     lib.ogl_unet_set_fused_stem.restype = i32
     lib.ogl_unet_set_fused_stem.argtypes = [vp, i32]
+    lib.ogl_unet_set_compose.restype = i32
+    lib.ogl_unet_set_compose.argtypes = [vp, i32]
     lib.ogl_unet_set_cta_pairs.restype = i32
     lib.ogl_unet_set_cta_pairs.argtypes = [vp, i32]
     lib.ogl_unet_set_repeat.restype = i32
@@ -156,6 +161,12 @@ def load() -> C.CDLL:
     lib.ogl_debug_s2d_layer.restype = i32
     lib.ogl_debug_s2d_layer.argtypes = [vp, i32, vp, i32, vp, _c_float_p, _c_float_p, _c_float_p,
                                         _c_float_p, i32, i32, i32, vp, vp, vp]
+    lib.ogl_debug_upcat_layer.restype = i32
+    lib.ogl_debug_upcat_layer.argtypes = [vp, vp, vp, _c_float_p, _c_float_p, _c_float_p, _c_float_p,
+                                          i32, i32, i32, i32, vp, vp]
+    lib.ogl_debug_upcat_program.restype = i32
+    lib.ogl_debug_upcat_program.argtypes = [_c_float_p, _c_float_p, _c_float_p, _c_float_p, i32, vp, vp,
+                                            vp, vp, vp]
     lib.ogl_debug_s2d_program.restype = i32
     lib.ogl_debug_s2d_program.argtypes = [_c_float_p, _c_float_p, i32, _c_float_p, _c_float_p, vp,
                                           sz, C.POINTER(sz), vp, i32, C.POINTER(i32), vp,

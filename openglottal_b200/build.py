@@ -10,10 +10,11 @@ PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_DIR = PKG_DIR / "lib"
 LIB_PATH = LIB_DIR / "libopenglottal_b200.so"
-SOURCES = ["api.cu", "conv_tc.cu", "conv_tc_f16.cu", "s2d_tc.cu", "s2d_tc_f16.cu", "stem_f32.cu",
-           "features.cu", "frame_ops.cu", "resize.cu"]
+SOURCES = ["api.cu", "conv_tc.cu", "conv_tc_f16.cu", "s2d_tc.cu", "s2d_tc_f16.cu", "upcat_tc.cu",
+           "upcat_tc_f16.cu", "stem_f32.cu", "features.cu", "frame_ops.cu", "resize.cu"]
 # units that #include another source (the f16 twins)
-INCLUDES = {"conv_tc_f16.cu": ["conv_tc.cu"], "s2d_tc_f16.cu": ["s2d_tc.cu"]}
+INCLUDES = {"conv_tc_f16.cu": ["conv_tc.cu"], "s2d_tc_f16.cu": ["s2d_tc.cu"],
+            "upcat_tc_f16.cu": ["upcat_tc.cu"]}
 HEADERS = ["internal.h", "ptx.cuh", "../../include/openglottal_b200.h"]
 
 NVCC_FLAGS = [

@@ -73,6 +73,8 @@ struct ogl_unet {
         // full-resolution level as space-to-depth GEMMs (s2d_tc.cu): downs.0.net.3 (+pool),
         // ups.6 (convT) composed into ups.7.net.0, ups.7.net.3 (+head)
         S2dLayer s2d_down, s2d_up0, s2d_up1;
+        // levels 3, 2, 1: ups.{0,2,4} (convT) composed into ups.{1,3,5}.net.0 (upcat_tc.cu)
+        UpcatLayer upcat[3];
     } pack[2];
     struct Folded {           // BN-folded fp32 weights on the host (PyTorch layouts)
         std::vector<float> dw[4][2], db[4][2], bw[2], bb[2], tw[4], tb[4], uw[4][2], ub[4][2];
@@ -81,6 +83,10 @@ struct ogl_unet {
     float head_w_host[32] = {0};
     float head_b = 0.f;
     bool use_s2d = true;
+    // ConvTranspose2d composed into the conv that follows it at levels 1-3 as well (upcat_tc.cu):
+    // 17 launches instead of 20, the `up` tensors never exist. 0: three transposed-conv launches +
+    // two-source convs (the round-1 schedule; kept for A/B runs and as an independent implementation)
+    bool compose_up = true;
     // u8 input: compute the stem inside the downs.0.net.3 kernel (its output never touches HBM:
     // 8.4 MB per frame less traffic). Bit-identical to the stand-alone stem; as fast or slightly
     // faster under the board's power cap.
@@ -269,6 +275,29 @@ int build_s2d_layer(ogl_unet* h, const std::vector<float>& w3, const std::vector
     return dev_upload(h, hs.btab, &L->btab);
 }
 
+int build_upcat_layer(ogl_unet* h, const std::vector<float>& w3, const std::vector<float>& b3,
+                      const std::vector<float>& wt, const std::vector<float>& bt, int f, UpcatLayer* L,
+                      bool f16) {
+    UpcatHost hs;
+    if (build_upcat_host(w3.data(), b3.data(), wt.data(), bt.data(), f, f16, &hs)) return 1;
+    *L = UpcatLayer();
+    L->f = hs.f;
+    L->N = hs.N;
+    L->npass = hs.npass;
+    auto up = [&](const std::vector<uint16_t>& v, uint8_t** out) {
+        uint16_t* d = nullptr;
+        if (dev_upload(h, v, &d)) return 1;
+        *out = reinterpret_cast<uint8_t*>(d);
+        return 0;
+    };
+    if (up(hs.wskip, &L->wskip) || up(hs.wskip_pair, &L->wskip2) || up(hs.wbelow, &L->wbelow) ||
+        up(hs.wbelow_pair, &L->wbelow2))
+        return 1;
+    if (dev_upload(h, hs.btab, &L->btab)) return 1;
+    std::vector<float> interior(hs.btab.begin() + 4 * f, hs.btab.begin() + 5 * f);   // class (1, 1)
+    return dev_upload(h, interior, &L->bias);
+}
+
 int build_f32_conv(ogl_unet* h, const std::vector<float>& w, const std::vector<float>& b, int cin,
                    int cout, F32Conv* L) {
     L->cin = cin;
@@ -312,6 +341,8 @@ int build_pack(ogl_unet* h, bool f16) {
             return 1;
         if (dev_upload(h, F.tb[k], &L->bias)) return 1;
         if (build_tc_conv(h, F.uw[k][0], F.ub[k][0], f, f, f, EPI_RELU, &P.up_c[k][0], f16)) return 1;
+        if (k < 3 && build_upcat_layer(h, F.uw[k][0], F.ub[k][0], F.tw[k], F.tb[k], f, &P.upcat[k], f16))
+            return 1;
         if (k == 3 && build_s2d_layer(h, F.uw[k][0], F.ub[k][0], 32, F.tw[k].data(), F.tb[k].data(),
                                       64, EPI_RELU, &P.s2d_up0, f16))
             return 1;
@@ -365,6 +396,8 @@ const char* const kDownC2[4] = {"downs.0.net.3+pool", "downs.1.net.3+pool", "dow
 const char* const kUpT[4] = {"ups.0(convT)", "ups.2(convT)", "ups.4(convT)", "ups.6(convT)"};
 const char* const kUpC1[4] = {"ups.1.net.0(cat)", "ups.3.net.0(cat)", "ups.5.net.0(cat)",
                               "ups.7.net.0(cat)"};
+const char* const kUpTC[3] = {"ups.0(convT)+ups.1.net.0(cat)", "ups.2(convT)+ups.3.net.0(cat)",
+                              "ups.4(convT)+ups.5.net.0(cat)"};
 const char* const kUpC2[4] = {"ups.1.net.3", "ups.3.net.3", "ups.5.net.3", "ups.7.net.3+head"};
 
 // closes the launch that was just enqueued: its name, and (when profiling) an event after it
@@ -396,11 +429,14 @@ int ogl_unet_create(ogl_unet** out, int device) {
     OGL_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10)
         return fail(std::string("openglottal_b200 is built for sm_100a (B200); found ") + prop.name);
-    if (conv_tc_init() || s2d_tc_init() || conv_tc_init_f16() || s2d_tc_init_f16()) return 1;
+    if (conv_tc_init() || s2d_tc_init() || upcat_tc_init() || conv_tc_init_f16() ||
+        s2d_tc_init_f16() || upcat_tc_init_f16())
+        return 1;
     ogl_unet* h = new ogl_unet();
     if (const char* e = getenv("OGL_S2D")) h->use_s2d = atoi(e) != 0;
     if (const char* e = getenv("OGL_CG")) h->cta_group = atoi(e);
     if (const char* e = getenv("OGL_FUSE_STEM")) h->fuse_stem = atoi(e);
+    if (const char* e = getenv("OGL_COMPOSE")) h->compose_up = atoi(e) != 0;
     h->device = device;
     h->num_sms = prop.multiProcessorCount;
     *out = h;
@@ -542,6 +578,8 @@ int ogl_unet_forward(ogl_unet* h, const void* frames_dev, int in_dtype, int n, i
         // the two operand types are the same kernels compiled twice (conv_tc_f16.cu, s2d_tc_f16.cu)
         auto conv_tc = [&](auto&&... a) { return f16 ? launch_conv_tc_f16(a...) : launch_conv_tc(a...); };
         auto s2d_tc = [&](auto&&... a) { return f16 ? launch_s2d_tc_f16(a...) : launch_s2d_tc(a...); };
+        auto upcat_tc = [&](auto&&... a) { return f16 ? launch_upcat_tc_f16(a...) : launch_upcat_tc(a...); };
+        const bool compose = h->compose_up;
         const Plan p = make_plan(n, H, W, 2);
         auto B = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(ws + off); };
         __nv_bfloat16* P[4] = {B(p.U[1]), B(p.U[2]), B(p.U[3]), B(p.P3)};
@@ -597,8 +635,9 @@ int ogl_unet_forward(ogl_unet* h, const void* frames_dev, int in_dtype, int n, i
                     if (l == 0 && s2d)
                         return s2d_tc(K.s2d_down, B(p.T[0]), nullptr, n, H, W, B(p.S[0]), P[0],
                                              nullptr, sms, stream, cg, nullptr, nullptr, rev);
+                    // composed decoder: the skip tensors of levels 1-3 are written space-to-depth
                     return conv_tc(K.down_c2[l], B(p.T[l]), nullptr, n, hh, ww, B(p.S[l]),
-                                          P[l], nullptr, sms, stream, cg, rev);
+                                          P[l], nullptr, sms, stream, cg, rev, compose && l >= 1);
                 }))
                 return 1;
         }
@@ -638,16 +677,24 @@ int ogl_unet_forward(ogl_unet* h, const void* frames_dev, int in_dtype, int n, i
                     return 1;
                 break;
             }
-            if (step(kUpT[k], [&] {
-                    return conv_tc(K.up_t[k], below, nullptr, n, hh / 2, ww / 2, B(p.U[l]),
-                                          nullptr, nullptr, sms, stream, cg, rev);
-                }))
-                return 1;
-            if (step(kUpC1[k], [&] {
-                    return conv_tc(K.up_c[k][0], B(p.S[l]), B(p.U[l]), n, hh, ww, B(p.T[l]),
-                                          nullptr, nullptr, sms, stream, cg, rev);
-                }))
-                return 1;
+            if (compose && l >= 1) {
+                // ups.{2k} is composed into ups.{2k+1}.net.0: reads the skip (S2D) and the tensor below
+                if (step(kUpTC[k], [&] {
+                        return upcat_tc(K.upcat[k], B(p.S[l]), below, n, hh, ww, B(p.T[l]), sms, stream, cg);
+                    }))
+                    return 1;
+            } else {
+                if (step(kUpT[k], [&] {
+                        return conv_tc(K.up_t[k], below, nullptr, n, hh / 2, ww / 2, B(p.U[l]),
+                                              nullptr, nullptr, sms, stream, cg, rev);
+                    }))
+                    return 1;
+                if (step(kUpC1[k], [&] {
+                        return conv_tc(K.up_c[k][0], B(p.S[l]), B(p.U[l]), n, hh, ww, B(p.T[l]),
+                                              nullptr, nullptr, sms, stream, cg, rev);
+                    }))
+                    return 1;
+            }
             if (step(kUpC2[k], [&] {
                     return conv_tc(K.up_c[k][1], B(p.T[l]), nullptr, n, hh, ww, B(p.U[l]),
                                           nullptr, k == 3 ? &hp : nullptr, sms, stream, cg, rev);
@@ -757,6 +804,12 @@ const char* ogl_unet_launch_name(const ogl_unet* h, int index) {
 int ogl_unet_set_schedule(ogl_unet* h, int s2d_level0) {
     if (!h) return fail("ogl_unet_set_schedule: NULL handle");
     h->use_s2d = s2d_level0 != 0;
+    return 0;
+}
+
+int ogl_unet_set_compose(ogl_unet* h, int enable) {
+    if (!h) return fail("ogl_unet_set_compose: NULL handle");
+    h->compose_up = enable != 0;
     return 0;
 }
 
@@ -985,6 +1038,92 @@ int ogl_debug_tc_layer(ogl_unet* h, int kind, const float* src0_dev, int c0, con
     cudaFree(d_s1);
     cudaFree(d_o);
     cudaFree(d_p);
+    return rc;
+}
+
+int ogl_debug_upcat_program(const float* w3_host, const float* b3_host, const float* wt_host,
+                            const float* bt_host, int f, uint16_t* wskip_out, uint16_t* wskip_pair_out,
+                            uint16_t* wbelow_out, uint16_t* wbelow_pair_out, float* btab_out) {
+    g_err.clear();
+    if (!w3_host || !b3_host || !wt_host || !bt_host)
+        return fail("ogl_debug_upcat_program: NULL argument");
+    UpcatHost hs;
+    if (build_upcat_host(w3_host, b3_host, wt_host, bt_host, f, false, &hs)) return 1;
+    if (wskip_out) memcpy(wskip_out, hs.wskip.data(), hs.wskip.size() * 2);
+    if (wskip_pair_out) memcpy(wskip_pair_out, hs.wskip_pair.data(), hs.wskip_pair.size() * 2);
+    if (wbelow_out) memcpy(wbelow_out, hs.wbelow.data(), hs.wbelow.size() * 2);
+    if (wbelow_pair_out) memcpy(wbelow_pair_out, hs.wbelow_pair.data(), hs.wbelow_pair.size() * 2);
+    if (btab_out) memcpy(btab_out, hs.btab.data(), hs.btab.size() * sizeof(float));
+    return 0;
+}
+
+int ogl_debug_upcat_layer(ogl_unet* h, const float* skip_dev, const float* below_dev,
+                          const float* w3_host, const float* b3_host, const float* wt_host,
+                          const float* bt_host, int f, int n, int height, int width, float* out_dev,
+                          void* stream_v) {
+    g_err.clear();
+    if (!h || !skip_dev || !below_dev || !w3_host || !b3_host || !wt_host || !bt_host || !out_dev)
+        return fail("ogl_debug_upcat_layer: NULL argument");
+    if (height % 2 || width % 2 || height < 2 || width < 2)
+        return fail("ogl_debug_upcat_layer: H and W must be even");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    OGL_CUDA(cudaSetDevice(h->device));
+    UpcatHost hs;
+    if (build_upcat_host(w3_host, b3_host, wt_host, bt_host, f, false, &hs)) return 1;
+    const size_t hw = static_cast<size_t>(height) * width;
+    std::vector<float> interior(hs.btab.begin() + 4 * f, hs.btab.begin() + 5 * f);
+    void *d_ws = nullptr, *d_ws2 = nullptr, *d_wb = nullptr, *d_wb2 = nullptr;
+    float *d_bt = nullptr, *d_bi = nullptr;
+    __nv_bfloat16 *d_s = nullptr, *d_b = nullptr, *d_o = nullptr;
+    int rc = 1;
+    do {
+        if (cudaMalloc(&d_ws, hs.wskip.size() * 2) != cudaSuccess) break;
+        if (cudaMalloc(&d_ws2, hs.wskip_pair.size() * 2) != cudaSuccess) break;
+        if (cudaMalloc(&d_wb, hs.wbelow.size() * 2) != cudaSuccess) break;
+        if (cudaMalloc(&d_wb2, hs.wbelow_pair.size() * 2) != cudaSuccess) break;
+        if (cudaMalloc(&d_bt, hs.btab.size() * 4) != cudaSuccess) break;
+        if (cudaMalloc(&d_bi, interior.size() * 4) != cudaSuccess) break;
+        if (cudaMalloc(&d_s, n * f * hw * 2) != cudaSuccess) break;
+        if (cudaMalloc(&d_b, n * 2 * f * hw / 4 * 2) != cudaSuccess) break;
+        if (cudaMalloc(&d_o, n * f * hw * 2) != cudaSuccess) break;
+        cudaMemcpyAsync(d_ws, hs.wskip.data(), hs.wskip.size() * 2, cudaMemcpyHostToDevice, stream);
+        cudaMemcpyAsync(d_ws2, hs.wskip_pair.data(), hs.wskip_pair.size() * 2, cudaMemcpyHostToDevice, stream);
+        cudaMemcpyAsync(d_wb, hs.wbelow.data(), hs.wbelow.size() * 2, cudaMemcpyHostToDevice, stream);
+        cudaMemcpyAsync(d_wb2, hs.wbelow_pair.data(), hs.wbelow_pair.size() * 2, cudaMemcpyHostToDevice, stream);
+        cudaMemcpyAsync(d_bt, hs.btab.data(), hs.btab.size() * 4, cudaMemcpyHostToDevice, stream);
+        cudaMemcpyAsync(d_bi, interior.data(), interior.size() * 4, cudaMemcpyHostToDevice, stream);
+        cudaStreamSynchronize(stream);
+        UpcatLayer L;
+        L.wskip = static_cast<uint8_t*>(d_ws);
+        L.wskip2 = static_cast<uint8_t*>(d_ws2);
+        L.wbelow = static_cast<uint8_t*>(d_wb);
+        L.wbelow2 = static_cast<uint8_t*>(d_wb2);
+        L.btab = d_bt;
+        L.bias = d_bi;
+        L.f = hs.f;
+        L.N = hs.N;
+        L.npass = hs.npass;
+        if (launch_nchw_to_c8(skip_dev, d_s, n, f, height, width, stream, true)) break;
+        if (launch_nchw_to_c8(below_dev, d_b, n, 2 * f, height / 2, width / 2, stream)) break;
+        if (launch_upcat_tc(L, d_s, d_b, n, height, width, d_o, h->num_sms, stream, h->cta_group)) break;
+        if (launch_c8_to_nchw(d_o, out_dev, n, f, height, width, stream)) break;
+        cudaError_t e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) {
+            fail_cuda(e, "ogl_debug_upcat_layer");
+            break;
+        }
+        rc = 0;
+    } while (0);
+    if (rc && g_err.empty()) fail("ogl_debug_upcat_layer: allocation or launch failed");
+    cudaFree(d_ws);
+    cudaFree(d_ws2);
+    cudaFree(d_wb);
+    cudaFree(d_wb2);
+    cudaFree(d_bt);
+    cudaFree(d_bi);
+    cudaFree(d_s);
+    cudaFree(d_b);
+    cudaFree(d_o);
     return rc;
 }
 

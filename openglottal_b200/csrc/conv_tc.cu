@@ -72,6 +72,8 @@ struct ConvParams {
     int reverse;     // walk the tiles from the last frame to the first (see launch_conv_tc)
     int split;       // N = 128, S = 2: per-accumulator barriers (see kSplit in the kernel)
     int acc_half;    // the other layers: one accumulator-empty barrier per (buffer, issuer half)
+    int out_s2d;     // `out` is written space-to-depth [frame][C/8][phase][H/2][W/2][8] (skip tensors
+                     // of levels 1-3, read by upcat_tc.cu); the pooled tensor stays plain
     int dbg;         // experiment switches (OGL_DBG): 1 no MMA, 2 no stores, 4 no epilogue math,
                      // 8 no activation TMA, 16 no weight copies. Results are garbage when set.
 };
@@ -517,9 +519,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                         }
                     } else {
                         const size_t plane = static_cast<size_t>(OH) * OW * 8;
+                        // position inside an 8-channel plane: row-major, or space-to-depth (the four
+                        // pixel phases as four quarter planes)
+                        const size_t pix =
+                            p.out_s2d ? (static_cast<size_t>((y & 1) * 2 + (x & 1)) * (OH >> 1) * (OW >> 1) +
+                                         static_cast<size_t>(y >> 1) * (OW >> 1) + (x >> 1))
+                                      : static_cast<size_t>(y) * OW + x;
                         __nv_bfloat16* optr =
-                            p.out + (static_cast<size_t>(t.n) * (p.cout >> 3) + (co0 >> 3)) * plane +
-                            (static_cast<size_t>(y) * OW + x) * 8;
+                            p.out + (static_cast<size_t>(t.n) * (p.cout >> 3) + (co0 >> 3)) * plane + pix * 8;
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
                             uint4 q4;
@@ -721,8 +728,10 @@ int conv_tc_init() {
 int launch_conv_tc(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloat16* src1, int B,
                    int H, int W, __nv_bfloat16* out, __nv_bfloat16* out_pool,
                    const HeadParams* head, int num_sms, cudaStream_t stream, int cta_group,
-                   bool reverse) {
+                   bool reverse, bool out_s2d) {
     if (!g_encode) return fail("conv_tc_init() was not called");
+    if (out_s2d && (L.epi == EPI_CONVT || L.epi == EPI_HEAD || H % 2 || W % 2))
+        return fail("space-to-depth output needs a conv3x3 layer with even H and W");
     if (H < 1 || W < 1) return fail("tensor-core conv needs a non-empty feature map");
     if (L.epi == EPI_RELU_POOL && (H % 2 || W % 2))
         return fail("fused 2x2 max-pool needs even H and W");
@@ -760,6 +769,7 @@ int launch_conv_tc(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloa
     // Tile order (experiment, api.cu OGL_PINGPONG): a launch that starts with the frames its
     // producer wrote last could find them still in the 126 MB L2; measured, no gain at batch 512.
     p.reverse = reverse ? 1 : 0;
+    p.out_s2d = out_s2d ? 1 : 0;
     // 2 sub-tiles (4 accumulators) per tile. Measured alternatives (experiment switches):
     // 1 sub-tile for N = 128 (OGL_S128=1) or for the transposed conv (OGL_ST=1) doubles the
     // weight traffic per pixel and is slower although TMEM could then be double-buffered.

@@ -61,11 +61,13 @@ int conv_tc_init_f16();   // the f16-operand twins (conv_tc_f16.cu, s2d_tc_f16.c
 int launch_conv_tc_f16(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloat16* src1, int B,
                        int H, int W, __nv_bfloat16* out, __nv_bfloat16* out_pool,
                        const HeadParams* head, int num_sms, cudaStream_t stream, int cta_group = 1,
-                       bool reverse = false);
+                       bool reverse = false, bool out_s2d = false);
 int launch_conv_tc(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloat16* src1, int B,
                    int H, int W, __nv_bfloat16* out, __nv_bfloat16* out_pool,
                    const HeadParams* head, int num_sms, cudaStream_t stream, int cta_group = 1,
-                   bool reverse = false);  // reverse: tiles from the last frame to the first
+                   bool reverse = false,   // reverse: tiles from the last frame to the first
+                   bool out_s2d = false);  // `out` (not the pooled tensor) is written space-to-depth:
+                                           // [frame][C/8][phase][H/2][W/2][8], the layout upcat_tc reads
 
 // stem: u8 / f32 gray -> conv3x3(1->32)+bias+ReLU in fp32 -> C8-planar bf16
 struct StemWeights {  // passed by value: lives in the kernel-parameter constant bank
@@ -174,6 +176,35 @@ int encode_bf16_map(void* tensor_map, const void* base, int rank, const uint64_t
                     const uint64_t* strides_bytes, const uint32_t* box);
 int encode_map(void* tensor_map, const void* base, int rank, const uint64_t* dims,
                const uint64_t* strides_bytes, const uint32_t* box, bool u8);
+
+// ------------------------------------------------------------------ decoder levels 1-3
+// ConvTranspose2d composed into the conv that follows it (upcat_tc.cu): the skip tensor is read in
+// the space-to-depth layout, the tensor below plain; weights per K block: 9 taps of the skip half,
+// 16 (output phase, half-resolution offset) pairs of the composed half.
+struct UpcatLayer {
+    uint8_t* wskip = nullptr;    // [pass][f/32][9][4][N][8]
+    uint8_t* wskip2 = nullptr;   // CTA-pair form [pass][f/32][rank][9][4][N/2][8]
+    uint8_t* wbelow = nullptr;   // [pass][2f/32][16][4][N][8]
+    uint8_t* wbelow2 = nullptr;  // [pass][2f/32][rank][16][4][N/2][8]
+    float* bias = nullptr;       // [f]: interior pixels (= btab[1][1])
+    float* btab = nullptr;       // [3][3][f]: bias per (row class, column class)
+    int f = 0, N = 0, npass = 0;
+};
+struct UpcatHost {
+    std::vector<uint16_t> wskip, wskip_pair, wbelow, wbelow_pair;
+    std::vector<float> btab;
+    int f = 0, N = 0, npass = 0;
+};
+int build_upcat_host(const float* w3, const float* b3, const float* wt, const float* bt, int f,
+                     bool f16, UpcatHost* out);
+int upcat_tc_init();
+int upcat_tc_init_f16();
+int launch_upcat_tc(const UpcatLayer& L, const __nv_bfloat16* skip_s2d, const __nv_bfloat16* below,
+                    int B, int H, int W, __nv_bfloat16* out, int num_sms, cudaStream_t stream,
+                    int cta_group = 1);
+int launch_upcat_tc_f16(const UpcatLayer& L, const __nv_bfloat16* skip_s2d, const __nv_bfloat16* below,
+                        int B, int H, int W, __nv_bfloat16* out, int num_sms, cudaStream_t stream,
+                        int cta_group = 1);
 
 int launch_stem(const void* frames, int in_dtype, const StemWeights& sw, int B, int H, int W,
                 __nv_bfloat16* out, bool s2d, cudaStream_t stream, bool f16 = false);

@@ -76,6 +76,9 @@ class UNet(nn.Module):
                                      # 0 separate kernel, 1 in-kernel on the CUDA cores (fp32),
                                      # 2 (default) in-kernel on the tensor cores (bf16 hi + lo
                                      # weights, fp32 accumulation)
+        self.compose_up = os.environ.get("OGL_COMPOSE", "1") != "0"   # decoder levels 1-3: every
+                                     # ConvTranspose2d composed into the conv after it (17 launches,
+                                     # no `up` tensor); False: the round-1 schedule (20 launches)
         self.use_graphs = True       # small batches: replay the forward's launches as one CUDA graph
         self.graph_max_batch = 128   # (a forward is ~20 launches; at batch 32 they take ~1 ms of
                                      # GPU time, the same order as enqueueing them one by one)
@@ -231,6 +234,7 @@ class UNet(nn.Module):
         _native.check(lib.ogl_unet_set_schedule(self._handle, 1 if self.schedule == "s2d" else 0))
         _native.check(lib.ogl_unet_set_cta_pairs(self._handle, int(self.cta_pairs)))
         _native.check(lib.ogl_unet_set_fused_stem(self._handle, int(self.fuse_stem)))
+        _native.check(lib.ogl_unet_set_compose(self._handle, int(bool(self.compose_up))))
         frames = frames.contiguous()
         prec = self._precision_code()
         if prec == _native.PRECISION_F16 and not self._f16_ready:
@@ -261,7 +265,8 @@ class UNet(nn.Module):
                 # host) are captured once per call signature and replayed; inputs and outputs of the
                 # captured launches are static buffers, copied from / into fresh tensors.
                 key = (n, hgt, wid, in_dtype, float(threshold), want_logits, want_mask, want_area, prec,
-                       self.schedule, int(self.cta_pairs), int(self.fuse_stem), ws.data_ptr())
+                       self.schedule, int(self.cta_pairs), int(self.fuse_stem), bool(self.compose_up),
+                       ws.data_ptr())
                 ent = self._graphs.get(key)
                 if ent is None:
                     ent = self._graphs[key] = [0, None, None, None]

@@ -83,7 +83,7 @@ def _f16(t: torch.Tensor) -> torch.Tensor:
 
 @torch.no_grad()
 def folded_forward(sd: dict, x: torch.Tensor, bf16: bool, composed_level0: bool = True,
-                   operand: str = "bf16") -> torch.Tensor:
+                   operand: str = "bf16", composed_up: bool = True) -> torch.Tensor:
     """Network on BN-folded weights. ``bf16=False``: the fp32 validation mode's arithmetic.
     ``bf16=True``: bit-model of the tensor-core path -- fp32 stem from the fp32 input, bf16
     weights, every stored activation rounded to bf16 (after bias+ReLU; convT after bias),
@@ -91,6 +91,7 @@ def folded_forward(sd: dict, x: torch.Tensor, bf16: bool, composed_level0: bool 
     ``composed_level0`` (the default "s2d" schedule): the last ConvTranspose2d is composed into
     the conv that follows it, so its output is never rounded (the composed weights are; that
     difference is inside the test tolerance and not modelled).
+    ``composed_up`` (the default decoder): the same at levels 1-3 (``compose_up`` of the model).
     ``operand="fp16"`` (with ``bf16=True``): the same rounding points with f16 operands -- the
     kernels' f16 precision mode."""
     fs = fold_state(sd)
@@ -113,7 +114,7 @@ def folded_forward(sd: dict, x: torch.Tensor, bf16: bool, composed_level0: bool 
     x = conv(x, "bottleneck.3")
     for k in range(4):
         up = F.conv_transpose2d(x, r(fs[f"ups.{2 * k}.w"]), fs[f"ups.{2 * k}.b"], stride=2)
-        x = up if (k == 3 and composed_level0) else r(up)
+        x = up if ((k == 3 and composed_level0) or (k < 3 and composed_up)) else r(up)
         x = torch.cat([skips[3 - k], x], dim=1)
         x = conv(x, f"ups.{2 * k + 1}.0")
         x = conv(x, f"ups.{2 * k + 1}.3", round_out=(k != 3))

@@ -250,3 +250,63 @@ def test_s2d_cta_pairs_bit_identical(lib, handle, kind, composed, n, hgt, wid):
     assert torch.equal(out1, out2)
     if kind == 1:
         assert torch.equal(pool1, pool2)
+
+
+UPCAT_CASES = [
+    # f, n, H, W (the level's own resolution)
+    (64, 2, 32, 32),
+    (64, 3, 48, 80),      # partial tiles in x and y
+    (64, 5, 128, 128),    # several tiles per frame
+    (128, 2, 32, 32),
+    (128, 3, 64, 16),
+    (256, 3, 32, 32),     # two output-channel passes
+    (256, 2, 16, 48),
+    (64, 1, 2, 2),        # a single half-resolution position
+]
+
+
+def _run_upcat(lib, handle, skip, below, w3, b3, wt, bt, f):
+    from openglottal_b200 import _native
+
+    n, _, hgt, wid = skip.shape
+    out = torch.full((n, f, hgt, wid), float("nan"), device="cuda")
+    host = [t.contiguous().cpu() for t in (w3, b3, wt, bt)]
+    fp = lambda t: C.cast(t.data_ptr(), C.POINTER(C.c_float))
+    _native.check(lib.ogl_debug_upcat_layer(handle, skip.data_ptr(), below.data_ptr(), fp(host[0]),
+                                            fp(host[1]), fp(host[2]), fp(host[3]), f, n, hgt, wid,
+                                            out.data_ptr(), None))
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("f,n,hgt,wid", UPCAT_CASES)
+def test_upcat_composed_convT_cat_conv(lib, handle, f, n, hgt, wid):
+    """ConvTranspose2d + cat + conv3x3 + bias + ReLU as ONE launch (unet.py:82-87) against torch in
+    fp64 on the same bf16-rounded activations; one CTA per tile and CTA pairs give the same bits."""
+    from openglottal_b200 import _native
+
+    g = torch.Generator().manual_seed(f * 3 + hgt + wid)
+    skip = _bf(torch.randn(n, f, hgt, wid, generator=g))
+    below = _bf(torch.randn(n, 2 * f, hgt // 2, wid // 2, generator=g))
+    w3 = torch.randn(f, 2 * f, 3, 3, generator=g) * (2.0 / (2 * f * 9)) ** 0.5
+    b3 = torch.randn(f, generator=g) * 0.1
+    wt = torch.randn(2 * f, f, 2, 2, generator=g) * (1.0 / (2 * f)) ** 0.5
+    bt = torch.randn(f, generator=g) * 0.5
+    up = F.conv_transpose2d(below.double(), wt.double(), bt.double(), stride=2)
+    ref = F.relu(F.conv2d(torch.cat([skip.double(), up], 1), w3.double(), b3.double(), padding=1)).float()
+    outs = []
+    try:
+        for mode in (1, 3):
+            _native.check(lib.ogl_unet_set_cta_pairs(handle, mode))
+            outs.append(_run_upcat(lib, handle, skip.cuda(), below.cuda(), w3, b3, wt, bt, f))
+    finally:
+        _native.check(lib.ogl_unet_set_cta_pairs(handle, 2))
+    # weights are rounded to bf16 AFTER the composition: |err| <= 2^-7 |ref| + a few weight ulps
+    err = (outs[0].cpu() - ref).abs()
+    tol = ref.abs() * 2.0 ** -7 + 2e-2
+    bad = err > tol
+    print(f"upcat f={f} {n}x{hgt}x{wid}: max|err|={err.max().item():.4g} mean={err.mean().item():.4g} "
+          f"nan={torch.isnan(outs[0]).sum().item()} bad={bad.sum().item()}")
+    assert not torch.isnan(outs[0]).any() and not bad.any()
+    assert err.mean().item() <= 3e-3
+    assert torch.equal(outs[0], outs[1])

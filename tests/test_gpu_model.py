@@ -85,12 +85,15 @@ def test_direct_schedule_matches_bitmodel_and_s2d(native_model, trained_sd):
     dev = torch.from_numpy(frames).cuda()
     lg_s2d, m_s2d, a_s2d = native_model.run(dev, want_logits=True)
     native_model.schedule = "direct"
+    native_model.compose_up = False      # every ConvTranspose2d its own launch, `up` rounded to bf16
     try:
         lg, m, a = native_model.run(dev, want_logits=True)
+        assert _native_launches(native_model) == 22
     finally:
         native_model.schedule = "s2d"
+        native_model.compose_up = True
     bit = uo.folded_forward(trained_sd, uo.frames_to_input(frames), bf16=True,
-                            composed_level0=False)[:, 0].numpy()
+                            composed_level0=False, composed_up=False)[:, 0].numpy()
     err = np.abs(lg.cpu().numpy() - bit)
     print("direct vs bit-model max|err|", err.max(), "mean", err.mean())
     assert err.max() <= 3e-2 and err.mean() <= 2e-3
@@ -99,6 +102,44 @@ def test_direct_schedule_matches_bitmodel_and_s2d(native_model, trained_sd):
     assert d.max().item() <= 5e-2 and d.mean().item() <= 3e-3
     assert (m != m_s2d).sum().item() <= 1e-4 * m.numel()
     assert np.array_equal(a.cpu().numpy(), (m.cpu().numpy() > 0).reshape(3, -1).sum(1))
+
+
+def _native_launches(model):
+    from openglottal_b200 import _native
+
+    return _native.load().ogl_unet_launch_count(model._handle)
+
+
+def test_composed_decoder_17_launches_and_agrees_with_separate_convT(native_model, trained_sd):
+    """Decoder levels 1-3 with every ConvTranspose2d composed into the conv after it (upcat_tc.cu,
+    the default: 17 launches, no `up` tensor) against the round-1 schedule (20 launches: separate
+    transposed convs, `up` rounded to bf16) and against the bit-model of each; incl. partial tiles,
+    a 512x256 batch and a batch with several tiles per SM (CTA pairs)."""
+    from oracle import unet_oracle as uo
+
+    for shape in ((3, 256, 256), (2, 48, 80), (1, 16, 16), (2, 512, 256), (40, 256, 256)):
+        frames = _clip(*shape)
+        dev = torch.from_numpy(frames).cuda()
+        lg_c, m_c, a_c = native_model.run(dev, want_logits=True)
+        assert _native_launches(native_model) == 17
+        native_model.compose_up = False
+        try:
+            lg_s, m_s, a_s = native_model.run(dev, want_logits=True)
+            assert _native_launches(native_model) == 20
+        finally:
+            native_model.compose_up = True
+        d = (lg_c - lg_s).abs()
+        print(shape, "composed vs separate convT: max|dz|", d.max().item(), "mean", d.mean().item())
+        assert d.max().item() <= 5e-2 and d.mean().item() <= 3e-3, shape
+        assert (m_c != m_s).sum().item() <= 1e-4 * m_c.numel() + 2, shape
+        assert torch.equal(a_c.cpu(), (m_c > 0).flatten(1).sum(1).to(torch.int32).cpu()), shape
+        if shape[0] <= 3:
+            x = uo.frames_to_input(frames)
+            for lg, comp in ((lg_c, True), (lg_s, False)):
+                bit = uo.folded_forward(trained_sd, x, bf16=True, composed_up=comp)[:, 0].numpy()
+                err = np.abs(lg.cpu().numpy() - bit)
+                print(shape, "composed" if comp else "separate", "vs its bit-model: max", err.max(), "mean", err.mean())
+                assert err.max() <= 3e-2 and err.mean() <= 2e-3, (shape, comp)
 
 
 def test_cta_pairs_bit_identical(native_model):
@@ -179,7 +220,7 @@ def test_repeated_launch_is_idempotent(native_model):
     ref = native_model.run(frames, want_logits=True)
     n_launch = lib.ogl_unet_launch_count(native_model._handle)
     try:
-        for idx in (0, 1, 9, 10, n_launch - 2):
+        for idx in (0, 1, 9, 11, n_launch - 2):   # fused stem, conv, composed convT+conv (x2), level 0
             _native.check(lib.ogl_unet_set_repeat(native_model._handle, idx, 3))
             got = native_model.run(frames, want_logits=True)
             assert torch.equal(ref[0], got[0]) and torch.equal(ref[1], got[1]), idx
