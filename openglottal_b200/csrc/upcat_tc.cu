@@ -27,10 +27,14 @@
 //   * weights: streamed per K block, [pass][kb][9 taps][4][N][8] for the skip half and
 //     [pass][kb][16 (phase, offset)][4][N][8] for the composed half, in stages of <= 36 KB.
 //   * warp roles as in conv_tc.cu. Issuer warp `me` owns the two accumulators of output row phase
-//     py = me, epilogue warp group `me` drains them (phases (py, 0) and (py, 1) of a position are two
-//     horizontally adjacent pixels: one 32-byte store per 8-channel group); each half has its own
-//     accumulator full / empty barriers, so the two MMA -> epilogue chains drift out of phase and one
-//     half's MMAs run while the other is drained (TMEM has no room for a second accumulator set).
+//     py = me, epilogue warp group `me` drains them.
+//     N = 64: two accumulator sets (2 x 4 x 64 columns), so the epilogue of a tile overlaps the MMAs
+//     of the next one; phases (py, 0) and (py, 1) of a position are two horizontally adjacent pixels
+//     and leave as one 32-byte store per 8-channel group.
+//     N = 128: the four accumulators fill TMEM. Each has its own full / empty barrier and a tile's K
+//     loop starts and ends with a group of the composed half issued ACCUMULATOR-MAJOR (px = 0, then
+//     px = 1; 32 MMAs = 2048 cycles each): accumulator (py, 0) is drained while the MMAs of (py, 1)
+//     finish the tile, and (py, 1) while those of the next tile's (py, 0) start it.
 //   * CG = 2: the two CTAs of a cluster take neighbouring tiles and run every MMA as one 256-row
 //     tcgen05.mma.cta_group::2, each staging half of the weight columns (as conv_tc.cu).
 #include "internal.h"
@@ -102,13 +106,12 @@ struct Smem {
 __host__ __device__ constexpr int src_phase(int p, int d) { return (p + d - 1) & 1; }
 __host__ __device__ constexpr int src_cell(int p, int d) { return (p + d + 1) >> 1; }
 
-// One issuer warp: ME = the output row phase py whose two accumulators (columns (2 ME + px) N) it owns.
+// One issuer warp: ME = the output row phase py whose two accumulators it owns.
 template <int N, int CG, int ME>
 __device__ __forceinline__ void issue_half(const UpcatParams& p, const Smem& s, uint32_t tmem_base,
                                            int item0, int items, int item_step) {
     constexpr int TPS = N == 64 ? 9 : 3;     // skip taps per weight stage
-    constexpr int TAPB = N == 64 ? 8 : 4;    // (phase, offset) pairs of the composed half per stage
-    constexpr int NSB = 16 / TAPB;
+    constexpr bool kDB = N == 64;            // two accumulator sets
     constexpr uint32_t nb = N / CG;          // weight columns staged per CTA
     constexpr uint32_t btap = 4u * nb;       // one tap of B, 16-byte units
     constexpr uint32_t bstep = 2u * nb;      // second K = 16 half of a 32-channel block
@@ -125,13 +128,87 @@ __device__ __forceinline__ void issue_half(const UpcatParams& p, const Smem& s, 
         if (CG == 2) umma_commit_pair(bar);
         else umma_commit(bar);
     };
-    const uint32_t d_me = tmem_base + static_cast<uint32_t>(2 * ME * N);
+    auto wait_acc_empty = [](uint32_t bar, uint32_t parity) {
+        if (CG == 2) mbar_wait_cluster(bar, parity);   // the peer's epilogue arrives remotely
+        else mbar_wait(bar, parity);
+        tc_fence_after();
+    };
     uint32_t ita = 0, itw = 0, li = 0;
     for (int item = item0; item < items; item += item_step, ++li) {
-        // this half's accumulators must have been drained by epilogue group ME
-        if (CG == 2) mbar_wait_cluster(s.acc_empty + 8u * ME, (li & 1u) ^ 1u);
-        else mbar_wait(s.acc_empty + 8u * ME, (li & 1u) ^ 1u);
-        tc_fence_after();
+        const uint32_t buf = kDB ? (li & 1u) : 0u;
+        const uint32_t aph = kDB ? ((li >> 1) & 1u) : (li & 1u);
+        const uint32_t d_me = tmem_base + buf * 256u + static_cast<uint32_t>(2 * ME * N);
+        // barrier index of accumulator (ME, px): kDB: one per (buffer, half); else one per accumulator
+        auto acc_bar = [&](int px) { return 8u * (kDB ? buf * 2u + ME : ME * 2u + px); };
+
+        // ---- composed half, one group of 4 K blocks. N = 64: per K block one stage per px with both
+        // py (8 pairs); N = 128: accumulator-major -- px outer, K block, then one stage per py.
+        auto below_group = [&](bool first_g, bool last_g) {
+            const uint32_t sa = ita % p.na;
+            mbar_wait(s.a_full + 8u * sa, (ita / p.na) & 1u);
+            const uint64_t ad = adesc_b + ((s.a_ring + sa * kStage) >> 4);
+            auto pair_mmas = [&](uint64_t bd, int px, int g4, int t0, bool first) {
+#pragma unroll
+                for (int o4 = 0; o4 < 4; ++o4) {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const uint32_t aoff =
+                            (g4 * 4 + 2 * j) * kPlaneU + (ME + (o4 >> 1)) * kHW + (px + (o4 & 1));
+                        mma(d_me + px * N, ad + aoff, bd + ((t0 + o4) * btap + j * bstep), idesc,
+                            (first && o4 == 0 && j == 0) ? 0u : 1u);
+                    }
+                }
+            };
+            if (kDB) {
+#pragma unroll
+                for (int g4 = 0; g4 < 4; ++g4) {
+#pragma unroll
+                    for (int px = 0; px < 2; ++px, ++itw) {
+                        const uint32_t sw = itw % p.nw;
+                        mbar_wait(s.w_full + 8u * sw, (itw / p.nw) & 1u);
+                        tc_fence_after();
+                        const uint64_t bd = bdesc0 + ((s.w_ring + sw * s.w_slot) >> 4);
+                        if (elect_one()) {
+                            pair_mmas(bd, px, g4, ME * 4, false);
+                            commit(s.w_empty + 8u * sw);
+                            if (g4 == 3 && px == 1) {
+                                commit(s.a_empty + 8u * sa);
+                                if (last_g) commit(s.acc_full + acc_bar(0));
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int px = 0; px < 2; ++px) {
+                    if (first_g) wait_acc_empty(s.acc_empty + acc_bar(px), aph ^ 1u);
+#pragma unroll
+                    for (int g4 = 0; g4 < 4; ++g4) {
+#pragma unroll
+                        for (int py = 0; py < 2; ++py, ++itw) {
+                            const uint32_t sw = itw % p.nw;
+                            mbar_wait(s.w_full + 8u * sw, (itw / p.nw) & 1u);
+                            tc_fence_after();
+                            const uint64_t bd = bdesc0 + ((s.w_ring + sw * s.w_slot) >> 4);
+                            if (elect_one()) {
+                                if (py == ME) pair_mmas(bd, px, g4, 0, first_g && g4 == 0);
+                                commit(s.w_empty + 8u * sw);
+                                if (g4 == 3 && py == 1) {
+                                    if (px == 1) commit(s.a_empty + 8u * sa);
+                                    if (last_g) commit(s.acc_full + acc_bar(px));
+                                }
+                            }
+                            __syncwarp();
+                        }
+                    }
+                }
+            }
+            ++ita;
+        };
+
+        if (kDB) wait_acc_empty(s.acc_empty + acc_bar(0), aph ^ 1u);
+        else below_group(true, false);         // N = 128: the tile starts accumulator-major
         // ---------------- skip half: kbS blocks x 9 taps, the same tap weights for all phases
         for (int kb = 0; kb < p.kbS; ++kb, ++ita) {
             const uint32_t sa = ita % p.na;
@@ -143,7 +220,7 @@ __device__ __forceinline__ void issue_half(const UpcatParams& p, const Smem& s, 
                 mbar_wait(s.w_full + 8u * sw, (itw / p.nw) & 1u);
                 tc_fence_after();
                 const uint64_t bd = bdesc0 + ((s.w_ring + sw * s.w_slot) >> 4);
-                const uint32_t first = (kb | tg) != 0 ? 1u : 0u;
+                const uint32_t first = (!kDB || (kb | tg) != 0) ? 1u : 0u;
                 if (elect_one()) {
 #pragma unroll
                     for (int t = 0; t < TPS; ++t) {
@@ -167,49 +244,8 @@ __device__ __forceinline__ void issue_half(const UpcatParams& p, const Smem& s, 
                 __syncwarp();
             }
         }
-        // ---------------- composed half: nG groups of 4 K blocks x (2 phases x 4 offsets) of this half
-        for (int g = 0; g < p.nG; ++g, ++ita) {
-            const uint32_t sa = ita % p.na;
-            mbar_wait(s.a_full + 8u * sa, (ita / p.na) & 1u);
-            const uint64_t ad = adesc_b + ((s.a_ring + sa * kStage) >> 4);
-            const bool last_g = g == p.nG - 1;
-#pragma unroll
-            for (int g4 = 0; g4 < 4; ++g4) {
-#pragma unroll
-                for (int sb = 0; sb < NSB; ++sb, ++itw) {
-                    const uint32_t sw = itw % p.nw;
-                    mbar_wait(s.w_full + 8u * sw, (itw / p.nw) & 1u);
-                    tc_fence_after();
-                    const uint64_t bd = bdesc0 + ((s.w_ring + sw * s.w_slot) >> 4);
-                    // pair index inside a K block: (px * 2 + py) * 4 + o4. N = 64: stage sb holds
-                    // px = sb, both py; N = 128: stage sb holds px = sb >> 1, py = sb & 1
-                    constexpr bool kBoth = N == 64;
-                    const int px = kBoth ? sb : sb >> 1;
-                    const bool mine = kBoth || (sb & 1) == ME;
-                    const int t0 = kBoth ? ME * 4 : 0;
-                    if (elect_one()) {
-                        if (mine) {
-#pragma unroll
-                            for (int o4 = 0; o4 < 4; ++o4) {
-#pragma unroll
-                                for (int j = 0; j < 2; ++j) {
-                                    const uint32_t aoff = (g4 * 4 + 2 * j) * kPlaneU +
-                                                          (ME + (o4 >> 1)) * kHW + (px + (o4 & 1));
-                                    mma(d_me + px * N, ad + aoff, bd + ((t0 + o4) * btap + j * bstep),
-                                        idesc, 1u);
-                                }
-                            }
-                        }
-                        commit(s.w_empty + 8u * sw);
-                        if (g4 == 3 && sb == NSB - 1) {
-                            commit(s.a_empty + 8u * sa);
-                            if (last_g) commit(s.acc_full + 8u * ME);
-                        }
-                    }
-                    __syncwarp();
-                }
-            }
-        }
+        // ---------------- the (other) groups of the composed half; the last one ends the tile
+        for (int g = kDB ? 0 : 1; g < p.nG; ++g) below_group(false, g == p.nG - 1);
     }
 }
 
@@ -220,8 +256,7 @@ upcat_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__
                 const UpcatParams p) {
     extern __shared__ uint8_t smem_raw[];
     constexpr int TPS = N == 64 ? 9 : 3;
-    constexpr int TAPB = N == 64 ? 8 : 4;
-    constexpr int NSB = 16 / TAPB;
+    constexpr int TAPB = N == 64 ? 8 : 4;    // (phase, offset) pairs of the composed half per stage
     constexpr uint32_t nb = N / CG;
     constexpr uint32_t w_tap_bytes = 64u * nb;
     constexpr uint32_t skip_bytes = TPS * w_tap_bytes, below_bytes = TAPB * w_tap_bytes;
@@ -237,8 +272,8 @@ upcat_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__
     s.w_full = s.a_empty + 8u * p.na;
     s.w_empty = s.w_full + 8u * p.nw;
     s.acc_full = s.w_empty + 8u * p.nw;
-    s.acc_empty = s.acc_full + 16u;
-    const uint32_t tmem_slot = s.acc_empty + 16u;
+    s.acc_empty = s.acc_full + 32u;
+    const uint32_t tmem_slot = s.acc_empty + 32u;
     const uint32_t bias_s = tmem_slot + 16u;
     uint8_t* gen = smem_raw - raw;   // generic pointer = gen + shared address
     float* bias_sp = reinterpret_cast<float*>(gen + bias_s);
@@ -274,7 +309,7 @@ upcat_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__
             mbar_init(s.w_full + 8u * i, 1);
             mbar_init(s.w_empty + 8u * i, 2);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < 4; ++i) {   // N = 64: (buffer, half); N = 128: (half, px)
             mbar_init(s.acc_full + 8u * i, 1);
             mbar_init(s.acc_empty + 8u * i, 128 * CG);   // one epilogue warp group (of both CTAs)
         }
@@ -298,7 +333,10 @@ upcat_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__
                 int tile = tile_of(item);
                 if (tile >= p.num_tiles) tile = p.num_tiles - 1;   // tail of the last pair: a duplicate
                 const Tile t = decode_tile(p, tile);
-                for (int k = 0; k < p.kbS + p.nG; ++k, ++it) {
+                for (int kk = 0; kk < p.kbS + p.nG; ++kk, ++it) {
+                    // N = 64: skip blocks, then the group of the tensor below; N = 128: group 0 of
+                    // the tensor below, the skip blocks, the other groups (k >= kbS: group k - kbS)
+                    const int k = N == 64 ? kk : (kk == 0 ? p.kbS : (kk <= p.kbS ? kk - 1 : kk));
                     const uint32_t slot = it % p.na;
                     mbar_wait_relaxed(s.a_empty + 8u * slot, ((it / p.na) & 1u) ^ 1u);
                     const uint32_t dst = s.a_ring + slot * kStage;
@@ -344,12 +382,25 @@ upcat_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__
             for (int item = item0; item < items; item += item_step) {
                 const uint32_t pass = static_cast<uint32_t>(pass_of(item));
                 // CG = 2 layouts: [pass][kb][rank][taps][4][N/2][8]
+                // the order the issuers consume (issue_half); pair index (px * 2 + py) * 4 + o4
+                auto group = [&](int g) {
+                    if (N == 64) {
+                        for (int g4 = 0; g4 < 4; ++g4)
+                            for (int px = 0; px < 2; ++px)
+                                stage(true, ((pass * kbB + g * 4 + g4) * CG + rank) * 16u + px * 8);
+                    } else {
+                        for (int px = 0; px < 2; ++px)
+                            for (int g4 = 0; g4 < 4; ++g4)
+                                for (int py = 0; py < 2; ++py)
+                                    stage(true, ((pass * kbB + g * 4 + g4) * CG + rank) * 16u +
+                                                    (px * 2 + py) * 4);
+                    }
+                };
+                if (N != 64) group(0);
                 for (int kb = 0; kb < p.kbS; ++kb)
                     for (int tg = 0; tg < 9 / TPS; ++tg)
                         stage(false, ((pass * p.kbS + kb) * CG + rank) * 9u + tg * TPS);
-                for (int kb = 0; kb < kbB; ++kb)
-                    for (int sb = 0; sb < NSB; ++sb)
-                        stage(true, ((pass * kbB + kb) * CG + rank) * 16u + sb * TAPB);
+                for (int g = N == 64 ? 0 : 1; g < p.nG; ++g) group(g);
             }
         }
     } else if ((warp == 1 || warp == 2) && rank == 0) {
@@ -366,6 +417,7 @@ upcat_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__
         const int H = 2 * p.H2, W = 2 * p.W2;
         const size_t plane = static_cast<size_t>(H) * W * 8;
         uint32_t li = 0;
+        constexpr bool kDB = N == 64;
         for (int item = item0; item < items; item += item_step, ++li) {
             const int tile = tile_of(item);
             const int pass = pass_of(item);
@@ -380,42 +432,84 @@ upcat_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__
             const int rx0 = X == 0 ? 0 : 1, rx1 = (2 * X + 1 == W - 1) ? 2 : 1;
             const bool interior = ry == 1 && rx0 == 1 && rx1 == 1;
             const bool plain = __all_sync(0xffffffffu, interior || !valid);
-            mbar_wait_relaxed(s.acc_full + 8u * py, li & 1u);
-            tc_fence_after();
-            const uint32_t tcol = tmem_base + lane_sel + static_cast<uint32_t>(2 * py * N);
+            const uint32_t buf = kDB ? (li & 1u) : 0u;
+            const uint32_t aph = kDB ? ((li >> 1) & 1u) : (li & 1u);
+            const uint32_t tcol = tmem_base + lane_sel + buf * 256u + static_cast<uint32_t>(2 * py * N);
+            __nv_bfloat16* orow = p.out + (static_cast<size_t>(t.n) * (p.cout >> 3)) * plane +
+                                  (static_cast<size_t>(y) * W + 2 * X) * 8;
+            auto release = [&](uint32_t bar) {
+                tc_fence_before();
+                if (CG == 2) mbar_arrive_cluster(map_to_cta(bar, 0));   // the leader's barrier
+                else mbar_arrive(bar);
+            };
+            if (kDB) {
+                // both pixels of a position together: one 32-byte store per 8-channel group
+                mbar_wait_relaxed(s.acc_full + 8u * (buf * 2u + py), aph);
+                tc_fence_after();
 #pragma unroll 1
-            for (int c0 = 0; c0 < N; c0 += 32) {
-                uint32_t r0[32], r1[32];
-                tmem_ld32(tcol + c0, r0);
-                tmem_ld32(tcol + N + c0, r1);
-                tmem_ld_wait();
-                const int co0 = pass * N + c0;
-                __nv_bfloat16* optr = p.out + (static_cast<size_t>(t.n) * (p.cout >> 3) + (co0 >> 3)) * plane +
-                                      (static_cast<size_t>(y) * W + 2 * X) * 8;
-                const float* b0p = bias_sp + co0;
-                const float* b1p = b0p;
-                if (!plain) {   // border classes straight from global memory (rare)
-                    b0p = p.btab + (ry * 3 + rx0) * p.cout + co0;
-                    b1p = p.btab + (ry * 3 + rx1) * p.cout + co0;
-                }
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    uint32_t q[8];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float2 a = *reinterpret_cast<const float2*>(b0p + g * 8 + 2 * e);
-                        const float2 b = *reinterpret_cast<const float2*>(b1p + g * 8 + 2 * e);
-                        q[e] = pack_relu_bf16x2(__uint_as_float(r0[g * 8 + 2 * e]) + a.x,
-                                                __uint_as_float(r0[g * 8 + 2 * e + 1]) + a.y);
-                        q[4 + e] = pack_relu_bf16x2(__uint_as_float(r1[g * 8 + 2 * e]) + b.x,
-                                                    __uint_as_float(r1[g * 8 + 2 * e + 1]) + b.y);
+                for (int c0 = 0; c0 < N; c0 += 32) {
+                    uint32_t r0[32], r1[32];
+                    tmem_ld32(tcol + c0, r0);
+                    tmem_ld32(tcol + N + c0, r1);
+                    tmem_ld_wait();
+                    const int co0 = pass * N + c0;
+                    const float* b0p = bias_sp + co0;
+                    const float* b1p = b0p;
+                    if (!plain) {   // border classes straight from global memory (rare)
+                        b0p = p.btab + (ry * 3 + rx0) * p.cout + co0;
+                        b1p = p.btab + (ry * 3 + rx1) * p.cout + co0;
                     }
-                    if (valid) st_global_256(optr + g * plane, q);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        uint32_t q[8];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 a = *reinterpret_cast<const float2*>(b0p + g * 8 + 2 * e);
+                            const float2 b = *reinterpret_cast<const float2*>(b1p + g * 8 + 2 * e);
+                            q[e] = pack_relu_bf16x2(__uint_as_float(r0[g * 8 + 2 * e]) + a.x,
+                                                    __uint_as_float(r0[g * 8 + 2 * e + 1]) + a.y);
+                            q[4 + e] = pack_relu_bf16x2(__uint_as_float(r1[g * 8 + 2 * e]) + b.x,
+                                                        __uint_as_float(r1[g * 8 + 2 * e + 1]) + b.y);
+                        }
+                        if (valid) st_global_256(orow + ((co0 >> 3) + g) * plane, q);
+                    }
+                }
+                release(s.acc_empty + 8u * (buf * 2u + py));
+            } else {
+                // one accumulator (= one pixel of the position) at a time, in the order the issuer
+                // finishes them
+#pragma unroll 1
+                for (int px = 0; px < 2; ++px) {
+                    mbar_wait_relaxed(s.acc_full + 8u * (py * 2 + px), aph);
+                    tc_fence_after();
+#pragma unroll 1
+                    for (int c0 = 0; c0 < N; c0 += 32) {
+                        uint32_t r[32];
+                        tmem_ld32(tcol + px * N + c0, r);
+                        tmem_ld_wait();
+                        const int co0 = pass * N + c0;
+                        const float* bp = plain ? bias_sp + co0
+                                                : p.btab + (ry * 3 + (px ? rx1 : rx0)) * p.cout + co0;
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            uint4 q4;
+                            const float4 a = *reinterpret_cast<const float4*>(bp + g * 8);
+                            const float4 b = *reinterpret_cast<const float4*>(bp + g * 8 + 4);
+                            q4.x = pack_relu_bf16x2(__uint_as_float(r[g * 8 + 0]) + a.x,
+                                                    __uint_as_float(r[g * 8 + 1]) + a.y);
+                            q4.y = pack_relu_bf16x2(__uint_as_float(r[g * 8 + 2]) + a.z,
+                                                    __uint_as_float(r[g * 8 + 3]) + a.w);
+                            q4.z = pack_relu_bf16x2(__uint_as_float(r[g * 8 + 4]) + b.x,
+                                                    __uint_as_float(r[g * 8 + 5]) + b.y);
+                            q4.w = pack_relu_bf16x2(__uint_as_float(r[g * 8 + 6]) + b.z,
+                                                    __uint_as_float(r[g * 8 + 7]) + b.w);
+                            if (valid)
+                                *reinterpret_cast<uint4*>(orow + ((co0 >> 3) + g) * plane + px * 8) = q4;
+                        }
+                    }
+                    release(s.acc_empty + 8u * (py * 2 + px));
                 }
             }
-            tc_fence_before();
-            if (CG == 2) mbar_arrive_cluster(map_to_cta(s.acc_empty + 8u * py, 0));  // the leader's barrier
-            else mbar_arrive(s.acc_empty + 8u * py);
         }
     }
 
@@ -435,7 +529,7 @@ size_t smem_need(int na, int nw, int cout) {
     constexpr size_t nb = N / CG;
     constexpr size_t skip = (N == 64 ? 9 : 3) * 64 * nb, below = (N == 64 ? 8 : 4) * 64 * nb;
     const size_t slot = skip > below ? skip : below;
-    return 128 + static_cast<size_t>(na) * kStage + nw * slot + 16 * (na + nw) + 32 + 16 + 16 +
+    return 128 + static_cast<size_t>(na) * kStage + nw * slot + 16 * (na + nw) + 64 + 16 + 16 +
            sizeof(float) * cout + 64;
 }
 

@@ -76,7 +76,8 @@ def test_bf16_matches_bitmodel(native_model, trained_sd):
     assert err.max() <= 3e-2 and err.mean() <= 2e-3
 
 
-def test_direct_schedule_matches_bitmodel_and_s2d(native_model, trained_sd):
+def test_direct_schedule_matches_bitmodel_and_s2d(eager_model, trained_sd):
+    native_model = eager_model
     """The per-tap form of the full-resolution level (schedule "direct") against its own
     bit-model, and the two schedules against each other (masks equal up to boundary pixels)."""
     from oracle import unet_oracle as uo
@@ -105,12 +106,24 @@ def test_direct_schedule_matches_bitmodel_and_s2d(native_model, trained_sd):
 
 
 def _native_launches(model):
+    """Launches of the most recent EAGER forward (a forward replayed as a CUDA graph -- small
+    batches, from the second call on -- does not pass through ogl_unet_forward)."""
     from openglottal_b200 import _native
 
     return _native.load().ogl_unet_launch_count(model._handle)
 
 
-def test_composed_decoder_17_launches_and_agrees_with_separate_convT(native_model, trained_sd):
+@pytest.fixture
+def eager_model(native_model):
+    native_model.use_graphs = False
+    try:
+        yield native_model
+    finally:
+        native_model.use_graphs = True
+
+
+def test_composed_decoder_17_launches_and_agrees_with_separate_convT(eager_model, trained_sd):
+    native_model = eager_model
     """Decoder levels 1-3 with every ConvTranspose2d composed into the conv after it (upcat_tc.cu,
     the default: 17 launches, no `up` tensor) against the round-1 schedule (20 launches: separate
     transposed convs, `up` rounded to bf16) and against the bit-model of each; incl. partial tiles,
@@ -209,7 +222,8 @@ def test_tensor_core_stem_matches_fp32_stem(native_model):
         assert torch.equal(got[2].cpu(), (got[1] > 0).flatten(1).sum(1).to(torch.int32).cpu()), shape
 
 
-def test_repeated_launch_is_idempotent(native_model):
+def test_repeated_launch_is_idempotent(eager_model):
+    native_model = eager_model
     """ogl_unet_set_repeat (the energy-measurement aid): enqueueing one launch of the schedule
     several times leaves logits and masks unchanged -- every launch reads and writes distinct
     tensors -- for each kind of launch (fused stem, conv, transposed conv, composed level-0 conv)."""
@@ -364,6 +378,30 @@ def test_unet_segment_frame_reference_semantics(native_model, trained_sd):
     d512 = ogl.dice(got, ref)
     print('512x256 single frame dice', d512, 'differing pixels', int((got != ref).sum()))
     assert d512 >= 0.999 or (got != ref).sum() <= 4    # one frame: 4 boundary pixels of ~1600
+
+
+def test_cuda_graph_replay_equals_eager(native_model):
+    """Small batches replay the forward's launches as one CUDA graph from the second call with the
+    same signature on: same logits, masks and areas as the eager launches, bit for bit; outputs are
+    fresh tensors (a later call does not overwrite an earlier result)."""
+    frames = torch.from_numpy(_clip(6)).cuda()
+    other = torch.from_numpy(_clip(6, seed=9)).cuda()
+    native_model.use_graphs = False
+    try:
+        ref = native_model.run(frames, want_logits=True)
+        ref_other = native_model.run(other, want_logits=True)
+    finally:
+        native_model.use_graphs = True
+    native_model._graphs = {}
+    first = native_model.run(frames, want_logits=True)        # eager (first sight of the signature)
+    second = native_model.run(frames, want_logits=True)       # captured, then replayed
+    third = native_model.run(other, want_logits=True)         # replayed with other frames
+    key = next(iter(native_model._graphs))
+    assert native_model._graphs[key][1] is not None
+    for got in (first, second):
+        assert all(torch.equal(a, b) for a, b in zip(ref, got))
+    assert all(torch.equal(a, b) for a, b in zip(ref_other, third))
+    assert all(torch.equal(a, b) for a, b in zip(ref, second))    # not overwritten by the third call
 
 
 def test_errors_are_loud(native_model):
