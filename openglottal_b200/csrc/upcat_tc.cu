@@ -537,14 +537,20 @@ template <int N, int CG>
 int launch_variant(const CUtensorMap& tmS, const CUtensorMap& tmB, const CUtensorMap& tmWs,
                    const CUtensorMap& tmWb, UpcatParams p, int num_sms, cudaStream_t stream) {
     // ring depths: 3 activation stages (2 when the unpaired weight slots are 36 KB), then as many
-    // weight slots as fit (at most 6)
-    p.na = 3;
-    p.nw = 6;
-    while (p.nw > 2 && smem_need<N, CG>(p.na, p.nw, p.cout) > static_cast<size_t>(kMaxSmem)) --p.nw;
+    // weight slots as fit (at most 8). OGL_UP_NA / OGL_UP_NW (experiments) override, clamped to what
+    // fits.
+    auto fit_nw = [&](int na, int want) {
+        int nw = want;
+        while (nw > 2 && smem_need<N, CG>(na, nw, p.cout) > static_cast<size_t>(kMaxSmem)) --nw;
+        return nw;
+    };
+    static const int na_env = getenv("OGL_UP_NA") ? atoi(getenv("OGL_UP_NA")) : 0;
+    static const int nw_env = getenv("OGL_UP_NW") ? atoi(getenv("OGL_UP_NW")) : 0;
+    p.na = (na_env >= 2 && na_env <= 4) ? na_env : 3;
+    p.nw = fit_nw(p.na, (nw_env >= 2 && nw_env <= 12) ? nw_env : 8);
     if (smem_need<N, CG>(p.na, p.nw, p.cout) > static_cast<size_t>(kMaxSmem) || p.nw < 3) {
         p.na = 2;
-        p.nw = 6;
-        while (p.nw > 2 && smem_need<N, CG>(p.na, p.nw, p.cout) > static_cast<size_t>(kMaxSmem)) --p.nw;
+        p.nw = fit_nw(2, (nw_env >= 2 && nw_env <= 12) ? nw_env : 8);
     }
     const size_t smem = smem_need<N, CG>(p.na, p.nw, p.cout);
     if (smem > static_cast<size_t>(kMaxSmem)) return fail("upcat layer: shared memory budget exceeded");
