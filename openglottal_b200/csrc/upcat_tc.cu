@@ -546,7 +546,9 @@ int launch_variant(const CUtensorMap& tmS, const CUtensorMap& tmB, const CUtenso
     };
     static const int na_env = getenv("OGL_UP_NA") ? atoi(getenv("OGL_UP_NA")) : 0;
     static const int nw_env = getenv("OGL_UP_NW") ? atoi(getenv("OGL_UP_NW")) : 0;
-    p.na = (na_env >= 2 && na_env <= 4) ? na_env : 3;
+    // measured (gpurun_out/r2_exp_upring.jsonl): N = 128 is faster with 2 activation stages and 8
+    // weight slots (0.977 -> 0.935 ms, 0.843 -> 0.818 ms), N = 64 with 3 and 5 (0.95 vs 1.08 ms)
+    p.na = (na_env >= 2 && na_env <= 4) ? na_env : (N == 128 ? 2 : 3);
     p.nw = fit_nw(p.na, (nw_env >= 2 && nw_env <= 12) ? nw_env : 8);
     if (smem_need<N, CG>(p.na, p.nw, p.cout) > static_cast<size_t>(kMaxSmem) || p.nw < 3) {
         p.na = 2;

@@ -15,9 +15,9 @@ rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, data = rows[0], rows[1], rows[2:]
 names = ["stem+downs.0.net.3+pool", "downs.1.net.0", "downs.1.net.3+pool", "downs.2.net.0",
          "downs.2.net.3+pool", "downs.3.net.0", "downs.3.net.3+pool", "bottleneck.net.0",
-         "bottleneck.net.3", "ups.0(convT)", "ups.1.net.0(cat)", "ups.1.net.3", "ups.2(convT)",
-         "ups.3.net.0(cat)", "ups.3.net.3", "ups.4(convT)", "ups.5.net.0(cat)", "ups.5.net.3",
-         "ups.6(convT)+ups.7.net.0(cat)", "ups.7.net.3+head"]
+         "bottleneck.net.3", "ups.0(convT)+ups.1.net.0(cat)", "ups.1.net.3",
+         "ups.2(convT)+ups.3.net.0(cat)", "ups.3.net.3", "ups.4(convT)+ups.5.net.0(cat)", "ups.5.net.3",
+         "ups.6(convT)+ups.7.net.0(cat)", "ups.7.net.3+head"]   # the 17 launches of the composed decoder
 want = ["Kernel Name", "launch__grid_size", "launch__cluster_dim_x", "launch__registers_per_thread",
         "gpu__time_duration.sum", "sm__cycles_active.avg", "dram__bytes_read.sum",
         "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
@@ -52,6 +52,7 @@ traffic = {
               "linearly with the batch, so the bench's batch-512 figure is this x 512 / batch",
     "batch": batch,
     "dram_bytes_per_launch": per,
+    "launches": len(names),
     "dram_bytes_per_launch_avg_batch512": tot / len(names) * 512 / batch,
     "dram_bytes_per_frame_tc_launches": tot / batch,
 }
