@@ -120,10 +120,11 @@ int ogl_unet_set_compose(ogl_unet* h, int enable);
 
 /* With u8 frames and the space-to-depth schedule, downs.0.net.0 (the Cin = 1 stem) can be computed
  * inside the downs.0.net.3 kernel, so that its output never touches HBM. 0: separate stem kernel;
- * 1: in-kernel on the CUDA cores in fp32 -- same results as 0 bit for bit; 2 (default): in-kernel
- * as a GEMM on the tensor cores (u8 taps exact in bf16, weights / 255 and bias split hi + lo in
- * bf16, fp32 accumulation) -- stem outputs within ~2^-17 relative of mode 1 before their rounding
- * to bf16, logits within the bf16 noise of the path. */
+ * 1: in-kernel on the CUDA cores in fp32 -- same results as 0 bit for bit; 2: in-kernel as a GEMM
+ * on the tensor cores (u8 taps exact in bf16, weights / 255 and bias split hi + lo in bf16, fp32
+ * accumulation) -- stem outputs within ~2^-17 relative of mode 1 before their rounding to bf16,
+ * logits within the bf16 noise of the path; 3 (default): the same GEMM with 16 instead of 8 stem
+ * warps and the im2col operand in f16 (u8 taps exact there too), built by byte permutes. */
 int ogl_unet_set_fused_stem(ogl_unet* h, int enable);
 
 /* CTA pairs for the conv3x3 layers with Cout >= 64: 1 = one CTA per tile; 2 = two CTAs of a

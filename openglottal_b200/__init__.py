@@ -12,6 +12,8 @@ from .utils import (
     unet_segment_frames,
     bgr_to_gray,
     load_frames_bgr,
+    load_frames_bgr_parallel,
+    video_info,
     dice,
     iou,
     dice_iou_batch,
@@ -29,6 +31,7 @@ from .features import (
     kinematic_features_device,
     segment_clip,
     masks_for_clip,
+    decode_gray_clip,
     extract_features_unet,
     extract_features_unet_frames,
     extract_features_yolo_crop_unet,
@@ -40,6 +43,9 @@ __all__ = [
     "unet_segment_frames",
     "bgr_to_gray",
     "load_frames_bgr",
+    "load_frames_bgr_parallel",
+    "video_info",
+    "decode_gray_clip",
     "dice",
     "iou",
     "dice_iou_batch",

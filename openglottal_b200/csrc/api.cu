@@ -90,8 +90,10 @@ struct ogl_unet {
     // u8 input: compute the stem inside the downs.0.net.3 kernel (its output never touches HBM:
     // 8.4 MB per frame less traffic). Bit-identical to the stand-alone stem; as fast or slightly
     // faster under the board's power cap.
-    int fuse_stem = 2;                 // 0 separate kernel, 1 in-kernel on CUDA cores, 2 on tensor cores
+    int fuse_stem = 3;                 // 0 separate kernel, 1 in-kernel on CUDA cores, 2 on tensor cores
+                                       // (8 stem warps, bf16 im2col), 3 the same with 16 warps / f16 im2col
     uint8_t* stem_tc = nullptr;        // B operands of the tensor-core stem (device)
+    uint8_t* stem_tc3 = nullptr;       // the same in the K order of the 16-warp form
     int cta_group = 2;  // 2: conv3x3 layers with N >= 64 run on CTA pairs (tcgen05 cta_group::2)
     // fp32 validation path
     F32Conv f_down[4][2], f_bott[2], f_up[4][2];
@@ -486,6 +488,8 @@ int ogl_unet_load_state(ogl_unet* h, const ogl_unet_state* st) {
     {
         std::vector<uint8_t> blob;
         if (build_stem_tc_blob(h->stem, &blob) || dev_upload(h, blob, &h->stem_tc)) return 1;
+        const bool b16 = getenv("OGL_STEM3_BFMT") && atoi(getenv("OGL_STEM3_BFMT"));   // experiment
+        if (build_stem_tc_blob(h->stem, &blob, true, !b16) || dev_upload(h, blob, &h->stem_tc3)) return 1;
     }
     fold_conv_bn(st->bottleneck[0], 512, 256, eps, &F.bw[0], &F.bb[0]);
     if (build_f32_conv(h, F.bw[0], F.bb[0], 256, 512, &h->f_bott[0])) return 1;
@@ -626,7 +630,10 @@ int ogl_unet_forward(ogl_unet* h, const void* frames_dev, int in_dtype, int n, i
                         return s2d_tc(K.s2d_down, nullptr, nullptr, n, H, W, B(p.S[0]), P[0],
                                              nullptr, sms, stream, cg,
                                              static_cast<const uint8_t*>(frames_dev), &h->stem, rev,
-                                             h->fuse_stem == 2 ? h->stem_tc : nullptr);
+                                             h->fuse_stem == 3   ? h->stem_tc3
+                                             : h->fuse_stem == 2 ? h->stem_tc
+                                                                 : nullptr,
+                                             h->fuse_stem == 3 ? 16 : 8);
                     }))
                     return 1;
                 continue;
@@ -815,7 +822,7 @@ int ogl_unet_set_compose(ogl_unet* h, int enable) {
 
 int ogl_unet_set_fused_stem(ogl_unet* h, int enable) {
     if (!h) return fail("ogl_unet_set_fused_stem: NULL handle");
-    if (enable < 0 || enable > 2) return fail("ogl_unet_set_fused_stem: mode must be 0, 1 or 2");
+    if (enable < 0 || enable > 3) return fail("ogl_unet_set_fused_stem: mode must be 0, 1, 2 or 3");
     h->fuse_stem = enable;
     return 0;
 }

@@ -161,14 +161,19 @@ int launch_s2d_tc(const S2dLayer& L, const __nv_bfloat16* src_s2d, const __nv_bf
                   int B, int H, int W, __nv_bfloat16* out_s2d, __nv_bfloat16* out_pool,
                   const HeadParams* head, int num_sms, cudaStream_t stream, int cta_group = 1,
                   const uint8_t* stem_frames = nullptr, const StemWeights* stem = nullptr,
-                  bool reverse = false, const uint8_t* stem_tc_blob = nullptr);
+                  bool reverse = false, const uint8_t* stem_tc_blob = nullptr,
+                  int stem_tc_warps = 8);
 int launch_s2d_tc_f16(const S2dLayer& L, const __nv_bfloat16* src_s2d, const __nv_bfloat16* below,
                       int B, int H, int W, __nv_bfloat16* out_s2d, __nv_bfloat16* out_pool,
                       const HeadParams* head, int num_sms, cudaStream_t stream, int cta_group = 1,
                       const uint8_t* stem_frames = nullptr, const StemWeights* stem = nullptr,
-                      bool reverse = false, const uint8_t* stem_tc_blob = nullptr);
-// (stem_tc_blob != null, from build_stem_tc_blob: the fused stem runs on the tensor cores)
-int build_stem_tc_blob(const StemWeights& sw, std::vector<uint8_t>* out);
+                      bool reverse = false, const uint8_t* stem_tc_blob = nullptr,
+                      int stem_tc_warps = 8);
+// (stem_tc_blob != null, from build_stem_tc_blob: the fused stem runs on the tensor cores, with 8
+//  stem warps and a bf16 im2col operand, or 16 warps and an f16 operand in the K order of
+//  build_stem_tc_blob(.., true))
+int build_stem_tc_blob(const StemWeights& sw, std::vector<uint8_t>* out, bool k_order3 = false,
+                       bool f16 = false);
 // (stem_frames != null: downs.0.net.3 with the stem fused in -- the A operand is computed from
 //  the u8 frames [B][H][W] inside the kernel and src_s2d is not read)
 // cuTensorMapEncodeTiled for a bf16 tensor (conv_tc.cu owns the driver entry point)

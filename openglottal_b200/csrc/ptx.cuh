@@ -73,6 +73,22 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// Register re-allocation between the warp groups of a CTA (all four warps of a group execute it)
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+// a * b + c on packed f16 pairs (HFMA2)
+__device__ __forceinline__ uint32_t fma_f16x2(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 // this translation unit's operand type
 __device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
     return pack_relu_x2<kF16>(lo, hi);
@@ -378,9 +394,13 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 }
 // Instruction descriptor for kind::f16: D = f32, A and B of format `fmt` (0 = f16, 1 = bf16), both
 // K-major, M = 128 (256 for a CTA pair: 128 rows in each CTA), N runtime.
-__host__ __device__ __forceinline__ uint32_t make_idesc_fmt(int n, uint32_t fmt, int m = 128) {
-    return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+__host__ __device__ __forceinline__ uint32_t make_idesc_ab(int n, uint32_t a_fmt, uint32_t b_fmt,
+                                                           int m = 128) {
+    return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
            (static_cast<uint32_t>(m >> 4) << 24);
+}
+__host__ __device__ __forceinline__ uint32_t make_idesc_fmt(int n, uint32_t fmt, int m = 128) {
+    return make_idesc_ab(n, fmt, fmt, m);
 }
 // ... with this translation unit's operand type
 __host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int n) {

@@ -135,11 +135,29 @@ constexpr int kStemABytes = 2 * kStemRows * 16;          // [K half][row][8 bf16
 constexpr int kStemBBytes = 2 * 2 * 32 * 16;             // B_hi, B_lo: [K half][32][8 bf16] each
 constexpr int kStemDSlots = 4;                           // 32-column accumulators, TMEM cols 384..511
 constexpr int kStemDCol = 384;
+// STEM = 3: the same GEMM with 16 stem warps (four groups of four, one accumulator slot each) and
+// an f16 im2col operand built without a single int -> float conversion (see the kernel).
+constexpr int kStem3Threads = 512;
+constexpr int kStemItems = 2 * kHW * kHH;                // 360 build items: (y phase, halo row, halo column)
+__host__ __device__ constexpr int stem_threads(int stem) {
+    return stem == 3 ? kStem3Threads : (stem ? kStemThreads : 0);
+}
+// K order of the STEM = 3 operand: k = 0..5 taps (0,0) (0,1) (1,0) (1,1) (2,0) (2,1), 6 tap (0,2),
+// 7 one (bias hi), 8 tap (1,2), 9 one (bias lo), 10 tap (2,2), 11..15 zero
+__host__ __device__ constexpr int stem3_k_of_tap(int tap) {
+    return tap % 3 < 2 ? 2 * (tap / 3) + tap % 3 : (tap == 2 ? 6 : (tap == 5 ? 8 : 10));
+}
+// register budget per role (setmaxnreg; the launch allocates 72 x 896 = 64512 registers)
+constexpr int kRegsLaunch3 = 72, kRegsCtl3 = 56, kRegsEpi3 = 96, kRegsStem3 = 64;
+static_assert(kRegsCtl3 * 128 + kRegsEpi3 * 256 + kRegsStem3 * kStem3Threads ==
+                  kRegsLaunch3 * (384 + kStem3Threads), "register pool of the STEM = 3 kernel");
 
 struct S2dParams {
     const uint8_t* frames;   // STEM: u8 gray frames [B][2 H2][2 W2]
     StemPairs stem;          // STEM = 1: folded stem weights / 255 and bias, as channel pairs
-    const uint8_t* stem_b;   // STEM = 2: B operands of the stem GEMM (build_stem_tc_blob), device
+    const uint8_t* stem_b;   // STEM >= 2: B operands of the stem GEMM (build_stem_tc_blob), device
+    uint32_t stem_idesc;     // ... and its instruction descriptor (operand formats)
+    int stem_lo;             // second MMA per chunk with the low parts of the split weights
     const uint8_t* wblob;
     const float* btab;     // [3][3][32]: bias per (row class, column class), border pixels only
     float bias[32];        // bias of interior pixels (= btab[1][1]); constant-bank operands
@@ -200,7 +218,7 @@ __device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) { return 
 // The weights are split w/255 = hi + lo in bf16 (two MMAs per 128 rows, fp32 accumulation), the
 // bias rides on two constant-one K columns the same way: within ~2^-17 relative of the fp32 stem.
 template <int EPI, int CG, int STEM>
-__global__ void __launch_bounds__(kThreads + (STEM ? kStemThreads : 0), 1)
+__global__ void __launch_bounds__(kThreads + stem_threads(STEM), 1)
 s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmB,
               const S2dParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -230,7 +248,7 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
     const uint32_t u8_s = (sd_empty + 8u * kStemDSlots + 127u) & ~127u;
     const uint32_t sA = u8_s + kU8Slots * kU8Slot;
     const uint32_t sB = sA + 2u * kStemABytes;
-    constexpr int kBufs = STEM == 2 ? 3 : kAccBufs;   // main accumulators (128 columns each)
+    constexpr int kBufs = STEM >= 2 ? 3 : kAccBufs;   // main accumulators (128 columns each)
     uint8_t* gen = smem_raw - raw;  // generic pointer = gen + shared address
     float* btab_sp = reinterpret_cast<float*>(gen + btab_s);
     volatile uint32_t* tmem_slot_p = reinterpret_cast<volatile uint32_t*>(gen + tmem_slot);
@@ -248,8 +266,8 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
     };
 
     // ---------------------------------------------------------------- setup
-    for (int i = threadIdx.x; i < 9 * 32; i += kThreads + (STEM ? kStemThreads : 0)) btab_sp[i] = p.btab[i];
-    if (STEM == 2) {
+    for (int i = threadIdx.x; i < 9 * 32; i += kThreads + stem_threads(STEM)) btab_sp[i] = p.btab[i];
+    if (STEM >= 2) {
         if (threadIdx.x < kStemBBytes / 16)
             *reinterpret_cast<uint4*>(gen + sB + 16u * threadIdx.x) =
                 reinterpret_cast<const uint4*>(p.stem_b)[threadIdx.x];
@@ -263,11 +281,11 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
         if (STEM)
             for (int i = 0; i < kU8Slots; ++i) {
                 mbar_init(u8_full + 8u * i, 1);
-                mbar_init(u8_empty + 8u * i, kStemThreads / 32);
+                mbar_init(u8_empty + 8u * i, stem_threads(STEM) / 32);
             }
-        if (STEM == 2) {
+        if (STEM >= 2) {
             for (int i = 0; i < 2; ++i) {
-                mbar_init(sa_full + 8u * i, kStemThreads / 32);
+                mbar_init(sa_full + 8u * i, stem_threads(STEM) / 32);
                 mbar_init(sa_empty + 8u * i, 1);
             }
             for (int i = 0; i < kStemDSlots; ++i) {
@@ -276,7 +294,8 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
             }
         }
         for (int i = 0; i < p.nslots; ++i) {
-            mbar_init(a_full + 8u * i, STEM ? kStemThreads / 32 : 1);   // one arrival per stem warp
+            // STEM 1, 2: one arrival per stem warp; STEM 3: one per (chunk, warp of its group)
+            mbar_init(a_full + 8u * i, STEM == 3 ? 4 * kStemChunks : (STEM ? kStemThreads / 32 : 1));
             mbar_init(a_empty + 8u * i, 1);
         }
         for (int i = 0; i < kBufs; ++i) {
@@ -294,409 +313,544 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
     if (CG == 2) cluster_sync_all();  // the peer's barriers exist before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_p;
-
-    if (STEM == 2 && warp >= kThreads / 32) {
-        // ============================ stem on the tensor cores: im2col in, A stages out
-        const int st = threadIdx.x - kThreads;
-        const int sw = st >> 5;            // stem warp 0..7; TMEM lane quarter = sw & 3 (= warp & 3)
-        const int grp = sw >> 2;           // drains the chunks j with (j & 1) == grp
-        const uint32_t lane_sel = static_cast<uint32_t>((sw & 3) * 32) << 16;
-        const int W = 2 * p.W2, H = 2 * p.H2;
-        // The rows a thread builds (st, st + 256, st + 512) are the same in every tile: their
-        // position inside the u8 region and the stage is computed once. Rows past the end (the
-        // third row of threads >= 208) read row 719 and store nothing.
-        constexpr int kRowsPerThread = (kStemRows + kStemThreads - 1) / kStemThreads;   // 3
-        int row_src[kRowsPerThread], row_ly[kRowsPerThread], row_lx[kRowsPerThread];
+    // STEM = 3: 896 threads leave 72 registers each; the control warps and the stem warps hand
+    // theirs to the two epilogue groups, whose 4 x 32 accumulator values per thread need 96. Each
+    // warp group re-allocates at the top of its own branch (setmaxnreg is per warp group, and
+    // ptxas budgets the code below each one accordingly).
+    if (warp >= kThreads / 32) {
+        if (STEM == 3) setmaxnreg_dec<kRegsStem3>();
+        if (STEM == 3) {
+            // ============== stem on the tensor cores, 16 warps: f16 im2col in, A stages out
+            // Build: one item = the two x phases of one (y phase, halo row, halo column): the 3 x 4
+            // bytes around it are read as aligned words (2 LDS.32 + 1 PRMT per window row, the
+            // selector fixed per thread), and every K pair of the operand is ONE byte permute that
+            // puts each u8 under the f16 exponent of 1024 (0x64 b = 1024 + b exactly) followed by ONE
+            // HFMA2, (1024 + b) * keep - 1024 * keep: no I2F, no F2FP, no separate masking (keep = 0
+            // outside the image, where the stem's OUTPUT is zero: conv2's padding). The constant-one K
+            // columns that carry the bias come out of the same permutes. 12 ALU instructions per
+            // operand row instead of 9 LDS.U8 + 9 I2F + 5 F2FP + 5 LOP3.
+            // Drain: group g = warps 4g..4g+3 owns accumulator slot g and every chunk c with
+            // c % 4 == g (6 chunks per tile), so per tile a warp builds one item and drains 1.5 chunks.
+            const int st = threadIdx.x - kThreads;
+            const int sw = st >> 5;
+            const uint32_t grp = static_cast<uint32_t>(sw >> 2);
+            const uint32_t lane_sel = static_cast<uint32_t>((sw & 3) * 32) << 16;
+            const int W = 2 * p.W2, H = 2 * p.H2;
+            const bool has_item = st < kStemItems;
+            const int item = has_item ? st : kStemItems - 1;
+            const int ipy = item / (kHW * kHH), irem = item - ipy * (kHW * kHH);
+            const int ihy = irem / kHW, ihx = irem - ihy * kHW;
+            const int ily = 2 * ihy + ipy, ilx = 2 * ihx;          // region pixel of (x phase 0, tap (0, 0))
+            const int boff = ily * kU8Row + kU8Off + ilx;           // its byte in the u8 box: odd
+            const int woff = boff & ~3;
+            const uint32_t wsel = (boff & 3) == 1 ? 0x4321u : 0x6543u;
+            const int row0 = 2 * ipy * (kHW * kHH) + irem;          // operand row of x phase 0 (+180: phase 1)
+            auto build = [&](uint32_t iu, int unit) {
+                const Tile t = decode_tile(p, tile_of(unit));
+                const int gy = 2 * t.y0 - 2 + ily, gx = 2 * t.x0 - 2 + ilx;
+                const uint32_t us = iu % kU8Slots;
+                const uint8_t* u8p = gen + u8_s + us * kU8Slot;
+                uint8_t* abuf = gen + sA + (iu & 1u) * kStemABytes;
+                mbar_wait_relaxed(u8_full + 8u * us, (iu / kU8Slots) & 1u);
+                mbar_wait_relaxed(sa_empty + 8u * (iu & 1u), ((iu >> 1) & 1u) ^ 1u);
+                if (has_item) {
+                    uint32_t lo[3], hi[3], wd[3];
 #pragma unroll
-        for (int rr = 0; rr < kRowsPerThread; ++rr) {
-            const int r = min(st + rr * kStemThreads, kStemRows - 1);
-            const int ph = r / (kHW * kHH), pos = r - ph * (kHW * kHH);
-            const int hy = pos / kHW, hx = pos - hy * kHW;
-            row_ly[rr] = 2 * hy + (ph >> 1);
-            row_lx[rr] = 2 * hx + (ph & 1);
-            row_src[rr] = row_ly[rr] * kU8Row + kU8Off + row_lx[rr];
-        }
-        // im2col of tile number iu of this CTA into buffer iu & 1
-        auto build = [&](uint32_t iu, int unit) {
-            const Tile t = decode_tile(p, tile_of(unit));
-            const int gy0 = 2 * t.y0 - 2, gx0 = 2 * t.x0 - 2;   // frame coordinates of stage pixel (0, 0)
-            const uint32_t us = iu % kU8Slots;
-            const uint8_t* u8p = gen + u8_s + us * kU8Slot;      // rows of kU8Row bytes (TMA box)
-            uint8_t* abuf = gen + sA + (iu & 1u) * kStemABytes;
-            mbar_wait_relaxed(u8_full + 8u * us, (iu / kU8Slots) & 1u);
-            mbar_wait_relaxed(sa_empty + 8u * (iu & 1u), ((iu >> 1) & 1u) ^ 1u);
-            // all 27 byte loads first, then the conversions, then the stores: three independent
-            // latency chains per thread instead of one after the other
-            uint32_t b[kRowsPerThread][9];
+                    for (int d = 0; d < 3; ++d) {
+                        lo[d] = *reinterpret_cast<const uint32_t*>(u8p + woff + d * kU8Row);
+                        hi[d] = *reinterpret_cast<const uint32_t*>(u8p + woff + d * kU8Row + 4);
+                    }
 #pragma unroll
-            for (int rr = 0; rr < kRowsPerThread; ++rr)
+                    for (int d = 0; d < 3; ++d) wd[d] = __byte_perm(lo[d], hi[d], wsel);
+                    const bool iny = gy >= 0 && gy < H && !(p.dbg & 64);
 #pragma unroll
-                for (int k = 0; k < 9; ++k) b[rr][k] = u8p[row_src[rr] + (k / 3) * kU8Row + (k % 3)];
+                    for (int px = 0; px < 2; ++px) {
+                        const bool in = iny && gx + px >= 0 && gx + px < W;
+                        const uint32_t keep = in ? 0x3c003c00u : 0u;        // (1, 1)
+                        const uint32_t off2 = in ? 0xe400e400u : 0u;        // (-1024, -1024)
+                        const uint32_t off1 = in ? 0x0000e400u : 0u;        // (-1024, 0)
+                        // bytes 4..7 of the permutes: 0x64 (f16 exponent of 1024), 0x00, 0x00, 0x3c
+                        const uint32_t pair_sel = px ? 0x4241u : 0x4140u;   // (b[px], b[px + 1])
+                        const uint32_t one_sel = px ? 0x7543u : 0x7542u;    // (b[px + 2], 1.0)
+                        const uint32_t zero_sel = px ? 0x5543u : 0x5542u;   // (b[px + 2], 0.0)
+                        uint4 k0, k1;
+                        k0.x = fma_f16x2(__byte_perm(wd[0], 0x64646464u, pair_sel), keep, off2);
+                        k0.y = fma_f16x2(__byte_perm(wd[1], 0x64646464u, pair_sel), keep, off2);
+                        k0.z = fma_f16x2(__byte_perm(wd[2], 0x64646464u, pair_sel), keep, off2);
+                        k0.w = fma_f16x2(__byte_perm(wd[0], 0x3c000064u, one_sel), keep, off1);
+                        k1.x = fma_f16x2(__byte_perm(wd[1], 0x3c000064u, one_sel), keep, off1);
+                        k1.y = fma_f16x2(__byte_perm(wd[2], 0x3c000064u, zero_sel), keep, off1);
+                        k1.z = 0u;
+                        k1.w = 0u;
+                        const int r = row0 + px * (kHW * kHH);
+                        if (p.dbg & 512) continue;
+                        *reinterpret_cast<uint4*>(abuf + r * 16) = k0;
+                        *reinterpret_cast<uint4*>(abuf + kStemRows * 16 + r * 16) = k1;
+                    }
+                }
+                fence_proxy_async();   // visible to the tensor core's reads
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(sa_full + 8u * (iu & 1u));
+                    mbar_arrive(u8_empty + 8u * us);
+                }
+            };
+            uint32_t c = grp, iu = 0;
+            int unit = unit0;
+            if (unit < num_units) build(0, unit);
+            for (; unit < num_units; unit += unit_step, ++iu) {
+                if (unit + unit_step < num_units) build(iu + 1, unit + unit_step);
+                const uint32_t it0 = 2u * iu, it1 = 2u * iu + 1u;
+                const uint32_t s0 = it0 % p.nslots, s1 = it1 % p.nslots;
+                mbar_wait_relaxed(a_empty + 8u * s0, ((it0 / p.nslots) & 1u) ^ 1u);
+                mbar_wait_relaxed(a_empty + 8u * s1, ((it1 / p.nslots) & 1u) ^ 1u);
+                uint8_t* stage0 = gen + a_ring + s0 * kSlot;
+                uint8_t* stage1 = gen + a_ring + s1 * kSlot;
+                for (; c < static_cast<uint32_t>(kStemChunks) * (iu + 1u); c += kStemDSlots) {
+                    const int j = static_cast<int>(c - static_cast<uint32_t>(kStemChunks) * iu);
+                    mbar_wait_relaxed(sd_full + 8u * grp, (c / kStemDSlots) & 1u);
+                    tc_fence_after();
+                    uint32_t v[32];
+                    if (p.dbg & 1024) {   // experiment: no TMEM read
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = 0u;
+                    } else {
+                        tmem_ld32(tmem_base + lane_sel + kStemDCol + grp * 32u, v);
+                        tmem_ld_wait();
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(sd_empty + 8u * grp);   // the values are in registers
+                    const int r = j * 128 + (sw & 3) * 32 + lane;
+                    if (r < kStemRows && !(p.dbg & 256)) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {   // 8-channel groups: (stage, plane group)
+                            const uint4 q = make_uint4(
+                                pack_relu_bf16x2(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1])),
+                                pack_relu_bf16x2(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])),
+                                pack_relu_bf16x2(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])),
+                                pack_relu_bf16x2(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
+                            uint8_t* dst = ((g >> 1) ? stage1 : stage0) + (g & 1) * 4 * kPlane + r * 16;
+                            *reinterpret_cast<uint4*>(dst) = q;
+                        }
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(a_full + 8u * s0);
+                        mbar_arrive(a_full + 8u * s1);
+                    }
+                }
+            }
+        } else if (STEM == 2) {
+            // ============================ stem on the tensor cores: im2col in, A stages out
+            const int st = threadIdx.x - kThreads;
+            const int sw = st >> 5;            // stem warp 0..7; TMEM lane quarter = sw & 3 (= warp & 3)
+            const int grp = sw >> 2;           // drains the chunks j with (j & 1) == grp
+            const uint32_t lane_sel = static_cast<uint32_t>((sw & 3) * 32) << 16;
+            const int W = 2 * p.W2, H = 2 * p.H2;
+            // The rows a thread builds (st, st + 256, st + 512) are the same in every tile: their
+            // position inside the u8 region and the stage is computed once. Rows past the end (the
+            // third row of threads >= 208) read row 719 and store nothing.
+            constexpr int kRowsPerThread = (kStemRows + kStemThreads - 1) / kStemThreads;   // 3
+            int row_src[kRowsPerThread], row_ly[kRowsPerThread], row_lx[kRowsPerThread];
 #pragma unroll
             for (int rr = 0; rr < kRowsPerThread; ++rr) {
-                const int r = st + rr * kStemThreads;
-                const int gy = gy0 + row_ly[rr], gx = gx0 + row_lx[rr];
-                // outside the image the stem's OUTPUT is zero (conv2's padding): a zero row,
-                // bias columns included
-                const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W && !(p.dbg & 64);
-                float v[9];
-#pragma unroll
-                for (int k = 0; k < 9; ++k) v[k] = static_cast<float>(b[rr][k]);
-                const uint32_t keep = in ? 0xffffffffu : 0u;
-                const uint4 k0 = make_uint4(pack_bf16x2(v[0], v[1]) & keep, pack_bf16x2(v[2], v[3]) & keep,
-                                            pack_bf16x2(v[4], v[5]) & keep, pack_bf16x2(v[6], v[7]) & keep);
-                const uint4 k1 = make_uint4(pack_bf16x2(v[8], 1.f) & keep, pack_bf16x2(1.f, 0.f) & keep, 0u, 0u);
-                if (r < kStemRows) {
-                    *reinterpret_cast<uint4*>(abuf + r * 16) = k0;
-                    *reinterpret_cast<uint4*>(abuf + kStemRows * 16 + r * 16) = k1;
-                }
+                const int r = min(st + rr * kStemThreads, kStemRows - 1);
+                const int ph = r / (kHW * kHH), pos = r - ph * (kHW * kHH);
+                const int hy = pos / kHW, hx = pos - hy * kHW;
+                row_ly[rr] = 2 * hy + (ph >> 1);
+                row_lx[rr] = 2 * hx + (ph & 1);
+                row_src[rr] = row_ly[rr] * kU8Row + kU8Off + row_lx[rr];
             }
-            fence_proxy_async();   // visible to the tensor core's reads
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(sa_full + 8u * (iu & 1u));
-                mbar_arrive(u8_empty + 8u * us);
-            }
-        };
-        // result of the stem GEMM: TMEM -> ReLU -> bf16 -> the tile's two A stages (row r of the
-        // GEMM is the 16-byte cell r of each 8-channel group of a stage). One chunk = 128 rows.
-        auto drain_chunk = [&](uint32_t iu, int j, uint8_t* stage0, uint8_t* stage1) {
-            const uint32_t c = static_cast<uint32_t>(kStemChunks) * iu + j;
-            const uint32_t slot = c % kStemDSlots;
-            mbar_wait_relaxed(sd_full + 8u * slot, (c / kStemDSlots) & 1u);
-            tc_fence_after();
-            uint32_t v[32];
-            tmem_ld32(tmem_base + lane_sel + kStemDCol + slot * 32u, v);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(sd_empty + 8u * slot);   // the values are in registers
-            const int r = j * 128 + (sw & 3) * 32 + lane;
-            if (r < kStemRows) {
+            // im2col of tile number iu of this CTA into buffer iu & 1
+            auto build = [&](uint32_t iu, int unit) {
+                const Tile t = decode_tile(p, tile_of(unit));
+                const int gy0 = 2 * t.y0 - 2, gx0 = 2 * t.x0 - 2;   // frame coordinates of stage pixel (0, 0)
+                const uint32_t us = iu % kU8Slots;
+                const uint8_t* u8p = gen + u8_s + us * kU8Slot;      // rows of kU8Row bytes (TMA box)
+                uint8_t* abuf = gen + sA + (iu & 1u) * kStemABytes;
+                mbar_wait_relaxed(u8_full + 8u * us, (iu / kU8Slots) & 1u);
+                mbar_wait_relaxed(sa_empty + 8u * (iu & 1u), ((iu >> 1) & 1u) ^ 1u);
+                // all 27 byte loads first, then the conversions, then the stores: three independent
+                // latency chains per thread instead of one after the other
+                uint32_t b[kRowsPerThread][9];
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {   // 8-channel groups: (stage, plane group)
-                    const uint4 q = make_uint4(
-                        pack_relu_bf16x2(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1])),
-                        pack_relu_bf16x2(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])),
-                        pack_relu_bf16x2(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])),
-                        pack_relu_bf16x2(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
-                    uint8_t* dst = ((g >> 1) ? stage1 : stage0) + (g & 1) * 4 * kPlane + r * 16;
-                    *reinterpret_cast<uint4*>(dst) = q;
-                }
-            }
-        };
-        // Per tile: first chunk, then the im2col of the NEXT tile, then the other two chunks. The
-        // accumulator ring has 4 slots for 6 chunks, so chunks 2..5 of a tile are issued only when
-        // earlier chunks have been drained: with this order their MMAs run while this warp builds.
-        uint32_t iu = 0;
-        int unit = unit0;
-        if (unit < num_units) build(0, unit);
-        for (; unit < num_units; unit += unit_step, ++iu) {
-            const uint32_t it0 = 2u * iu, it1 = 2u * iu + 1u;
-            const uint32_t s0 = it0 % p.nslots, s1 = it1 % p.nslots;
-            mbar_wait_relaxed(a_empty + 8u * s0, ((it0 / p.nslots) & 1u) ^ 1u);
-            mbar_wait_relaxed(a_empty + 8u * s1, ((it1 / p.nslots) & 1u) ^ 1u);
-            uint8_t* stage0 = gen + a_ring + s0 * kSlot;
-            uint8_t* stage1 = gen + a_ring + s1 * kSlot;
-            drain_chunk(iu, grp, stage0, stage1);
-            if (unit + unit_step < num_units) build(iu + 1, unit + unit_step);
-            drain_chunk(iu, grp + 2, stage0, stage1);
-            drain_chunk(iu, grp + 4, stage0, stage1);
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(a_full + 8u * s0);
-                mbar_arrive(a_full + 8u * s1);
-            }
-        }
-    } else if (STEM == 1 && warp >= kThreads / 32) {
-        // ====================================== stem: compute the A stages from the u8 frame
-        // A tile needs the stem output on 10 x 18 half-resolution positions x 4 phases, of which
-        // the outermost ring is read through one phase only: 34 x 18 full-resolution pixels.
-        // Per pixel and stage 16 channels = 144 FFMAs with constant-bank weights, bias, ReLU,
-        // bf16, two 16-byte stores into the operand layout.
-        const int st = threadIdx.x - kThreads;
-        const int W = 2 * p.W2, H = 2 * p.H2;
-        constexpr int kNeedH = 2 * kHH - 2, kNeedW = 2 * kHW - 2;   // 34 x 18
-        uint32_t it = 0, iu = 0;
-        for (int unit = unit0; unit < num_units; unit += unit_step, ++iu) {
-            const Tile t = decode_tile(p, tile_of(unit));
-            const int gy0 = 2 * t.y0 - 3, gx0 = 2 * t.x0 - 3;   // frame coordinates of u8p[0][0]
-            const uint32_t us = iu % kU8Slots;
-            const uint8_t* u8p = gen + u8_s + us * kU8Slot;      // rows of kU8Row bytes (TMA box)
-            mbar_wait_relaxed(u8_full + 8u * us, (iu / kU8Slots) & 1u);
-            // One work item = 3 horizontally adjacent pixels of one row (34 rows x 6 triples = 204
-            // items per tile, thread st takes item st): every weight fetched from the constant
-            // bank feeds 3 FFMAs, the 3x5 input window is read once.
-            constexpr int kItems = kNeedH * (kNeedW / 3);
-            static_assert(kNeedW % 3 == 0 && kItems <= kStemThreads, "stem work split");
-            const bool active = st < kItems;
-            const int ly = 1 + st / (kNeedW / 3), lx0 = 1 + 3 * (st % (kNeedW / 3));
-            const int gy = gy0 + 1 + ly;
-            unsigned long long in[3][5];   // each input value in both halves of a register pair
-            uint32_t inside[3];   // all-ones inside the image, 0 outside (a mask, not a branch:
-                                  // the six accumulator chains of an item stay interleaved)
-            if (active) {
+                for (int rr = 0; rr < kRowsPerThread; ++rr)
 #pragma unroll
-                for (int dy = 0; dy < 3; ++dy)
+                    for (int k = 0; k < 9; ++k) b[rr][k] = u8p[row_src[rr] + (k / 3) * kU8Row + (k % 3)];
 #pragma unroll
-                    for (int dx = 0; dx < 5; ++dx)
-                        in[dy][dx] =
-                            dup2(static_cast<float>(u8p[(ly + dy) * kU8Row + kU8Off + lx0 + dx]));
+                for (int rr = 0; rr < kRowsPerThread; ++rr) {
+                    const int r = st + rr * kStemThreads;
+                    const int gy = gy0 + row_ly[rr], gx = gx0 + row_lx[rr];
+                    // outside the image the stem's OUTPUT is zero (conv2's padding): a zero row,
+                    // bias columns included
+                    const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W && !(p.dbg & 64);
+                    float v[9];
 #pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    const int gx = gx0 + 1 + lx0 + q;
-                    inside[q] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? 0xffffffffu : 0u;
-                }
-            }
-#pragma unroll   // `half` must be a compile-time constant: weights are constant-bank operands
-            for (int half = 0; half < 2; ++half, ++it) {
-                const uint32_t slot = it % p.nslots;
-                mbar_wait_relaxed(a_empty + 8u * slot, ((it / p.nslots) & 1u) ^ 1u);
-                uint8_t* stage = gen + a_ring + slot * kSlot;
-                if (active && !(p.dbg & 64)) {
-#pragma unroll
-                    for (int g = 0; g < 2; ++g) {
-                        uint32_t pk[3][4];
-#pragma unroll
-                        for (int c2 = 0; c2 < 4; ++c2) {
-                            // channel pair (2 cp, 2 cp + 1) of the 3 pixels: packed FFMA2s
-                            const int cp = half * 8 + g * 4 + c2;
-                            unsigned long long a[3];
-#pragma unroll
-                            for (int q = 0; q < 3; ++q) a[q] = as_u64(p.stem.bp[cp]);
-#pragma unroll
-                            for (int k = 0; k < 9; ++k) {
-                                const unsigned long long w = as_u64(p.stem.wp[cp * 9 + k]);
-#pragma unroll
-                                for (int q = 0; q < 3; ++q) a[q] = fma2(in[k / 3][k % 3 + q], w, a[q]);
-                            }
-#pragma unroll
-                            for (int q = 0; q < 3; ++q) {   // zero outside the image: conv2's padding
-                                const float lo = __uint_as_float(static_cast<uint32_t>(a[q]));
-                                const float hi = __uint_as_float(static_cast<uint32_t>(a[q] >> 32));
-                                pk[q][c2] = pack_relu_bf16x2(lo, hi) & inside[q];
-                            }
-                        }
-#pragma unroll
-                        for (int q = 0; q < 3; ++q) {
-                            const int lx = lx0 + q;
-                            uint8_t* dst = stage + ((ly & 1) * 2 + (lx & 1)) * kPlane +
-                                           ((ly >> 1) * kHW + (lx >> 1)) * 16 + g * 4 * kPlane;
-                            *reinterpret_cast<uint4*>(dst) =
-                                make_uint4(pk[q][0], pk[q][1], pk[q][2], pk[q][3]);
-                        }
+                    for (int k = 0; k < 9; ++k) v[k] = static_cast<float>(b[rr][k]);
+                    const uint32_t keep = in ? 0xffffffffu : 0u;
+                    const uint4 k0 = make_uint4(pack_bf16x2(v[0], v[1]) & keep, pack_bf16x2(v[2], v[3]) & keep,
+                                                pack_bf16x2(v[4], v[5]) & keep, pack_bf16x2(v[6], v[7]) & keep);
+                    const uint4 k1 = make_uint4(pack_bf16x2(v[8], 1.f) & keep, pack_bf16x2(1.f, 0.f) & keep, 0u, 0u);
+                    if (r < kStemRows) {
+                        *reinterpret_cast<uint4*>(abuf + r * 16) = k0;
+                        *reinterpret_cast<uint4*>(abuf + kStemRows * 16 + r * 16) = k1;
                     }
                 }
-                fence_proxy_async();   // this thread's stores visible to the tensor core's reads
+                fence_proxy_async();   // visible to the tensor core's reads
                 __syncwarp();
-                if (lane == 0) mbar_arrive(a_full + 8u * slot);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(u8_empty + 8u * us);
-        }
-    } else if (warp == 0 && STEM) {
-        // ================================ u8 regions of the tiles, by TMA, ahead of the stem warps
-        // box = 48 x 38 bytes at (2 X0 - 16, 2 Y0 - 3): conv1's zero padding is the OOB fill
-        if (lane == 0) {
+                if (lane == 0) {
+                    mbar_arrive(sa_full + 8u * (iu & 1u));
+                    mbar_arrive(u8_empty + 8u * us);
+                }
+            };
+            // result of the stem GEMM: TMEM -> ReLU -> bf16 -> the tile's two A stages (row r of the
+            // GEMM is the 16-byte cell r of each 8-channel group of a stage). One chunk = 128 rows.
+            auto drain_chunk = [&](uint32_t iu, int j, uint8_t* stage0, uint8_t* stage1) {
+                const uint32_t c = static_cast<uint32_t>(kStemChunks) * iu + j;
+                const uint32_t slot = c % kStemDSlots;
+                mbar_wait_relaxed(sd_full + 8u * slot, (c / kStemDSlots) & 1u);
+                tc_fence_after();
+                uint32_t v[32];
+                tmem_ld32(tmem_base + lane_sel + kStemDCol + slot * 32u, v);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(sd_empty + 8u * slot);   // the values are in registers
+                const int r = j * 128 + (sw & 3) * 32 + lane;
+                if (r < kStemRows) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {   // 8-channel groups: (stage, plane group)
+                        const uint4 q = make_uint4(
+                            pack_relu_bf16x2(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1])),
+                            pack_relu_bf16x2(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])),
+                            pack_relu_bf16x2(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])),
+                            pack_relu_bf16x2(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
+                        uint8_t* dst = ((g >> 1) ? stage1 : stage0) + (g & 1) * 4 * kPlane + r * 16;
+                        *reinterpret_cast<uint4*>(dst) = q;
+                    }
+                }
+            };
+            // Per tile: first chunk, then the im2col of the NEXT tile, then the other two chunks. The
+            // accumulator ring has 4 slots for 6 chunks, so chunks 2..5 of a tile are issued only when
+            // earlier chunks have been drained: with this order their MMAs run while this warp builds.
             uint32_t iu = 0;
+            int unit = unit0;
+            if (unit < num_units) build(0, unit);
+            for (; unit < num_units; unit += unit_step, ++iu) {
+                const uint32_t it0 = 2u * iu, it1 = 2u * iu + 1u;
+                const uint32_t s0 = it0 % p.nslots, s1 = it1 % p.nslots;
+                mbar_wait_relaxed(a_empty + 8u * s0, ((it0 / p.nslots) & 1u) ^ 1u);
+                mbar_wait_relaxed(a_empty + 8u * s1, ((it1 / p.nslots) & 1u) ^ 1u);
+                uint8_t* stage0 = gen + a_ring + s0 * kSlot;
+                uint8_t* stage1 = gen + a_ring + s1 * kSlot;
+                drain_chunk(iu, grp, stage0, stage1);
+                if (unit + unit_step < num_units) build(iu + 1, unit + unit_step);
+                drain_chunk(iu, grp + 2, stage0, stage1);
+                drain_chunk(iu, grp + 4, stage0, stage1);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(a_full + 8u * s0);
+                    mbar_arrive(a_full + 8u * s1);
+                }
+            }
+        } else if (STEM == 1) {
+            // ====================================== stem: compute the A stages from the u8 frame
+            // A tile needs the stem output on 10 x 18 half-resolution positions x 4 phases, of which
+            // the outermost ring is read through one phase only: 34 x 18 full-resolution pixels.
+            // Per pixel and stage 16 channels = 144 FFMAs with constant-bank weights, bias, ReLU,
+            // bf16, two 16-byte stores into the operand layout.
+            const int st = threadIdx.x - kThreads;
+            const int W = 2 * p.W2, H = 2 * p.H2;
+            constexpr int kNeedH = 2 * kHH - 2, kNeedW = 2 * kHW - 2;   // 34 x 18
+            uint32_t it = 0, iu = 0;
             for (int unit = unit0; unit < num_units; unit += unit_step, ++iu) {
                 const Tile t = decode_tile(p, tile_of(unit));
+                const int gy0 = 2 * t.y0 - 3, gx0 = 2 * t.x0 - 3;   // frame coordinates of u8p[0][0]
                 const uint32_t us = iu % kU8Slots;
-                mbar_wait_relaxed(u8_empty + 8u * us, ((iu / kU8Slots) & 1u) ^ 1u);
-                mbar_arrive_expect_tx(u8_full + 8u * us, kU8Bytes);
-                tma_load_3d(u8_s + us * kU8Slot, &tmS, u8_full + 8u * us, 2 * t.x0 - 16, 2 * t.y0 - 3,
-                            t.n);
+                const uint8_t* u8p = gen + u8_s + us * kU8Slot;      // rows of kU8Row bytes (TMA box)
+                mbar_wait_relaxed(u8_full + 8u * us, (iu / kU8Slots) & 1u);
+                // One work item = 3 horizontally adjacent pixels of one row (34 rows x 6 triples = 204
+                // items per tile, thread st takes item st): every weight fetched from the constant
+                // bank feeds 3 FFMAs, the 3x5 input window is read once.
+                constexpr int kItems = kNeedH * (kNeedW / 3);
+                static_assert(kNeedW % 3 == 0 && kItems <= kStemThreads, "stem work split");
+                const bool active = st < kItems;
+                const int ly = 1 + st / (kNeedW / 3), lx0 = 1 + 3 * (st % (kNeedW / 3));
+                const int gy = gy0 + 1 + ly;
+                unsigned long long in[3][5];   // each input value in both halves of a register pair
+                uint32_t inside[3];   // all-ones inside the image, 0 outside (a mask, not a branch:
+                                      // the six accumulator chains of an item stay interleaved)
+                if (active) {
+#pragma unroll
+                    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                        for (int dx = 0; dx < 5; ++dx)
+                            in[dy][dx] =
+                                dup2(static_cast<float>(u8p[(ly + dy) * kU8Row + kU8Off + lx0 + dx]));
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        const int gx = gx0 + 1 + lx0 + q;
+                        inside[q] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? 0xffffffffu : 0u;
+                    }
+                }
+#pragma unroll   // `half` must be a compile-time constant: weights are constant-bank operands
+                for (int half = 0; half < 2; ++half, ++it) {
+                    const uint32_t slot = it % p.nslots;
+                    mbar_wait_relaxed(a_empty + 8u * slot, ((it / p.nslots) & 1u) ^ 1u);
+                    uint8_t* stage = gen + a_ring + slot * kSlot;
+                    if (active && !(p.dbg & 64)) {
+#pragma unroll
+                        for (int g = 0; g < 2; ++g) {
+                            uint32_t pk[3][4];
+#pragma unroll
+                            for (int c2 = 0; c2 < 4; ++c2) {
+                                // channel pair (2 cp, 2 cp + 1) of the 3 pixels: packed FFMA2s
+                                const int cp = half * 8 + g * 4 + c2;
+                                unsigned long long a[3];
+#pragma unroll
+                                for (int q = 0; q < 3; ++q) a[q] = as_u64(p.stem.bp[cp]);
+#pragma unroll
+                                for (int k = 0; k < 9; ++k) {
+                                    const unsigned long long w = as_u64(p.stem.wp[cp * 9 + k]);
+#pragma unroll
+                                    for (int q = 0; q < 3; ++q) a[q] = fma2(in[k / 3][k % 3 + q], w, a[q]);
+                                }
+#pragma unroll
+                                for (int q = 0; q < 3; ++q) {   // zero outside the image: conv2's padding
+                                    const float lo = __uint_as_float(static_cast<uint32_t>(a[q]));
+                                    const float hi = __uint_as_float(static_cast<uint32_t>(a[q] >> 32));
+                                    pk[q][c2] = pack_relu_bf16x2(lo, hi) & inside[q];
+                                }
+                            }
+#pragma unroll
+                            for (int q = 0; q < 3; ++q) {
+                                const int lx = lx0 + q;
+                                uint8_t* dst = stage + ((ly & 1) * 2 + (lx & 1)) * kPlane +
+                                               ((ly >> 1) * kHW + (lx >> 1)) * 16 + g * 4 * kPlane;
+                                *reinterpret_cast<uint4*>(dst) =
+                                    make_uint4(pk[q][0], pk[q][1], pk[q][2], pk[q][3]);
+                            }
+                        }
+                    }
+                    fence_proxy_async();   // this thread's stores visible to the tensor core's reads
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(a_full + 8u * slot);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(u8_empty + 8u * us);
             }
         }
-    } else if (warp == 0 && !STEM) {
-        // ================================================ activation producer
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int unit = unit0; unit < num_units; unit += unit_step) {
-                int tile = tile_of(unit);
-                if (tile >= p.num_tiles) tile = p.num_tiles - 1;   // tail of the last pair: a duplicate
-                const Tile t = decode_tile(p, tile);
-                for (int s = 0; s < p.n_stages; ++s, ++it) {
-                    const uint32_t slot = it % p.nslots;
-                    const uint32_t ph = (it / p.nslots) & 1u;
-                    mbar_wait_relaxed(a_empty + 8u * slot, ph ^ 1u);
-                    const uint32_t dst = a_ring + slot * kSlot;
-                    if (CG == 1 && (p.dbg & 8)) {   // experiment: no activation loads
-                        mbar_arrive(a_full + 8u * slot);
-                        continue;
-                    }
-                    if (CG == 1) {
-                        const uint32_t full = a_full + 8u * slot;
-                        mbar_arrive_expect_tx(full, kSlot);
-                        if (p.stage_src[s] == 0)
-                            tma_load_5d(dst, &tmS, full, (t.x0 - 1) * 8, t.y0 - 1, 0,
-                                        p.stage_plane0[s], t.n);
-                        else
-                            tma_load_4d(dst, &tmB, full, (t.x0 - 1) * 8, t.y0 - 1,
-                                        p.stage_plane0[s], t.n);
-                    } else {
-                        // the leader's barrier counts the bytes of both CTAs
-                        if (rank == 0) mbar_arrive_expect_tx(a_full + 8u * slot, 2u * kSlot);
-                        const uint32_t full = map_to_cta(a_full + 8u * slot, 0);
-                        if (p.stage_src[s] == 0)
-                            tma_load_5d_pair(dst, &tmS, full, (t.x0 - 1) * 8, t.y0 - 1, 0,
-                                             p.stage_plane0[s], t.n);
-                        else
-                            tma_load_4d_pair(dst, &tmB, full, (t.x0 - 1) * 8, t.y0 - 1,
-                                             p.stage_plane0[s], t.n);
+    } else if (warp < 4) {
+        if (STEM == 3) setmaxnreg_dec<kRegsCtl3>();
+        if (warp == 0 && STEM) {
+            // ================================ u8 regions of the tiles, by TMA, ahead of the stem warps
+            // box = 48 x 38 bytes at (2 X0 - 16, 2 Y0 - 3): conv1's zero padding is the OOB fill
+            if (lane == 0) {
+                uint32_t iu = 0;
+                for (int unit = unit0; unit < num_units; unit += unit_step, ++iu) {
+                    const Tile t = decode_tile(p, tile_of(unit));
+                    const uint32_t us = iu % kU8Slots;
+                    mbar_wait_relaxed(u8_empty + 8u * us, ((iu / kU8Slots) & 1u) ^ 1u);
+                    mbar_arrive_expect_tx(u8_full + 8u * us, kU8Bytes);
+                    tma_load_3d(u8_s + us * kU8Slot, &tmS, u8_full + 8u * us, 2 * t.x0 - 16, 2 * t.y0 - 3,
+                                t.n);
+                }
+            }
+        } else if (warp == 0 && !STEM) {
+            // ================================================ activation producer
+            if (lane == 0) {
+                uint32_t it = 0;
+                for (int unit = unit0; unit < num_units; unit += unit_step) {
+                    int tile = tile_of(unit);
+                    if (tile >= p.num_tiles) tile = p.num_tiles - 1;   // tail of the last pair: a duplicate
+                    const Tile t = decode_tile(p, tile);
+                    for (int s = 0; s < p.n_stages; ++s, ++it) {
+                        const uint32_t slot = it % p.nslots;
+                        const uint32_t ph = (it / p.nslots) & 1u;
+                        mbar_wait_relaxed(a_empty + 8u * slot, ph ^ 1u);
+                        const uint32_t dst = a_ring + slot * kSlot;
+                        if (CG == 1 && (p.dbg & 8)) {   // experiment: no activation loads
+                            mbar_arrive(a_full + 8u * slot);
+                            continue;
+                        }
+                        if (CG == 1) {
+                            const uint32_t full = a_full + 8u * slot;
+                            mbar_arrive_expect_tx(full, kSlot);
+                            if (p.stage_src[s] == 0)
+                                tma_load_5d(dst, &tmS, full, (t.x0 - 1) * 8, t.y0 - 1, 0,
+                                            p.stage_plane0[s], t.n);
+                            else
+                                tma_load_4d(dst, &tmB, full, (t.x0 - 1) * 8, t.y0 - 1,
+                                            p.stage_plane0[s], t.n);
+                        } else {
+                            // the leader's barrier counts the bytes of both CTAs
+                            if (rank == 0) mbar_arrive_expect_tx(a_full + 8u * slot, 2u * kSlot);
+                            const uint32_t full = map_to_cta(a_full + 8u * slot, 0);
+                            if (p.stage_src[s] == 0)
+                                tma_load_5d_pair(dst, &tmS, full, (t.x0 - 1) * 8, t.y0 - 1, 0,
+                                                 p.stage_plane0[s], t.n);
+                            else
+                                tma_load_4d_pair(dst, &tmB, full, (t.x0 - 1) * 8, t.y0 - 1,
+                                                 p.stage_plane0[s], t.n);
+                        }
                     }
                 }
             }
-        }
-    } else if (warp == 3) {
-        // ================================================== weights, once per CTA
-        // (CG = 2: the blob holds rank 0's halves, then rank 1's)
-        if (lane == 0) {
-            const uint8_t* src = p.wblob + static_cast<size_t>(rank) * wbytes;
-            mbar_arrive_expect_tx(w_full, wbytes);
-            for (uint32_t off = 0; off < wbytes; off += kWChunk) {
-                const uint32_t n = wbytes - off < kWChunk ? wbytes - off : kWChunk;
-                bulk_load(w_s + off, src + off, n, w_full);
+        } else if (warp == 3) {
+            // ================================================== weights, once per CTA
+            // (CG = 2: the blob holds rank 0's halves, then rank 1's)
+            if (lane == 0) {
+                const uint8_t* src = p.wblob + static_cast<size_t>(rank) * wbytes;
+                mbar_arrive_expect_tx(w_full, wbytes);
+                for (uint32_t off = 0; off < wbytes; off += kWChunk) {
+                    const uint32_t n = wbytes - off < kWChunk ? wbytes - off : kWChunk;
+                    bulk_load(w_s + off, src + off, n, w_full);
+                }
+                if (CG == 2 && rank == 1) {
+                    // tell the leader that this CTA's weights are resident too
+                    mbar_wait(w_full, 0);
+                    mbar_arrive_cluster(map_to_cta(w_peer, 0));
+                }
             }
-            if (CG == 2 && rank == 1) {
-                // tell the leader that this CTA's weights are resident too
-                mbar_wait(w_full, 0);
-                mbar_arrive_cluster(map_to_cta(w_peer, 0));
-            }
-        }
-        if (STEM == 2) {
-            // ============================================== issuer of the stem GEMM
-            // per tile 6 x (A[128 rows x 16] x B_hi, then x B_lo) into a ring of four 32-column
-            // accumulators; the whole warp walks the loop, one elected lane issues
-            __syncwarp();
-            constexpr uint32_t a_hi_s = (128u >> 4) | (1u << 14);                 // SBO = 8 rows
-            constexpr uint32_t a_lbo_s = (static_cast<uint32_t>(kStemRows * 16) >> 4) << 16;
-            constexpr uint64_t b_hi_s = static_cast<uint64_t>((128u >> 4) | (1u << 14)) << 32;
-            const uint64_t bd_hi = b_hi_s | ((sB >> 4) | (32u << 16));            // LBO = 16 N = 512 B
-            const uint64_t bd_lo = bd_hi + (1024u >> 4);
-            uint32_t c = 0, iu = 0;
-            for (int unit = unit0; unit < num_units; unit += unit_step, ++iu) {
-                const uint32_t b = iu & 1u;
-                mbar_wait(sa_full + 8u * b, (iu >> 1) & 1u);
-                tc_fence_after();
-#pragma unroll 1
-                for (int j = 0; j < kStemChunks; ++j, ++c) {
-                    const uint32_t slot = c % kStemDSlots;
-                    mbar_wait(sd_empty + 8u * slot, ((c / kStemDSlots) & 1u) ^ 1u);
+            if (STEM >= 2) {
+                // ============================================== issuer of the stem GEMM
+                // per tile 6 x (A[128 rows x 16] x B_hi, then x B_lo) into a ring of four 32-column
+                // accumulators; the whole warp walks the loop, one elected lane issues
+                __syncwarp();
+                constexpr uint32_t a_hi_s = (128u >> 4) | (1u << 14);                 // SBO = 8 rows
+                constexpr uint32_t a_lbo_s = (static_cast<uint32_t>(kStemRows * 16) >> 4) << 16;
+                constexpr uint64_t b_hi_s = static_cast<uint64_t>((128u >> 4) | (1u << 14)) << 32;
+                const uint64_t bd_hi = b_hi_s | ((sB >> 4) | (32u << 16));            // LBO = 16 N = 512 B
+                const uint64_t bd_lo = bd_hi + (1024u >> 4);
+                uint32_t c = 0, iu = 0;
+                for (int unit = unit0; unit < num_units; unit += unit_step, ++iu) {
+                    const uint32_t b = iu & 1u;
+                    mbar_wait(sa_full + 8u * b, (iu >> 1) & 1u);
                     tc_fence_after();
-                    if (elect_one()) {
-                        const uint64_t ad =
-                            (static_cast<uint64_t>(a_hi_s) << 32) |
-                            (((sA + b * kStemABytes + static_cast<uint32_t>(j) * 2048u) >> 4) | a_lbo_s);
-                        const uint32_t d = tmem_base + kStemDCol + slot * 32u;
-                        if (!(p.dbg & 1)) {
-                            umma_bf16(d, ad, bd_hi, make_idesc_fmt(32, 1u), 0u);   // bf16 x bf16 in
-                            umma_bf16(d, ad, bd_lo, make_idesc_fmt(32, 1u), 1u);   // either unit
+#pragma unroll 1
+                    for (int j = 0; j < kStemChunks; ++j, ++c) {
+                        const uint32_t slot = c % kStemDSlots;
+                        mbar_wait(sd_empty + 8u * slot, ((c / kStemDSlots) & 1u) ^ 1u);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint64_t ad =
+                                (static_cast<uint64_t>(a_hi_s) << 32) |
+                                (((sA + b * kStemABytes + static_cast<uint32_t>(j) * 2048u) >> 4) | a_lbo_s);
+                            const uint32_t d = tmem_base + kStemDCol + slot * 32u;
+                            // STEM 2: bf16 x bf16 (in either translation unit); STEM 3: f16 x f16
+                            const uint32_t idesc = p.stem_idesc;
+                            if (!(p.dbg & 1)) {
+                                umma_bf16(d, ad, bd_hi, idesc, 0u);
+                                if (p.stem_lo) umma_bf16(d, ad, bd_lo, idesc, 1u);
+                            }
+                            umma_commit(sd_full + 8u * slot);
+                            if (j == kStemChunks - 1) umma_commit(sa_empty + 8u * b);
                         }
-                        umma_commit(sd_full + 8u * slot);
-                        if (j == kStemChunks - 1) umma_commit(sa_empty + 8u * b);
+                        __syncwarp();
+                    }
+                }
+            }
+        } else if (rank == 0) {
+            // ================================================= MMA issuers (two warps)
+            // The tensor pipe accepts an MMA only when the previous one is (nearly) done, and a wait
+            // on an mbarrier costs the issuing warp ~120 cycles even when the phase completed long
+            // ago, so with ONE issuer every barrier wait between two groups of MMAs is a bubble in the
+            // pipe (measured: 82 instead of 48 cycles per N = 64 MMA with a wait every 4 MMAs;
+            // profiles/microbench_mma_issuer_bubbles_r01.txt). Two warps issue alternate tiles (into
+            // different accumulator buffers, so the summation order inside a tile is unchanged):
+            // while one waits, the other's MMAs keep the pipe full -- 48.0 cycles in the same test.
+            // An issuer may then wait for a ring slot's NEXT use while the other issuer has not yet
+            // seen its current one; mbarrier parities tell phases apart only one step, so this needs
+            // a ring of at least two tiles (p.dual is 0 otherwise and warp 2 idles).
+            // The whole warp walks the loops (all values warp-uniform); one elected lane issues.
+            const uint32_t me = static_cast<uint32_t>(warp - 1);
+            // descriptor halves that never change: A (two LBOs: S2D stage / plain stage), B
+            constexpr uint32_t a_hi = ((kHW * 16u) >> 4) | (1u << 14);           // SBO = one halo row
+            constexpr uint32_t a_lbo_s2d = ((4u * kPlane) >> 4) << 16;          // plane pair of a phase
+            constexpr uint32_t a_lbo_plain = (static_cast<uint32_t>(kPlane) >> 4) << 16;
+            constexpr uint64_t b_hi = static_cast<uint64_t>((128u >> 4) | (1u << 14)) << 32;
+            const uint32_t w_lo = w_s >> 4;
+            // CG = 2: every B block is half as wide in this CTA, so offsets, slab sizes and LBO halve
+            auto mma = [](uint32_t d, uint64_t a, uint64_t b, int n, uint32_t acc) {
+                if (CG == 2) umma_bf16_pair(d, a, b, make_idesc_bf16_pair(n), acc);
+                else umma_bf16(d, a, b, make_idesc_bf16(n), acc);
+            };
+            auto commit = [](uint32_t bar) {
+                if (CG == 2) umma_commit_pair(bar);
+                else umma_commit(bar);
+            };
+            mbar_wait(w_full, 0);
+            if (CG == 2) mbar_wait_cluster(w_peer, 0);
+            uint32_t ita = 0, li = 0;
+            for (int unit = unit0; unit < num_units; unit += unit_step, ++li) {
+                if (p.dual ? (li & 1u) != me : me != 0u) continue;   // the other issuer's tile
+                ita = li * static_cast<uint32_t>(p.n_stages);       // its stages in the ring
+                const uint32_t buf = li % kBufs;
+                const uint32_t aph = (li / kBufs) & 1u;
+                if (CG == 2) mbar_wait_cluster(acc_empty + 8u * buf, aph ^ 1u);
+                else mbar_wait(acc_empty + 8u * buf, aph ^ 1u);
+                tc_fence_after();
+                const uint32_t d0 = tmem_base + buf * 128u;
+                for (int s = 0; s < p.n_s2d; ++s, ++ita) {
+                    const uint32_t slot = ita % p.nslots;
+                    // fused stem: the CUDA-core stem warps are the critical path, not the issuers
+                    if (STEM && c_wait_cfg[3]) mbar_wait_relaxed(a_full + 8u * slot, (ita / p.nslots) & 1u);
+                    else mbar_wait(a_full + 8u * slot, (ita / p.nslots) & 1u);
+                    tc_fence_after();
+                    const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) |
+                                        (((a_ring + slot * kSlot) >> 4) | a_lbo_s2d);
+                    const uint64_t bd = b_hi | (w_lo + static_cast<uint32_t>(s) * (kS2dSlabUnits / CG));
+                    const uint32_t first = s != 0 ? 1u : 0u;
+                    const bool last = (s == p.n_s2d - 1) && !p.has_below;
+                    if (elect_one()) {
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) {
+                            if (p.dbg & 1) break;
+                            const OpShape sh = s2d_shape(c);
+                            // LBO of B = 16 * N bytes -> (N) in the descriptor's bits 16..29
+                            mma(d0 + sh.dcol, ad + sh.a_off,
+                                bd + (s2d_boff(c) / CG + (static_cast<uint32_t>(sh.n / CG) << 16)), sh.n,
+                                c ? 1u : first);
+                        }
+                        commit(a_empty + 8u * slot);
+                        if (last) commit(acc_full + 8u * buf);
                     }
                     __syncwarp();
                 }
-            }
-        }
-    } else if ((warp == 1 || warp == 2) && rank == 0) {
-        // ================================================= MMA issuers (two warps)
-        // The tensor pipe accepts an MMA only when the previous one is (nearly) done, and a wait
-        // on an mbarrier costs the issuing warp ~120 cycles even when the phase completed long
-        // ago, so with ONE issuer every barrier wait between two groups of MMAs is a bubble in the
-        // pipe (measured: 82 instead of 48 cycles per N = 64 MMA with a wait every 4 MMAs;
-        // profiles/microbench_mma_issuer_bubbles_r01.txt). Two warps issue alternate tiles (into
-        // different accumulator buffers, so the summation order inside a tile is unchanged):
-        // while one waits, the other's MMAs keep the pipe full -- 48.0 cycles in the same test.
-        // An issuer may then wait for a ring slot's NEXT use while the other issuer has not yet
-        // seen its current one; mbarrier parities tell phases apart only one step, so this needs
-        // a ring of at least two tiles (p.dual is 0 otherwise and warp 2 idles).
-        // The whole warp walks the loops (all values warp-uniform); one elected lane issues.
-        const uint32_t me = static_cast<uint32_t>(warp - 1);
-        // descriptor halves that never change: A (two LBOs: S2D stage / plain stage), B
-        constexpr uint32_t a_hi = ((kHW * 16u) >> 4) | (1u << 14);           // SBO = one halo row
-        constexpr uint32_t a_lbo_s2d = ((4u * kPlane) >> 4) << 16;          // plane pair of a phase
-        constexpr uint32_t a_lbo_plain = (static_cast<uint32_t>(kPlane) >> 4) << 16;
-        constexpr uint64_t b_hi = static_cast<uint64_t>((128u >> 4) | (1u << 14)) << 32;
-        const uint32_t w_lo = w_s >> 4;
-        // CG = 2: every B block is half as wide in this CTA, so offsets, slab sizes and LBO halve
-        auto mma = [](uint32_t d, uint64_t a, uint64_t b, int n, uint32_t acc) {
-            if (CG == 2) umma_bf16_pair(d, a, b, make_idesc_bf16_pair(n), acc);
-            else umma_bf16(d, a, b, make_idesc_bf16(n), acc);
-        };
-        auto commit = [](uint32_t bar) {
-            if (CG == 2) umma_commit_pair(bar);
-            else umma_commit(bar);
-        };
-        mbar_wait(w_full, 0);
-        if (CG == 2) mbar_wait_cluster(w_peer, 0);
-        uint32_t ita = 0, li = 0;
-        for (int unit = unit0; unit < num_units; unit += unit_step, ++li) {
-            if (p.dual ? (li & 1u) != me : me != 0u) continue;   // the other issuer's tile
-            ita = li * static_cast<uint32_t>(p.n_stages);       // its stages in the ring
-            const uint32_t buf = li % kBufs;
-            const uint32_t aph = (li / kBufs) & 1u;
-            if (CG == 2) mbar_wait_cluster(acc_empty + 8u * buf, aph ^ 1u);
-            else mbar_wait(acc_empty + 8u * buf, aph ^ 1u);
-            tc_fence_after();
-            const uint32_t d0 = tmem_base + buf * 128u;
-            for (int s = 0; s < p.n_s2d; ++s, ++ita) {
-                const uint32_t slot = ita % p.nslots;
-                // fused stem: the CUDA-core stem warps are the critical path, not the issuers
-                if (STEM && c_wait_cfg[3]) mbar_wait_relaxed(a_full + 8u * slot, (ita / p.nslots) & 1u);
-                else mbar_wait(a_full + 8u * slot, (ita / p.nslots) & 1u);
-                tc_fence_after();
-                const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) |
-                                    (((a_ring + slot * kSlot) >> 4) | a_lbo_s2d);
-                const uint64_t bd = b_hi | (w_lo + static_cast<uint32_t>(s) * (kS2dSlabUnits / CG));
-                const uint32_t first = s != 0 ? 1u : 0u;
-                const bool last = (s == p.n_s2d - 1) && !p.has_below;
-                if (elect_one()) {
+                if (p.has_below) {
+                    const uint32_t slot = ita % p.nslots;
+                    mbar_wait(a_full + 8u * slot, (ita / p.nslots) & 1u);
+                    tc_fence_after();
+                    const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) |
+                                        (((a_ring + slot * kSlot) >> 4) | a_lbo_plain);
+                    const uint64_t bd =
+                        b_hi | (w_lo + static_cast<uint32_t>(p.n_s2d) * (kS2dSlabUnits / CG));
+                    if (elect_one()) {
 #pragma unroll
-                    for (int c = 0; c < 16; ++c) {
-                        if (p.dbg & 1) break;
-                        const OpShape sh = s2d_shape(c);
-                        // LBO of B = 16 * N bytes -> (N) in the descriptor's bits 16..29
-                        mma(d0 + sh.dcol, ad + sh.a_off,
-                            bd + (s2d_boff(c) / CG + (static_cast<uint32_t>(sh.n / CG) << 16)), sh.n,
-                            c ? 1u : first);
-                    }
-                    commit(a_empty + 8u * slot);
-                    if (last) commit(acc_full + 8u * buf);
-                }
-                __syncwarp();
-            }
-            if (p.has_below) {
-                const uint32_t slot = ita % p.nslots;
-                mbar_wait(a_full + 8u * slot, (ita / p.nslots) & 1u);
-                tc_fence_after();
-                const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) |
-                                    (((a_ring + slot * kSlot) >> 4) | a_lbo_plain);
-                const uint64_t bd =
-                    b_hi | (w_lo + static_cast<uint32_t>(p.n_s2d) * (kS2dSlabUnits / CG));
-                if (elect_one()) {
+                        for (int k16 = 0; k16 < 4; ++k16) {
 #pragma unroll
-                    for (int k16 = 0; k16 < 4; ++k16) {
-#pragma unroll
-                        for (int i = 0; i < 9; ++i) {
-                            if (p.dbg & 1) break;
-                            const OpShape sh = below_shape(i);
-                            mma(d0 + sh.dcol, ad + (2 * k16 * (kPlane / 16) + sh.a_off),
-                                bd + ((k16 * kBelowSlabUnits + below_boff(i)) / CG +
-                                      (static_cast<uint32_t>(sh.n / CG) << 16)),
-                                sh.n, 1u);
+                            for (int i = 0; i < 9; ++i) {
+                                if (p.dbg & 1) break;
+                                const OpShape sh = below_shape(i);
+                                mma(d0 + sh.dcol, ad + (2 * k16 * (kPlane / 16) + sh.a_off),
+                                    bd + ((k16 * kBelowSlabUnits + below_boff(i)) / CG +
+                                          (static_cast<uint32_t>(sh.n / CG) << 16)),
+                                    sh.n, 1u);
+                            }
                         }
+                        commit(a_empty + 8u * slot);
+                        commit(acc_full + 8u * buf);
                     }
-                    commit(a_empty + 8u * slot);
-                    commit(acc_full + 8u * buf);
+                    __syncwarp();
+                    ++ita;
                 }
-                __syncwarp();
-                ++ita;
             }
         }
-    } else if (warp >= 4) {
+    } else {
+        if (STEM == 3) setmaxnreg_inc<kRegsEpi3>();
         // =========================================================== epilogue
         const int et = (threadIdx.x - 128) & 127;   // TMEM lane = position inside the tile
         const int grp = (threadIdx.x - 128) >> 7;   // takes tiles with (li & 1) == grp
@@ -850,10 +1004,18 @@ inline uint16_t operand_bits(double v, bool f16) {
 // B operands of the tensor-core stem: [B_hi, B_lo][K half][n = 32 channels][8 K elements] bf16.
 // K rows 0..8 = the taps' weights / 255 (the fp32 value of the CUDA-core stem, split hi + lo),
 // row 9 = bias (hi), row 10 = bias (lo) -- the im2col operand holds ones there -- rows 11..15 zero.
-int build_stem_tc_blob(const StemWeights& sw, std::vector<uint8_t>* out) {
+// `k_order3`: the K order of the STEM = 3 operand (stem3_k_of_tap; ones at K = 7 and 9).
+int build_stem_tc_blob(const StemWeights& sw, std::vector<uint8_t>* out, bool k_order3, bool f16) {
     out->assign(kStemBBytes, 0);
     uint16_t* B = reinterpret_cast<uint16_t*>(out->data());
-    auto split = [](float v, uint16_t* hi, uint16_t* lo) {
+    auto split = [f16](float v, uint16_t* hi, uint16_t* lo) {
+        if (f16) {   // 11 + 11 significant bits; the low part may be subnormal (spacing 2^-24)
+            const __half h = __float2half_rn(v);
+            const __half l = __float2half_rn(v - __half2float(h));
+            memcpy(hi, &h, 2);
+            memcpy(lo, &l, 2);
+            return;
+        }
         const __nv_bfloat16 h = __float2bfloat16_rn(v);
         const float rest = v - __bfloat162float(h);
         const __nv_bfloat16 l = __float2bfloat16_rn(rest);
@@ -866,9 +1028,10 @@ int build_stem_tc_blob(const StemWeights& sw, std::vector<uint8_t>* out) {
     for (int n = 0; n < 32; ++n) {
         for (int k = 0; k < 9; ++k) {
             const float w = static_cast<float>(static_cast<double>(sw.w[n * 9 + k]) / 255.0);
-            split(w, &at(0, k, n), &at(1, k, n));
+            const int kk = k_order3 ? stem3_k_of_tap(k) : k;
+            split(w, &at(0, kk, n), &at(1, kk, n));
         }
-        split(sw.b[n], &at(0, 9, n), &at(0, 10, n));
+        split(sw.b[n], &at(0, k_order3 ? 7 : 9, n), &at(0, k_order3 ? 9 : 10, n));
     }
     return 0;
 }
@@ -1049,6 +1212,8 @@ int s2d_tc_init() {
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     OGL_CUDA(cudaFuncSetAttribute(s2d_tc_kernel<EPI_RELU_POOL, 1, 2>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    OGL_CUDA(cudaFuncSetAttribute(s2d_tc_kernel<EPI_RELU_POOL, 1, 3>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     return set_attr<EPI_RELU>() || set_attr<EPI_RELU_POOL>() || set_attr<EPI_HEAD>();
 }
 
@@ -1056,7 +1221,7 @@ int launch_s2d_tc(const S2dLayer& L, const __nv_bfloat16* src_s2d, const __nv_bf
                   int B, int H, int W, __nv_bfloat16* out_s2d, __nv_bfloat16* out_pool,
                   const HeadParams* head, int num_sms, cudaStream_t stream, int cta_group,
                   const uint8_t* stem_frames, const StemWeights* stem, bool reverse,
-                  const uint8_t* stem_tc_blob) {
+                  const uint8_t* stem_tc_blob, int stem_tc_warps) {
     if (H < 2 || W < 2 || H % 2 || W % 2) return fail("s2d layer needs even, non-empty H and W");
     if ((W / 2) % 8) return fail("s2d layer needs W to be a multiple of 16");
     const bool fused_stem = stem_frames != nullptr;
@@ -1088,7 +1253,14 @@ int launch_s2d_tc(const S2dLayer& L, const __nv_bfloat16* src_s2d, const __nv_bf
         // they are: utils.py:235 folded into downs.0.net.0
         p.frames = stem_frames;
         p.stem = make_stem_pairs(*stem);
-        p.stem_b = stem_tc_blob;   // non-null: the stem runs on the tensor cores (STEM = 2)
+        p.stem_b = stem_tc_blob;   // non-null: the stem runs on the tensor cores (STEM >= 2)
+        // 8 warps: bf16 im2col x bf16 weights; 16 warps: f16 im2col x f16 weights (a mixed
+        // f16 x bf16 descriptor, OGL_STEM3_BFMT=1 with a bf16 blob, traps: illegal instruction)
+        static const int bfmt_env = getenv("OGL_STEM3_BFMT") ? atoi(getenv("OGL_STEM3_BFMT")) : 0;
+        static const int lo_env = getenv("OGL_STEM_LO") ? atoi(getenv("OGL_STEM_LO")) : 1;
+        p.stem_lo = lo_env;
+        p.stem_idesc = stem_tc_warps == 16 ? make_idesc_ab(32, 0u, bfmt_env ? 1u : 0u)
+                                           : make_idesc_fmt(32, 1u);
     }
     p.btab = L.btab;
     p.border_bias = L.cin_b > 0 ? 1 : 0;
@@ -1155,8 +1327,12 @@ int launch_s2d_tc(const S2dLayer& L, const __nv_bfloat16* src_s2d, const __nv_bf
         const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
         if (tc_stem) {
             if (nslots < 4) return fail("s2d layer: the tensor-core stem needs 4 activation stages");
-            s2d_tc_kernel<EPI_RELU_POOL, 1, 2>
-                <<<grid, kThreads + kStemThreads, smem, stream>>>(tmS, tmB, p);
+            if (stem_tc_warps == 16)
+                s2d_tc_kernel<EPI_RELU_POOL, 1, 3>
+                    <<<grid, kThreads + kStem3Threads, smem, stream>>>(tmS, tmB, p);
+            else
+                s2d_tc_kernel<EPI_RELU_POOL, 1, 2>
+                    <<<grid, kThreads + kStemThreads, smem, stream>>>(tmS, tmB, p);
         } else {
             s2d_tc_kernel<EPI_RELU_POOL, 1, 1>
                 <<<grid, kThreads + kStemThreads, smem, stream>>>(tmS, tmB, p);

@@ -15,7 +15,8 @@ import torch
 
 from . import _native, sharding
 from .unet import UNet
-from .utils import _require_native, bgr_to_gray, load_frames_bgr
+from .utils import (RangeDecoder, _require_native, _silence_stderr, bgr_to_gray, decode_workers,
+                    load_frames_bgr, parallel_decodable, video_info)
 
 _FEATURE_KEYS = ("area_mean", "area_std", "area_range", "open_quotient", "f0", "periodicity", "cv")
 
@@ -186,6 +187,79 @@ def gray_clip_from_bgr(frames_bgr: list, dev: torch.device, chunk: int = 2048) -
     return gray
 
 
+def decode_gray_clip(avi_path: str, dev: torch.device, workers: int | None = None,
+                     chunk: int = 1024, timings: dict | None = None) -> torch.Tensor | None:
+    """Video file -> ``(N, H, W)`` uint8 gray CUDA tensor, or ``None`` for a file without frames:
+    ``load_frames_bgr`` + ``cvtColor`` of /root/reference/openglottal/features.py:226,235 as a
+    pipeline. Intra-only codecs (MJPG, FFV1, raw) are decoded by ``workers`` threads, each with
+    its own ``VideoCapture`` on a contiguous frame range, straight into two pinned BGR chunk
+    buffers; while the next chunk decodes, the previous one crosses PCIe and becomes gray on the
+    GPU (OpenCV's integer coefficients, bit-exact). The frames are those the reference's
+    sequential loop decodes (same decoder, frame-exact seeks; checked in tests). Other codecs, a
+    header without a plausible frame count, or any short read fall back to the sequential loop.
+    ``timings`` (optional dict) receives ``decode_s`` / ``total_s`` / ``workers`` / ``mode``."""
+    import time
+    from concurrent.futures import ThreadPoolExecutor
+
+    t_start = time.perf_counter()
+    workers = decode_workers(workers)
+    info = video_info(avi_path)
+
+    def sequential():
+        frames_bgr = load_frames_bgr(avi_path)
+        t_dec = time.perf_counter()
+        gray = gray_clip_from_bgr(frames_bgr, dev) if frames_bgr else None
+        if timings is not None:
+            torch.cuda.synchronize(dev)
+            timings.update(mode="sequential", workers=1, decode_s=t_dec - t_start,
+                           total_s=time.perf_counter() - t_start)
+        return gray
+
+    if not parallel_decodable(info, workers):
+        return sequential()
+    n, hgt, wid = info["frames"], info["height"], info["width"]
+    chunk = max(workers, min(chunk, n))
+    gray = torch.empty((n, hgt, wid), dtype=torch.uint8, device=dev)
+    bufs = [torch.empty((chunk, hgt, wid, 3), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+    views = [b.numpy() for b in bufs]
+    copy = torch.cuda.Stream(device=dev)
+    freed = [torch.cuda.Event(), torch.cuda.Event()]
+    decode_s, ok = 0.0, True
+    with _silence_stderr(), ThreadPoolExecutor(workers) as pool:
+        decs = list(pool.map(lambda _: RangeDecoder(avi_path), range(workers)))
+        try:
+            for k, i0 in enumerate(range(0, n, chunk)):
+                m, b = min(chunk, n - i0), k % 2
+                if k >= 2:
+                    freed[b].synchronize()        # the copy that read this buffer has finished
+                cut = [m * w // workers for w in range(workers + 1)]
+                t0 = time.perf_counter()
+                got = list(pool.map(lambda w: decs[w].read_into(i0 + cut[w], i0 + cut[w + 1],
+                                                                views[b][cut[w]:cut[w + 1]]),
+                                    range(workers)))
+                decode_s += time.perf_counter() - t0
+                if any(g != cut[w + 1] - cut[w] for w, g in enumerate(got)):
+                    ok = False
+                    break
+                with torch.cuda.stream(copy):
+                    part = bufs[b][:m].to(dev, non_blocking=True)
+                    gray[i0:i0 + m] = bgr_to_gray(part)
+                    freed[b].record(copy)
+            if ok and decs[-1].pos == n and decs[-1].cap.read()[0]:
+                ok = False       # frames beyond the header's count: the sequential loop reads them
+        finally:
+            for d in decs:
+                d.release()
+    torch.cuda.current_stream(dev).wait_stream(copy)
+    if not ok:
+        return sequential()
+    if timings is not None:
+        torch.cuda.synchronize(dev)
+        timings.update(mode="parallel", workers=workers, decode_s=decode_s,
+                       total_s=time.perf_counter() - t_start)
+    return gray
+
+
 def extract_features_unet_frames(frames_gray, model: UNet, batch: int = 512,
                                  threshold: float = 0.5, group=None) -> dict | None:
     """unet-only pipeline on raw gray frames ``(N, H, W)`` uint8 (H, W multiples of 16).
@@ -247,19 +321,20 @@ def extract_features_unet(avi_path: str, detector, model, device=None) -> dict |
 
     model = _require_native(model)
     dev = model._device()
+    if detector is None:
+        # unet-only: no consumer of the BGR frames on the host, so they are never held as a list
+        gray = decode_gray_clip(avi_path, dev)
+        if gray is None:
+            return None
+        area, _ = masks_for_clip(gray, model)
+        return kinematic_features_device(area)
     frames_bgr = load_frames_bgr(avi_path)
     if not frames_bgr:
         return None
-    boxes = None
-    if detector is not None:
-        detector.reset()
-        boxes = [detector.detect(frm) for frm in frames_bgr]
-
-    area, masks = masks_for_clip(gray_clip_from_bgr(frames_bgr, dev), model,
-                                 want_masks=boxes is not None)
-    if boxes is not None:
-        area = gated_area(masks, boxes)
-    return kinematic_features_device(area)
+    detector.reset()
+    boxes = [detector.detect(frm) for frm in frames_bgr]
+    _, masks = masks_for_clip(gray_clip_from_bgr(frames_bgr, dev), model, want_masks=True)
+    return kinematic_features_device(gated_area(masks, boxes))
 
 
 def extract_features_yolo_crop_unet(avi_path: str, detector, model, device=None,

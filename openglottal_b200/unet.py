@@ -72,10 +72,11 @@ class UNet(nn.Module):
         self.cta_pairs = int(os.environ.get("OGL_CG", "2"))   # 1: one CTA per tile; 2: CTA pairs
                                      # (tcgen05 cta_group::2) for the Cout >= 64 conv layers when
                                      # a launch has a tile per SM; 3: pairs whenever possible
-        self.fuse_stem = int(os.environ.get("OGL_FUSE_STEM", "2"))   # stem inside downs.0.net.3:
+        self.fuse_stem = int(os.environ.get("OGL_FUSE_STEM", "3"))   # stem inside downs.0.net.3:
                                      # 0 separate kernel, 1 in-kernel on the CUDA cores (fp32),
-                                     # 2 (default) in-kernel on the tensor cores (bf16 hi + lo
-                                     # weights, fp32 accumulation)
+                                     # 2 in-kernel on the tensor cores (bf16 hi + lo weights, fp32
+                                     # accumulation; 8 stem warps), 3 (default) the same GEMM with
+                                     # 16 stem warps and an f16 im2col operand
         self.compose_up = os.environ.get("OGL_COMPOSE", "1") != "0"   # decoder levels 1-3: every
                                      # ConvTranspose2d composed into the conv after it (17 launches,
                                      # no `up` tensor); False: the round-1 schedule (20 launches)

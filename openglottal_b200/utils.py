@@ -54,6 +54,120 @@ def load_frames_bgr(avi_path: str) -> list[np.ndarray]:
     return frames
 
 
+# Codecs whose every frame is a key frame: a seek to frame k lands exactly on frame k, so
+# contiguous frame ranges can be decoded by independent VideoCapture instances. (Anything else --
+# H.264, MPEG-4 ... -- is decoded sequentially: OpenCV's seek is not frame-exact there.)
+_INTRA_ONLY_FOURCC = {"MJPG", "mjpg", "FFV1", "ffv1", "HFYU", "hfyu", "FFVH", "Y800", "GREY",
+                      "DIB ", "RAW ", "I420", "IYUV", "YV12", "YUY2", "UYVY", "\0\0\0\0"}
+
+
+def video_info(avi_path: str) -> dict:
+    """``{"frames", "height", "width", "fourcc"}`` of a video as OpenCV reports them (``frames``
+    is the container's count and may be 0 / wrong for broken headers)."""
+    import cv2
+
+    with _silence_stderr():
+        cap = cv2.VideoCapture(str(avi_path))
+        code = int(cap.get(cv2.CAP_PROP_FOURCC))
+        info = {"frames": int(cap.get(cv2.CAP_PROP_FRAME_COUNT)),
+                "height": int(cap.get(cv2.CAP_PROP_FRAME_HEIGHT)),
+                "width": int(cap.get(cv2.CAP_PROP_FRAME_WIDTH)),
+                "fourcc": "".join(chr((code >> (8 * i)) & 0xFF) for i in range(4))}
+        cap.release()
+    return info
+
+
+class RangeDecoder:
+    """One ``VideoCapture`` that decodes frame ranges straight into caller-owned arrays (no
+    per-frame allocation: at ~200 KB per frame every fresh numpy array is an mmap/munmap pair,
+    which serialises concurrent decoders on the process's memory map)."""
+
+    def __init__(self, avi_path: str):
+        import cv2
+
+        self.cap = cv2.VideoCapture(str(avi_path))
+        self.pos = 0
+
+    def read_into(self, start: int, stop: int, dst: np.ndarray) -> int:
+        """Frames ``[start, stop)`` into ``dst[0:stop-start]`` (``(.., H, W, 3)`` uint8); returns
+        how many were read (short on a failed seek, a read error or a frame of another shape)."""
+        import cv2
+
+        if self.pos != start:
+            if not self.cap.set(cv2.CAP_PROP_POS_FRAMES, start) or \
+                    int(self.cap.get(cv2.CAP_PROP_POS_FRAMES)) != start:
+                return 0
+            self.pos = start
+        for i in range(stop - start):
+            ok, frm = self.cap.read(dst[i])
+            if not ok or frm.shape != dst[i].shape:
+                return i
+            if frm.ctypes.data != dst[i].ctypes.data:   # OpenCV allocated its own: copy
+                dst[i] = frm
+            self.pos += 1
+        return stop - start
+
+    def release(self) -> None:
+        self.cap.release()
+
+
+def decode_workers(default: int | None = None) -> int:
+    """Decoder threads: ``OGL_DECODE_WORKERS`` or the host cores this process may use (max 32)."""
+    env = os.environ.get("OGL_DECODE_WORKERS")
+    if env:
+        return max(1, int(env))
+    if default:
+        return default
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    return max(1, min(32, cores))
+
+
+def load_frames_bgr_parallel(avi_path: str, workers: int | None = None,
+                             min_frames: int = 256) -> list[np.ndarray]:
+    """``load_frames_bgr`` with the decode spread over ``workers`` threads (OpenCV releases the GIL
+    inside ``read``), each decoding one contiguous frame range with its own ``VideoCapture``. Only
+    for intra-only codecs (MJPG, FFV1, raw ...), where a seek is frame-exact and every decoder
+    produces the very frames the sequential loop of /root/reference/openglottal/utils.py:43-54
+    does; anything else, short clips, wrong frame counts or a failed seek fall back to that loop.
+    After the GPU path the CPU decode is the end-to-end bottleneck by more than 10x."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    workers = decode_workers(workers)
+    info = video_info(avi_path)
+    n = info["frames"]
+    if not parallel_decodable(info, workers, min_frames):
+        return load_frames_bgr(avi_path)
+    clip = np.empty((n, info["height"], info["width"], 3), np.uint8)
+    bounds = [n * w // workers for w in range(workers + 1)]
+
+    def work(w):
+        dec = RangeDecoder(avi_path)
+        try:
+            got = dec.read_into(bounds[w], bounds[w + 1], clip[bounds[w]:bounds[w + 1]])
+            if w == workers - 1 and got == bounds[w + 1] - bounds[w]:
+                got += dec.cap.read()[0]     # a frame beyond the header's count: not trustworthy
+            return got
+        finally:
+            dec.release()
+
+    with _silence_stderr(), ThreadPoolExecutor(workers) as pool:
+        counts = list(pool.map(work, range(workers)))
+    if any(c != bounds[w + 1] - bounds[w] for w, c in enumerate(counts)):
+        return load_frames_bgr(avi_path)      # header count or seek not trustworthy
+    return list(clip)
+
+
+def parallel_decodable(info: dict, workers: int, min_frames: int = 256) -> bool:
+    """Whether a clip (``video_info``) is decoded by several ``RangeDecoder``s: an intra-only
+    codec, a plausible header and enough frames to be worth it."""
+    return (workers >= 2 and info["frames"] >= max(min_frames, 2 * workers)
+            and info["height"] > 0 and info["width"] > 0
+            and info["fourcc"] in _INTRA_ONLY_FOURCC)
+
+
 def bgr_to_gray(frames_bgr: torch.Tensor) -> torch.Tensor:
     """``(N, H, W, 3)`` uint8 BGR CUDA tensor -> ``(N, H, W)`` uint8 gray, bit-exact with
     ``cv2.cvtColor(..., COLOR_BGR2GRAY)`` (/root/reference/openglottal/features.py:235)."""

@@ -60,3 +60,21 @@ def native_model(lib, trained_sd):
     m.load_state_dict(trained_sd, strict=True)
     m.eval()
     return m
+
+
+@pytest.fixture(scope="session")
+def write_clip():
+    """``write_clip(path, fourcc, n, hgt=64, wid=48)``: a synthetic glottis clip as a video file."""
+    def _write(path, fourcc: str, n: int, hgt: int = 64, wid: int = 48):
+        import cv2
+
+        from oracle import synth
+
+        frames, _ = synth.glottis_clip(n, hgt, wid, seed=11, period=9.0)
+        wr = cv2.VideoWriter(str(path), cv2.VideoWriter_fourcc(*fourcc), 25.0, (wid, hgt))
+        assert wr.isOpened()
+        for f in frames:
+            wr.write(cv2.cvtColor(f, cv2.COLOR_GRAY2BGR))
+        wr.release()
+
+    return _write

@@ -205,21 +205,26 @@ def test_tensor_core_stem_matches_fp32_stem(native_model):
             frames = torch.randint(0, 256, (4, 256, 256), dtype=torch.uint8, generator=g).cuda()
         else:
             frames = torch.from_numpy(_clip(*shape)).cuda()
-        try:
-            native_model.fuse_stem = 1
-            ref = native_model.run(frames, want_logits=True)
-            native_model.fuse_stem = 2
-            got = native_model.run(frames, want_logits=True)
-            again = native_model.run(frames, want_logits=True)
-        finally:
-            native_model.fuse_stem = default
-        assert all(torch.equal(a, b) for a, b in zip(got, again)), shape     # deterministic
-        d = (ref[0] - got[0]).abs()
-        scale = max(1.0, ref[0].abs().max().item())
-        print(shape, "tc stem vs fp32 stem: max|dz|", d.max().item(), "mean", d.mean().item())
-        assert d.max().item() <= 2e-2 * scale and d.mean().item() <= 1e-3 * scale, shape
-        assert (ref[1] != got[1]).sum().item() <= 1e-4 * ref[1].numel() + 2, shape
-        assert torch.equal(got[2].cpu(), (got[1] > 0).flatten(1).sum(1).to(torch.int32).cpu()), shape
+        # mode 2: 8 stem warps, bf16 im2col operand; mode 3 (default): 16 stem warps, f16 im2col
+        # operand built by byte permutes (u8 values are exact in either type), other K order
+        for mode in (2, 3):
+            try:
+                native_model.fuse_stem = 1
+                ref = native_model.run(frames, want_logits=True)
+                native_model.fuse_stem = mode
+                got = native_model.run(frames, want_logits=True)
+                again = native_model.run(frames, want_logits=True)
+            finally:
+                native_model.fuse_stem = default
+            assert all(torch.equal(a, b) for a, b in zip(got, again)), (shape, mode)   # deterministic
+            d = (ref[0] - got[0]).abs()
+            scale = max(1.0, ref[0].abs().max().item())
+            print(shape, "tc stem mode", mode, "vs fp32 stem: max|dz|", d.max().item(), "mean",
+                  d.mean().item())
+            assert d.max().item() <= 2e-2 * scale and d.mean().item() <= 1e-3 * scale, (shape, mode)
+            assert (ref[1] != got[1]).sum().item() <= 1e-4 * ref[1].numel() + 2, (shape, mode)
+            assert torch.equal(got[2].cpu(),
+                               (got[1] > 0).flatten(1).sum(1).to(torch.int32).cpu()), (shape, mode)
 
 
 def test_repeated_launch_is_idempotent(eager_model):

@@ -265,3 +265,26 @@ def test_unet_only_pipeline_on_512x256_video_reference_resize(lib, native_model,
     err = np.abs(got["_area"] - want)
     print("512x256 reference-resize areas", got["_area"], want)
     assert (err <= np.maximum(4.0, 0.005 * want)).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fourcc", ["MJPG", "FFV1"])
+def test_decode_gray_clip_equals_cv2(tmp_path, fourcc, write_clip):
+    """The streaming ingestion (threads decoding frame ranges into pinned chunk buffers, H2D and
+    BGR->gray on the GPU) gives exactly cv2.cvtColor of the reference's sequentially decoded
+    frames (features.py:226,235), incl. a last partial chunk; a missing file gives None."""
+    import cv2
+
+    import openglottal_b200 as ogl
+    from openglottal_b200.features import decode_gray_clip
+
+    clip = tmp_path / f"c_{fourcc}.avi"
+    write_clip(clip, fourcc, 700, 64, 48)
+    want = np.stack([cv2.cvtColor(f, cv2.COLOR_BGR2GRAY) for f in ogl.load_frames_bgr(str(clip))])
+    t = {}
+    got = decode_gray_clip(str(clip), torch.device("cuda:0"), workers=4, chunk=256, timings=t)
+    assert t["mode"] == "parallel" and got.shape == want.shape
+    assert np.array_equal(got.cpu().numpy(), want)
+    seq = decode_gray_clip(str(clip), torch.device("cuda:0"), workers=1)
+    assert np.array_equal(seq.cpu().numpy(), want)
+    assert decode_gray_clip(str(tmp_path / "missing.avi"), torch.device("cuda:0")) is None

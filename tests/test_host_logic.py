@@ -164,3 +164,34 @@ def test_reference_arm_prints_the_contract_line():
     assert line["config"]["config_index"] == 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert line["e2e"]["value"] == line["value"]
+
+
+@pytest.mark.parametrize("fourcc", ["MJPG", "FFV1"])
+def test_parallel_decode_equals_the_sequential_loop(tmp_path, fourcc, write_clip):
+    """Frame ranges decoded by independent VideoCapture instances (intra-only codecs: frame-exact
+    seeks) are the frames of the reference's sequential loop (utils.py:43-54), for worker counts
+    that do and do not divide the frame count; short clips and other codecs take that loop."""
+    import numpy as np
+
+    from openglottal_b200 import utils
+
+    clip = tmp_path / f"clip_{fourcc}.avi"
+    write_clip(clip, fourcc, 103)
+    want = utils.load_frames_bgr(str(clip))
+    assert len(want) == 103
+    info = utils.video_info(str(clip))
+    assert info["frames"] == 103 and (info["height"], info["width"]) == (64, 48)
+    for workers in (2, 3, 8):
+        got = utils.load_frames_bgr_parallel(str(clip), workers=workers, min_frames=16)
+        assert len(got) == len(want)
+        assert all(np.array_equal(a, b) for a, b in zip(got, want)), workers
+    # ranges decoded in place, out of order, by one decoder (the streaming path's access pattern)
+    dec = utils.RangeDecoder(str(clip))
+    buf = np.empty((20, 64, 48, 3), np.uint8)
+    for start in (60, 5, 83):
+        assert dec.read_into(start, start + 20, buf) == 20
+        assert all(np.array_equal(buf[i], want[start + i]) for i in range(20))
+    assert dec.read_into(95, 115, buf) == 8        # past the end: a short count, not an error
+    dec.release()
+    assert not utils.parallel_decodable({"frames": 5000, "height": 64, "width": 48, "fourcc": "avc1"}, 8)
+    assert not utils.parallel_decodable({"frames": 0, "height": 64, "width": 48, "fourcc": "MJPG"}, 8)
