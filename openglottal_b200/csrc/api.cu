@@ -606,6 +606,11 @@ int ogl_unet_forward(ogl_unet* h, const void* frames_dev, int in_dtype, int n, i
         auto step = [&](const char* name, auto&& launch) {
             const int idx = launch_idx++;
             rev = pingpong && (idx & 1);
+            // a repeated head launch would add every frame's popcount rep_n times (the area vector
+            // is zeroed once per forward): a measurement aid must not return wrong areas
+            if (idx == h->rep_launch && h->rep_n > 1 && area_dev && strstr(name, "head"))
+                return fail("ogl_unet_forward: the head launch is repeated (ogl_unet_set_repeat); "
+                            "pass area = NULL or reset the repetition");
             for (int r = idx == h->rep_launch ? h->rep_n : 1; r > 0; --r)
                 if (launch()) return 1;
             mark(h, stream, name);

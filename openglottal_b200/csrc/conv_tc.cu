@@ -795,7 +795,7 @@ int launch_conv_tc(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloa
     p.acc_bufs = (2 * p.S * p.N <= 256) ? 2 : 1;
     static const int split_env = getenv("OGL_SPLIT") ? atoi(getenv("OGL_SPLIT")) : 1;
     p.split = split_env;
-    static const int dbg_env = getenv("OGL_DBG") ? atoi(getenv("OGL_DBG")) : 0;
+    static const int dbg_env = experiment_dbg();
     p.dbg = dbg_env;
     static const int half_env = getenv("OGL_ACC_HALF") ? atoi(getenv("OGL_ACC_HALF")) : 1;
     p.acc_half = half_env;

@@ -1,5 +1,6 @@
 // Internal (non-ABI) declarations shared by the translation units of libopenglottal_b200.so.
 #pragma once
+#include <cstdlib>
 #include <cstddef>
 #include <cstdint>
 #include <cuda_bf16.h>
@@ -129,6 +130,15 @@ struct S2dOp {        // one tcgen05.mma of the per-tile program, as the host pa
     uint32_t idesc;   // instruction descriptor (carries N)
     uint32_t pad;
 };
+// OGL_DBG switches parts of the tensor-core kernels OFF for timing experiments (results are
+// garbage): honoured only together with OGL_EXPERIMENT=1, so that a stray variable in a production
+// environment cannot silently corrupt masks and areas.
+inline int experiment_dbg() {
+    const char* dbg = getenv("OGL_DBG");
+    const char* on = getenv("OGL_EXPERIMENT");
+    return (dbg && on && atoi(on) != 0) ? atoi(dbg) : 0;
+}
+
 constexpr int kS2dMaxStages = 8;
 struct S2dLayer {
     uint8_t* wblob = nullptr;  // device: B tiles in op order

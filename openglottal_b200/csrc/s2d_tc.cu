@@ -31,6 +31,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #ifdef OGL_F16   // s2d_tc_f16.cu: the same kernels with f16 operands, exported under other names
@@ -137,7 +138,12 @@ constexpr int kStemDSlots = 4;                           // 32-column accumulato
 constexpr int kStemDCol = 384;
 // STEM = 3: the same GEMM with 16 stem warps (four groups of four, one accumulator slot each) and
 // an f16 im2col operand built without a single int -> float conversion (see the kernel).
+constexpr uint32_t kTraceTiles = 96;
+constexpr int kTraceRoles = 8;
 constexpr int kStem3Threads = 512;
+constexpr int kStem3BuildWarps = 4;                      // the other 12 stem warps drain
+constexpr int kStem3DSlots = 4;                          // 32-column accumulators, TMEM cols 384..511
+constexpr int kStem3DCol = 384;                          // (three main accumulators below them)
 constexpr int kStemItems = 2 * kHW * kHH;                // 360 build items: (y phase, halo row, halo column)
 __host__ __device__ constexpr int stem_threads(int stem) {
     return stem == 3 ? kStem3Threads : (stem ? kStemThreads : 0);
@@ -148,8 +154,8 @@ __host__ __device__ constexpr int stem3_k_of_tap(int tap) {
     return tap % 3 < 2 ? 2 * (tap / 3) + tap % 3 : (tap == 2 ? 6 : (tap == 5 ? 8 : 10));
 }
 // register budget per role (setmaxnreg; the launch allocates 72 x 896 = 64512 registers)
-constexpr int kRegsLaunch3 = 72, kRegsCtl3 = 56, kRegsEpi3 = 96, kRegsStem3 = 64;
-static_assert(kRegsCtl3 * 128 + kRegsEpi3 * 256 + kRegsStem3 * kStem3Threads ==
+constexpr int kRegsLaunch3 = 72, kRegsCtl3 = 56, kRegsEpi3 = 96, kRegsBuild3 = 40;   // drain: 72
+static_assert(kRegsCtl3 * 128 + kRegsEpi3 * 256 + kRegsBuild3 * 128 + kRegsLaunch3 * 384 ==
                   kRegsLaunch3 * (384 + kStem3Threads), "register pool of the STEM = 3 kernel");
 
 struct S2dParams {
@@ -158,6 +164,7 @@ struct S2dParams {
     const uint8_t* stem_b;   // STEM >= 2: B operands of the stem GEMM (build_stem_tc_blob), device
     uint32_t stem_idesc;     // ... and its instruction descriptor (operand formats)
     int stem_lo;             // second MMA per chunk with the low parts of the split weights
+    unsigned long long* trace;   // debug (OGL_TRACE=file): clock64 of CTA 0's hand-offs, [role][tile][8]
     const uint8_t* wblob;
     const float* btab;     // [3][3][32]: bias per (row class, column class), border pixels only
     float bias[32];        // bias of interior pixels (= btab[1][1]); constant-bank operands
@@ -179,6 +186,7 @@ struct S2dParams {
     int nslots;
     int reverse;  // walk the tiles from the last frame to the first (L2 reuse, see conv_tc.cu)
     int dual;   // two MMA issuer warps on alternate tiles (needs nslots >= 2 * n_stages)
+    int wait_all;   // an issuer waits for all stages of a tile before its first MMA
     int dbg;  // 1 no MMA, 2 no stores, 4 no epilogue work, 8 no activation loads (1-CTA form)
 };
 
@@ -248,7 +256,10 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
     const uint32_t u8_s = (sd_empty + 8u * kStemDSlots + 127u) & ~127u;
     const uint32_t sA = u8_s + kU8Slots * kU8Slot;
     const uint32_t sB = sA + 2u * kStemABytes;
-    constexpr int kBufs = STEM >= 2 ? 3 : kAccBufs;   // main accumulators (128 columns each)
+    // main accumulators (128 columns each) and, above them, the stem GEMM's 32-column ones
+    constexpr int kBufs = STEM >= 2 ? 3 : kAccBufs;
+    constexpr uint32_t kDSlots = STEM == 3 ? kStem3DSlots : kStemDSlots;
+    constexpr uint32_t kDCol = STEM == 3 ? kStem3DCol : kStemDCol;
     uint8_t* gen = smem_raw - raw;  // generic pointer = gen + shared address
     float* btab_sp = reinterpret_cast<float*>(gen + btab_s);
     volatile uint32_t* tmem_slot_p = reinterpret_cast<volatile uint32_t*>(gen + tmem_slot);
@@ -281,21 +292,25 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
         if (STEM)
             for (int i = 0; i < kU8Slots; ++i) {
                 mbar_init(u8_full + 8u * i, 1);
-                mbar_init(u8_empty + 8u * i, stem_threads(STEM) / 32);
+                mbar_init(u8_empty + 8u * i, STEM == 3 ? kStem3BuildWarps : kStemThreads / 32);
             }
         if (STEM >= 2) {
             for (int i = 0; i < 2; ++i) {
-                mbar_init(sa_full + 8u * i, stem_threads(STEM) / 32);
+                mbar_init(sa_full + 8u * i, STEM == 3 ? kStem3BuildWarps : kStemThreads / 32);
                 mbar_init(sa_empty + 8u * i, 1);
             }
-            for (int i = 0; i < kStemDSlots; ++i) {
+            for (int i = 0; i < static_cast<int>(kDSlots); ++i) {
                 mbar_init(sd_full + 8u * i, 1);
-                mbar_init(sd_empty + 8u * i, 4);   // the four warps of the draining group
+                // STEM 2: slot i is free again (the four warps of the draining group). STEM 3:
+                // entries 0 / 1: chunks 2..5 of an even / odd tile are in registers (4 x 4 warps),
+                // entries 2 / 3: chunks 0, 1 (2 x 4 warps)
+                mbar_init(sd_empty + 8u * i, STEM == 3 ? (i < 2 ? 16 : 8) : 4);
             }
         }
         for (int i = 0; i < p.nslots; ++i) {
-            // STEM 1, 2: one arrival per stem warp; STEM 3: one per (chunk, warp of its group)
-            mbar_init(a_full + 8u * i, STEM == 3 ? 4 * kStemChunks : (STEM ? kStemThreads / 32 : 1));
+            // one arrival per stem warp that writes the stages (STEM 3: the 12 drain warps)
+            mbar_init(a_full + 8u * i, STEM == 3 ? kStem3Threads / 32 - kStem3BuildWarps
+                                                 : (STEM ? kStemThreads / 32 : 1));
             mbar_init(a_empty + 8u * i, 1);
         }
         for (int i = 0; i < kBufs; ++i) {
@@ -313,125 +328,173 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
     if (CG == 2) cluster_sync_all();  // the peer's barriers exist before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_p;
+    // debug timeline of CTA 0 (STEM = 3 only): role r, its tile number i < kTraceTiles, event e < 8
+    auto trace = [&](int r, uint32_t i, int e) {
+        if (STEM == 3 && p.trace && blockIdx.x == 0 && lane == 0 && i < kTraceTiles)
+            p.trace[(static_cast<uint32_t>(r) * kTraceTiles + i) * 8u + e] = clock64();
+    };
     // STEM = 3: 896 threads leave 72 registers each; the control warps and the stem warps hand
     // theirs to the two epilogue groups, whose 4 x 32 accumulator values per thread need 96. Each
     // warp group re-allocates at the top of its own branch (setmaxnreg is per warp group, and
     // ptxas budgets the code below each one accordingly).
     if (warp >= kThreads / 32) {
-        if (STEM == 3) setmaxnreg_dec<kRegsStem3>();
         if (STEM == 3) {
             // ============== stem on the tensor cores, 16 warps: f16 im2col in, A stages out
+            // The stem is a chain of hand-offs per tile (u8 region -> im2col -> MMAs -> TMEM ->
+            // A stages -> main MMAs), and what bounds the launch is how far the chains of consecutive
+            // tiles overlap, not the work in them (measured: with every MMA, every TMEM read and the
+            // epilogue switched off the 8-warp form still needed 2 800 cycles per tile). So the roles
+            // are separated and every buffer between them holds more than one tile:
+            //   * warps 0-3 BUILD only, one tile ahead (two im2col buffers);
+            //   * warps 4-15 DRAIN only: three groups of four, group g takes the chunks c with
+            //     c % 3 == g (two per tile) out of a ring of four 32-column accumulators;
+            //   * the issuer (warp 3) waits for accumulator slots twice per tile, not per chunk.
             // Build: one item = the two x phases of one (y phase, halo row, halo column): the 3 x 4
             // bytes around it are read as aligned words (2 LDS.32 + 1 PRMT per window row, the
-            // selector fixed per thread), and every K pair of the operand is ONE byte permute that
+            // selector fixed per item), and every K pair of the operand is ONE byte permute that
             // puts each u8 under the f16 exponent of 1024 (0x64 b = 1024 + b exactly) followed by ONE
             // HFMA2, (1024 + b) * keep - 1024 * keep: no I2F, no F2FP, no separate masking (keep = 0
             // outside the image, where the stem's OUTPUT is zero: conv2's padding). The constant-one K
             // columns that carry the bias come out of the same permutes. 12 ALU instructions per
             // operand row instead of 9 LDS.U8 + 9 I2F + 5 F2FP + 5 LOP3.
-            // Drain: group g = warps 4g..4g+3 owns accumulator slot g and every chunk c with
-            // c % 4 == g (6 chunks per tile), so per tile a warp builds one item and drains 1.5 chunks.
             const int st = threadIdx.x - kThreads;
             const int sw = st >> 5;
-            const uint32_t grp = static_cast<uint32_t>(sw >> 2);
-            const uint32_t lane_sel = static_cast<uint32_t>((sw & 3) * 32) << 16;
             const int W = 2 * p.W2, H = 2 * p.H2;
-            const bool has_item = st < kStemItems;
-            const int item = has_item ? st : kStemItems - 1;
-            const int ipy = item / (kHW * kHH), irem = item - ipy * (kHW * kHH);
-            const int ihy = irem / kHW, ihx = irem - ihy * kHW;
-            const int ily = 2 * ihy + ipy, ilx = 2 * ihx;          // region pixel of (x phase 0, tap (0, 0))
-            const int boff = ily * kU8Row + kU8Off + ilx;           // its byte in the u8 box: odd
-            const int woff = boff & ~3;
-            const uint32_t wsel = (boff & 3) == 1 ? 0x4321u : 0x6543u;
-            const int row0 = 2 * ipy * (kHW * kHH) + irem;          // operand row of x phase 0 (+180: phase 1)
-            auto build = [&](uint32_t iu, int unit) {
-                const Tile t = decode_tile(p, tile_of(unit));
-                const int gy = 2 * t.y0 - 2 + ily, gx = 2 * t.x0 - 2 + ilx;
-                const uint32_t us = iu % kU8Slots;
-                const uint8_t* u8p = gen + u8_s + us * kU8Slot;
-                uint8_t* abuf = gen + sA + (iu & 1u) * kStemABytes;
-                mbar_wait_relaxed(u8_full + 8u * us, (iu / kU8Slots) & 1u);
-                mbar_wait_relaxed(sa_empty + 8u * (iu & 1u), ((iu >> 1) & 1u) ^ 1u);
-                if (has_item) {
-                    uint32_t lo[3], hi[3], wd[3];
+            if (sw < kStem3BuildWarps) {
+                setmaxnreg_dec<kRegsBuild3>();   // (the drain warps keep the launch value)
+                constexpr int kRounds = (kStemItems + 32 * kStem3BuildWarps - 1) / (32 * kStem3BuildWarps);
+                int woff[kRounds], row0[kRounds], ily[kRounds], ilx[kRounds];
+                uint32_t wsel[kRounds];
 #pragma unroll
-                    for (int d = 0; d < 3; ++d) {
-                        lo[d] = *reinterpret_cast<const uint32_t*>(u8p + woff + d * kU8Row);
-                        hi[d] = *reinterpret_cast<const uint32_t*>(u8p + woff + d * kU8Row + 4);
-                    }
-#pragma unroll
-                    for (int d = 0; d < 3; ++d) wd[d] = __byte_perm(lo[d], hi[d], wsel);
-                    const bool iny = gy >= 0 && gy < H && !(p.dbg & 64);
-#pragma unroll
-                    for (int px = 0; px < 2; ++px) {
-                        const bool in = iny && gx + px >= 0 && gx + px < W;
-                        const uint32_t keep = in ? 0x3c003c00u : 0u;        // (1, 1)
-                        const uint32_t off2 = in ? 0xe400e400u : 0u;        // (-1024, -1024)
-                        const uint32_t off1 = in ? 0x0000e400u : 0u;        // (-1024, 0)
-                        // bytes 4..7 of the permutes: 0x64 (f16 exponent of 1024), 0x00, 0x00, 0x3c
-                        const uint32_t pair_sel = px ? 0x4241u : 0x4140u;   // (b[px], b[px + 1])
-                        const uint32_t one_sel = px ? 0x7543u : 0x7542u;    // (b[px + 2], 1.0)
-                        const uint32_t zero_sel = px ? 0x5543u : 0x5542u;   // (b[px + 2], 0.0)
-                        uint4 k0, k1;
-                        k0.x = fma_f16x2(__byte_perm(wd[0], 0x64646464u, pair_sel), keep, off2);
-                        k0.y = fma_f16x2(__byte_perm(wd[1], 0x64646464u, pair_sel), keep, off2);
-                        k0.z = fma_f16x2(__byte_perm(wd[2], 0x64646464u, pair_sel), keep, off2);
-                        k0.w = fma_f16x2(__byte_perm(wd[0], 0x3c000064u, one_sel), keep, off1);
-                        k1.x = fma_f16x2(__byte_perm(wd[1], 0x3c000064u, one_sel), keep, off1);
-                        k1.y = fma_f16x2(__byte_perm(wd[2], 0x3c000064u, zero_sel), keep, off1);
-                        k1.z = 0u;
-                        k1.w = 0u;
-                        const int r = row0 + px * (kHW * kHH);
-                        if (p.dbg & 512) continue;
-                        *reinterpret_cast<uint4*>(abuf + r * 16) = k0;
-                        *reinterpret_cast<uint4*>(abuf + kStemRows * 16 + r * 16) = k1;
-                    }
+                for (int rr = 0; rr < kRounds; ++rr) {
+                    const int item = min(st + rr * 32 * kStem3BuildWarps, kStemItems - 1);
+                    const int ipy = item / (kHW * kHH), irem = item - ipy * (kHW * kHH);
+                    const int ihy = irem / kHW, ihx = irem - ihy * kHW;
+                    ily[rr] = 2 * ihy + ipy;
+                    ilx[rr] = 2 * ihx;   // region pixel of (x phase 0, tap (0, 0))
+                    const int boff = ily[rr] * kU8Row + kU8Off + ilx[rr];   // its byte in the u8 box: odd
+                    woff[rr] = boff & ~3;
+                    wsel[rr] = (boff & 3) == 1 ? 0x4321u : 0x6543u;
+                    row0[rr] = 2 * ipy * (kHW * kHH) + irem;   // operand row of x phase 0 (+180: phase 1)
                 }
-                fence_proxy_async();   // visible to the tensor core's reads
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(sa_full + 8u * (iu & 1u));
-                    mbar_arrive(u8_empty + 8u * us);
-                }
-            };
-            uint32_t c = grp, iu = 0;
-            int unit = unit0;
-            if (unit < num_units) build(0, unit);
-            for (; unit < num_units; unit += unit_step, ++iu) {
-                if (unit + unit_step < num_units) build(iu + 1, unit + unit_step);
-                const uint32_t it0 = 2u * iu, it1 = 2u * iu + 1u;
-                const uint32_t s0 = it0 % p.nslots, s1 = it1 % p.nslots;
-                mbar_wait_relaxed(a_empty + 8u * s0, ((it0 / p.nslots) & 1u) ^ 1u);
-                mbar_wait_relaxed(a_empty + 8u * s1, ((it1 / p.nslots) & 1u) ^ 1u);
-                uint8_t* stage0 = gen + a_ring + s0 * kSlot;
-                uint8_t* stage1 = gen + a_ring + s1 * kSlot;
-                for (; c < static_cast<uint32_t>(kStemChunks) * (iu + 1u); c += kStemDSlots) {
-                    const int j = static_cast<int>(c - static_cast<uint32_t>(kStemChunks) * iu);
-                    mbar_wait_relaxed(sd_full + 8u * grp, (c / kStemDSlots) & 1u);
-                    tc_fence_after();
-                    uint32_t v[32];
-                    if (p.dbg & 1024) {   // experiment: no TMEM read
+                uint32_t iu = 0;
+                for (int unit = unit0; unit < num_units; unit += unit_step, ++iu) {
+                    const Tile t = decode_tile(p, tile_of(unit));
+                    const uint32_t us = iu % kU8Slots;
+                    const uint8_t* u8p = gen + u8_s + us * kU8Slot;
+                    uint8_t* abuf = gen + sA + (iu & 1u) * kStemABytes;
+                    mbar_wait_relaxed(u8_full + 8u * us, (iu / kU8Slots) & 1u);
+                    if (sw == 0) trace(0, iu, 0);
+                    mbar_wait_relaxed(sa_empty + 8u * (iu & 1u), ((iu >> 1) & 1u) ^ 1u);
+                    if (sw == 0) trace(0, iu, 1);
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = 0u;
-                    } else {
-                        tmem_ld32(tmem_base + lane_sel + kStemDCol + grp * 32u, v);
-                        tmem_ld_wait();
+                    for (int rr = 0; rr < kRounds; ++rr) {
+                        if (st + rr * 32 * kStem3BuildWarps >= kStemItems) break;
+                        const int gy = 2 * t.y0 - 2 + ily[rr], gx = 2 * t.x0 - 2 + ilx[rr];
+                        uint32_t lo[3], hi[3], wd[3];
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) {
+                            lo[d] = *reinterpret_cast<const uint32_t*>(u8p + woff[rr] + d * kU8Row);
+                            hi[d] = *reinterpret_cast<const uint32_t*>(u8p + woff[rr] + d * kU8Row + 4);
+                        }
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) wd[d] = __byte_perm(lo[d], hi[d], wsel[rr]);
+                        const bool iny = gy >= 0 && gy < H && !(p.dbg & 64);
+#pragma unroll
+                        for (int px = 0; px < 2; ++px) {
+                            const bool in = iny && gx + px >= 0 && gx + px < W;
+                            const uint32_t keep = in ? 0x3c003c00u : 0u;        // (1, 1)
+                            const uint32_t off2 = in ? 0xe400e400u : 0u;        // (-1024, -1024)
+                            const uint32_t off1 = in ? 0x0000e400u : 0u;        // (-1024, 0)
+                            // bytes 4..7 of the permutes: 0x64 (f16 exponent of 1024), 0x00, 0x00, 0x3c
+                            const uint32_t pair_sel = px ? 0x4241u : 0x4140u;   // (b[px], b[px + 1])
+                            const uint32_t one_sel = px ? 0x7543u : 0x7542u;    // (b[px + 2], 1.0)
+                            const uint32_t zero_sel = px ? 0x5543u : 0x5542u;   // (b[px + 2], 0.0)
+                            uint4 k0, k1;
+                            k0.x = fma_f16x2(__byte_perm(wd[0], 0x64646464u, pair_sel), keep, off2);
+                            k0.y = fma_f16x2(__byte_perm(wd[1], 0x64646464u, pair_sel), keep, off2);
+                            k0.z = fma_f16x2(__byte_perm(wd[2], 0x64646464u, pair_sel), keep, off2);
+                            k0.w = fma_f16x2(__byte_perm(wd[0], 0x3c000064u, one_sel), keep, off1);
+                            k1.x = fma_f16x2(__byte_perm(wd[1], 0x3c000064u, one_sel), keep, off1);
+                            k1.y = fma_f16x2(__byte_perm(wd[2], 0x3c000064u, zero_sel), keep, off1);
+                            k1.z = 0u;
+                            k1.w = 0u;
+                            const int r = row0[rr] + px * (kHW * kHH);
+                            if (p.dbg & 512) continue;
+                            *reinterpret_cast<uint4*>(abuf + r * 16) = k0;
+                            *reinterpret_cast<uint4*>(abuf + kStemRows * 16 + r * 16) = k1;
+                        }
                     }
-                    tc_fence_before();
+                    fence_proxy_async();   // visible to the tensor core's reads
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(sd_empty + 8u * grp);   // the values are in registers
-                    const int r = j * 128 + (sw & 3) * 32 + lane;
-                    if (r < kStemRows && !(p.dbg & 256)) {
+                    if (lane == 0) {
+                        mbar_arrive(sa_full + 8u * (iu & 1u));
+                        mbar_arrive(u8_empty + 8u * us);
+                    }
+                    if (sw == 0) trace(0, iu, 2);
+                }
+            } else {
+                // Drain, in two steps per tile so that the A stages are busy as briefly as possible:
+                // (1) both chunks of this group leave TMEM as soon as their MMAs are done -- ReLU,
+                // bf16, 2 x 4 packed 16-byte cells kept in registers -- which also frees the
+                // accumulator slots for the issuer early; (2) only the eight stores wait for the two
+                // stages of the ring (CTA 0's timeline, scripts/stem_trace.py: with load and store
+                // both behind the stage wait a tile's stages were refilled 3 300 cycles after the main
+                // MMAs had released them, and the ring holds two tiles).
+                const uint32_t dg = static_cast<uint32_t>(sw - kStem3BuildWarps) >> 2;   // 0..2
+                const uint32_t lane_sel = static_cast<uint32_t>((sw & 3) * 32) << 16;
+                const bool trd = sw == kStem3BuildWarps;
+                uint32_t iu = 0;
+                for (int unit = unit0; unit < num_units; unit += unit_step, ++iu) {
+                    uint4 q[2][4];
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) {   // 8-channel groups: (stage, plane group)
-                            const uint4 q = make_uint4(
+                    for (int h = 0; h < 2; ++h) {
+                        const uint32_t j = dg + 3u * h;
+                        const uint32_t c = static_cast<uint32_t>(kStemChunks) * iu + j;
+                        const uint32_t slot = c % kStem3DSlots;
+                        mbar_wait_relaxed(sd_full + 8u * slot, (c / kStem3DSlots) & 1u);
+                        if (trd) trace(1, iu, h ? 4 : 1);
+                        tc_fence_after();
+                        uint32_t v[32];
+                        if (p.dbg & 1024) {   // experiment: no TMEM read
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = 0u;
+                        } else {
+                            tmem_ld32(tmem_base + lane_sel + kStem3DCol + slot * 32u, v);
+                            tmem_ld_wait();
+                        }
+                        tc_fence_before();
+                        __syncwarp();
+                        // the values are in registers. Slot (6 T + k) % 4 of tile T was last used by
+                        // chunk 6 T + k - 4: chunks 2..5 of tile T - 1 for k = 0..3, chunks 0, 1 of
+                        // tile T itself for k = 4, 5 -- TWO barrier waits per tile for the issuer
+                        // instead of six.
+                        if (lane == 0) mbar_arrive(sd_empty + 8u * ((j < 2 ? 2u : 0u) + (iu & 1u)));
+                        if (trd) trace(1, iu, h ? 5 : 2);
+#pragma unroll
+                        for (int g = 0; g < 4; ++g)   // 8-channel groups: (stage, plane group)
+                            q[h][g] = make_uint4(
                                 pack_relu_bf16x2(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1])),
                                 pack_relu_bf16x2(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3])),
                                 pack_relu_bf16x2(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])),
                                 pack_relu_bf16x2(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
-                            uint8_t* dst = ((g >> 1) ? stage1 : stage0) + (g & 1) * 4 * kPlane + r * 16;
-                            *reinterpret_cast<uint4*>(dst) = q;
+                    }
+                    const uint32_t it0 = 2u * iu, it1 = 2u * iu + 1u;
+                    const uint32_t s0 = it0 % p.nslots, s1 = it1 % p.nslots;
+                    mbar_wait_relaxed(a_empty + 8u * s0, ((it0 / p.nslots) & 1u) ^ 1u);
+                    mbar_wait_relaxed(a_empty + 8u * s1, ((it1 / p.nslots) & 1u) ^ 1u);
+                    if (trd) trace(1, iu, 0);
+                    uint8_t* stage0 = gen + a_ring + s0 * kSlot;
+                    uint8_t* stage1 = gen + a_ring + s1 * kSlot;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int r = static_cast<int>(dg + 3u * h) * 128 + (sw & 3) * 32 + lane;
+                        if (r < kStemRows && !(p.dbg & 256)) {
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                uint8_t* dst = ((g >> 1) ? stage1 : stage0) + (g & 1) * 4 * kPlane + r * 16;
+                                *reinterpret_cast<uint4*>(dst) = q[h][g];
+                            }
                         }
                     }
                     fence_proxy_async();
@@ -440,6 +503,7 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
                         mbar_arrive(a_full + 8u * s0);
                         mbar_arrive(a_full + 8u * s1);
                     }
+                    if (trd) trace(1, iu, 6);
                 }
             }
         } else if (STEM == 2) {
@@ -654,6 +718,7 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
                     const Tile t = decode_tile(p, tile_of(unit));
                     const uint32_t us = iu % kU8Slots;
                     mbar_wait_relaxed(u8_empty + 8u * us, ((iu / kU8Slots) & 1u) ^ 1u);
+                    trace(7, iu, 0);
                     mbar_arrive_expect_tx(u8_full + 8u * us, kU8Bytes);
                     tma_load_3d(u8_s + us * kU8Slot, &tmS, u8_full + 8u * us, 2 * t.x0 - 16, 2 * t.y0 - 3,
                                 t.n);
@@ -725,31 +790,91 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
                 constexpr uint64_t b_hi_s = static_cast<uint64_t>((128u >> 4) | (1u << 14)) << 32;
                 const uint64_t bd_hi = b_hi_s | ((sB >> 4) | (32u << 16));            // LBO = 16 N = 512 B
                 const uint64_t bd_lo = bd_hi + (1024u >> 4);
-                uint32_t c = 0, iu = 0;
-                for (int unit = unit0; unit < num_units; unit += unit_step, ++iu) {
-                    const uint32_t b = iu & 1u;
-                    mbar_wait(sa_full + 8u * b, (iu >> 1) & 1u);
-                    tc_fence_after();
-#pragma unroll 1
-                    for (int j = 0; j < kStemChunks; ++j, ++c) {
-                        const uint32_t slot = c % kStemDSlots;
-                        mbar_wait(sd_empty + 8u * slot, ((c / kStemDSlots) & 1u) ^ 1u);
-                        tc_fence_after();
-                        if (elect_one()) {
-                            const uint64_t ad =
-                                (static_cast<uint64_t>(a_hi_s) << 32) |
-                                (((sA + b * kStemABytes + static_cast<uint32_t>(j) * 2048u) >> 4) | a_lbo_s);
-                            const uint32_t d = tmem_base + kStemDCol + slot * 32u;
-                            // STEM 2: bf16 x bf16 (in either translation unit); STEM 3: f16 x f16
-                            const uint32_t idesc = p.stem_idesc;
-                            if (!(p.dbg & 1)) {
-                                umma_bf16(d, ad, bd_hi, idesc, 0u);
-                                if (p.stem_lo) umma_bf16(d, ad, bd_lo, idesc, 1u);
+                if (STEM == 3) {
+                    // Two slot waits per tile (plus the im2col buffer) and the tile's 6 x 2 MMAs and 7
+                    // commits as straight-line code: the slot of chunk j of tile T is (6 T + j) % 4,
+                    // which depends on T % 2 only, so both variants are unrolled with compile-time
+                    // descriptor offsets (operands in uniform registers, as in the main issuers).
+                    // Measured before (CTA 0's timeline, scripts/stem_trace.py): with a wait + elect +
+                    // issue round per chunk this warp needed ~3 800 cycles per tile and paced the
+                    // whole kernel (period 4 300 cycles per tile).
+                    const uint32_t idesc = p.stem_idesc;
+                    const bool lo = p.stem_lo != 0, no_mma = (p.dbg & 1) != 0;
+                    const uint64_t ad0 = (static_cast<uint64_t>(a_hi_s) << 32) | ((sA >> 4) | a_lbo_s);
+                    const uint32_t d0 = tmem_base + kStem3DCol;
+                    auto issue = [&](auto ph_tag, auto j0_tag, auto j1_tag) {
+                        constexpr uint32_t PH = decltype(ph_tag)::value;   // T % 2
+                        constexpr uint32_t kTileA = PH * (kStemABytes >> 4);
+#pragma unroll
+                        for (uint32_t j = decltype(j0_tag)::value; j < decltype(j1_tag)::value; ++j) {
+                            const uint32_t slot = (2u * PH + j) & 3u;
+                            const uint64_t ad = ad0 + (kTileA + j * (2048u >> 4));
+                            if (!no_mma) {
+                                umma_bf16(d0 + slot * 32u, ad, bd_hi, idesc, 0u);
+                                if (lo) umma_bf16(d0 + slot * 32u, ad, bd_lo, idesc, 1u);
                             }
                             umma_commit(sd_full + 8u * slot);
-                            if (j == kStemChunks - 1) umma_commit(sa_empty + 8u * b);
+                        }
+                        if (decltype(j1_tag)::value == kStemChunks) umma_commit(sa_empty + 8u * PH);
+                    };
+                    using U0 = std::integral_constant<uint32_t, 0>;
+                    using U1 = std::integral_constant<uint32_t, 1>;
+                    using U4 = std::integral_constant<uint32_t, 4>;
+                    using U6 = std::integral_constant<uint32_t, 6>;
+                    uint32_t iu = 0;
+                    for (int unit = unit0; unit < num_units; unit += unit_step, ++iu) {
+                        const uint32_t par = iu & 1u;
+                        mbar_wait(sa_full + 8u * par, (iu >> 1) & 1u);
+                        trace(2, iu, 0);
+                        if (iu) mbar_wait(sd_empty + 8u * (par ^ 1u), ((iu - 1u) >> 1) & 1u);
+                        trace(2, iu, 1);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            if (par) issue(U1{}, U0{}, U4{});
+                            else issue(U0{}, U0{}, U4{});
                         }
                         __syncwarp();
+                        trace(2, iu, 2);
+                        mbar_wait(sd_empty + 8u * (2u + par), (iu >> 1) & 1u);
+                        trace(2, iu, 3);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            if (par) issue(U1{}, U4{}, U6{});
+                            else issue(U0{}, U4{}, U6{});
+                        }
+                        __syncwarp();
+                        trace(2, iu, 4);
+                    }
+                } else {
+                    uint32_t c = 0, iu = 0;
+                    for (int unit = unit0; unit < num_units; unit += unit_step, ++iu) {
+                        const uint32_t b = iu & 1u;
+                        mbar_wait(sa_full + 8u * b, (iu >> 1) & 1u);
+                        trace(2, iu, 0);
+                        tc_fence_after();
+#pragma unroll 1
+                        for (int j = 0; j < kStemChunks; ++j, ++c) {
+                            const uint32_t slot = c % kDSlots;
+                            mbar_wait(sd_empty + 8u * slot, ((c / kDSlots) & 1u) ^ 1u);
+                            if (j == 0 || j == kStemChunks - 1) trace(2, iu, j == 0 ? 1 : 3);
+                            tc_fence_after();
+                            if (elect_one()) {
+                                const uint64_t ad =
+                                    (static_cast<uint64_t>(a_hi_s) << 32) |
+                                    (((sA + b * kStemABytes + static_cast<uint32_t>(j) * 2048u) >> 4) | a_lbo_s);
+                                const uint32_t d = tmem_base + kDCol + slot * 32u;
+                                // STEM 2: bf16 x bf16 (in either translation unit); STEM 3: f16 x f16
+                                const uint32_t idesc = p.stem_idesc;
+                                if (!(p.dbg & 1)) {
+                                    umma_bf16(d, ad, bd_hi, idesc, 0u);
+                                    if (p.stem_lo) umma_bf16(d, ad, bd_lo, idesc, 1u);
+                                }
+                                umma_commit(sd_full + 8u * slot);
+                                if (j == kStemChunks - 1) umma_commit(sa_empty + 8u * b);
+                            }
+                            __syncwarp();
+                            if (j == 0 || j == kStemChunks - 1) trace(2, iu, j == 0 ? 2 : 4);
+                        }
                     }
                 }
             }
@@ -792,13 +917,26 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
                 const uint32_t aph = (li / kBufs) & 1u;
                 if (CG == 2) mbar_wait_cluster(acc_empty + 8u * buf, aph ^ 1u);
                 else mbar_wait(acc_empty + 8u * buf, aph ^ 1u);
+                trace(3 + static_cast<int>(me), li, 0);
                 tc_fence_after();
                 const uint32_t d0 = tmem_base + buf * 128u;
+                // All stages of the tile first, then its MMAs without a barrier wait between them:
+                // every wait of an issuer is a hole in the tensor pipe (~500 cycles between the two
+                // slabs of a tile in CTA 0's timeline, scripts/stem_trace.py), and the producers run
+                // a tile ahead anyway (the in-kernel stem even completes both stages together).
+                if (p.wait_all)
+                    for (int s = 0; s < p.n_stages; ++s) {
+                        const uint32_t it = ita + static_cast<uint32_t>(s);
+                        mbar_wait(a_full + 8u * (it % p.nslots), (it / p.nslots) & 1u);
+                    }
                 for (int s = 0; s < p.n_s2d; ++s, ++ita) {
                     const uint32_t slot = ita % p.nslots;
-                    // fused stem: the CUDA-core stem warps are the critical path, not the issuers
-                    if (STEM && c_wait_cfg[3]) mbar_wait_relaxed(a_full + 8u * slot, (ita / p.nslots) & 1u);
-                    else mbar_wait(a_full + 8u * slot, (ita / p.nslots) & 1u);
+                    if (!p.wait_all) {
+                        // fused stem: the CUDA-core stem warps are the critical path, not the issuers
+                        if (STEM && c_wait_cfg[3]) mbar_wait_relaxed(a_full + 8u * slot, (ita / p.nslots) & 1u);
+                        else mbar_wait(a_full + 8u * slot, (ita / p.nslots) & 1u);
+                    }
+                    trace(3 + static_cast<int>(me), li, 1 + 2 * s);
                     tc_fence_after();
                     const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) |
                                         (((a_ring + slot * kSlot) >> 4) | a_lbo_s2d);
@@ -819,10 +957,11 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
                         if (last) commit(acc_full + 8u * buf);
                     }
                     __syncwarp();
+                    trace(3 + static_cast<int>(me), li, 2 + 2 * s);
                 }
                 if (p.has_below) {
                     const uint32_t slot = ita % p.nslots;
-                    mbar_wait(a_full + 8u * slot, (ita / p.nslots) & 1u);
+                    if (!p.wait_all) mbar_wait(a_full + 8u * slot, (ita / p.nslots) & 1u);
                     tc_fence_after();
                     const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) |
                                         (((a_ring + slot * kSlot) >> 4) | a_lbo_plain);
@@ -869,6 +1008,7 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
             const int Y = t.y0 + py, X = t.x0 + px;
             const bool valid = in_range && Y < p.H2 && X < p.W2 && !(p.dbg & 2);
             mbar_wait_relaxed(acc_full + 8u * buf, aph);
+            if ((warp & 3) == 0) trace(5 + grp, li, 0);
             tc_fence_after();
             const uint32_t tcol = tmem_base + lane_sel + buf * 128u;
             uint32_t mx[16];
@@ -967,6 +1107,7 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
             tc_fence_before();
             if (CG == 2) mbar_arrive_cluster(map_to_cta(acc_empty + 8u * buf, 0));
             else mbar_arrive(acc_empty + 8u * buf);
+            if ((warp & 3) == 0) trace(5 + grp, li, 1);
         }
     }
 
@@ -1287,7 +1428,7 @@ int launch_s2d_tc(const S2dLayer& L, const __nv_bfloat16* src_s2d, const __nv_bf
     p.num_tiles = static_cast<int>(total);
     p.magic_tx = ((1ull << 40) / static_cast<unsigned long long>(p.tiles_x)) + 1;
     p.magic_tpf = ((1ull << 40) / static_cast<unsigned long long>(p.tiles_x * p.tiles_y)) + 1;
-    static const int dbg_env = getenv("OGL_DBG") ? atoi(getenv("OGL_DBG")) : 0;
+    static const int dbg_env = experiment_dbg();
     p.dbg = dbg_env;
     p.reverse = reverse ? 1 : 0;
 
@@ -1314,6 +1455,8 @@ int launch_s2d_tc(const S2dLayer& L, const __nv_bfloat16* src_s2d, const __nv_bf
     p.nslots = nslots;
     static const int dual_env = getenv("OGL_DUAL") ? atoi(getenv("OGL_DUAL")) : 1;
     p.dual = (dual_env && nslots >= 2 * p.n_stages) ? 1 : 0;
+    static const int wait_all_env = getenv("OGL_S2D_WAITALL") ? atoi(getenv("OGL_S2D_WAITALL")) : 0;
+    p.wait_all = (wait_all_env && nslots >= p.n_stages) ? 1 : 0;
 
     CUtensorMap tmS, tmB;
     if (fused_stem) {
@@ -1325,6 +1468,14 @@ int launch_s2d_tc(const S2dLayer& L, const __nv_bfloat16* src_s2d, const __nv_bf
         if (encode_map(&tmS, stem_frames, 3, dims, str, box, true)) return 1;
         memset(&tmB, 0, sizeof tmB);
         const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+        static const char* trace_env = getenv("OGL_TRACE");   // debug: file for CTA 0's timeline
+        static unsigned long long* trace_dev = nullptr;
+        const size_t trace_n = static_cast<size_t>(kTraceRoles) * kTraceTiles * 8;
+        if (trace_env && tc_stem && stem_tc_warps == 16) {
+            if (!trace_dev) OGL_CUDA(cudaMalloc(&trace_dev, trace_n * 8));
+            OGL_CUDA(cudaMemsetAsync(trace_dev, 0, trace_n * 8, stream));
+            p.trace = trace_dev;
+        }
         if (tc_stem) {
             if (nslots < 4) return fail("s2d layer: the tensor-core stem needs 4 activation stages");
             if (stem_tc_warps == 16)
@@ -1338,6 +1489,15 @@ int launch_s2d_tc(const S2dLayer& L, const __nv_bfloat16* src_s2d, const __nv_bf
                 <<<grid, kThreads + kStemThreads, smem, stream>>>(tmS, tmB, p);
         }
         OGL_CUDA(cudaGetLastError());
+        if (p.trace) {   // debug only: synchronises
+            std::vector<unsigned long long> host(trace_n);
+            OGL_CUDA(cudaStreamSynchronize(stream));
+            OGL_CUDA(cudaMemcpy(host.data(), trace_dev, trace_n * 8, cudaMemcpyDeviceToHost));
+            if (FILE* f = fopen(trace_env, "wb")) {
+                fwrite(host.data(), 8, trace_n, f);
+                fclose(f);
+            }
+        }
         return 0;
     }
     {

@@ -187,44 +187,36 @@ def gray_clip_from_bgr(frames_bgr: list, dev: torch.device, chunk: int = 2048) -
     return gray
 
 
-def decode_gray_clip(avi_path: str, dev: torch.device, workers: int | None = None,
-                     chunk: int = 1024, timings: dict | None = None) -> torch.Tensor | None:
-    """Video file -> ``(N, H, W)`` uint8 gray CUDA tensor, or ``None`` for a file without frames:
-    ``load_frames_bgr`` + ``cvtColor`` of /root/reference/openglottal/features.py:226,235 as a
-    pipeline. Intra-only codecs (MJPG, FFV1, raw) are decoded by ``workers`` threads, each with
-    its own ``VideoCapture`` on a contiguous frame range, straight into two pinned BGR chunk
-    buffers; while the next chunk decodes, the previous one crosses PCIe and becomes gray on the
-    GPU (OpenCV's integer coefficients, bit-exact). The frames are those the reference's
-    sequential loop decodes (same decoder, frame-exact seeks; checked in tests). Other codecs, a
-    header without a plausible frame count, or any short read fall back to the sequential loop.
-    ``timings`` (optional dict) receives ``decode_s`` / ``total_s`` / ``workers`` / ``mode``."""
+class _DecodeFallback(Exception):
+    """The parallel decoder met something it does not trust; the caller restarts sequentially."""
+
+
+def iter_gray_chunks(avi_path: str, dev: torch.device, workers: int | None = None,
+                     chunk: int = 1024, out: torch.Tensor | None = None, stats: dict | None = None):
+    """Generator over ``(first frame index, (m, H, W) uint8 gray CUDA tensor)`` of a video whose
+    codec is intra-only (``parallel_decodable``), in order. ``workers`` threads, each with its own
+    ``VideoCapture`` on a contiguous frame range, decode straight into two pinned BGR chunk
+    buffers; the chunk crosses PCIe and becomes gray (OpenCV's integer coefficients, bit-exact) on
+    a side stream, and the yielded tensor is ordered after that on the CURRENT stream -- so a
+    consumer that enqueues GPU work per chunk overlaps it with the decode of the next chunk.
+    ``out``: an ``(N, H, W)`` tensor to fill (slices are yielded) instead of one tensor per chunk.
+    Raises ``_DecodeFallback`` (before or between chunks) when a read comes back short or the
+    container holds more frames than its header says."""
     import time
     from concurrent.futures import ThreadPoolExecutor
 
-    t_start = time.perf_counter()
     workers = decode_workers(workers)
     info = video_info(avi_path)
-
-    def sequential():
-        frames_bgr = load_frames_bgr(avi_path)
-        t_dec = time.perf_counter()
-        gray = gray_clip_from_bgr(frames_bgr, dev) if frames_bgr else None
-        if timings is not None:
-            torch.cuda.synchronize(dev)
-            timings.update(mode="sequential", workers=1, decode_s=t_dec - t_start,
-                           total_s=time.perf_counter() - t_start)
-        return gray
-
     if not parallel_decodable(info, workers):
-        return sequential()
+        raise _DecodeFallback("not an intra-only clip with a plausible header")
     n, hgt, wid = info["frames"], info["height"], info["width"]
     chunk = max(workers, min(chunk, n))
-    gray = torch.empty((n, hgt, wid), dtype=torch.uint8, device=dev)
     bufs = [torch.empty((chunk, hgt, wid, 3), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
     views = [b.numpy() for b in bufs]
     copy = torch.cuda.Stream(device=dev)
     freed = [torch.cuda.Event(), torch.cuda.Event()]
-    decode_s, ok = 0.0, True
+    if stats is not None:
+        stats.update(frames=n, height=hgt, width=wid, workers=workers, decode_s=0.0)
     with _silence_stderr(), ThreadPoolExecutor(workers) as pool:
         decs = list(pool.map(lambda _: RangeDecoder(avi_path), range(workers)))
         try:
@@ -237,25 +229,57 @@ def decode_gray_clip(avi_path: str, dev: torch.device, workers: int | None = Non
                 got = list(pool.map(lambda w: decs[w].read_into(i0 + cut[w], i0 + cut[w + 1],
                                                                 views[b][cut[w]:cut[w + 1]]),
                                     range(workers)))
-                decode_s += time.perf_counter() - t0
+                if stats is not None:
+                    stats["decode_s"] += time.perf_counter() - t0
                 if any(g != cut[w + 1] - cut[w] for w, g in enumerate(got)):
-                    ok = False
-                    break
+                    raise _DecodeFallback("short read")
+                if i0 + m == n and decs[-1].cap.read()[0]:
+                    raise _DecodeFallback("frames beyond the header's count")
+                cur = torch.cuda.current_stream(dev)
+                gray = out[i0:i0 + m] if out is not None else torch.empty(
+                    (m, hgt, wid), dtype=torch.uint8, device=dev)
+                copy.wait_stream(cur)             # earlier users of this memory are done
                 with torch.cuda.stream(copy):
-                    part = bufs[b][:m].to(dev, non_blocking=True)
-                    gray[i0:i0 + m] = bgr_to_gray(part)
+                    gray.copy_(bgr_to_gray(bufs[b][:m].to(dev, non_blocking=True)))
                     freed[b].record(copy)
-            if ok and decs[-1].pos == n and decs[-1].cap.read()[0]:
-                ok = False       # frames beyond the header's count: the sequential loop reads them
+                cur.wait_stream(copy)
+                yield i0, gray
         finally:
             for d in decs:
                 d.release()
-    torch.cuda.current_stream(dev).wait_stream(copy)
-    if not ok:
-        return sequential()
+
+
+def decode_gray_clip(avi_path: str, dev: torch.device, workers: int | None = None,
+                     chunk: int = 1024, timings: dict | None = None) -> torch.Tensor | None:
+    """Video file -> ``(N, H, W)`` uint8 gray CUDA tensor, or ``None`` for a file without frames:
+    ``load_frames_bgr`` + ``cvtColor`` of /root/reference/openglottal/features.py:226,235.
+    Intra-only codecs (MJPG, FFV1, raw) go through ``iter_gray_chunks`` -- the frames are those
+    the reference's sequential loop decodes (same decoder, frame-exact seeks; checked in tests) --
+    anything else, or anything that decoder does not trust, through the sequential loop.
+    ``timings`` (optional dict) receives ``decode_s`` / ``total_s`` / ``workers`` / ``mode``."""
+    import time
+
+    t_start = time.perf_counter()
+    stats: dict = {}
+    try:
+        info = video_info(avi_path)
+        gray = torch.empty((max(info["frames"], 0), max(info["height"], 0), max(info["width"], 0)),
+                           dtype=torch.uint8, device=dev)
+        for _ in iter_gray_chunks(avi_path, dev, workers, chunk, out=gray, stats=stats):
+            pass
+        if timings is not None:
+            torch.cuda.synchronize(dev)
+            timings.update(mode="parallel", workers=stats["workers"], decode_s=stats["decode_s"],
+                           total_s=time.perf_counter() - t_start)
+        return gray
+    except _DecodeFallback:
+        pass
+    frames_bgr = load_frames_bgr(avi_path)
+    t_dec = time.perf_counter()
+    gray = gray_clip_from_bgr(frames_bgr, dev) if frames_bgr else None
     if timings is not None:
         torch.cuda.synchronize(dev)
-        timings.update(mode="parallel", workers=workers, decode_s=decode_s,
+        timings.update(mode="sequential", workers=1, decode_s=t_dec - t_start,
                        total_s=time.perf_counter() - t_start)
     return gray
 
@@ -322,8 +346,18 @@ def extract_features_unet(avi_path: str, detector, model, device=None) -> dict |
     model = _require_native(model)
     dev = model._device()
     if detector is None:
-        # unet-only: no consumer of the BGR frames on the host, so they are never held as a list
-        gray = decode_gray_clip(avi_path, dev)
+        # unet-only: no consumer of the BGR frames on the host, so they are never held as a list.
+        # Intra-only clips stream: chunk k is segmented on the GPU while chunk k + 1 decodes.
+        try:
+            area = None
+            for i0, part in iter_gray_chunks(avi_path, dev):
+                if area is None:
+                    area = torch.empty(video_info(avi_path)["frames"], dtype=torch.int32, device=dev)
+                area[i0:i0 + part.shape[0]] = masks_for_clip(part, model)[0]
+            return kinematic_features_device(area)
+        except _DecodeFallback:
+            pass
+        gray = decode_gray_clip(avi_path, dev, workers=1)
         if gray is None:
             return None
         area, _ = masks_for_clip(gray, model)

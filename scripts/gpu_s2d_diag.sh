@@ -3,8 +3,8 @@ timeout 300 python -m pytest tests/test_gpu_layers.py tests/test_gpu_model.py -q
 rm -f gpurun_out/exp_diag.jsonl gpurun_out/exp_diag.err
 run() { env "$@" timeout 120 python scripts/layer_times.py 512 3 "$*" >> gpurun_out/exp_diag.jsonl 2>> gpurun_out/exp_diag.err; }
 run OGL_FUSE_STEM=0 OGL_CG=1
-run OGL_FUSE_STEM=0 OGL_CG=1 OGL_DBG=12
-run OGL_FUSE_STEM=0 OGL_CG=1 OGL_DBG=13
+run OGL_FUSE_STEM=0 OGL_CG=1 OGL_EXPERIMENT=1 OGL_DBG=12
+run OGL_FUSE_STEM=0 OGL_CG=1 OGL_EXPERIMENT=1 OGL_DBG=13
 run OGL_FUSE_STEM=1 OGL_CG=2
 run OGL_FUSE_STEM=1 OGL_CG=2
 python - <<'PY'

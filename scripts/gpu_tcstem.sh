@@ -10,5 +10,5 @@ run OGL_FUSE_STEM=1
 run OGL_FUSE_STEM=2
 run OGL_FUSE_STEM=1
 run OGL_FUSE_STEM=2
-run OGL_FUSE_STEM=2 OGL_DBG=64
+run OGL_FUSE_STEM=2 OGL_EXPERIMENT=1 OGL_DBG=64
 python scripts/show_exp.py gpurun_out/exp_tcstem.jsonl | cut -c1-120; tail -3 gpurun_out/exp_tcstem.err

@@ -59,6 +59,8 @@ seq_fps = m / (time.perf_counter() - t0)
 cap.release()
 
 ogl.decode_gray_clip(str(clip), dev, workers=workers)          # warm (page cache, pinned pools)
+ogl.masks_for_clip(torch.zeros((1024, 256, 256), dtype=torch.uint8, device=dev), model)   # workspace
+torch.cuda.synchronize()
 tim = {}
 gray = ogl.decode_gray_clip(str(clip), dev, workers=workers, timings=tim)
 torch.cuda.synchronize()
@@ -72,6 +74,17 @@ t0 = time.perf_counter()
 feats_e2e = ogl.extract_features_unet(str(clip), None, model)
 torch.cuda.synchronize()
 e2e_s = time.perf_counter() - t0
+# the same streaming loop by hand, with the decoder's own statistics and per-chunk wall times
+from openglottal_b200.features import iter_gray_chunks  # noqa: E402
+st, marks = {}, []
+t0 = time.perf_counter()
+area2 = torch.empty(n, dtype=torch.int32, device=dev)
+for i0, part in iter_gray_chunks(str(clip), dev, workers=workers, stats=st):
+    t1 = time.perf_counter()
+    area2[i0:i0 + part.shape[0]] = ogl.masks_for_clip(part, model)[0]
+    marks.append((round(t1 - t0, 4), round(time.perf_counter() - t1, 4)))
+torch.cuda.synchronize()
+stream_s = time.perf_counter() - t0
 same = all(feats[k] == feats_e2e[k] for k in ("area_mean", "area_std", "f0", "periodicity"))
 
 def have(lib):
@@ -94,6 +107,8 @@ print(json.dumps({
     "unet_area_features_on_resident_clip": {"fps": round(n / seg_s), "seconds": round(seg_s, 3)},
     "extract_features_unet_end_to_end": {"fps": round(n / e2e_s), "seconds": round(e2e_s, 3),
                                          "same_features_as_staged_run": bool(same)},
+    "streaming_loop": {"seconds": round(stream_s, 3), "decode_wait_seconds": round(st["decode_s"], 3),
+                       "chunk_yield_time_and_enqueue_seconds": marks[:6]},
     "bottleneck": "decode" if tim["total_s"] > seg_s else "unet",
     "hardware_decoders": {"libnvcuvid": have("nvcuvid"), "libnvjpeg": have("nvjpeg"),
                           "cv2_cudacodec": hasattr(cv2, "cudacodec")},

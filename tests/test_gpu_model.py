@@ -245,6 +245,13 @@ def test_repeated_launch_is_idempotent(eager_model):
             assert torch.equal(ref[0], got[0]) and torch.equal(ref[1], got[1]), idx
             assert torch.equal(ref[2], got[2]), idx
         assert lib.ogl_unet_set_repeat(native_model._handle, 0, 0) != 0      # times out of range
+        # the head launch adds popcounts to the area vector: repeating it with an area output
+        # would multiply the areas, so the forward refuses (and runs without one)
+        _native.check(lib.ogl_unet_set_repeat(native_model._handle, n_launch - 1, 2))
+        with pytest.raises(RuntimeError, match="head launch is repeated"):
+            native_model.run(frames)
+        got = native_model.run(frames, want_logits=True, want_area=False)
+        assert torch.equal(ref[0], got[0]) and torch.equal(ref[1], got[1])
     finally:
         _native.check(lib.ogl_unet_set_repeat(native_model._handle, -1, 1))
 
