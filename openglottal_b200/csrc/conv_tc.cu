@@ -196,12 +196,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     if (warp == 0) {
         // ================================================ activation producer
         if (lane == 0) {
-            uint32_t it = 0;
+            Ring ra;
             for (int item = item0; item < items; item += item_step) {
                 const int tile = tile_of(item);
-                for (int kb = 0; kb < kb_total; ++kb, ++it) {
-                    const uint32_t s = it % p.na;
-                    const uint32_t ph = (it / p.na) & 1u;
+                for (int kb = 0; kb < kb_total; ++kb, ra.next(p.na)) {
+                    const uint32_t s = ra.slot;
+                    const uint32_t ph = ra.phase;
                     mbar_wait_relaxed(a_empty + 8u * s, ph ^ 1u);
                     if (CG == 1 && (p.dbg & 8)) {
                         mbar_arrive(a_full + 8u * s);
@@ -234,14 +234,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     } else if (warp == 3) {
         // ==================================================== weight producer
         if (lane == 0) {
-            uint32_t it = 0;
+            Ring rw;
             const uint8_t* wbytes = reinterpret_cast<const uint8_t*>(p.wpack);
+            const int tgs = p.taps / TPS;
             for (int item = item0; item < items; item += item_step) {
                 const int pass = pass_of(item);
                 for (int kb = 0; kb < kb_total; ++kb) {
-                    for (int tg = 0; tg < p.taps / TPS; ++tg, ++it) {
-                        const uint32_t s = it % p.nw;
-                        const uint32_t ph = (it / p.nw) & 1u;
+                    for (int tg = 0; tg < tgs; ++tg, rw.next(p.nw)) {
+                        const uint32_t s = rw.slot;
+                        const uint32_t ph = rw.phase;
                         mbar_wait_relaxed(w_empty + 8u * s, ph ^ 1u);
                         if (CG == 1 && (p.dbg & 16)) {
                             mbar_arrive(w_full + 8u * s);
@@ -305,10 +306,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             if (CG == 2) mbar_wait_cluster(bar, parity);   // the peer's epilogue arrives remotely
             else mbar_wait(bar, parity);
         };
-        uint32_t ita = 0, itw = 0, li = 0;
-        for (int item = item0; item < items; item += item_step, ++li) {
-            const uint32_t buf = kSplit ? 0u : li % p.acc_bufs;
-            const uint32_t aph = kSplit ? (li & 1u) : (li / p.acc_bufs) & 1u;
+        // ring positions advanced without integer division (ptx.cuh: Ring)
+        Ring ra, rw, rb;
+        const int tgs = p.taps / TPS;
+        uint32_t li = 0;
+        for (int item = item0; item < items; item += item_step, ++li, rb.next(p.acc_bufs)) {
+            const uint32_t buf = kSplit ? 0u : rb.slot;
+            const uint32_t aph = kSplit ? (li & 1u) : rb.phase;
             if (!kSplit) {
                 // acc_half: only this issuer's half of the tile has to be drained, so the two
                 // halves run as independent MMA -> epilogue chains that fall out of phase and keep
@@ -317,18 +321,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 tc_fence_after();
             }
             const uint32_t d0 = tmem_base + buf * acc_cols;
-            for (int kb = 0; kb < kb_total; ++kb, ++ita) {
-                const uint32_t sa = ita % p.na;
-                mbar_wait(a_full + 8u * sa, (ita / p.na) & 1u);
+            for (int kb = 0; kb < kb_total; ++kb, ra.next(p.na)) {
+                const uint32_t sa = ra.slot;
+                mbar_wait(a_full + 8u * sa, ra.phase);
                 const uint32_t abase = a_ring + sa * a_stage_bytes;
                 if (kSplit && (kb == 0 || kb == kb_total - 1)) {
                     // accumulator-major K block: its three weight stages (one per tap row)
                     // are held together; needs nw >= 3
                     uint32_t wst[3];
 #pragma unroll
-                    for (int tg = 0; tg < 3; ++tg) {
-                        wst[tg] = (itw + tg) % p.nw;
-                        mbar_wait(w_full + 8u * wst[tg], ((itw + tg) / p.nw) & 1u);
+                    for (int tg = 0; tg < 3; ++tg, rw.next(p.nw)) {
+                        wst[tg] = rw.slot;
+                        mbar_wait(w_full + 8u * wst[tg], rw.phase);
                     }
                     tc_fence_after();
                     for (int m = 0; m < 2; ++m) {
@@ -365,12 +369,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                         commit(a_empty + 8u * sa);
                     }
                     __syncwarp();
-                    itw += 3;
                     continue;
                 }
-                for (int tg = 0; tg < p.taps / TPS; ++tg, ++itw) {
-                    const uint32_t sw = itw % p.nw;
-                    mbar_wait(w_full + 8u * sw, (itw / p.nw) & 1u);
+                for (int tg = 0; tg < tgs; ++tg, rw.next(p.nw)) {
+                    const uint32_t sw = rw.slot;
+                    mbar_wait(w_full + 8u * sw, rw.phase);
                     tc_fence_after();
                     // TPS == 9: all taps unrolled; TPS == 3: tg is the tap row dy; TPS == 1: convT
                     const uint32_t row_off =
@@ -378,7 +381,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     const uint64_t ad = adesc0 + ((abase + row_off) >> 4);
                     const uint64_t bd = bdesc0 + ((w_ring + sw * w_stage_bytes) >> 4);
                     const uint32_t first = (kb | tg) != 0 ? 1u : 0u;
-                    const bool last_tg = tg == p.taps / TPS - 1;
+                    const bool last_tg = tg == tgs - 1;
                     if (elect_one()) {
 #pragma unroll
                         for (int t = 0; t < TPS; ++t) {
@@ -420,15 +423,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int OH = EPI == EPI_CONVT ? 2 * p.H : p.H;
         const int OW = EPI == EPI_CONVT ? 2 * p.W : p.W;
         uint32_t li = 0;
+        Ring rb;
         auto release_acc = [](uint32_t bar) {
             if (CG == 2) mbar_arrive_cluster(map_to_cta(bar, 0));  // the leader's barrier
             else mbar_arrive(bar);
         };
-        for (int item = item0; item < items; item += item_step, ++li) {
+        for (int item = item0; item < items; item += item_step, ++li, rb.next(p.acc_bufs)) {
             const int tile = tile_of(item);
             const int pass = pass_of(item);
-            const uint32_t buf = kSplit ? 0u : li % p.acc_bufs;
-            const uint32_t aph = kSplit ? (li & 1u) : (li / p.acc_bufs) & 1u;
+            const uint32_t buf = kSplit ? 0u : rb.slot;
+            const uint32_t aph = kSplit ? (li & 1u) : rb.phase;
             if (!kSplit) {
                 mbar_wait_relaxed(acc_full + 8u * (buf * 2u + egrp), aph);   // the issuer of this half
                 tc_fence_after();

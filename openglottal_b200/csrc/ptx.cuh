@@ -89,6 +89,23 @@ __device__ __forceinline__ uint32_t fma_f16x2(uint32_t a, uint32_t b, uint32_t c
     return d;
 }
 
+// Position in a ring of `n` stages and the mbarrier phase parity of its current pass, advanced
+// without integer division: `it % n` / `(it / n) & 1` with a run-time n are ~40 dependent
+// instructions (I2F, MUFU.RCP, F2I, IMADs), which in an MMA issuer's loop sit between two groups of
+// MMAs (CTA 0's timeline, scripts/stem_trace.py: ~450 cycles per barrier wait of an issuer).
+struct Ring {
+    uint32_t slot = 0, phase = 0;
+    __device__ __forceinline__ void next(uint32_t n) {
+        if (++slot == n) {
+            slot = 0;
+            phase ^= 1u;
+        }
+    }
+    __device__ __forceinline__ void skip(uint32_t n, int count) {
+        for (int i = 0; i < count; ++i) next(n);
+    }
+};
+
 // this translation unit's operand type
 __device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
     return pack_relu_x2<kF16>(lo, hi);

@@ -186,7 +186,6 @@ struct S2dParams {
     int nslots;
     int reverse;  // walk the tiles from the last frame to the first (L2 reuse, see conv_tc.cu)
     int dual;   // two MMA issuer warps on alternate tiles (needs nslots >= 2 * n_stages)
-    int wait_all;   // an issuer waits for all stages of a tile before its first MMA
     int dbg;  // 1 no MMA, 2 no stores, 4 no epilogue work, 8 no activation loads (1-CTA form)
 };
 
@@ -328,9 +327,9 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
     if (CG == 2) cluster_sync_all();  // the peer's barriers exist before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_p;
-    // debug timeline of CTA 0 (STEM = 3 only): role r, its tile number i < kTraceTiles, event e < 8
+    // debug timeline of CTA 0: role r, its tile number i < kTraceTiles, event e < 8
     auto trace = [&](int r, uint32_t i, int e) {
-        if (STEM == 3 && p.trace && blockIdx.x == 0 && lane == 0 && i < kTraceTiles)
+        if (p.trace && blockIdx.x == 0 && lane == 0 && i < kTraceTiles)
             p.trace[(static_cast<uint32_t>(r) * kTraceTiles + i) * 8u + e] = clock64();
     };
     // STEM = 3: 896 threads leave 72 registers each; the control warps and the stem warps hand
@@ -445,6 +444,7 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
                 const uint32_t lane_sel = static_cast<uint32_t>((sw & 3) * 32) << 16;
                 const bool trd = sw == kStem3BuildWarps;
                 uint32_t iu = 0;
+                Ring rs;
                 for (int unit = unit0; unit < num_units; unit += unit_step, ++iu) {
                     uint4 q[2][4];
 #pragma unroll
@@ -479,10 +479,12 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
                                 pack_relu_bf16x2(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5])),
                                 pack_relu_bf16x2(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
                     }
-                    const uint32_t it0 = 2u * iu, it1 = 2u * iu + 1u;
-                    const uint32_t s0 = it0 % p.nslots, s1 = it1 % p.nslots;
-                    mbar_wait_relaxed(a_empty + 8u * s0, ((it0 / p.nslots) & 1u) ^ 1u);
-                    mbar_wait_relaxed(a_empty + 8u * s1, ((it1 / p.nslots) & 1u) ^ 1u);
+                    const uint32_t s0 = rs.slot, ph0 = rs.phase;
+                    rs.next(p.nslots);
+                    const uint32_t s1 = rs.slot, ph1 = rs.phase;
+                    rs.next(p.nslots);
+                    mbar_wait_relaxed(a_empty + 8u * s0, ph0 ^ 1u);
+                    mbar_wait_relaxed(a_empty + 8u * s1, ph1 ^ 1u);
                     if (trd) trace(1, iu, 0);
                     uint8_t* stage0 = gen + a_ring + s0 * kSlot;
                     uint8_t* stage1 = gen + a_ring + s1 * kSlot;
@@ -727,15 +729,17 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
         } else if (warp == 0 && !STEM) {
             // ================================================ activation producer
             if (lane == 0) {
-                uint32_t it = 0;
-                for (int unit = unit0; unit < num_units; unit += unit_step) {
+                Ring rs;
+                uint32_t ti = 0;
+                for (int unit = unit0; unit < num_units; unit += unit_step, ++ti) {
                     int tile = tile_of(unit);
                     if (tile >= p.num_tiles) tile = p.num_tiles - 1;   // tail of the last pair: a duplicate
                     const Tile t = decode_tile(p, tile);
-                    for (int s = 0; s < p.n_stages; ++s, ++it) {
-                        const uint32_t slot = it % p.nslots;
-                        const uint32_t ph = (it / p.nslots) & 1u;
+                    for (int s = 0; s < p.n_stages; ++s, rs.next(p.nslots)) {
+                        const uint32_t slot = rs.slot;
+                        const uint32_t ph = rs.phase;
                         mbar_wait_relaxed(a_empty + 8u * slot, ph ^ 1u);
+                        trace(7, ti, s);
                         const uint32_t dst = a_ring + slot * kSlot;
                         if (CG == 1 && (p.dbg & 8)) {   // experiment: no activation loads
                             mbar_arrive(a_full + 8u * slot);
@@ -909,33 +913,28 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
             };
             mbar_wait(w_full, 0);
             if (CG == 2) mbar_wait_cluster(w_peer, 0);
-            uint32_t ita = 0, li = 0;
-            for (int unit = unit0; unit < num_units; unit += unit_step, ++li) {
-                if (p.dual ? (li & 1u) != me : me != 0u) continue;   // the other issuer's tile
-                ita = li * static_cast<uint32_t>(p.n_stages);       // its stages in the ring
-                const uint32_t buf = li % kBufs;
-                const uint32_t aph = (li / kBufs) & 1u;
+            // ring positions without integer division (ptx.cuh: Ring); a tile of the other issuer
+            // advances them too
+            Ring rs, rb;
+            const bool relaxed = STEM && c_wait_cfg[3] != 0;
+            uint32_t li = 0;
+            for (int unit = unit0; unit < num_units; unit += unit_step, ++li, rb.next(kBufs)) {
+                if (p.dual ? (li & 1u) != me : me != 0u) {   // the other issuer's tile
+                    rs.skip(p.nslots, p.n_stages);
+                    continue;
+                }
+                const uint32_t buf = rb.slot;
+                const uint32_t aph = rb.phase;
                 if (CG == 2) mbar_wait_cluster(acc_empty + 8u * buf, aph ^ 1u);
                 else mbar_wait(acc_empty + 8u * buf, aph ^ 1u);
                 trace(3 + static_cast<int>(me), li, 0);
                 tc_fence_after();
                 const uint32_t d0 = tmem_base + buf * 128u;
-                // All stages of the tile first, then its MMAs without a barrier wait between them:
-                // every wait of an issuer is a hole in the tensor pipe (~500 cycles between the two
-                // slabs of a tile in CTA 0's timeline, scripts/stem_trace.py), and the producers run
-                // a tile ahead anyway (the in-kernel stem even completes both stages together).
-                if (p.wait_all)
-                    for (int s = 0; s < p.n_stages; ++s) {
-                        const uint32_t it = ita + static_cast<uint32_t>(s);
-                        mbar_wait(a_full + 8u * (it % p.nslots), (it / p.nslots) & 1u);
-                    }
-                for (int s = 0; s < p.n_s2d; ++s, ++ita) {
-                    const uint32_t slot = ita % p.nslots;
-                    if (!p.wait_all) {
-                        // fused stem: the CUDA-core stem warps are the critical path, not the issuers
-                        if (STEM && c_wait_cfg[3]) mbar_wait_relaxed(a_full + 8u * slot, (ita / p.nslots) & 1u);
-                        else mbar_wait(a_full + 8u * slot, (ita / p.nslots) & 1u);
-                    }
+                for (int s = 0; s < p.n_s2d; ++s, rs.next(p.nslots)) {
+                    const uint32_t slot = rs.slot;
+                    // fused stem: the CUDA-core stem warps are the critical path, not the issuers
+                    if (relaxed) mbar_wait_relaxed(a_full + 8u * slot, rs.phase);
+                    else mbar_wait(a_full + 8u * slot, rs.phase);
                     trace(3 + static_cast<int>(me), li, 1 + 2 * s);
                     tc_fence_after();
                     const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) |
@@ -960,8 +959,8 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
                     trace(3 + static_cast<int>(me), li, 2 + 2 * s);
                 }
                 if (p.has_below) {
-                    const uint32_t slot = ita % p.nslots;
-                    if (!p.wait_all) mbar_wait(a_full + 8u * slot, (ita / p.nslots) & 1u);
+                    const uint32_t slot = rs.slot;
+                    mbar_wait(a_full + 8u * slot, rs.phase);
                     tc_fence_after();
                     const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) |
                                         (((a_ring + slot * kSlot) >> 4) | a_lbo_plain);
@@ -984,7 +983,7 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
                         commit(acc_full + 8u * buf);
                     }
                     __syncwarp();
-                    ++ita;
+                    rs.next(p.nslots);
                 }
             }
         }
@@ -998,10 +997,11 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
         const int H = 2 * p.H2, W = 2 * p.W2;
         const size_t plane = static_cast<size_t>(p.H2) * p.W2 * 8;  // one phase of one 8-ch group
         uint32_t li = 0;
-        for (int unit = unit0; unit < num_units; unit += unit_step, ++li) {
+        Ring rb;
+        for (int unit = unit0; unit < num_units; unit += unit_step, ++li, rb.next(kBufs)) {
             if (static_cast<int>(li & 1u) != grp) continue;
-            const uint32_t buf = li % kBufs;
-            const uint32_t aph = (li / kBufs) & 1u;
+            const uint32_t buf = rb.slot;
+            const uint32_t aph = rb.phase;
             const int tile = tile_of(unit);
             const bool in_range = tile < p.num_tiles;   // false only for the tail of the last pair
             const Tile t = decode_tile(p, in_range ? tile : p.num_tiles - 1);
@@ -1347,6 +1347,36 @@ int launch_kernel(bool pair, int grid, size_t smem, cudaStream_t stream, const C
 }
 }  // namespace
 
+namespace {
+// Debug timeline (OGL_TRACE=file, OGL_TRACE_LAUNCH=stem|head|up|down, default stem): CTA 0 of the
+// chosen space-to-depth launch writes clock64 at its hand-offs; the launch then synchronises and the
+// buffer is dumped. scripts/stem_trace.py reads it.
+unsigned long long* g_trace_dev = nullptr;
+int trace_begin(const char* which, cudaStream_t stream, S2dParams* p) {
+    static const char* file = getenv("OGL_TRACE");
+    static const char* want = getenv("OGL_TRACE_LAUNCH") ? getenv("OGL_TRACE_LAUNCH") : "stem";
+    p->trace = nullptr;
+    if (!file || strcmp(which, want) != 0) return 0;
+    const size_t n = static_cast<size_t>(kTraceRoles) * kTraceTiles * 8;
+    if (!g_trace_dev) OGL_CUDA(cudaMalloc(&g_trace_dev, n * 8));
+    OGL_CUDA(cudaMemsetAsync(g_trace_dev, 0, n * 8, stream));
+    p->trace = g_trace_dev;
+    return 0;
+}
+int trace_end(cudaStream_t stream, const S2dParams& p) {
+    if (!p.trace) return 0;
+    const size_t n = static_cast<size_t>(kTraceRoles) * kTraceTiles * 8;
+    std::vector<unsigned long long> host(n);
+    OGL_CUDA(cudaStreamSynchronize(stream));
+    OGL_CUDA(cudaMemcpy(host.data(), g_trace_dev, n * 8, cudaMemcpyDeviceToHost));
+    if (FILE* f = fopen(getenv("OGL_TRACE"), "wb")) {
+        fwrite(host.data(), 8, n, f);
+        fclose(f);
+    }
+    return 0;
+}
+}  // namespace
+
 int s2d_tc_init() {
     OGL_CUDA(set_wait_cfg());
     OGL_CUDA(cudaFuncSetAttribute(s2d_tc_kernel<EPI_RELU_POOL, 1, 1>,
@@ -1455,8 +1485,6 @@ int launch_s2d_tc(const S2dLayer& L, const __nv_bfloat16* src_s2d, const __nv_bf
     p.nslots = nslots;
     static const int dual_env = getenv("OGL_DUAL") ? atoi(getenv("OGL_DUAL")) : 1;
     p.dual = (dual_env && nslots >= 2 * p.n_stages) ? 1 : 0;
-    static const int wait_all_env = getenv("OGL_S2D_WAITALL") ? atoi(getenv("OGL_S2D_WAITALL")) : 0;
-    p.wait_all = (wait_all_env && nslots >= p.n_stages) ? 1 : 0;
 
     CUtensorMap tmS, tmB;
     if (fused_stem) {
@@ -1468,14 +1496,7 @@ int launch_s2d_tc(const S2dLayer& L, const __nv_bfloat16* src_s2d, const __nv_bf
         if (encode_map(&tmS, stem_frames, 3, dims, str, box, true)) return 1;
         memset(&tmB, 0, sizeof tmB);
         const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-        static const char* trace_env = getenv("OGL_TRACE");   // debug: file for CTA 0's timeline
-        static unsigned long long* trace_dev = nullptr;
-        const size_t trace_n = static_cast<size_t>(kTraceRoles) * kTraceTiles * 8;
-        if (trace_env && tc_stem && stem_tc_warps == 16) {
-            if (!trace_dev) OGL_CUDA(cudaMalloc(&trace_dev, trace_n * 8));
-            OGL_CUDA(cudaMemsetAsync(trace_dev, 0, trace_n * 8, stream));
-            p.trace = trace_dev;
-        }
+        if (trace_begin(tc_stem && stem_tc_warps == 16 ? "stem" : "", stream, &p)) return 1;
         if (tc_stem) {
             if (nslots < 4) return fail("s2d layer: the tensor-core stem needs 4 activation stages");
             if (stem_tc_warps == 16)
@@ -1489,15 +1510,7 @@ int launch_s2d_tc(const S2dLayer& L, const __nv_bfloat16* src_s2d, const __nv_bf
                 <<<grid, kThreads + kStemThreads, smem, stream>>>(tmS, tmB, p);
         }
         OGL_CUDA(cudaGetLastError());
-        if (p.trace) {   // debug only: synchronises
-            std::vector<unsigned long long> host(trace_n);
-            OGL_CUDA(cudaStreamSynchronize(stream));
-            OGL_CUDA(cudaMemcpy(host.data(), trace_dev, trace_n * 8, cudaMemcpyDeviceToHost));
-            if (FILE* f = fopen(trace_env, "wb")) {
-                fwrite(host.data(), 8, trace_n, f);
-                fclose(f);
-            }
-        }
+        if (trace_end(stream, p)) return 1;
         return 0;
     }
     {
@@ -1520,11 +1533,14 @@ int launch_s2d_tc(const S2dLayer& L, const __nv_bfloat16* src_s2d, const __nv_bf
         tmB = tmS;
     }
     const int grid = pair ? (num_sms & ~1) : (p.num_tiles < num_sms ? p.num_tiles : num_sms);
-    if (L.epi == EPI_RELU) return launch_kernel<EPI_RELU>(pair, grid, smem, stream, tmS, tmB, p);
-    if (L.epi == EPI_RELU_POOL)
-        return launch_kernel<EPI_RELU_POOL>(pair, grid, smem, stream, tmS, tmB, p);
-    if (L.epi == EPI_HEAD) return launch_kernel<EPI_HEAD>(pair, grid, smem, stream, tmS, tmB, p);
-    return fail("s2d layer: unknown epilogue");
+    if (trace_begin(L.epi == EPI_HEAD ? "head" : (L.cin_b > 0 ? "up" : "down"), stream, &p)) return 1;
+    int rc;
+    if (L.epi == EPI_RELU) rc = launch_kernel<EPI_RELU>(pair, grid, smem, stream, tmS, tmB, p);
+    else if (L.epi == EPI_RELU_POOL)
+        rc = launch_kernel<EPI_RELU_POOL>(pair, grid, smem, stream, tmS, tmB, p);
+    else if (L.epi == EPI_HEAD) rc = launch_kernel<EPI_HEAD>(pair, grid, smem, stream, tmS, tmB, p);
+    else return fail("s2d layer: unknown epilogue");
+    return rc ? rc : trace_end(stream, p);
 }
 
 }  // namespace ogl

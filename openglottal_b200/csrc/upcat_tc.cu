@@ -133,7 +133,9 @@ __device__ __forceinline__ void issue_half(const UpcatParams& p, const Smem& s, 
         else mbar_wait(bar, parity);
         tc_fence_after();
     };
-    uint32_t ita = 0, itw = 0, li = 0;
+    // ring positions advanced without integer division (ptx.cuh: Ring)
+    Ring ra, rw;
+    uint32_t li = 0;
     for (int item = item0; item < items; item += item_step, ++li) {
         const uint32_t buf = kDB ? (li & 1u) : 0u;
         const uint32_t aph = kDB ? ((li >> 1) & 1u) : (li & 1u);
@@ -144,8 +146,8 @@ __device__ __forceinline__ void issue_half(const UpcatParams& p, const Smem& s, 
         // ---- composed half, one group of 4 K blocks. N = 64: per K block one stage per px with both
         // py (8 pairs); N = 128: accumulator-major -- px outer, K block, then one stage per py.
         auto below_group = [&](bool first_g, bool last_g) {
-            const uint32_t sa = ita % p.na;
-            mbar_wait(s.a_full + 8u * sa, (ita / p.na) & 1u);
+            const uint32_t sa = ra.slot;
+            mbar_wait(s.a_full + 8u * sa, ra.phase);
             const uint64_t ad = adesc_b + ((s.a_ring + sa * kStage) >> 4);
             auto pair_mmas = [&](uint64_t bd, int px, int g4, int t0, bool first) {
 #pragma unroll
@@ -163,9 +165,9 @@ __device__ __forceinline__ void issue_half(const UpcatParams& p, const Smem& s, 
 #pragma unroll
                 for (int g4 = 0; g4 < 4; ++g4) {
 #pragma unroll
-                    for (int px = 0; px < 2; ++px, ++itw) {
-                        const uint32_t sw = itw % p.nw;
-                        mbar_wait(s.w_full + 8u * sw, (itw / p.nw) & 1u);
+                    for (int px = 0; px < 2; ++px, rw.next(p.nw)) {
+                        const uint32_t sw = rw.slot;
+                        mbar_wait(s.w_full + 8u * sw, rw.phase);
                         tc_fence_after();
                         const uint64_t bd = bdesc0 + ((s.w_ring + sw * s.w_slot) >> 4);
                         if (elect_one()) {
@@ -186,9 +188,9 @@ __device__ __forceinline__ void issue_half(const UpcatParams& p, const Smem& s, 
 #pragma unroll
                     for (int g4 = 0; g4 < 4; ++g4) {
 #pragma unroll
-                        for (int py = 0; py < 2; ++py, ++itw) {
-                            const uint32_t sw = itw % p.nw;
-                            mbar_wait(s.w_full + 8u * sw, (itw / p.nw) & 1u);
+                        for (int py = 0; py < 2; ++py, rw.next(p.nw)) {
+                            const uint32_t sw = rw.slot;
+                            mbar_wait(s.w_full + 8u * sw, rw.phase);
                             tc_fence_after();
                             const uint64_t bd = bdesc0 + ((s.w_ring + sw * s.w_slot) >> 4);
                             if (elect_one()) {
@@ -204,20 +206,20 @@ __device__ __forceinline__ void issue_half(const UpcatParams& p, const Smem& s, 
                     }
                 }
             }
-            ++ita;
+            ra.next(p.na);
         };
 
         if (kDB) wait_acc_empty(s.acc_empty + acc_bar(0), aph ^ 1u);
         else below_group(true, false);         // N = 128: the tile starts accumulator-major
         // ---------------- skip half: kbS blocks x 9 taps, the same tap weights for all phases
-        for (int kb = 0; kb < p.kbS; ++kb, ++ita) {
-            const uint32_t sa = ita % p.na;
-            mbar_wait(s.a_full + 8u * sa, (ita / p.na) & 1u);
+        for (int kb = 0; kb < p.kbS; ++kb, ra.next(p.na)) {
+            const uint32_t sa = ra.slot;
+            mbar_wait(s.a_full + 8u * sa, ra.phase);
             const uint64_t ad = adesc_s + ((s.a_ring + sa * kStage) >> 4);
 #pragma unroll
-            for (int tg = 0; tg < 9 / TPS; ++tg, ++itw) {
-                const uint32_t sw = itw % p.nw;
-                mbar_wait(s.w_full + 8u * sw, (itw / p.nw) & 1u);
+            for (int tg = 0; tg < 9 / TPS; ++tg, rw.next(p.nw)) {
+                const uint32_t sw = rw.slot;
+                mbar_wait(s.w_full + 8u * sw, rw.phase);
                 tc_fence_after();
                 const uint64_t bd = bdesc0 + ((s.w_ring + sw * s.w_slot) >> 4);
                 const uint32_t first = (!kDB || (kb | tg) != 0) ? 1u : 0u;
@@ -328,17 +330,17 @@ upcat_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__
     if (warp == 0) {
         // ================================================ activation producer
         if (lane == 0) {
-            uint32_t it = 0;
+            Ring ra;
             for (int item = item0; item < items; item += item_step) {
                 int tile = tile_of(item);
                 if (tile >= p.num_tiles) tile = p.num_tiles - 1;   // tail of the last pair: a duplicate
                 const Tile t = decode_tile(p, tile);
-                for (int kk = 0; kk < p.kbS + p.nG; ++kk, ++it) {
+                for (int kk = 0; kk < p.kbS + p.nG; ++kk, ra.next(p.na)) {
                     // N = 64: skip blocks, then the group of the tensor below; N = 128: group 0 of
                     // the tensor below, the skip blocks, the other groups (k >= kbS: group k - kbS)
                     const int k = N == 64 ? kk : (kk == 0 ? p.kbS : (kk <= p.kbS ? kk - 1 : kk));
-                    const uint32_t slot = it % p.na;
-                    mbar_wait_relaxed(s.a_empty + 8u * slot, ((it / p.na) & 1u) ^ 1u);
+                    const uint32_t slot = ra.slot;
+                    mbar_wait_relaxed(s.a_empty + 8u * slot, ra.phase ^ 1u);
                     const uint32_t dst = s.a_ring + slot * kStage;
                     uint32_t full = s.a_full + 8u * slot;
                     if (CG == 1) {
@@ -361,11 +363,11 @@ upcat_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__
     } else if (warp == 3) {
         // ==================================================== weight producer
         if (lane == 0) {
-            uint32_t it = 0;
+            Ring rw;
             constexpr uint32_t rows_per_tap = w_tap_bytes >> 8;   // CG = 2: the blobs as rows of 256 B
             auto stage = [&](bool below, uint32_t tap0) {   // tap0: first tap of the stage in its blob
-                const uint32_t slot = it % p.nw;
-                mbar_wait_relaxed(s.w_empty + 8u * slot, ((it / p.nw) & 1u) ^ 1u);
+                const uint32_t slot = rw.slot;
+                mbar_wait_relaxed(s.w_empty + 8u * slot, rw.phase ^ 1u);
                 const uint32_t bytes = below ? below_bytes : skip_bytes;
                 const uint32_t dst = s.w_ring + slot * w_slot;
                 if (CG == 1) {
@@ -377,7 +379,7 @@ upcat_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__
                     tma_load_2d_pair(dst, below ? &tmWb : &tmWs, map_to_cta(s.w_full + 8u * slot, 0), 0,
                                      static_cast<int>(tap0 * rows_per_tap));
                 }
-                ++it;
+                rw.next(p.nw);
             };
             for (int item = item0; item < items; item += item_step) {
                 const uint32_t pass = static_cast<uint32_t>(pass_of(item));

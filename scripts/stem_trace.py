@@ -17,6 +17,8 @@ import bench  # noqa: E402
 import openglottal_b200 as ogl  # noqa: E402
 
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+which = sys.argv[2] if len(sys.argv) > 2 else "stem"
+os.environ["OGL_TRACE_LAUNCH"] = which
 sd, _ = bench.bench_state()
 model = ogl.UNet().to("cuda")
 model.load_state_dict(sd)
@@ -36,6 +38,11 @@ ev = {0: ["u8_full", "sa_empty", "done"],
       3: ["acc_empty", "a_full s0", "issued s0", "a_full s1", "issued s1"],
       4: ["acc_empty", "a_full s0", "issued s0", "a_full s1", "issued s1"],
       5: ["acc_full", "done"], 6: ["acc_full", "done"], 7: ["u8_empty"]}
+if which != "stem":     # TMA producer instead of the stem roles; up to three stages per tile
+    roles[7] = "producer"
+    ev[7] = ["slot s0", "slot s1", "slot s2"]
+    for r in (3, 4):
+        ev[r] = ["acc_empty", "a_full s0", "issued s0", "a_full s1", "issued s1", "-", "-", "-"]
 t0 = t[t > 0].min()
 print("per-tile period (cycles), tiles 20..80, by role (first event of each tile):")
 for r, name in enumerate(roles):
