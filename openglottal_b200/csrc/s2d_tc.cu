@@ -1476,15 +1476,22 @@ int launch_s2d_tc(const S2dLayer& L, const __nv_bfloat16* src_s2d, const __nv_bf
     const size_t fixed = 128 + ((wres + 127u) & ~static_cast<size_t>(127)) + 9 * 32 * 4 + 8 +
                          16 * kAccBufs + 16 + 16 + 16 * kU8Slots + 32 + 16 * kStemDSlots + 128 +
                          kU8Slots * kU8Slot + (tc_stem ? 2 * kStemABytes + kStemBBytes : 0) + 64;
-    int nslots = 6;
+    // Ring depth and issuers per layer (same-call A/Bs, profiles/exp_r02_s2d_rings.jsonl): a
+    // two-stage tile runs best with a ring of two tiles (the head: 0.70 instead of 0.735 ms with
+    // three) and two issuer warps; the three-stage tile of the composed layer (CTA pair, HBM-bound)
+    // with ONE issuer over its six stages (1.16 instead of 1.25 ms).
+    int nslots = L.cin_b > 0 ? 6 : 4;
     static const int ns_env = getenv("OGL_S2D_SLOTS") ? atoi(getenv("OGL_S2D_SLOTS")) : 0;
+    static const int ns_head_env = getenv("OGL_S2D_SLOTS_HEAD") ? atoi(getenv("OGL_S2D_SLOTS_HEAD")) : 0;
     if (ns_env > 0) nslots = ns_env;
+    if (ns_head_env > 0 && L.cin_b == 0 && !fused_stem) nslots = ns_head_env;
     while (nslots > 2 && fixed + static_cast<size_t>(nslots) * (kSlot + 16) > kMaxSmem) --nslots;
     const size_t smem = fixed + static_cast<size_t>(nslots) * (kSlot + 16);
     if (smem > static_cast<size_t>(kMaxSmem)) return fail("s2d layer: shared memory budget exceeded");
     p.nslots = nslots;
     static const int dual_env = getenv("OGL_DUAL") ? atoi(getenv("OGL_DUAL")) : 1;
-    p.dual = (dual_env && nslots >= 2 * p.n_stages) ? 1 : 0;
+    static const int dual_below_env = getenv("OGL_DUAL_BELOW") ? atoi(getenv("OGL_DUAL_BELOW")) : 0;
+    p.dual = (dual_env && nslots >= 2 * p.n_stages && (L.cin_b == 0 || dual_below_env)) ? 1 : 0;
 
     CUtensorMap tmS, tmB;
     if (fused_stem) {
