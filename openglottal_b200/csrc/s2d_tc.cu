@@ -142,8 +142,14 @@ constexpr uint32_t kTraceTiles = 96;
 constexpr int kTraceRoles = 8;
 constexpr int kStem3Threads = 512;
 constexpr int kStem3BuildWarps = 4;                      // the other 12 stem warps drain
-constexpr int kStem3DSlots = 4;                          // 32-column accumulators, TMEM cols 384..511
-constexpr int kStem3DCol = 384;                          // (three main accumulators below them)
+#ifdef OGL_STEM3_SLOTS8   // experiment build: eight stem accumulators above TWO main ones
+constexpr bool kS8 = true;
+#else
+constexpr bool kS8 = false;
+#endif
+constexpr int kStem3DSlots = kS8 ? 8 : 4;                // 32-column accumulators, TMEM cols 384..511
+constexpr int kStem3DCol = kS8 ? 256 : 384;              // (three main accumulators below them)
+constexpr int kSdMax = 8;                                // entries of the sd_full / sd_empty arrays
 constexpr int kStemItems = 2 * kHW * kHH;                // 360 build items: (y phase, halo row, halo column)
 __host__ __device__ constexpr int stem_threads(int stem) {
     return stem == 3 ? kStem3Threads : (stem ? kStemThreads : 0);
@@ -251,12 +257,12 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
     const uint32_t sa_full = u8_empty + 8u * kU8Slots;
     const uint32_t sa_empty = sa_full + 16u;
     const uint32_t sd_full = sa_empty + 16u;
-    const uint32_t sd_empty = sd_full + 8u * kStemDSlots;
-    const uint32_t u8_s = (sd_empty + 8u * kStemDSlots + 127u) & ~127u;
+    const uint32_t sd_empty = sd_full + 8u * kSdMax;
+    const uint32_t u8_s = (sd_empty + 8u * kSdMax + 127u) & ~127u;
     const uint32_t sA = u8_s + kU8Slots * kU8Slot;
     const uint32_t sB = sA + 2u * kStemABytes;
     // main accumulators (128 columns each) and, above them, the stem GEMM's 32-column ones
-    constexpr int kBufs = STEM >= 2 ? 3 : kAccBufs;
+    constexpr int kBufs = STEM >= 2 ? ((STEM == 3 && kS8) ? 2 : 3) : kAccBufs;
     constexpr uint32_t kDSlots = STEM == 3 ? kStem3DSlots : kStemDSlots;
     constexpr uint32_t kDCol = STEM == 3 ? kStem3DCol : kStemDCol;
     uint8_t* gen = smem_raw - raw;  // generic pointer = gen + shared address
@@ -303,7 +309,7 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
                 // STEM 2: slot i is free again (the four warps of the draining group). STEM 3:
                 // entries 0 / 1: chunks 2..5 of an even / odd tile are in registers (4 x 4 warps),
                 // entries 2 / 3: chunks 0, 1 (2 x 4 warps)
-                mbar_init(sd_empty + 8u * i, STEM == 3 ? (i < 2 ? 16 : 8) : 4);
+                mbar_init(sd_empty + 8u * i, STEM == 3 ? ((i < 2 || kS8) ? 16 : 8) : 4);
             }
         }
         for (int i = 0; i < p.nslots; ++i) {
@@ -469,7 +475,14 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
                         // chunk 6 T + k - 4: chunks 2..5 of tile T - 1 for k = 0..3, chunks 0, 1 of
                         // tile T itself for k = 4, 5 -- TWO barrier waits per tile for the issuer
                         // instead of six.
-                        if (lane == 0) mbar_arrive(sd_empty + 8u * ((j < 2 ? 2u : 0u) + (iu & 1u)));
+                        // (kS8, eight slots: slot (6 T + k) % 8 was last used by chunks 4, 5 of T - 2
+                        //  for k = 0, 1 and chunks 0..3 of T - 1 for k = 2..5; a group drains its chunk
+                        //  of T - 2 before that of T - 1, so "chunks 0..3 of T - 1" frees all six: ONE wait)
+                        if (kS8) {
+                            if (lane == 0 && j < 4) mbar_arrive(sd_empty + 8u * (iu & 1u));
+                        } else if (lane == 0) {
+                            mbar_arrive(sd_empty + 8u * ((j < 2 ? 2u : 0u) + (iu & 1u)));
+                        }
                         if (trd) trace(1, iu, h ? 5 : 2);
 #pragma unroll
                         for (int g = 0; g < 4; ++g)   // 8-channel groups: (stage, plane group)
@@ -807,11 +820,11 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
                     const uint64_t ad0 = (static_cast<uint64_t>(a_hi_s) << 32) | ((sA >> 4) | a_lbo_s);
                     const uint32_t d0 = tmem_base + kStem3DCol;
                     auto issue = [&](auto ph_tag, auto j0_tag, auto j1_tag) {
-                        constexpr uint32_t PH = decltype(ph_tag)::value;   // T % 2
-                        constexpr uint32_t kTileA = PH * (kStemABytes >> 4);
+                        constexpr uint32_t PH = decltype(ph_tag)::value;   // T % 4
+                        constexpr uint32_t kTileA = (PH & 1u) * (kStemABytes >> 4);
 #pragma unroll
                         for (uint32_t j = decltype(j0_tag)::value; j < decltype(j1_tag)::value; ++j) {
-                            const uint32_t slot = (2u * PH + j) & 3u;
+                            const uint32_t slot = (6u * PH + j) & static_cast<uint32_t>(kStem3DSlots - 1);
                             const uint64_t ad = ad0 + (kTileA + j * (2048u >> 4));
                             if (!no_mma) {
                                 umma_bf16(d0 + slot * 32u, ad, bd_hi, idesc, 0u);
@@ -819,12 +832,22 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
                             }
                             umma_commit(sd_full + 8u * slot);
                         }
-                        if (decltype(j1_tag)::value == kStemChunks) umma_commit(sa_empty + 8u * PH);
+                        if (decltype(j1_tag)::value == kStemChunks) umma_commit(sa_empty + 8u * (PH & 1u));
                     };
                     using U0 = std::integral_constant<uint32_t, 0>;
                     using U1 = std::integral_constant<uint32_t, 1>;
+                    using U2 = std::integral_constant<uint32_t, 2>;
+                    using U3 = std::integral_constant<uint32_t, 3>;
                     using U4 = std::integral_constant<uint32_t, 4>;
                     using U6 = std::integral_constant<uint32_t, 6>;
+                    auto issue_ph = [&](uint32_t ph, auto j0_tag, auto j1_tag) {
+                        switch (ph) {
+                            case 0: issue(U0{}, j0_tag, j1_tag); break;
+                            case 1: issue(U1{}, j0_tag, j1_tag); break;
+                            case 2: issue(U2{}, j0_tag, j1_tag); break;
+                            default: issue(U3{}, j0_tag, j1_tag); break;
+                        }
+                    };
                     uint32_t iu = 0;
                     for (int unit = unit0; unit < num_units; unit += unit_step, ++iu) {
                         const uint32_t par = iu & 1u;
@@ -833,19 +856,19 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
                         if (iu) mbar_wait(sd_empty + 8u * (par ^ 1u), ((iu - 1u) >> 1) & 1u);
                         trace(2, iu, 1);
                         tc_fence_after();
-                        if (elect_one()) {
-                            if (par) issue(U1{}, U0{}, U4{});
-                            else issue(U0{}, U0{}, U4{});
+                        if (kS8) {
+                            if (elect_one()) issue_ph(iu & 3u, U0{}, U6{});
+                            __syncwarp();
+                            trace(2, iu, 4);
+                            continue;
                         }
+                        if (elect_one()) issue_ph(iu & 3u, U0{}, U4{});
                         __syncwarp();
                         trace(2, iu, 2);
                         mbar_wait(sd_empty + 8u * (2u + par), (iu >> 1) & 1u);
                         trace(2, iu, 3);
                         tc_fence_after();
-                        if (elect_one()) {
-                            if (par) issue(U1{}, U4{}, U6{});
-                            else issue(U0{}, U4{}, U6{});
-                        }
+                        if (elect_one()) issue_ph(iu & 3u, U4{}, U6{});
                         __syncwarp();
                         trace(2, iu, 4);
                     }
@@ -1021,6 +1044,13 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
                 uint32_t r[32];
                 tmem_ld32(tcol + ph * 32, r);
                 tmem_ld_wait();
+                if (ph == 3) {
+                    // the last phase is in registers: the accumulator goes back to the issuers
+                    // before this phase's arithmetic and stores, not after them
+                    tc_fence_before();
+                    if (CG == 2) mbar_arrive_cluster(map_to_cta(acc_empty + 8u * buf, 0));
+                    else mbar_arrive(acc_empty + 8u * buf);
+                }
                 const int y = 2 * Y + (ph >> 1), x = 2 * X + (ph & 1);
                 const int ry = y == 0 ? 0 : (y == H - 1 ? 2 : 1);
                 const int rx = x == 0 ? 0 : (x == W - 1 ? 2 : 1);
@@ -1104,9 +1134,11 @@ s2d_tc_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ C
             if (EPI == EPI_HEAD) {
                 if (lane == 0 && p.area && cnt) atomicAdd(p.area + t.n, cnt);
             }
-            tc_fence_before();
-            if (CG == 2) mbar_arrive_cluster(map_to_cta(acc_empty + 8u * buf, 0));
-            else mbar_arrive(acc_empty + 8u * buf);
+            if (p.dbg & 4) {   // experiment without epilogue work: nothing was loaded
+                tc_fence_before();
+                if (CG == 2) mbar_arrive_cluster(map_to_cta(acc_empty + 8u * buf, 0));
+                else mbar_arrive(acc_empty + 8u * buf);
+            }
             if ((warp & 3) == 0) trace(5 + grp, li, 1);
         }
     }
@@ -1474,7 +1506,7 @@ int launch_s2d_tc(const S2dLayer& L, const __nv_bfloat16* src_s2d, const __nv_bf
     const size_t wres = L.wbytes / (pair ? 2 : 1);
     const bool tc_stem = fused_stem && stem_tc_blob != nullptr;
     const size_t fixed = 128 + ((wres + 127u) & ~static_cast<size_t>(127)) + 9 * 32 * 4 + 8 +
-                         16 * kAccBufs + 16 + 16 + 16 * kU8Slots + 32 + 16 * kStemDSlots + 128 +
+                         16 * kAccBufs + 16 + 16 + 16 * kU8Slots + 32 + 16 * kSdMax + 128 +
                          kU8Slots * kU8Slot + (tc_stem ? 2 * kStemABytes + kStemBBytes : 0) + 64;
     // Ring depth and issuers per layer (same-call A/Bs, profiles/exp_r02_s2d_rings.jsonl): a
     // two-stage tile runs best with a ring of two tiles (the head: 0.70 instead of 0.735 ms with
