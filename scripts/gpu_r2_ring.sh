@@ -1,4 +1,4 @@
-# Ring counters instead of run-time div/mod in the issuers / producers: whole GPU suite, then a
+# A new build against the previous one (openglottal_b200/lib/libopenglottal_b200_prev.so): whole GPU suite, then a
 # same-call A/B against the previous build (openglottal_b200/lib/libopenglottal_b200_prev.so)
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest_v3.log 2>&1; rc=$?; echo "all gpu tests rc=$rc"; tail -3 gpurun_out/r2_pytest_v3.log
@@ -19,7 +19,7 @@ for n in names:
 print('%-36s' % 'step', *['%12.3f' % r['ms_step'] for r in rows])
 print('%-36s' % 'sm MHz', *['%12d' % r['clocks']['sm_mhz'] for r in rows])
 PY
-for v in new prev new prev; do
+for v in new prev new prev new prev; do
   if [ $v = prev ]; then export OGL_LIB=$PREV; else unset OGL_LIB; fi
   timeout 300 python bench.py --no-cpu-baseline > gpurun_out/r2_bench_ring_$v.json 2> gpurun_out/r2_bench_ring_$v.err
   python -c "
