@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <nvtx3/nvToolsExt.h>   // header-only: ranges cost nothing unless a tool is attached
 #include <string>
 #include <vector>
 
@@ -611,8 +612,13 @@ int ogl_unet_forward(ogl_unet* h, const void* frames_dev, int in_dtype, int n, i
             if (idx == h->rep_launch && h->rep_n > 1 && area_dev && strstr(name, "head"))
                 return fail("ogl_unet_forward: the head launch is repeated (ogl_unet_set_repeat); "
                             "pass area = NULL or reset the repetition");
+            nvtxRangePushA(name);   // the reference layer names in nsys / ncu timelines
             for (int r = idx == h->rep_launch ? h->rep_n : 1; r > 0; --r)
-                if (launch()) return 1;
+                if (launch()) {
+                    nvtxRangePop();
+                    return 1;
+                }
+            nvtxRangePop();
             mark(h, stream, name);
             return 0;
         };
