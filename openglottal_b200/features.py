@@ -332,14 +332,16 @@ def masks_for_clip(frames_gray, model: UNet, threshold: float = 0.5, want_masks:
     return torch.cat(areas), (torch.cat(masks) if want_masks else None)
 
 
-def extract_features_unet(avi_path: str, detector, model, device=None) -> dict | None:
+def extract_features_unet(avi_path: str, detector, model, device=None, *,
+                          decode_chunk: int = 1024) -> dict | None:
     """Drop-in for ``openglottal.extract_features_unet`` (features.py:202-247).
 
     ``detector is None`` (unet-only) is the accelerated path. With a detector the masks come
     from the native kernels in batches, the detector (the reference's Ultralytics
     ``TemporalDetector``, or anything with ``reset()`` / ``detect(frame_bgr)``) is called once
     per frame in order as the reference does, and the bbox gating of features.py:240-245 runs
-    as one CUDA reduction over the batch of masks.
+    as one CUDA reduction over the batch of masks. ``decode_chunk`` (keyword only, not in the
+    reference): frames per pinned staging buffer of the streaming reader.
     """
     from .utils import gated_area
 
@@ -350,7 +352,7 @@ def extract_features_unet(avi_path: str, detector, model, device=None) -> dict |
         # Intra-only clips stream: chunk k is segmented on the GPU while chunk k + 1 decodes.
         try:
             area = None
-            for i0, part in iter_gray_chunks(avi_path, dev):
+            for i0, part in iter_gray_chunks(avi_path, dev, chunk=decode_chunk):
                 if area is None:
                     area = torch.empty(video_info(avi_path)["frames"], dtype=torch.int32, device=dev)
                 area[i0:i0 + part.shape[0]] = masks_for_clip(part, model)[0]

@@ -288,3 +288,29 @@ def test_decode_gray_clip_equals_cv2(tmp_path, fourcc, write_clip):
     seq = decode_gray_clip(str(clip), torch.device("cuda:0"), workers=1)
     assert np.array_equal(seq.cpu().numpy(), want)
     assert decode_gray_clip(str(tmp_path / "missing.avi"), torch.device("cuda:0")) is None
+
+
+@pytest.mark.gpu
+def test_streamed_extract_features_equals_staged(tmp_path, write_clip, native_model):
+    """``extract_features_unet`` on an MJPG file streams: frame ranges decode on several threads
+    while earlier chunks are segmented. Its features (and ``_area``) equal those of the staged run
+    -- sequential ``load_frames_bgr``, ``cv2.cvtColor``, one ``masks_for_clip`` over the whole clip --
+    for a chunk size that does not divide the frame count; 256 x 256 frames take the native
+    kernels, 64 x 48 ones the reference-resize path."""
+    import cv2
+
+    import openglottal_b200 as ogl
+
+    for hgt, wid, n in ((256, 256, 300), (64, 48, 650)):
+        clip = tmp_path / f"s_{hgt}x{wid}.avi"
+        write_clip(clip, "MJPG", n, hgt, wid)
+        frames = ogl.load_frames_bgr(str(clip))
+        gray = np.stack([cv2.cvtColor(f, cv2.COLOR_BGR2GRAY) for f in frames])
+        area, _ = ogl.masks_for_clip(torch.from_numpy(gray).cuda(), native_model)
+        want = ogl.kinematic_features_device(area)
+        got = ogl.extract_features_unet(str(clip), None, native_model, decode_chunk=256)
+        assert (want is None) == (got is None)
+        if want is not None:
+            assert np.array_equal(got["_area"], want["_area"])
+            for k in ("area_mean", "area_std", "area_range", "open_quotient", "f0", "periodicity", "cv"):
+                assert got[k] == want[k], k
