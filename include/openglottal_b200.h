@@ -89,7 +89,13 @@ size_t ogl_unet_workspace_bytes(const ogl_unet* h, int n, int height, int width,
 /* UNet forward + sigmoid/threshold + per-frame area for n gray frames [n][height][width]
  * (u8 in 0..255, or f32 already scaled). Any of logits_dev [n][h][w] f32, mask_dev [n][h][w]
  * u8 {0,255}, area_dev [n] int32 may be NULL. `threshold` is on the probability (0.5 in the
- * reference); the kernel compares the fp32 logit against logit(threshold). */
+ * reference); the kernel compares the fp32 logit against logit(threshold).
+ * Concurrency: a handle and a workspace are single-stream objects. The handle's device must be
+ * the current device (checked). Calls on one handle must be serialised by the caller; two
+ * forwards may overlap only if they use different handles AND different workspaces (the
+ * activation tensors of a forward live in the workspace until its last kernel has run). The
+ * Python layer keeps one handle and one workspace per UNet module, i.e. a module is driven from
+ * one stream at a time. */
 int ogl_unet_forward(ogl_unet* h, const void* frames_dev, int in_dtype, int n, int height,
                      int width, void* workspace_dev, size_t workspace_bytes, float* logits_dev,
                      uint8_t* mask_dev, int32_t* area_dev, float threshold, int precision,

@@ -89,8 +89,9 @@ struct ogl_unet {
     // two-source convs (the round-1 schedule; kept for A/B runs and as an independent implementation)
     bool compose_up = true;
     // u8 input: compute the stem inside the downs.0.net.3 kernel (its output never touches HBM:
-    // 8.4 MB per frame less traffic). Bit-identical to the stand-alone stem; as fast or slightly
-    // faster under the board's power cap.
+    // 8.4 MB per frame less traffic). Mode 1 (fp32 on the CUDA cores) is bit-identical to the
+    // stand-alone stem; modes 2 and 3 (a K = 16 GEMM on the tensor cores, weights split hi + lo)
+    // agree with it to ~2^-17 relative before the rounding to bf16, i.e. NOT bit for bit.
     int fuse_stem = 3;                 // 0 separate kernel, 1 in-kernel on CUDA cores, 2 on tensor cores
                                        // (8 stem warps, bf16 im2col), 3 the same with 16 warps / f16 im2col
     uint8_t* stem_tc = nullptr;        // B operands of the tensor-core stem (device)

@@ -204,6 +204,8 @@ class UNet(nn.Module):
         kernel, /root/reference/openglottal/utils.py:235) or float32 already scaled.
         Returns f32 logits ``(N, H, W)``, u8 masks in {0, 255}
         (utils.py:241) and int32 per-frame areas (features.py:238).
+        The module owns ONE activation workspace: drive it from one stream at a time (calls on
+        the same stream queue up correctly; concurrent streams need one module each).
         """
         if self.training:
             raise RuntimeError("openglottal_b200.UNet is inference-only: call .eval() first "
