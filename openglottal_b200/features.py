@@ -16,7 +16,7 @@ import torch
 from . import _native, sharding
 from .unet import UNet
 from .utils import (RangeDecoder, _require_native, _silence_stderr, bgr_to_gray, decode_workers,
-                    load_frames_bgr, parallel_decodable, video_info)
+                    load_frames_bgr, parallel_decodable, seekable_clip, video_info)
 
 _FEATURE_KEYS = ("area_mean", "area_std", "area_range", "open_quotient", "f0", "periodicity", "cv")
 
@@ -192,7 +192,8 @@ class _DecodeFallback(Exception):
 
 
 def iter_gray_chunks(avi_path: str, dev: torch.device, workers: int | None = None,
-                     chunk: int = 1024, out: torch.Tensor | None = None, stats: dict | None = None):
+                     chunk: int = 1024, out: torch.Tensor | None = None, stats: dict | None = None,
+                     frame_range: tuple[int, int] | None = None):
     """Generator over ``(first frame index, (m, H, W) uint8 gray CUDA tensor)`` of a video whose
     codec is intra-only (``parallel_decodable``), in order. ``workers`` threads, each with its own
     ``VideoCapture`` on a contiguous frame range, decode straight into two pinned BGR chunk
@@ -200,6 +201,8 @@ def iter_gray_chunks(avi_path: str, dev: torch.device, workers: int | None = Non
     a side stream, and the yielded tensor is ordered after that on the CURRENT stream -- so a
     consumer that enqueues GPU work per chunk overlaps it with the decode of the next chunk.
     ``out``: an ``(N, H, W)`` tensor to fill (slices are yielded) instead of one tensor per chunk.
+    ``frame_range = (lo, hi)``: only those frames (a rank's shard; indices stay absolute) -- the
+    frames outside it are never decoded.
     Raises ``_DecodeFallback`` (before or between chunks) when a read comes back short or the
     container holds more frames than its header says."""
     import time
@@ -207,10 +210,13 @@ def iter_gray_chunks(avi_path: str, dev: torch.device, workers: int | None = Non
 
     workers = decode_workers(workers)
     info = video_info(avi_path)
-    if not parallel_decodable(info, workers):
+    # a rank's shard is read by range even with one decoder thread (the alternative is decoding the
+    # whole file on every rank); a whole clip only when several threads make it worth it
+    if not (seekable_clip(info) if frame_range is not None else parallel_decodable(info, workers)):
         raise _DecodeFallback("not an intra-only clip with a plausible header")
     n, hgt, wid = info["frames"], info["height"], info["width"]
-    chunk = max(workers, min(chunk, n))
+    lo, hi = (0, n) if frame_range is None else (max(0, frame_range[0]), min(n, frame_range[1]))
+    chunk = max(workers, min(chunk, max(hi - lo, 1)))
     bufs = [torch.empty((chunk, hgt, wid, 3), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
     views = [b.numpy() for b in bufs]
     copy = torch.cuda.Stream(device=dev)
@@ -220,8 +226,8 @@ def iter_gray_chunks(avi_path: str, dev: torch.device, workers: int | None = Non
     with _silence_stderr(), ThreadPoolExecutor(workers) as pool:
         decs = list(pool.map(lambda _: RangeDecoder(avi_path), range(workers)))
         try:
-            for k, i0 in enumerate(range(0, n, chunk)):
-                m, b = min(chunk, n - i0), k % 2
+            for k, i0 in enumerate(range(lo, hi, chunk)):
+                m, b = min(chunk, hi - i0), k % 2
                 if k >= 2:
                     freed[b].synchronize()        # the copy that read this buffer has finished
                 cut = [m * w // workers for w in range(workers + 1)]
@@ -233,7 +239,7 @@ def iter_gray_chunks(avi_path: str, dev: torch.device, workers: int | None = Non
                     stats["decode_s"] += time.perf_counter() - t0
                 if any(g != cut[w + 1] - cut[w] for w, g in enumerate(got)):
                     raise _DecodeFallback("short read")
-                if i0 + m == n and decs[-1].cap.read()[0]:
+                if i0 + m == n and decs[-1].pos == n and decs[-1].cap.read()[0]:
                     raise _DecodeFallback("frames beyond the header's count")
                 cur = torch.cuda.current_stream(dev)
                 gray = out[i0:i0 + m] if out is not None else torch.empty(
@@ -332,16 +338,27 @@ def masks_for_clip(frames_gray, model: UNet, threshold: float = 0.5, want_masks:
     return torch.cat(areas), (torch.cat(masks) if want_masks else None)
 
 
+def _local_world(world: int) -> int:
+    """Ranks sharing this host (torchrun's LOCAL_WORLD_SIZE; all of them when it is not set)."""
+    import os
+
+    try:
+        return max(1, min(world, int(os.environ.get("LOCAL_WORLD_SIZE", world))))
+    except ValueError:
+        return max(1, world)
+
+
 def extract_features_unet(avi_path: str, detector, model, device=None, *,
-                          decode_chunk: int = 1024) -> dict | None:
+                          decode_chunk: int = 1024, group=None) -> dict | None:
     """Drop-in for ``openglottal.extract_features_unet`` (features.py:202-247).
 
     ``detector is None`` (unet-only) is the accelerated path. With a detector the masks come
     from the native kernels in batches, the detector (the reference's Ultralytics
     ``TemporalDetector``, or anything with ``reset()`` / ``detect(frame_bgr)``) is called once
     per frame in order as the reference does, and the bbox gating of features.py:240-245 runs
-    as one CUDA reduction over the batch of masks. ``decode_chunk`` (keyword only, not in the
-    reference): frames per pinned staging buffer of the streaming reader.
+    as one CUDA reduction over the batch of masks. ``decode_chunk`` / ``group`` (keyword only,
+    not in the reference): frames per pinned staging buffer of the streaming reader; the process
+    group the frames are sharded over (default: the world, when torch.distributed is initialised).
     """
     from .utils import gated_area
 
@@ -350,20 +367,33 @@ def extract_features_unet(avi_path: str, detector, model, device=None, *,
     if detector is None:
         # unet-only: no consumer of the BGR frames on the host, so they are never held as a list.
         # Intra-only clips stream: chunk k is segmented on the GPU while chunk k + 1 decodes.
+        # With torch.distributed initialised (one process per GPU) every rank decodes and
+        # segments only its contiguous frame range (sharding.shard_range: a seek, the frames of
+        # the other ranks are never decoded), with its share of the host's decoder threads; the
+        # int32 areas are all-gathered, so every rank returns the same dict.
+        rank, world = sharding.rank_world(group)
         try:
-            area = None
-            for i0, part in iter_gray_chunks(avi_path, dev, chunk=decode_chunk):
-                if area is None:
-                    area = torch.empty(video_info(avi_path)["frames"], dtype=torch.int32, device=dev)
-                area[i0:i0 + part.shape[0]] = masks_for_clip(part, model)[0]
-            return kinematic_features_device(area)
+            n = video_info(avi_path)["frames"]
+            lo, hi = sharding.shard_range(n, rank, world)
+            local = torch.empty(hi - lo, dtype=torch.int32, device=dev)
+            workers = max(1, decode_workers() // _local_world(world))
+            for i0, part in iter_gray_chunks(avi_path, dev, workers=workers, chunk=decode_chunk,
+                                             frame_range=(lo, hi) if world > 1 else None):
+                local[i0 - lo:i0 - lo + part.shape[0]] = masks_for_clip(part, model)[0]
+            return kinematic_features_device(sharding.gather_area(local, n, group))
         except _DecodeFallback:
             pass
+        # sequential decode (any codec): every rank reads the file, segments its own range
         gray = decode_gray_clip(avi_path, dev, workers=1)
         if gray is None:
             return None
-        area, _ = masks_for_clip(gray, model)
-        return kinematic_features_device(area)
+        n = gray.shape[0]
+        lo, hi = sharding.shard_range(n, rank, world)
+        if hi > lo:
+            local, _ = masks_for_clip(gray[lo:hi], model)
+        else:
+            local = torch.empty(0, dtype=torch.int32, device=dev)
+        return kinematic_features_device(sharding.gather_area(local, n, group))
     frames_bgr = load_frames_bgr(avi_path)
     if not frames_bgr:
         return None

@@ -160,12 +160,17 @@ def load_frames_bgr_parallel(avi_path: str, workers: int | None = None,
     return list(clip)
 
 
-def parallel_decodable(info: dict, workers: int, min_frames: int = 256) -> bool:
-    """Whether a clip (``video_info``) is decoded by several ``RangeDecoder``s: an intra-only
-    codec, a plausible header and enough frames to be worth it."""
-    return (workers >= 2 and info["frames"] >= max(min_frames, 2 * workers)
-            and info["height"] > 0 and info["width"] > 0
+def seekable_clip(info: dict) -> bool:
+    """Whether a clip (``video_info``) can be read by frame ranges: an intra-only codec (a seek is
+    frame-exact) and a plausible header."""
+    return (info["frames"] > 0 and info["height"] > 0 and info["width"] > 0
             and info["fourcc"] in _INTRA_ONLY_FOURCC)
+
+
+def parallel_decodable(info: dict, workers: int, min_frames: int = 256) -> bool:
+    """Whether a clip is decoded by several ``RangeDecoder``s: seekable and enough frames to be
+    worth it."""
+    return workers >= 2 and info["frames"] >= max(min_frames, 2 * workers) and seekable_clip(info)
 
 
 def bgr_to_gray(frames_bgr: torch.Tensor) -> torch.Tensor:
