@@ -99,10 +99,11 @@ class RangeDecoder:
                 return 0
             self.pos = start
         for i in range(stop - start):
-            ok, frm = self.cap.read(dst[i])
-            if not ok or frm.shape != dst[i].shape:
+            view = dst[i]
+            ok, frm = self.cap.read(view)
+            if not ok or frm.shape != view.shape:
                 return i
-            if frm.ctypes.data != dst[i].ctypes.data:   # OpenCV allocated its own: copy
+            if frm is not view:   # OpenCV allocated its own array: copy
                 dst[i] = frm
             self.pos += 1
         return stop - start
