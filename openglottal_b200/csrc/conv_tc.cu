@@ -777,8 +777,8 @@ int launch_conv_tc(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloa
     // 2 sub-tiles (4 accumulators) per tile. Measured alternatives (experiment switches):
     // 1 sub-tile for N = 128 (OGL_S128=1) or for the transposed conv (OGL_ST=1) doubles the
     // weight traffic per pixel and is slower although TMEM could then be double-buffered.
-    static const int s_env = getenv("OGL_S128") ? atoi(getenv("OGL_S128")) : 2;
-    static const int st_env = getenv("OGL_ST") ? atoi(getenv("OGL_ST")) : 2;
+    static const int s_env = env_knob("OGL_S128", 2, 1, 2);
+    static const int st_env = env_knob("OGL_ST", 2, 1, 2);
     p.S = (L.taps == 1 && L.N == 128) ? st_env : ((L.N == 128) ? s_env : 2);
     p.tiles_x = (W + 15) / 16;
     p.tiles_y = (H + 15) / 16;
@@ -786,7 +786,7 @@ int launch_conv_tc(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloa
     // Transposed conv on CTA pairs (OGL_CONVT_PAIR=1, experiment): ONE sub-tile per CTA, so that
     // TMEM holds two accumulator sets and the pixel-shuffle epilogue of a tile overlaps the MMAs
     // of the next one, while the pair still fetches each weight column once per 512 pixels.
-    static const int convt_pair_env = getenv("OGL_CONVT_PAIR") ? atoi(getenv("OGL_CONVT_PAIR")) : 0;
+    static const int convt_pair_env = env_knob("OGL_CONVT_PAIR", 0, 0, 1);
     const bool convt_pair = convt_pair_env && L.epi == EPI_CONVT && L.N == 128 && L.wpack2 &&
                             cta_group >= 2 && num_sms >= 2 &&
                             p.total_sub >= (cta_group == 3 ? 2 : num_sms);
@@ -797,18 +797,18 @@ int launch_conv_tc(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloa
     if (static_cast<unsigned long long>(p.total_sub) * (p.tiles_x * p.tiles_y) >= (1ull << 40))
         return fail("batch too large for the tile decoder");
     p.acc_bufs = (2 * p.S * p.N <= 256) ? 2 : 1;
-    static const int split_env = getenv("OGL_SPLIT") ? atoi(getenv("OGL_SPLIT")) : 1;
+    static const int split_env = env_knob("OGL_SPLIT", 1, 0, 1);
     p.split = split_env;
     static const int dbg_env = experiment_dbg();
     p.dbg = dbg_env;
-    static const int half_env = getenv("OGL_ACC_HALF") ? atoi(getenv("OGL_ACC_HALF")) : 1;
+    static const int half_env = env_knob("OGL_ACC_HALF", 1, 0, 1);
     p.acc_half = half_env;
     const int tps = taps_per_stage(L);
     // CTA pairs (cta_group::2) for the conv3x3 layers with N >= 64 when there is enough work
     // (cta_group 2), or whenever possible (cta_group 3: unit tests on small inputs)
     // Layers with a single 32-channel K block (downs.1.net.0) are faster unpaired (measured):
     // the pair's per-tile hand-shakes are not amortised over so short a K loop.
-    static const int minkb_env = getenv("OGL_CG_MINKB") ? atoi(getenv("OGL_CG_MINKB")) : 2;
+    static const int minkb_env = env_knob("OGL_CG_MINKB", 2, 1, 64);
     const bool pair = convt_pair ||
                       (cta_group >= 2 && L.wpack2 && L.taps == 9 && (L.N == 64 || L.N == 128) &&
                        (L.epi == EPI_RELU || L.epi == EPI_RELU_POOL) && p.S == 2 &&
@@ -834,10 +834,10 @@ int launch_conv_tc(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloa
     // transposed conv: a K block is only 2 x 16 KB and the two halves of a tile drift apart by at
     // most the ring's depth (acc_half), so its ring may be deeper (OGL_NA_CONVT)
     // (measured: ups.4 0.39 -> 0.36 ms with 4..6 stages)
-    static const int na_convt_env = getenv("OGL_NA_CONVT") ? atoi(getenv("OGL_NA_CONVT")) : 5;
+    static const int na_convt_env = env_knob("OGL_NA_CONVT", 5, 2, 8);
     if (L.epi == EPI_CONVT && na_convt_env > 0) p.na = na_convt_env;
-    static const int na_env = getenv("OGL_NA") ? atoi(getenv("OGL_NA")) : 0;
-    static const int nw_env = getenv("OGL_NW") ? atoi(getenv("OGL_NW")) : 0;
+    static const int na_env = env_knob("OGL_NA", 0, 2, 8);   // 0: automatic
+    static const int nw_env = env_knob("OGL_NW", 0, 2, 8);
     if (na_env > 0) p.na = na_env;
     if (nw_env > 0) p.nw = nw_env;
     while (p.nw > 2 && smem_need(p.na, p.nw) > static_cast<size_t>(kMaxSmem)) --p.nw;
@@ -873,7 +873,7 @@ int launch_conv_tc(const TcLayer& L, const __nv_bfloat16* src0, const __nv_bfloa
     }
     const int items = p.npass * p.num_tiles;
     const int grid = items < num_sms ? items : num_sms;
-    static const int pf_env = getenv("OGL_PASSFAST") ? atoi(getenv("OGL_PASSFAST")) : 1;
+    static const int pf_env = env_knob("OGL_PASSFAST", 1, 0, 1);
     p.pass_fast = (pf_env && p.npass > 1 && grid % p.npass == 0) ? 1 : 0;
     if (L.epi == EPI_CONVT) return launch_epi<EPI_CONVT, 1>(tm0, tm1, p, grid, smem, stream);
     if (L.epi == EPI_HEAD) return launch_epi<EPI_HEAD, 9>(tm0, tm1, p, grid, smem, stream);

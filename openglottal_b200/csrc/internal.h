@@ -1,5 +1,6 @@
 // Internal (non-ABI) declarations shared by the translation units of libopenglottal_b200.so.
 #pragma once
+#include <cstdio>
 #include <cstdlib>
 #include <cstddef>
 #include <cstdint>
@@ -137,6 +138,22 @@ inline int experiment_dbg() {
     const char* dbg = getenv("OGL_DBG");
     const char* on = getenv("OGL_EXPERIMENT");
     return (dbg && on && atoi(on) != 0) ? atoi(dbg) : 0;
+}
+
+// Experiment knobs (ring depths, issuer counts, ...) come from the environment, read once per process.
+// A value outside [lo, hi] is refused (the default is used and one line goes to stderr): a stray or
+// mistyped variable must not be able to build a ring the kernels' barrier protocol cannot run.
+inline int env_knob(const char* name, int dflt, int lo, int hi) {
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    char* end = nullptr;
+    const long x = strtol(v, &end, 10);
+    if (end == v || *end != '\0' || x < lo || x > hi) {
+        fprintf(stderr, "openglottal_b200: %s=%s ignored (allowed %d..%d, default %d)\n", name, v, lo,
+                hi, dflt);
+        return dflt;
+    }
+    return static_cast<int>(x);
 }
 
 constexpr int kS2dMaxStages = 8;

@@ -1459,8 +1459,8 @@ int launch_s2d_tc(const S2dLayer& L, const __nv_bfloat16* src_s2d, const __nv_bf
         p.stem_b = stem_tc_blob;   // non-null: the stem runs on the tensor cores (STEM >= 2)
         // 8 warps: bf16 im2col x bf16 weights; 16 warps: f16 im2col x f16 weights (a mixed
         // f16 x bf16 descriptor, OGL_STEM3_BFMT=1 with a bf16 blob, traps: illegal instruction)
-        static const int bfmt_env = getenv("OGL_STEM3_BFMT") ? atoi(getenv("OGL_STEM3_BFMT")) : 0;
-        static const int lo_env = getenv("OGL_STEM_LO") ? atoi(getenv("OGL_STEM_LO")) : 1;
+        static const int bfmt_env = env_knob("OGL_STEM3_BFMT", 0, 0, 1);
+        static const int lo_env = env_knob("OGL_STEM_LO", 1, 0, 1);
         p.stem_lo = lo_env;
         p.stem_idesc = stem_tc_warps == 16 ? make_idesc_ab(32, 0u, bfmt_env ? 1u : 0u)
                                            : make_idesc_fmt(32, 1u);
@@ -1498,7 +1498,7 @@ int launch_s2d_tc(const S2dLayer& L, const __nv_bfloat16* src_s2d, const __nv_bf
     // weights leave one CTA only 3 activation stages (measured 1.57 -> 1.12 ms; the HBM-bound
     // downs.0.net.3 is slower paired, 0.85 -> 1.05 ms, and ups.7.net.3 unchanged), when there
     // is a tile per SM. cta_group 3 (unit tests): whenever there are two tiles.
-    static const int pair_all_env = getenv("OGL_S2D_PAIR_ALL") ? atoi(getenv("OGL_S2D_PAIR_ALL")) : 0;
+    static const int pair_all_env = env_knob("OGL_S2D_PAIR_ALL", 0, 0, 1);
     const bool pair = !fused_stem && cta_group >= 2 && L.wblob2 && num_sms >= 2 &&
                       (cta_group == 3 ? p.num_tiles >= 2
                                       : (p.num_tiles >= num_sms && (L.cin_b > 0 || pair_all_env)));
@@ -1513,16 +1513,18 @@ int launch_s2d_tc(const S2dLayer& L, const __nv_bfloat16* src_s2d, const __nv_bf
     // three) and two issuer warps; the three-stage tile of the composed layer (CTA pair, HBM-bound)
     // with ONE issuer over its six stages (1.16 instead of 1.25 ms).
     int nslots = L.cin_b > 0 ? 6 : 4;
-    static const int ns_env = getenv("OGL_S2D_SLOTS") ? atoi(getenv("OGL_S2D_SLOTS")) : 0;
-    static const int ns_head_env = getenv("OGL_S2D_SLOTS_HEAD") ? atoi(getenv("OGL_S2D_SLOTS_HEAD")) : 0;
+    static const int ns_env = env_knob("OGL_S2D_SLOTS", 0, 2, kSdMax);   // 0: per layer
+    static const int ns_head_env = env_knob("OGL_S2D_SLOTS_HEAD", 0, 2, kSdMax);
     if (ns_env > 0) nslots = ns_env;
     if (ns_head_env > 0 && L.cin_b == 0 && !fused_stem) nslots = ns_head_env;
     while (nslots > 2 && fixed + static_cast<size_t>(nslots) * (kSlot + 16) > kMaxSmem) --nslots;
     const size_t smem = fixed + static_cast<size_t>(nslots) * (kSlot + 16);
     if (smem > static_cast<size_t>(kMaxSmem)) return fail("s2d layer: shared memory budget exceeded");
+    if (nslots < p.n_stages)
+        return fail("s2d layer: the activation ring must hold at least one tile's stages");
     p.nslots = nslots;
-    static const int dual_env = getenv("OGL_DUAL") ? atoi(getenv("OGL_DUAL")) : 1;
-    static const int dual_below_env = getenv("OGL_DUAL_BELOW") ? atoi(getenv("OGL_DUAL_BELOW")) : 0;
+    static const int dual_env = env_knob("OGL_DUAL", 1, 0, 1);
+    static const int dual_below_env = env_knob("OGL_DUAL_BELOW", 0, 0, 1);
     p.dual = (dual_env && nslots >= 2 * p.n_stages && (L.cin_b == 0 || dual_below_env)) ? 1 : 0;
 
     CUtensorMap tmS, tmB;
