@@ -372,6 +372,7 @@ def extract_features_unet(avi_path: str, detector, model, device=None, *,
         # the other ranks are never decoded), with its share of the host's decoder threads; the
         # int32 areas are all-gathered, so every rank returns the same dict.
         rank, world = sharding.rank_world(group)
+        fell_back = False
         try:
             n = video_info(avi_path)["frames"]
             lo, hi = sharding.shard_range(n, rank, world)
@@ -380,9 +381,12 @@ def extract_features_unet(avi_path: str, detector, model, device=None, *,
             for i0, part in iter_gray_chunks(avi_path, dev, workers=workers, chunk=decode_chunk,
                                              frame_range=(lo, hi) if world > 1 else None):
                 local[i0 - lo:i0 - lo + part.shape[0]] = masks_for_clip(part, model)[0]
-            return kinematic_features_device(sharding.gather_area(local, n, group))
         except _DecodeFallback:
-            pass
+            fell_back = True
+        # a short read or a wrong header shows up only on the rank whose range it falls into: the
+        # ranks agree before the gather, or they would wait for each other in different collectives
+        if not sharding.agree_any(fell_back, dev, group):
+            return kinematic_features_device(sharding.gather_area(local, n, group))
         # sequential decode (any codec): every rank reads the file, segments its own range
         gray = decode_gray_clip(avi_path, dev, workers=1)
         if gray is None:

@@ -33,6 +33,18 @@ def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
     return lo, hi
 
 
+def agree_any(flag: bool, device, group=None) -> bool:
+    """True on every rank when ``flag`` is true on ANY rank (one 4-byte all-reduce; no collective
+    with a single rank). Ranks that must take the same branch before a collective -- e.g. "my part
+    of the file could not be read by range, decode sequentially" -- agree through this."""
+    _, world = rank_world(group)
+    if world == 1:
+        return bool(flag)
+    t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return bool(t.item())
+
+
 def gather_area(local: torch.Tensor, n: int, group=None) -> torch.Tensor:
     """All-gather the per-rank int32 area shards into the full ``(n,)`` waveform, in frame
     order, on every rank. Shards are padded to ceil(n/R) so one ``all_gather_into_tensor``

@@ -83,6 +83,7 @@ class UNet(nn.Module):
         self.use_graphs = True       # small batches: replay the forward's launches as one CUDA graph
         self.graph_max_batch = 128   # (a forward is ~20 launches; at batch 32 they take ~1 ms of
                                      # GPU time, the same order as enqueueing them one by one)
+        self.graph_cache_entries = 16   # captured call signatures kept (each owns static buffers)
         self._handle = None
         self._handle_device = None
         self._packed_sig = None
@@ -272,6 +273,10 @@ class UNet(nn.Module):
                        ws.data_ptr())
                 ent = self._graphs.get(key)
                 if ent is None:
+                    if len(self._graphs) >= self.graph_cache_entries:
+                        # every entry owns static input / output buffers: a caller that walks many
+                        # batch sizes must not accumulate them (oldest signature goes first)
+                        self._graphs.pop(next(iter(self._graphs)))
                     ent = self._graphs[key] = [0, None, None, None]
                 ent[0] += 1
                 if ent[0] == 2:          # second call with this signature: capture

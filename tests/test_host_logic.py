@@ -105,6 +105,9 @@ for n in (9, 10, 1, 1001):
     lo, hi = sharding.shard_range(n, rank, world)
     got = sharding.gather_area(full[lo:hi].clone(), n)
     assert torch.equal(got, full), (n, rank, got[:5])
+# ranks agree on a branch before a collective (extract_features_unet's decode fallback)
+assert sharding.agree_any(rank == world - 1, "cpu") is True
+assert sharding.agree_any(False, "cpu") is False
 dist.barrier()
 dist.destroy_process_group()
 print("ok", rank)
