@@ -15,6 +15,10 @@ Outputs (all small, committed):
   overlay.npz              reference `_draw_overlay` (scripts/infer.py) on a seeded frame and mask
   gated.json               reference `extract_features_unet(clip, detector, model, cpu)` with a
                            scripted detector (boxes listed in the file)
+  gaw_512x256.json         reference `extract_gaw_features` (scripts/analyze_gaw.py:75-100) on a
+                           seeded 512(H) x 256(W) clip (frames regenerated from the seed), scripted
+                           boxes, capture rate 4000 fps: the BAGLS-shaped reference-resize path
+                           (`python tests/golden/make_golden.py gaw` writes this file alone)
 
 The state dict is regenerated from its seed at test time (oracle.synth.calibrated_state uses only
 a CPU torch.Generator), so no weights are committed.
@@ -152,7 +156,32 @@ def overlay_golden():
     np.savez_compressed(HERE / "overlay.npz", **out)
 
 
+def gaw_golden():
+    """scripts/analyze_gaw.py:75-100 on BAGLS-shaped frames: every frame is squashed to 256 x 256
+    and the probability resized back (utils.py:234-240), the area is counted inside the box, f0 is
+    converted to Hz."""
+    sys.path.insert(0, "/root/reference/scripts")
+    from analyze_gaw import extract_gaw_features
+
+    sd = synth.calibrated_state(0)
+    model = UNet(1, 1, (32, 64, 128, 256))
+    model.load_state_dict(sd)
+    model.eval()
+    n, hgt, wid, seed, period, fps = 16, 512, 256, 91, 5.0, 4000.0
+    clip, _ = synth.glottis_clip(n, hgt, wid, seed=seed, period=period)
+    boxes = scripted_boxes(n, hgt, wid, seed=92)
+    frames_bgr = [cv2.cvtColor(f, cv2.COLOR_GRAY2BGR) for f in clip]
+    feats = extract_gaw_features(frames_bgr, fps, ScriptedDetector(boxes), model, torch.device("cpu"))
+    (HERE / "gaw_512x256.json").write_text(json.dumps({
+        "clip": {"n": n, "height": hgt, "width": wid, "seed": seed, "period": period},
+        "capture_fps": fps, "boxes": boxes, "features": jsonable(feats)}))
+
+
 def main():
+    if sys.argv[1:] == ["gaw"]:
+        gaw_golden()
+        return
+    gaw_golden()
     features_kat()
     crops_and_metrics()
     overlay_golden()

@@ -246,6 +246,45 @@ def test_gaw_features_and_annotation(lib, native_model, trained_sd, tmp_path):
     assert ok and frm.shape == (256, 256, 3)
 
 
+def test_gaw_features_512x256_match_reference_golden(lib, calibrated_sd):
+    """extract_gaw_features on BAGLS-shaped 512(H) x 256(W) frames against the reference's own
+    output (gaw_512x256.json, scripts/analyze_gaw.py:75-100): the frames must go through the
+    reference's resize -> forward -> resize(prob) -> threshold order (the helpers in
+    analysis.py once ran the network at the frames' own size). Calibrated RANDOM weights, hence the
+    fp32 validation mode, as for gated.json; annotate_unet_only shares the same masks."""
+    import cv2
+    import openglottal_b200 as ogl
+    from openglottal_b200.analysis import annotate_unet_only, extract_gaw_features
+    from oracle import synth
+
+    ref = json.loads((GOLDEN / "gaw_512x256.json").read_text())
+    c = ref["clip"]
+    clip, _ = synth.glottis_clip(c["n"], c["height"], c["width"], seed=c["seed"], period=c["period"])
+    frames_bgr = [cv2.cvtColor(f, cv2.COLOR_GRAY2BGR) for f in clip]
+    boxes = [None if b is None else tuple(b) for b in ref["boxes"]]
+    m = ogl.UNet().to("cuda")
+    m.load_state_dict(calibrated_sd)
+    m.eval()
+    m.precision = "fp32"
+    det = ScriptedDetector(boxes)
+    got = extract_gaw_features(frames_bgr, ref["capture_fps"], det, m)
+    assert det.resets == 1 and det.i == len(boxes)
+    want = ref["features"]
+    area = np.array(want["_area"])
+    err = np.abs(got["_area"] - area)
+    print("gaw 512x256 area max abs err", err.max(), "max area", area.max())
+    # fp32 kernels vs torch CPU fp32 on random weights: a handful of pixels of 131 072 sit within
+    # rounding of the threshold (running at the frames' own size instead would be off by hundreds)
+    assert err.max() <= 4.0
+    assert got["f0"] == pytest.approx(want["f0"], rel=1e-9)          # Hz
+    for k in ("area_mean", "area_std", "open_quotient", "periodicity"):
+        assert got[k] == pytest.approx(want[k], rel=5e-3, abs=1e-3), k
+    # the overlay path segments the same way: its ungated waveform bounds the gated one
+    annotated, wave = annotate_unet_only(frames_bgr, m)
+    assert annotated[0].shape == (c["height"], c["width"], 3)
+    assert all(w + 4.0 >= a for w, a in zip(wave, area))
+
+
 def test_unet_only_pipeline_on_512x256_video_reference_resize(lib, native_model, trained_sd, tmp_path):
     """BASELINE.json configs[2] through the pipeline: BAGLS-shaped 512(H) x 256(W) frames take the
     reference's resize path (utils.py:234-241: squash to 256x256, upsample the probability), here

@@ -249,3 +249,24 @@ def test_resize_oracle_reproduces_reference_masks(calibrated_sd):
     logits = uo.ref_forward(calibrated_sd, uo.frames_to_input(small[None]))[0, 0].numpy()
     got = ro.segment_frame_restated(logits, 96, 128) > 0
     assert (got != ref).sum() <= 2
+
+
+def test_gaw_oracle_matches_reference_512x256(calibrated_sd):
+    """gaw_512x256.json: the reference's extract_gaw_features (scripts/analyze_gaw.py:75-100) on
+    BAGLS-shaped frames -- squash to 256 x 256, probability resized back, gated count, f0 in Hz."""
+    from oracle import pipeline_oracle as po, synth, unet_oracle as uo
+    from oracle.features_oracle import kinematic_features
+
+    ref = json.loads((GOLDEN / "gaw_512x256.json").read_text())
+    c = ref["clip"]
+    clip, _ = synth.glottis_clip(c["n"], c["height"], c["width"], seed=c["seed"], period=c["period"])
+    boxes = [None if b is None else tuple(b) for b in ref["boxes"]]
+    masks = [uo.segment_frame(calibrated_sd, f) for f in clip]
+    assert masks[0].shape == (c["height"], c["width"])
+    wave = po.gated_area_wave(masks, boxes)
+    want = ref["features"]
+    assert np.abs(np.array(wave) - np.array(want["_area"])).max() <= 2
+    feats = kinematic_features(want["_area"])
+    assert feats["f0"] * ref["capture_fps"] == pytest.approx(want["f0"], rel=1e-12)
+    for k in ("area_mean", "area_std", "open_quotient", "periodicity", "cv"):
+        assert feats[k] == pytest.approx(want[k], rel=1e-12, abs=1e-12), k
