@@ -1520,8 +1520,6 @@ int launch_s2d_tc(const S2dLayer& L, const __nv_bfloat16* src_s2d, const __nv_bf
     while (nslots > 2 && fixed + static_cast<size_t>(nslots) * (kSlot + 16) > kMaxSmem) --nslots;
     const size_t smem = fixed + static_cast<size_t>(nslots) * (kSlot + 16);
     if (smem > static_cast<size_t>(kMaxSmem)) return fail("s2d layer: shared memory budget exceeded");
-    if (nslots < p.n_stages)
-        return fail("s2d layer: the activation ring must hold at least one tile's stages");
     p.nslots = nslots;
     static const int dual_env = env_knob("OGL_DUAL", 1, 0, 1);
     static const int dual_below_env = env_knob("OGL_DUAL_BELOW", 0, 0, 1);

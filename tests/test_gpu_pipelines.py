@@ -275,7 +275,7 @@ def test_gaw_features_512x256_match_reference_golden(lib, calibrated_sd):
     print("gaw 512x256 area max abs err", err.max(), "max area", area.max())
     # fp32 kernels vs torch CPU fp32 on random weights: a handful of pixels of 131 072 sit within
     # rounding of the threshold (running at the frames' own size instead would be off by hundreds)
-    assert err.max() <= 4.0
+    assert err.max() <= 2.0      # measured 0.0 on B200 (profiles/pytest_gpu_r02_v4.log)
     assert got["f0"] == pytest.approx(want["f0"], rel=1e-9)          # Hz
     for k in ("area_mean", "area_std", "open_quotient", "periodicity"):
         assert got[k] == pytest.approx(want[k], rel=5e-3, abs=1e-3), k
