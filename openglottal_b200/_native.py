@@ -98,6 +98,13 @@ def load() -> C.CDLL:
             f"{lib_path} is missing: run `python -m openglottal_b200.build` (needs nvcc). "
             "openglottal_b200 has no CPU or PyTorch fallback."
         )
+    _lib = load_path(lib_path)
+    return _lib
+
+
+def load_path(lib_path) -> C.CDLL:
+    """Bind the C ABI of the library at ``lib_path`` (not cached: same-process comparisons of two
+    builds, scripts/byte_ops_bench.py)."""
     lib = C.CDLL(str(lib_path))
     vp, i32, i64, sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
     lib.ogl_version.restype = i32
@@ -171,7 +178,6 @@ def load() -> C.CDLL:
     lib.ogl_debug_s2d_program.argtypes = [_c_float_p, _c_float_p, i32, _c_float_p, _c_float_p, vp,
                                           sz, C.POINTER(sz), vp, i32, C.POINTER(i32), vp,
                                           C.POINTER(i32), vp]
-    _lib = lib
     return lib
 
 

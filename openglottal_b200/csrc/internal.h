@@ -156,6 +156,17 @@ inline int env_knob(const char* name, int dflt, int lo, int hi) {
     return static_cast<int>(x);
 }
 
+// grid.x of the per-frame byte kernels (grid.y = frame): `units` work items per frame (16-byte words,
+// 4-pixel groups ...), `per_thread` of them per thread of a 256-thread block when the batch fills
+// the GPU, fewer per thread (more blocks) when it does not.
+inline int frame_chunks(long long units, int per_thread, int n) {
+    long long c = (units + 256LL * per_thread - 1) / (256LL * per_thread);
+    const long long cmax = (units + 255) / 256;
+    while (c < cmax && c * n < 148 * 8) c *= 2;
+    if (c > cmax) c = cmax;
+    return static_cast<int>(c < 1 ? 1 : (c > 64 ? 64 : c));
+}
+
 constexpr int kS2dMaxStages = 8;
 struct S2dLayer {
     uint8_t* wblob = nullptr;  // device: B tiles in op order

@@ -87,6 +87,69 @@ resize_u8_linear_kernel(const uint8_t* __restrict__ src, int SH, int SW, uint8_t
     }
 }
 
+// The same arithmetic with the per-column and per-row (index, coefficient) pairs computed once per
+// block into shared memory -- lin_pos is a double-precision division, two per pixel before -- and
+// four output bytes per store. tab[0..DW) = columns {s0, s1, a0, a1}, tab[DW..DW+DH) = rows
+// {s0, s1, b0, b1}. DW % 4 == 0, dst 4-byte aligned.
+__global__ void __launch_bounds__(256)
+resize_u8_linear_tab_kernel(const uint8_t* __restrict__ src, int SH, int SW,
+                            uint8_t* __restrict__ dst, int DH, int DW) {
+    extern __shared__ int4 tab_u8[];
+    for (int i = threadIdx.x; i < DW + DH; i += blockDim.x) {
+        const Lin l = i < DW ? lin_x(i, SW, DW) : lin_y(i - DW, SH, DH);
+        tab_u8[i] = make_int4(l.s0, l.s1, coef11(__fsub_rn(1.f, l.f)), coef11(l.f));
+    }
+    __syncthreads();
+    const int n = blockIdx.y;
+    const uint8_t* s = src + static_cast<size_t>(n) * SH * SW;
+    uint32_t* d = reinterpret_cast<uint32_t*>(dst + static_cast<size_t>(n) * DH * DW);
+    const int quads = DW >> 2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < DH * quads; i += gridDim.x * blockDim.x) {
+        const int y = i / quads, x0 = (i - y * quads) << 2;
+        const int4 ty = tab_u8[DW + y];
+        const uint8_t* r0p = s + static_cast<size_t>(ty.x) * SW;
+        const uint8_t* r1p = s + static_cast<size_t>(ty.y) * SW;
+        uint32_t out = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int4 tx = tab_u8[x0 + j];
+            const int r0 = r0p[tx.x] * tx.z + r0p[tx.y] * tx.w;
+            const int r1 = r1p[tx.x] * tx.z + r1p[tx.y] * tx.w;
+            const int v = (((ty.z * (r0 >> 4)) >> 16) + ((ty.w * (r1 >> 4)) >> 16) + 2) >> 2;
+            out |= static_cast<uint32_t>(v < 0 ? 0 : (v > 255 ? 255 : v)) << (8 * j);
+        }
+        d[i] = out;
+    }
+}
+
+// src = 2 dst on both axes (cv2's 2x2 area mean): 8 source bytes of two rows per thread, 4 output
+// bytes per store. SW % 8 == 0, src 8-byte and dst 4-byte aligned.
+__global__ void __launch_bounds__(256)
+resize_u8_area2x2_vec_kernel(const uint8_t* __restrict__ src, int SW, uint8_t* __restrict__ dst,
+                             int DH, int DW) {
+    const int n = blockIdx.y;
+    const uint8_t* s = src + static_cast<size_t>(n) * (2 * DH) * SW;
+    uint32_t* d = reinterpret_cast<uint32_t*>(dst + static_cast<size_t>(n) * DH * DW);
+    const int quads = DW >> 2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < DH * quads; i += gridDim.x * blockDim.x) {
+        const int y = i / quads, xq = i - y * quads;
+        const uint2 a = __ldg(reinterpret_cast<const uint2*>(s + static_cast<size_t>(2 * y) * SW) + xq);
+        const uint2 b = __ldg(reinterpret_cast<const uint2*>(s + static_cast<size_t>(2 * y + 1) * SW) + xq);
+        const uint32_t aw[2] = {a.x, a.y}, bw[2] = {b.x, b.y};
+        uint32_t out = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = 2 * j;                           // first of the two source columns
+            const uint32_t t = ((aw[k >> 2] >> (8 * (k & 3))) & 0xffu) +
+                               ((aw[(k + 1) >> 2] >> (8 * ((k + 1) & 3))) & 0xffu) +
+                               ((bw[k >> 2] >> (8 * (k & 3))) & 0xffu) +
+                               ((bw[(k + 1) >> 2] >> (8 * ((k + 1) & 3))) & 0xffu);
+            out |= ((t + 2u) >> 2) << (8 * j);
+        }
+        d[i] = out;
+    }
+}
+
 __device__ __forceinline__ float sigmoidf(float z) { return 1.f / (1.f + expf(-z)); }
 
 // grid = (chunks, n). identity (DH, DW) == (SH, SW): the reference skips the resize.
@@ -129,6 +192,61 @@ prob_resize_mask_kernel(const float* __restrict__ logits, int SH, int SW, int DH
     }
 }
 
+// The resizing case with the (index, fraction) pairs of the columns and rows in shared memory
+// (tab[0..DW) columns, tab[DW..DW+DH) rows; .z holds the bits of the f32 fraction) and four mask
+// bytes per store. Same products and sums in the same order as above. DW % 4 == 0, mask 4-byte
+// aligned (or absent).
+__global__ void __launch_bounds__(256)
+prob_resize_mask_tab_kernel(const float* __restrict__ logits, int SH, int SW, int DH, int DW,
+                            float threshold, uint8_t* __restrict__ mask, int32_t* __restrict__ area) {
+    extern __shared__ int4 tab_f32[];
+    __shared__ int scratch[8];
+    for (int i = threadIdx.x; i < DW + DH; i += blockDim.x) {
+        const Lin l = i < DW ? lin_x(i, SW, DW) : lin_y(i - DW, SH, DH);
+        tab_f32[i] = make_int4(l.s0, l.s1, __float_as_int(l.f), 0);
+    }
+    __syncthreads();
+    const int n = blockIdx.y;
+    const float* z = logits + static_cast<size_t>(n) * SH * SW;
+    uint32_t* m = mask ? reinterpret_cast<uint32_t*>(mask + static_cast<size_t>(n) * DH * DW) : nullptr;
+    const int quads = DW >> 2;
+    int cnt = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < DH * quads; i += gridDim.x * blockDim.x) {
+        const int y = i / quads, x0 = (i - y * quads) << 2;
+        const int4 ty = tab_f32[DW + y];
+        const float fy = __int_as_float(ty.z);
+        const float b0 = __fsub_rn(1.f, fy), b1 = fy;
+        const float* r0p = z + static_cast<size_t>(ty.x) * SW;
+        const float* r1p = z + static_cast<size_t>(ty.y) * SW;
+        uint32_t out = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int4 tx = tab_f32[x0 + j];
+            const float fx = __int_as_float(tx.z);
+            const float a0 = __fsub_rn(1.f, fx), a1 = fx;
+            const float r0 = __fadd_rn(__fmul_rn(sigmoidf(r0p[tx.x]), a0), __fmul_rn(sigmoidf(r0p[tx.y]), a1));
+            const float r1 = __fadd_rn(__fmul_rn(sigmoidf(r1p[tx.x]), a0), __fmul_rn(sigmoidf(r1p[tx.y]), a1));
+            const float v = __fadd_rn(__fmul_rn(r0, b0), __fmul_rn(r1, b1));
+            if (v > threshold) {
+                out |= 0xffu << (8 * j);
+                ++cnt;
+            }
+        }
+        if (m) m[i] = out;
+    }
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0 && area) {
+        int t = 0;
+        for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) t += scratch[w];
+        if (t) atomicAdd(area + n, t);
+    }
+}
+
+constexpr size_t kMaxTabBytes = 40 * 1024;   // index tables in (default-limit) shared memory
+inline bool aligned_to(const void* p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+
 inline int chunks_for(long long work) {
     long long c = (work + 256 * 8 - 1) / (256 * 8);
     return static_cast<int>(c < 1 ? 1 : (c > 64 ? 64 : c));
@@ -145,7 +263,17 @@ int launch_resize_u8_linear(const uint8_t* src, int n, int SH, int SW, uint8_t* 
     }
     const int area2x2 = (SH == 2 * DH && SW == 2 * DW) ? 1 : 0;
     dim3 grid(chunks_for(static_cast<long long>(DH) * DW), n);
-    resize_u8_linear_kernel<<<grid, 256, 0, stream>>>(src, SH, SW, dst, DH, DW, area2x2);
+    const size_t tab = sizeof(int4) * (static_cast<size_t>(DW) + DH);
+    const long long quads = static_cast<long long>(DH) * (DW / 4);
+    if (area2x2 && SW % 8 == 0 && aligned_to(src, 8) && aligned_to(dst, 4)) {
+        grid.x = frame_chunks(quads, 4, n);
+        resize_u8_area2x2_vec_kernel<<<grid, 256, 0, stream>>>(src, SW, dst, DH, DW);
+    } else if (!area2x2 && DW % 4 == 0 && tab <= kMaxTabBytes && aligned_to(dst, 4)) {
+        grid.x = frame_chunks(quads, 8, n);
+        resize_u8_linear_tab_kernel<<<grid, 256, tab, stream>>>(src, SH, SW, dst, DH, DW);
+    } else {
+        resize_u8_linear_kernel<<<grid, 256, 0, stream>>>(src, SH, SW, dst, DH, DW, area2x2);
+    }
     OGL_CUDA(cudaGetLastError());
     return 0;
 }
@@ -154,7 +282,15 @@ int launch_prob_resize_mask(const float* logits, int n, int SH, int SW, int DH, 
                             float threshold, uint8_t* mask, int32_t* area, cudaStream_t stream) {
     if (area) OGL_CUDA(cudaMemsetAsync(area, 0, sizeof(int32_t) * n, stream));
     dim3 grid(chunks_for(static_cast<long long>(DH) * DW), n);
-    prob_resize_mask_kernel<<<grid, 256, 0, stream>>>(logits, SH, SW, DH, DW, threshold, mask, area);
+    const size_t tab = sizeof(int4) * (static_cast<size_t>(DW) + DH);
+    const bool identity = SH == DH && SW == DW;
+    if (!identity && DW % 4 == 0 && tab <= kMaxTabBytes && (!mask || aligned_to(mask, 4))) {
+        grid.x = frame_chunks(static_cast<long long>(DH) * (DW / 4), 8, n);
+        prob_resize_mask_tab_kernel<<<grid, 256, tab, stream>>>(logits, SH, SW, DH, DW, threshold,
+                                                                mask, area);
+    } else {
+        prob_resize_mask_kernel<<<grid, 256, 0, stream>>>(logits, SH, SW, DH, DW, threshold, mask, area);
+    }
     OGL_CUDA(cudaGetLastError());
     return 0;
 }
