@@ -53,14 +53,16 @@ def ck(lib, rc):
         raise RuntimeError((lib.ogl_last_error() or b"?").decode())
 
 
-def random_boxes(n, hgt, wid, rng, exotic=False):
+def random_boxes(n, hgt, wid, rng, exotic=False, min_side=1):
+    """Every ninth box is None. ``min_side`` >= 8 keeps a crop from collapsing under letterboxing
+    (cv2.resize to a zero-sized image fails in the reference, _crop_geometry raises)."""
     boxes = []
     for i in range(n):
         if i % 9 == 4:
             boxes.append(None)
             continue
         x1, y1 = int(rng.integers(0, wid - 8)), int(rng.integers(0, hgt - 8))
-        x2, y2 = int(rng.integers(x1 + 1, wid + 1)), int(rng.integers(y1 + 1, hgt + 1))
+        x2, y2 = int(rng.integers(x1 + min_side, wid + 1)), int(rng.integers(y1 + min_side, hgt + 1))
         if exotic and i % 5 == 0:
             x1, x2 = x1 - wid, x2 if x2 < wid else wid + 7      # negative start, end past the edge
         if exotic and i % 11 == 3:
@@ -206,7 +208,7 @@ def main() -> None:
     del gt
 
     gray = u8((n, 256, 256))
-    lb_boxes = random_boxes(n, 256, 256, rng)
+    lb_boxes = random_boxes(n, 256, 256, rng, min_side=8)
     geom, geom_d = geom_for(lb_boxes, 256, 256, 256)
     crop_px = int(((geom[:, 2] - geom[:, 0]) * (geom[:, 3] - geom[:, 1])).sum())
     cont_px = int((geom[:, 6] * geom[:, 7]).sum())
@@ -248,10 +250,20 @@ def main() -> None:
              lambda o: o.overlap(m_odd, m_odd.flip(0).contiguous()), timing=False)
         g_odd = u8((6, 250, 300))
         for size in (256, 250, 64):
-            gm, gm_d = geom_for(random_boxes(6, 250, 300, rng), 250, 300, size)
+            gm, gm_d = geom_for(random_boxes(6, 250, 300, rng, min_side=8), 250, 300, size)
             cs = u8((6, size, size), sparse=True)
             case(f"letterbox_crops / unletterbox_area 250x300, size {size}", "ragged", 0,
                  lambda o: (o.letterbox(g_odd, gm_d, size), o.unletterbox(cs, gm_d, 250, 300)), timing=False)
+        for (sh, sw), (dh, dw) in (((256, 256), (512, 256)), ((96, 128), (384, 512)), ((480, 640), (120, 160)),
+                                   ((300, 200), (256, 256)), ((64, 64), (1024, 64)), ((1024, 64), (64, 64))):
+            lg = torch.randn((3, sh, sw), device=dev, generator=g) * 4
+            lg[0, 0, :7] = torch.tensor([float("inf"), float("-inf"), float("nan"), 0.0, -0.0, 88.0, -104.0],
+                                        device=dev)[: min(7, sw)]
+            case(f"prob_resize_mask {sh}x{sw} -> {dh}x{dw} (incl. inf / nan logits)", "ragged", 0,
+                 lambda o: o.prob(lg, dh, dw), timing=False)
+            src = u8((3, sh, sw))
+            case(f"resize_u8_linear {sh}x{sw} -> {dh}x{dw}", "ragged", 0, lambda o: o.resize(src, dh, dw),
+                 timing=False)
         flat = u8((3 * 100_003 + 64,))
         for off_s, off_d, px in ((0, 0, 100_003), (1, 0, 99_999), (0, 3, 4096), (16, 16, 15), (0, 0, 16)):
             def call(o, off_s=off_s, off_d=off_d, px=px):
