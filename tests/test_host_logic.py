@@ -169,6 +169,25 @@ def test_reference_arm_prints_the_contract_line():
     assert line["e2e"]["value"] == line["value"]
 
 
+def test_batched_cpu_figure_of_the_bench(calibrated_sd):
+    """bench.py's cpu_baseline.batch32 leg (a batched fp32 CPU forward beside the
+    reference's batch-1 loop): runs the reference module from oracle/_ref and returns (fps, frames);
+    None when the reference package is not vendored."""
+    sys.path.insert(0, str(ROOT))
+    import bench
+    from oracle import synth
+
+    frames, _ = synth.glottis_clip(2, 64, 64, seed=5)
+    got = bench.cpu_batched_fps(calibrated_sd, frames, seconds=0.01, batch=2)
+    if (ROOT / "oracle" / "_ref" / "openglottal").is_dir():
+        assert got is not None and got[0] > 0 and got[1] >= 2 and got[1] % 2 == 0
+    else:
+        assert got is None
+    # the algorithmic FLOPs the roofline is credited with: SURVEY App. A (reference formulation)
+    assert sum(bench.module_flops(256, 256).values()) == 24_066_916_352
+    assert sum(bench.module_flops(512, 256).values()) == 48_133_832_704
+
+
 @pytest.mark.parametrize("fourcc", ["MJPG", "FFV1"])
 def test_parallel_decode_equals_the_sequential_loop(tmp_path, fourcc, write_clip):
     """Frame ranges decoded by independent VideoCapture instances (intra-only codecs: frame-exact
